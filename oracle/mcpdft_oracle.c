@@ -1,0 +1,528 @@
+/*
+ * oracle/mcpdft_oracle.c -- TEST INFRASTRUCTURE ONLY.  Never linked into, imported by or
+ * executed from the product (openrdm_b200/); only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may use it, and only as the checker.
+ *
+ * A plain-C, serial restatement of OpenRDM's MC-PDFT energy hot path
+ *   mcpdft::mcpdft_energy            /root/reference/src/libmcpdft/energy.cc:27-188
+ *   mcpdft::MCPDFT::build_* / translate   src/libmcpdft/mcpdft.cc:35-416
+ *   mcpdft::Functional::E*           src/libfunc/functional.cc:12-309
+ * Each function cites the reference lines it follows and keeps the reference's loop order
+ * and operation order, so that on identical inputs it agrees with the reference's own
+ * compiled code (oracle/_ref, built from the sources under /root/reference by the Makefile
+ * here) to rounding.
+ *
+ * PARITY PINNING: the reference's golden values (tests/h2_t*_sto3g/eref.txt) cannot be
+ * reproduced in this checkout -- the quadrature weights (grids.txt) and gradients.txt are
+ * missing blobs (.MISSING_LARGE_BLOBS:1-3).  This port is therefore pinned against outputs
+ * of the reference itself run here (oracle/_ref; tests/test_oracle_vs_ref.py) and against
+ * fixtures generated from it (tests/golden/, made by tests/golden/make_golden.py).
+ *
+ * Storage convention = the reference's: matrices are column-major, phi(p,mu) at
+ * phi[p + mu*npts] (arma::mat(npts,nbfs), mcpdft.h:184); D2ab is (n*n) x (n*n) column-major
+ * with row = nu*n+mu, col = sigma*n+lambda (mcpdft.cc:204).
+ */
+#include <math.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+#define ORC_TOL 1.0e-20 /* mcpdft.cc:295,347; functional.cc:39,106,185 */
+
+typedef struct {
+  double e_tot, ex, ec, eclass;
+  double n_tot, n_a, n_b;       /* "Integrated total/alpha/beta density", mcpdft.cc:100-104 */
+  double trn_tot, trn_a, trn_b; /* "Integrated translated ... density", mcpdft.cc:339-343 */
+} orc_result;
+
+/* order of the optional per-point output vectors (orc_energy*'s `vecs` argument) */
+enum {
+  ORC_RHOA, ORC_RHOB, ORC_RHO,
+  ORC_RHOA_X, ORC_RHOA_Y, ORC_RHOA_Z, ORC_RHOB_X, ORC_RHOB_Y, ORC_RHOB_Z,
+  ORC_SIGMA_AA, ORC_SIGMA_AB, ORC_SIGMA_BB,
+  ORC_PI, ORC_R, ORC_TR_RHOA, ORC_TR_RHOB,
+  ORC_TR_SIGMA_AA, ORC_TR_SIGMA_AB, ORC_TR_SIGMA_BB,
+  ORC_PI_X, ORC_PI_Y, ORC_PI_Z,
+  ORC_NVEC
+};
+
+/* ------------------------------------------------------------------------------------------
+ * rho_a, rho_b, rho and the three integrated densities.   mcpdft.cc:42-105 (loop 74-94)
+ * sums[0..2] = { integral rho, integral rho_a, integral rho_b } accumulated in point order.
+ * ---------------------------------------------------------------------------------------- */
+void orc_density(size_t npts, int n, const double* phi, const double* D1a, const double* D1b,
+                 const double* w, double* rhoa, double* rhob, double* rho, double* sums) {
+  double acc_a = 0.0, acc_b = 0.0, acc_t = 0.0;
+  for (size_t p = 0; p < npts; ++p) {
+    double ta = 0.0, tb = 0.0;
+    for (int mu = 0; mu < n; ++mu) {
+      const double fm = phi[p + (size_t)mu * npts];
+      for (int nu = 0; nu < n; ++nu) {
+        const double fn = phi[p + (size_t)nu * npts];
+        ta += D1a[mu + nu * n] * fm * fn; /* mcpdft.cc:83 */
+        tb += D1b[mu + nu * n] * fm * fn; /* mcpdft.cc:84 */
+      }
+    }
+    rhoa[p] = ta;
+    rhob[p] = tb;
+    rho[p] = ta + tb; /* mcpdft.cc:89 */
+    if (w) {
+      acc_a += ta * w[p];        /* mcpdft.cc:91 */
+      acc_b += tb * w[p];        /* mcpdft.cc:92 */
+      acc_t += (ta + tb) * w[p]; /* mcpdft.cc:93 */
+    }
+  }
+  if (sums) {
+    sums[0] = acc_t;
+    sums[1] = acc_a;
+    sums[2] = acc_b;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Spin-density gradients and sigma_aa/ab/bb.   mcpdft.cc:107-176 (loop 130-165)
+ * g[0..5] = d/dx,y,z rho_a then d/dx,y,z rho_b.  D1 is not assumed symmetric (148-153).
+ * ---------------------------------------------------------------------------------------- */
+void orc_density_gradients(size_t npts, int n, const double* phi, const double* phix,
+                           const double* phiy, const double* phiz, const double* D1a,
+                           const double* D1b, double* const* g, double* saa, double* sab,
+                           double* sbb) {
+  for (size_t p = 0; p < npts; ++p) {
+    double ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0;
+    for (int s = 0; s < n; ++s) {
+      const size_t os = p + (size_t)s * npts;
+      for (int nu = 0; nu < n; ++nu) {
+        const size_t on = p + (size_t)nu * npts;
+        const double da = D1a[s + nu * n], db = D1b[s + nu * n];
+        const double tx = phix[os] * phi[on] + phi[os] * phix[on];
+        const double ty = phiy[os] * phi[on] + phi[os] * phiy[on];
+        const double tz = phiz[os] * phi[on] + phi[os] * phiz[on];
+        ax += tx * da; bx += tx * db; /* mcpdft.cc:148-149 */
+        ay += ty * da; by += ty * db; /* mcpdft.cc:150-151 */
+        az += tz * da; bz += tz * db; /* mcpdft.cc:152-153 */
+      }
+    }
+    g[0][p] = ax; g[1][p] = ay; g[2][p] = az;
+    g[3][p] = bx; g[4][p] = by; g[5][p] = bz;
+    saa[p] = (ax * ax) + (ay * ay) + (az * az); /* mcpdft.cc:162 */
+    sbb[p] = (bx * bx) + (by * by) + (bz * bz); /* mcpdft.cc:163 */
+    sab[p] = (ax * bx) + (ay * by) + (az * bz); /* mcpdft.cc:164 */
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * On-top pair density, dense 4-index sum.   mcpdft.cc:185-212 (loop 200-207)
+ * ---------------------------------------------------------------------------------------- */
+void orc_pi(size_t npts, int n, const double* phi, const double* D2ab, double* pi) {
+  const size_t n2 = (size_t)n * n;
+  for (size_t p = 0; p < npts; ++p) {
+    double acc = 0.0;
+    for (int mu = 0; mu < n; ++mu)
+      for (int nu = 0; nu < n; ++nu)
+        for (int la = 0; la < n; ++la)
+          for (int si = 0; si < n; ++si)
+            acc += phi[p + (size_t)mu * npts] * phi[p + (size_t)nu * npts] *
+                   phi[p + (size_t)la * npts] * phi[p + (size_t)si * npts] *
+                   D2ab[((size_t)nu * n + mu) + ((size_t)si * n + la) * n2]; /* mcpdft.cc:204 */
+    pi[p] = acc;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Gradient of the on-top pair density (product rule, four terms).   mcpdft.cc:214-270
+ * The reference stores only pi_x and pi_z (line 268 writes pi_y into the pi_z slot and
+ * line 269 overwrites it); all three components are returned here.
+ * ---------------------------------------------------------------------------------------- */
+void orc_pi_gradients(size_t npts, int n, const double* phi, const double* phix,
+                      const double* phiy, const double* phiz, const double* D2ab, double* pix,
+                      double* piy, double* piz) {
+  const size_t n2 = (size_t)n * n;
+  const double* comp[3] = {phix, phiy, phiz};
+  double* out[3] = {pix, piy, piz};
+  for (size_t p = 0; p < npts; ++p) {
+    double acc[3] = {0, 0, 0};
+    for (int mu = 0; mu < n; ++mu)
+      for (int nu = 0; nu < n; ++nu)
+        for (int la = 0; la < n; ++la)
+          for (int si = 0; si < n; ++si) {
+            const double d = D2ab[((size_t)nu * n + mu) + ((size_t)si * n + la) * n2];
+            const double fm = phi[p + (size_t)mu * npts], fn = phi[p + (size_t)nu * npts];
+            const double fl = phi[p + (size_t)la * npts], fs = phi[p + (size_t)si * npts];
+            for (int c = 0; c < 3; ++c) {
+              const double* q = comp[c];
+              const double gm = q[p + (size_t)mu * npts], gn = q[p + (size_t)nu * npts];
+              const double gl = q[p + (size_t)la * npts], gs = q[p + (size_t)si * npts];
+              /* mcpdft.cc:244-247 (x), 249-252 (y), 254-257 (z) */
+              acc[c] += (gm * fl * fs * fn + fm * gl * fs * fn + fm * fl * gs * fn + fm * fl * fs * gn) * d;
+            }
+          }
+    for (int c = 0; c < 3; ++c) out[c][p] = acc[c];
+  }
+}
+
+/* R(r) = 4 Pi / rho^2, unguarded.   mcpdft.cc:272-285 (line 282) */
+void orc_R(size_t npts, const double* pi, const double* rho, double* R) {
+  for (size_t p = 0; p < npts; ++p) R[p] = 4.0 * pi[p] / (rho[p] * rho[p]);
+}
+
+/* zeta of the (singly) translated scheme.   mcpdft.cc:319-325 */
+static double orc_zeta(double R) { return ((1.0 - R) > ORC_TOL) ? sqrt(1.0 - R) : 0.0; }
+
+/* ------------------------------------------------------------------------------------------
+ * Translated spin densities.   mcpdft.cc:294-344 (loop 314-335)
+ * sums[0..2] = integrated translated total / alpha / beta density.
+ * ---------------------------------------------------------------------------------------- */
+void orc_translate(size_t npts, const double* rho, const double* pi, const double* R,
+                   const double* w, double* tra, double* trb, double* sums) {
+  double acc_a = 0, acc_b = 0, acc_t = 0;
+  for (size_t p = 0; p < npts; ++p) {
+    if (!(rho[p] < ORC_TOL) && !(pi[p] < 0.0)) {
+      const double z = orc_zeta(R[p]);
+      tra[p] = (1.0 + z) * (rho[p] / 2.0); /* mcpdft.cc:326 */
+      trb[p] = (1.0 - z) * (rho[p] / 2.0); /* mcpdft.cc:327 */
+    } else {
+      tra[p] = 0.0;
+      trb[p] = 0.0;
+    }
+    if (w) {
+      acc_a += tra[p] * w[p];
+      acc_b += trb[p] * w[p];
+      acc_t += (tra[p] + trb[p]) * w[p]; /* mcpdft.cc:332-334 */
+    }
+  }
+  if (sums) {
+    sums[0] = acc_t;
+    sums[1] = acc_a;
+    sums[2] = acc_b;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Translated gradients -> translated sigma.   mcpdft.cc:346-416 (loop 378-412)
+ * g[0..5] as in orc_density_gradients.
+ * ---------------------------------------------------------------------------------------- */
+void orc_translate_gradients(size_t npts, const double* rho, const double* pi, const double* R,
+                             double* const* g, double* tsaa, double* tsab, double* tsbb) {
+  for (size_t p = 0; p < npts; ++p) {
+    const double rx = g[0][p] + g[3][p], ry = g[1][p] + g[4][p], rz = g[2][p] + g[5][p];
+    double ax = 0, ay = 0, az = 0, bx = 0, by = 0, bz = 0;
+    if (!(rho[p] < ORC_TOL) && !(pi[p] < 0.0)) {
+      const double z = orc_zeta(R[p]);
+      ax = (1.0 + z) * (rx / 2.0); bx = (1.0 - z) * (rx / 2.0); /* mcpdft.cc:391-392 */
+      ay = (1.0 + z) * (ry / 2.0); by = (1.0 - z) * (ry / 2.0);
+      az = (1.0 + z) * (rz / 2.0); bz = (1.0 - z) * (rz / 2.0);
+    }
+    tsaa[p] = (ax * ax) + (ay * ay) + (az * az); /* mcpdft.cc:407 */
+    tsab[p] = (ax * bx) + (ay * by) + (az * bz); /* mcpdft.cc:408 */
+    tsbb[p] = (bx * bx) + (by * by) + (bz * bz); /* mcpdft.cc:409 */
+  }
+}
+
+/* ==========================================================================================
+ *                                libfunc: exchange
+ * ======================================================================================== */
+
+/* Slater exchange, no density threshold.   functional.cc:12-29 */
+double orc_ex_lsda(size_t npts, const double* ra, const double* rb, const double* w) {
+  const double alpha = 2.0 / 3.0;
+  const double Cx = (9.0 / 8.0) * alpha * pow(3.0 / M_PI, 1.0 / 3.0);
+  double e = 0.0;
+  for (size_t p = 0; p < npts; ++p) {
+    const double xa = pow(2.0, 1.0 / 3.0) * Cx * pow(ra[p], 4.0 / 3.0);
+    const double xb = pow(2.0, 1.0 / 3.0) * Cx * pow(rb[p], 4.0 / 3.0);
+    e += -(xa + xb) * w[p]; /* functional.cc:26 */
+  }
+  return e;
+}
+
+static double pbe_kF(double rho) { return pow(3.0 * M_PI * M_PI * rho, 1.0 / 3.0); } /* functional.cc:41-44 */
+static double pbe_eX(double rho) { return -(3.0 * pbe_kF(rho)) / (4.0 * M_PI); }     /* :46-49 */
+static double pbe_S(double rho, double sig) { return sqrt(sig) / (2.0 * pbe_kF(rho) * rho); } /* :57-60 */
+static double pbe_FX(double s) {                                                              /* :51-54 */
+  const double beta = 0.06672455060314922, mu = (1.0 / 3.0) * beta * M_PI * M_PI, kappa = 0.804;
+  return 1.0 + kappa - kappa * pow(1.0 + (mu * pow(s, 2.0)) / kappa, -1.0);
+}
+
+/* spin-scaled PBE exchange.   functional.cc:31-99 (loop 66-97) */
+double orc_ex_pbe(size_t npts, const double* ra, const double* rb, const double* saa,
+                  const double* sbb, const double* w) {
+  double e = 0.0;
+  for (size_t p = 0; p < npts; ++p) {
+    const double a = ra[p], b = rb[p];
+    double rho = a + b;
+    if (rho > ORC_TOL) {
+      if (a < ORC_TOL) { /* functional.cc:75-81 */
+        rho = b;
+        const double sg = fmax(0.0, sbb[p]);
+        e += rho * (pbe_eX(2.0 * rho) * pbe_FX(pbe_S(2.0 * rho, 4.0 * sg))) * w[p];
+      } else if (b < ORC_TOL) { /* functional.cc:82-87 */
+        rho = a;
+        const double sg = fmax(0.0, saa[p]);
+        e += rho * (pbe_eX(2.0 * rho) * pbe_FX(pbe_S(2.0 * rho, 4.0 * sg))) * w[p];
+      } else { /* functional.cc:88-93: sigma not clamped here */
+        const double za = a * pbe_eX(2.0 * a) * pbe_FX(pbe_S(2.0 * a, 4.0 * saa[p]));
+        const double zb = b * pbe_eX(2.0 * b) * pbe_FX(pbe_S(2.0 * b, 4.0 * sbb[p]));
+        e += (za + zb) * w[p];
+      }
+    }
+  }
+  return e;
+}
+
+/* ==========================================================================================
+ *                                libfunc: correlation
+ * ======================================================================================== */
+
+/* spin-interpolation function f(zeta).   functional.cc:125-128, 225-228 */
+static double spin_f(double z) {
+  return (pow(1.0 + z, 4.0 / 3.0) + pow(1.0 - z, 4.0 / 3.0) - 2.0) / (2.0 * pow(2.0, 1.0 / 3.0) - 2.0);
+}
+
+/* VWN "q" function.   functional.cc:137-142 ; argument names as in the reference lambda:
+ * q(RHO, A, p, c, d) is called with (A, x0, b, c) of Vosko-Wilk-Nusair. */
+static double vwn_q(double rho, double A, double p, double c, double d) {
+  const double rs = pow(3.0 / (4.0 * M_PI * rho), 1.0 / 3.0);
+  const double x = sqrt(rs); /* functional.cc:120-124 */
+  const double Xx = pow(x, 2.0) + c * x + d, Xp = pow(p, 2.0) + c * p + d; /* :129-132 */
+  const double Q = sqrt(4 * d - pow(c, 2.0));                              /* :133-136 */
+  const double at = atan(Q / (2.0 * x + c));
+  return A * (log(pow(x, 2.0) / Xx) + 2.0 * c * at * pow(Q, -1.0) -
+              c * p * (log(pow(x - p, 2.0) / Xx) + 2.0 * (c + 2.0 * p) * at * pow(Q, -1.0)) * pow(Xp, -1.0));
+}
+
+/* VWN-RPA ("VWN3" in the reference) correlation.   functional.cc:103-177 (loop 154-175) */
+double orc_ec_vwn3(size_t npts, const double* ra, const double* rb, const double* w) {
+  double e = 0.0;
+  for (size_t p = 0; p < npts; ++p) {
+    const double a = ra[p], b = rb[p];
+    double rho = a + b, zeta;
+    if (rho > ORC_TOL) {
+      if (a < ORC_TOL) { rho = b; zeta = 1.0; }
+      else if (b < ORC_TOL) { rho = a; zeta = 1.0; }
+      else zeta = (a - b) / rho;
+      const double eP = vwn_q(rho, 0.03109070000, -0.409286, 13.0720, 42.7198);  /* functional.cc:108-111 */
+      const double eF = vwn_q(rho, 0.01554535000, -0.743294, 20.1231, 101.578);  /* functional.cc:112-115 */
+      e += rho * (eP + spin_f(zeta) * (eF - eP)) * w[p];                         /* functional.cc:169-170 */
+    }
+  }
+  return e;
+}
+
+/* PW92 "G" function.   functional.cc:237-241 */
+static double pw92_G(double r, double T, double a1, double b1, double b2, double b3, double b4, double p) {
+  return -2.0 * T * (1.0 + a1 * r) *
+         log(1.0 + 0.5 * pow(T * (b1 * sqrt(r) + b2 * r + b3 * pow(r, 3.0 / 2.0) + b4 * pow(r, p + 1.0)), -1.0));
+}
+
+/* PW92 eps_c(rs, zeta).   functional.cc:243-261 */
+static double pw92_Ec(double r, double z) {
+  const double d2Fz = 1.7099209341613656173;
+  const double mAc = pw92_G(r, 0.0168869, 0.11125, 10.357, 3.6231, 0.88026, 0.49671, 1.0);  /* = -Ac(r) */
+  const double eP = pw92_G(r, 0.0310907, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294, 1.0);
+  const double eF = pw92_G(r, 0.01554535, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517, 1.0);
+  const double fz = spin_f(z);
+  return eP + ((-mAc) * fz * (1.0 - pow(z, 4.0))) / d2Fz + (eF - eP) * fz * pow(z, 4.0); /* :259 */
+}
+
+static double pbe_phi(double z) { return 0.5 * (pow(1.0 + z, 2.0 / 3.0) + pow(1.0 - z, 2.0 / 3.0)); } /* :210-213 */
+
+/* PBE gradient correction H.   functional.cc:263-271 */
+static double pbe_H(double rho, double sig, double r, double z) {
+  const double BETA = 0.06672455060314922, GAMMA = 0.0310906908696549;
+  const double fi = pbe_phi(z);
+  const double ks = sqrt(4.0 * pbe_kF(rho) / M_PI);         /* :220-223 */
+  const double t = sqrt(sig) / (2.0 * ks * fi * rho);       /* :230-233 */
+  const double A = (BETA / GAMMA) * pow(exp(-pw92_Ec(r, z) / (pow(fi, 3.0) * GAMMA)) - 1.0, -1.0); /* :263-266 */
+  const double t2 = pow(t, 2.0), t4 = pow(t, 4.0);
+  return pow(fi, 3.0) * GAMMA *
+         log(1.0 + (BETA / GAMMA) * t2 * (1.0 + A * t2) / (1.0 + A * t2 + pow(A, 2.0) * t4)); /* :268-271 */
+}
+
+/* PBE correlation.   functional.cc:179-309 (loop 275-307).  zeta and rs are formed from the
+ * total density *before* the single-spin branches re-point rho (lines 278-280). */
+double orc_ec_pbe(size_t npts, const double* ra, const double* rb, const double* saa,
+                  const double* sab, const double* sbb, const double* w) {
+  double e = 0.0;
+  for (size_t p = 0; p < npts; ++p) {
+    const double a = ra[p], b = rb[p];
+    double rho = a + b;
+    double zeta = (a - b) / rho;
+    const double rs = pow(3.0 / (4.0 * M_PI * rho), 1.0 / 3.0);
+    double sig;
+    if (rho > ORC_TOL) {
+      if (a < ORC_TOL) { rho = b; sig = fmax(0.0, sbb[p]); zeta = 1.0; }       /* :286-290 */
+      else if (b < ORC_TOL) { rho = a; sig = fmax(0.0, saa[p]); zeta = 1.0; }  /* :291-295 */
+      else sig = fmax(0.0, saa[p]) + fmax(0.0, sbb[p]) + 2.0 * sab[p];         /* :296-300 */
+      e += rho * (pbe_H(rho, sig, rs, zeta) + pw92_Ec(rs, zeta)) * w[p];       /* :301-302 */
+    }
+  }
+  return e;
+}
+
+/* ==========================================================================================
+ *                 mcpdft_energy: orchestration.   energy.cc:27-188
+ * ======================================================================================== */
+
+static double* pick(double** vecs, int id, size_t npts, double** owned, int* nowned) {
+  if (vecs && vecs[id]) return vecs[id];
+  double* v = (double*)calloc(npts ? npts : 1, sizeof(double));
+  owned[(*nowned)++] = v;
+  return v;
+}
+
+/* Steps shared by the dense and the core/active drivers once rho, grad rho and Pi exist:
+ * build_R (energy.cc:55), translate (energy.cc:58), functional dispatch (energy.cc:110-122:
+ * "SVWN" -> EX_LSDA+EC_VWN3, anything else -> EX_PBE+EC_PBE), total (energy.cc:181-183). */
+static void orc_finish(size_t npts, int is_gga, int functional_is_svwn, const double* w,
+                       double eclass, double** v, orc_result* out) {
+  double tsum[3];
+  orc_R(npts, v[ORC_PI], v[ORC_RHO], v[ORC_R]);
+  orc_translate(npts, v[ORC_RHO], v[ORC_PI], v[ORC_R], w, v[ORC_TR_RHOA], v[ORC_TR_RHOB], tsum);
+  if (is_gga) {
+    double* g[6] = {v[ORC_RHOA_X], v[ORC_RHOA_Y], v[ORC_RHOA_Z], v[ORC_RHOB_X], v[ORC_RHOB_Y], v[ORC_RHOB_Z]};
+    orc_translate_gradients(npts, v[ORC_RHO], v[ORC_PI], v[ORC_R], g, v[ORC_TR_SIGMA_AA],
+                            v[ORC_TR_SIGMA_AB], v[ORC_TR_SIGMA_BB]);
+  } /* else tr_sigma stay zero (energy.cc:63-65) */
+  double ex, ec;
+  if (functional_is_svwn) {
+    ex = orc_ex_lsda(npts, v[ORC_TR_RHOA], v[ORC_TR_RHOB], w);
+    ec = orc_ec_vwn3(npts, v[ORC_TR_RHOA], v[ORC_TR_RHOB], w);
+  } else {
+    ex = orc_ex_pbe(npts, v[ORC_TR_RHOA], v[ORC_TR_RHOB], v[ORC_TR_SIGMA_AA], v[ORC_TR_SIGMA_BB], w);
+    ec = orc_ec_pbe(npts, v[ORC_TR_RHOA], v[ORC_TR_RHOB], v[ORC_TR_SIGMA_AA], v[ORC_TR_SIGMA_AB],
+                    v[ORC_TR_SIGMA_BB], w);
+  }
+  out->ex = ex;
+  out->ec = ec;
+  out->eclass = eclass;
+  out->e_tot = 0.0;
+  out->e_tot += eclass;
+  out->e_tot += ex;
+  out->e_tot += ec;
+  out->trn_tot = tsum[0];
+  out->trn_a = tsum[1];
+  out->trn_b = tsum[2];
+}
+
+/*
+ * Dense driver: exactly the reference's operator surface (all n orbitals in D1a, D1b and the
+ * (n^2)x(n^2) D2ab).  `vecs` is NULL or an array of ORC_NVEC pointers, each NULL or an
+ * npts-long output buffer.  with_pi_grad != 0 also evaluates grad Pi as the reference does
+ * for GGA (mcpdft.cc:178-183) -- its result does not enter the energy.
+ */
+int orc_energy(size_t npts, int n, int is_gga, int functional_is_svwn, const double* w,
+               const double* phi, const double* phix, const double* phiy, const double* phiz,
+               const double* D1a, const double* D1b, const double* D2ab, double eclass,
+               int with_pi_grad, orc_result* out, double** vecs) {
+  double* owned[ORC_NVEC];
+  int nowned = 0;
+  double* v[ORC_NVEC];
+  for (int i = 0; i < ORC_NVEC; ++i) v[i] = pick(vecs, i, npts, owned, &nowned);
+  double s[3];
+  orc_density(npts, n, phi, D1a, D1b, w, v[ORC_RHOA], v[ORC_RHOB], v[ORC_RHO], s); /* energy.cc:49 */
+  out->n_tot = s[0];
+  out->n_a = s[1];
+  out->n_b = s[2];
+  if (is_gga)
+    orc_density_gradients(npts, n, phi, phix, phiy, phiz, D1a, D1b, &v[ORC_RHOA_X], v[ORC_SIGMA_AA],
+                          v[ORC_SIGMA_AB], v[ORC_SIGMA_BB]);
+  orc_pi(npts, n, phi, D2ab, v[ORC_PI]); /* energy.cc:52 */
+  if (is_gga && with_pi_grad)
+    orc_pi_gradients(npts, n, phi, phix, phiy, phiz, D2ab, v[ORC_PI_X], v[ORC_PI_Y], v[ORC_PI_Z]);
+  orc_finish(npts, is_gga, functional_is_svwn, w, eclass, v, out);
+  for (int i = 0; i < nowned; ++i) free(owned[i]);
+  return 0;
+}
+
+/*
+ * Core/active driver (block rules as in src/libpyscf/libpyscf.py:143-173).
+ * phi has ncore+nact columns; D1s = I (core) (+) As (active, nact x nact); the 2-RDM is given on
+ * the active block only, D2act (nact^2 x nact^2, reference index convention), and the core
+ * contributions are closed-form:
+ *     rho_s = rho_c + rho_t,s          rho_c = sum_core phi_i^2
+ *     Pi    = rho_c^2 + rho_c*rho_t,b + rho_t,a*rho_c + Pi_act
+ * Identical to orc_energy() on the equivalent full-size D1/D2ab up to summation order; that
+ * equivalence is itself tested against oracle/_ref at small sizes.
+ */
+int orc_energy_coreactive(size_t npts, int ncore, int nact, int is_gga, int functional_is_svwn,
+                          const double* w, const double* phi, const double* phix,
+                          const double* phiy, const double* phiz, const double* A1a,
+                          const double* A1b, const double* D2act, double eclass, int with_pi_grad,
+                          orc_result* out, double** vecs) {
+  double* owned[ORC_NVEC + 16];
+  int nowned = 0;
+  double* v[ORC_NVEC];
+  for (int i = 0; i < ORC_NVEC; ++i) v[i] = pick(vecs, i, npts, owned, &nowned);
+  const size_t off = (size_t)ncore * npts;
+  const double *pa = phi + off, *pax = phix ? phix + off : 0, *pay = phiy ? phiy + off : 0,
+               *paz = phiz ? phiz + off : 0;
+  /* active-space pieces through the dense routines */
+  orc_density(npts, nact, pa, A1a, A1b, 0, v[ORC_RHOA], v[ORC_RHOB], v[ORC_RHO], 0);
+  if (is_gga)
+    orc_density_gradients(npts, nact, pa, pax, pay, paz, A1a, A1b, &v[ORC_RHOA_X], v[ORC_SIGMA_AA],
+                          v[ORC_SIGMA_AB], v[ORC_SIGMA_BB]);
+  orc_pi(npts, nact, pa, D2act, v[ORC_PI]);
+  if (is_gga && with_pi_grad)
+    orc_pi_gradients(npts, nact, pa, pax, pay, paz, D2act, v[ORC_PI_X], v[ORC_PI_Y], v[ORC_PI_Z]);
+  /* closed-form core contributions */
+  double na = 0, nb = 0, nt = 0;
+  for (size_t p = 0; p < npts; ++p) {
+    double rc = 0, cx = 0, cy = 0, cz = 0;
+    for (int i = 0; i < ncore; ++i) {
+      const size_t o = p + (size_t)i * npts;
+      rc += phi[o] * phi[o];
+      if (is_gga) {
+        cx += phix[o] * phi[o] + phi[o] * phix[o];
+        cy += phiy[o] * phi[o] + phi[o] * phiy[o];
+        cz += phiz[o] * phi[o] + phi[o] * phiz[o];
+      }
+    }
+    const double ta = v[ORC_RHOA][p], tb = v[ORC_RHOB][p];
+    if (is_gga && with_pi_grad) {
+      /* d(Pi) = 2 rc drc + drc (ta+tb) + rc (dta + dtb) + dPi_act */
+      const double dc[3] = {cx, cy, cz};
+      for (int c = 0; c < 3; ++c) {
+        const double dta = v[ORC_RHOA_X + c][p], dtb = v[ORC_RHOB_X + c][p];
+        v[ORC_PI_X + c][p] += 2.0 * rc * dc[c] + dc[c] * (ta + tb) + rc * (dta + dtb);
+      }
+    }
+    v[ORC_PI][p] = rc * rc + rc * tb + ta * rc + v[ORC_PI][p];
+    v[ORC_RHOA][p] = rc + ta;
+    v[ORC_RHOB][p] = rc + tb;
+    v[ORC_RHO][p] = v[ORC_RHOA][p] + v[ORC_RHOB][p];
+    if (is_gga) {
+      double* g = 0;
+      g = v[ORC_RHOA_X]; g[p] += cx; g = v[ORC_RHOA_Y]; g[p] += cy; g = v[ORC_RHOA_Z]; g[p] += cz;
+      g = v[ORC_RHOB_X]; g[p] += cx; g = v[ORC_RHOB_Y]; g[p] += cy; g = v[ORC_RHOB_Z]; g[p] += cz;
+      const double ax = v[ORC_RHOA_X][p], ay = v[ORC_RHOA_Y][p], az = v[ORC_RHOA_Z][p];
+      const double bx = v[ORC_RHOB_X][p], by = v[ORC_RHOB_Y][p], bz = v[ORC_RHOB_Z][p];
+      v[ORC_SIGMA_AA][p] = (ax * ax) + (ay * ay) + (az * az);
+      v[ORC_SIGMA_BB][p] = (bx * bx) + (by * by) + (bz * bz);
+      v[ORC_SIGMA_AB][p] = (ax * bx) + (ay * by) + (az * bz);
+    }
+    na += v[ORC_RHOA][p] * w[p];
+    nb += v[ORC_RHOB][p] * w[p];
+    nt += (v[ORC_RHOA][p] + v[ORC_RHOB][p]) * w[p];
+  }
+  out->n_tot = nt;
+  out->n_a = na;
+  out->n_b = nb;
+  orc_finish(npts, is_gga, functional_is_svwn, w, eclass, v, out);
+  for (int i = 0; i < nowned; ++i) free(owned[i]);
+  return 0;
+}
+
+/* D2ab = kron(D1a, D1b): the compound-index convention of build_tpdm.   mcpdft.cc:640-652
+ * D2ab(i*n+k, j*n+l) = D1a(i,j) * D1b(k,l). */
+void orc_kron_tpdm(int n, const double* D1a, const double* D1b, double* D2ab) {
+  const size_t n2 = (size_t)n * n;
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i)
+      for (int l = 0; l < n; ++l)
+        for (int k = 0; k < n; ++k)
+          D2ab[((size_t)i * n + k) + ((size_t)j * n + l) * n2] = D1a[i + j * n] * D1b[k + l * n];
+}
