@@ -1,0 +1,176 @@
+/*
+ * openrdm_b200.h -- C ABI of the B200-native MC-PDFT energy engine.
+ *
+ * This is the drop-in boundary for OpenRDM's MC-PDFT energy hot path
+ *     mcpdft::mcpdft_energy()                   /root/reference/src/libmcpdft/energy.cc:27-188
+ *     mcpdft::MCPDFT::build_rho/build_pi/build_R/translate   src/libmcpdft/mcpdft.cc:35-416
+ *     mcpdft::Functional::EX_LSDA/EC_VWN3/EX_PBE/EC_PBE       src/libfunc/functional.cc:12-309
+ * OpenRDM itself has no C ABI on this path (it is a C++ static library, CMakeLists.txt:23-24);
+ * the host-side C++ mirror of its classes (openrdm_b200/host/) and any other binding sit on
+ * top of exactly these entry points.  Plain pointers and sizes only; no CUDA / torch types.
+ *
+ * Conventions (the reference's): all matrices are column-major FP64;
+ *   phi(p,mu) at phi[p + mu*ld]            (arma::mat(npts,nbfs), mcpdft.h:184)
+ *   D1(mu,nu) at D1[mu + nu*n]
+ *   D2ab is (n*n) x (n*n), element (nu*n+mu, sigma*n+lambda) multiplies
+ *        phi_mu phi_nu phi_lambda phi_sigma  (mcpdft.cc:204; build_tpdm = kron(D1a,D1b), :640-652)
+ *
+ * Every function returns ORDM_OK (0) or an error code; ordm_last_error() gives the text.
+ * There is no CPU fallback anywhere: without a CUDA device every compute call fails loudly.
+ * A context is bound to one device and is not thread-safe; use one context per host thread.
+ */
+#ifndef OPENRDM_B200_H
+#define OPENRDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ordm_ctx ordm_ctx;
+
+enum ordm_status {
+  ORDM_OK = 0,
+  ORDM_ERR_INVALID = 1, /* bad argument */
+  ORDM_ERR_STATE = 2,   /* call order: inputs missing for the requested stage */
+  ORDM_ERR_CUDA = 3,    /* CUDA runtime error (no device, launch failure, out of memory) */
+  ORDM_ERR_NCCL = 4,    /* NCCL not loadable / communicator error */
+  ORDM_ERR_UNSUPPORTED = 5
+};
+
+/* energy.cc:114-120 dispatches on the string "SVWN"; every other string means PBE. */
+enum ordm_functional { ORDM_FUNC_SVWN = 0, ORDM_FUNC_PBE = 1 };
+
+/* The four libfunc entry points (functional.h:17-43). */
+enum ordm_xc_term { ORDM_EX_LSDA = 0, ORDM_EC_VWN3 = 1, ORDM_EX_PBE = 2, ORDM_EC_PBE = 3 };
+
+/* Per-point vectors held by the engine = the arma::vec members of mcpdft::MCPDFT
+ * (mcpdft.h:216-305) that the path reads or writes. */
+enum ordm_vector {
+  ORDM_VEC_RHOA = 0, ORDM_VEC_RHOB, ORDM_VEC_RHO,
+  ORDM_VEC_RHOA_X, ORDM_VEC_RHOA_Y, ORDM_VEC_RHOA_Z,
+  ORDM_VEC_RHOB_X, ORDM_VEC_RHOB_Y, ORDM_VEC_RHOB_Z,
+  ORDM_VEC_SIGMA_AA, ORDM_VEC_SIGMA_AB, ORDM_VEC_SIGMA_BB,
+  ORDM_VEC_PI, ORDM_VEC_R, ORDM_VEC_TR_RHOA, ORDM_VEC_TR_RHOB,
+  ORDM_VEC_TR_SIGMA_AA, ORDM_VEC_TR_SIGMA_AB, ORDM_VEC_TR_SIGMA_BB,
+  ORDM_VEC_PI_X, ORDM_VEC_PI_Y, ORDM_VEC_PI_Z,
+  ORDM_VEC_W,
+  ORDM_VEC_COUNT
+};
+
+/* option bits for ordm_set_options */
+enum {
+  ORDM_OPT_DIAGNOSTICS = 1, /* keep every per-point vector (getters work); off = energy-only mode */
+  ORDM_OPT_PI_GRADIENT = 2  /* also build grad Pi (mcpdft.cc:214-270); never enters the energy */
+};
+
+/* What mcpdft_energy returns or prints: energy.cc:175-183, mcpdft.cc:100-104,339-343. */
+typedef struct {
+  double e_tot, ex, ec, eclass;
+  double n_tot, n_a, n_b;       /* integrated total / alpha / beta density */
+  double trn_tot, trn_a, trn_b; /* integrated translated densities */
+  /* CUDA-event times of the last ordm_energy call on this context's stream, milliseconds */
+  double ms_density, ms_pi, ms_xc, ms_reduce, ms_total;
+  uint64_t npts;          /* points this context (shard) processed */
+  uint32_t gpu_launches;  /* kernels launched by that call */
+  uint32_t reserved;
+} ordm_result;
+
+/* ---- lifecycle ----------------------------------------------------------------------- */
+const char* ordm_version(void);
+int ordm_device_count(void);
+/* replaces `new MCPDFT(...)` / `delete mc` (tests/main.cc:17,46) */
+int ordm_create(int device, ordm_ctx** out);
+void ordm_destroy(ordm_ctx* ctx);
+/* ctx may be NULL: returns the last error of the calling thread's most recent failing call */
+const char* ordm_last_error(const ordm_ctx* ctx);
+/* use an existing cudaStream_t (passed as void*) instead of the context's own stream */
+int ordm_set_stream(ordm_ctx* ctx, void* cuda_stream);
+int ordm_set_options(ordm_ctx* ctx, unsigned flags);
+int ordm_synchronize(ordm_ctx* ctx);
+
+/* page-locked host memory, so that the H2D copies of set_* / energy_host run at PCIe speed */
+int ordm_host_alloc(size_t bytes, void** out);
+int ordm_host_free(void* p);
+
+/* ---- inputs (host pointers; copied, never retained) ---------------------------------- */
+/* MCPDFT::set_npts + set_w (mcpdft.h:112,114); reader: read_grids_from_file, utility.cc:5-34 */
+int ordm_set_grid(ordm_ctx* ctx, size_t npts, const double* w);
+/* MCPDFT::set_nbfs + set_phi/_x/_y/_z (mcpdft.h:113,118-121).  phi_x/y/z NULL = LDA only. */
+int ordm_set_orbitals(ordm_ctx* ctx, size_t npts, int n, size_t ld, const double* phi,
+                      const double* phi_x, const double* phi_y, const double* phi_z);
+/* MCPDFT::set_D1a + set_D1b (mcpdft.h:125-126).  n x n, not assumed symmetric (mcpdft.cc:148). */
+int ordm_set_rdm1(ordm_ctx* ctx, int n, const double* D1a, const double* D1b);
+/* the D2ab argument of mcpdft_energy / build_pi (energy.h:14-18, mcpdft.h:35); dense
+ * (n^2)x(n^2) in the reference's index convention, n = all orbitals of ordm_set_orbitals. */
+int ordm_set_rdm2ab_dense(ordm_ctx* ctx, int n, const double* D2ab);
+/* Extension (no reference counterpart): the orbitals are
+ * [ncore doubly-occupied | nact active]; A1a/A1b are the nact x nact active 1-RDM blocks and
+ * D2act the (nact^2)x(nact^2) active alpha-beta 2-RDM.  Equivalent to the dense calls above
+ * with D1 = I (+) A and the core-expanded D2ab, without ever forming the (n^2)^2 matrix. */
+int ordm_set_active_space(ordm_ctx* ctx, int ncore, int nact, const double* A1a, const double* A1b,
+                          const double* D2act);
+
+/* ---- stages = the public methods of mcpdft::MCPDFT ------------------------------------ */
+int ordm_build_rho(ordm_ctx* ctx);   /* MCPDFT::build_rho,  mcpdft.cc:35-40  */
+int ordm_build_pi(ordm_ctx* ctx);    /* MCPDFT::build_pi,   mcpdft.cc:178-183 (D2ab from set_rdm2ab_*) */
+int ordm_build_R(ordm_ctx* ctx);     /* MCPDFT::build_R,    mcpdft.cc:272-285 */
+int ordm_translate(ordm_ctx* ctx);   /* MCPDFT::translate,  mcpdft.cc:287-292 */
+/* the integrated densities the reference prints after build_rho / translate */
+int ordm_integrated_densities(ordm_ctx* ctx, double out_n[3], double out_trn[3]);
+
+/* Functional::EX_LSDA / EC_VWN3 / EX_PBE / EC_PBE on caller-provided vectors
+ * (functional.h:17-43): npts-long host arrays, weights from ordm_set_grid.  Unused sigma
+ * arguments may be NULL. */
+int ordm_functional(ordm_ctx* ctx, int term, size_t npts, const double* rho_a, const double* rho_b,
+                    const double* sigma_aa, const double* sigma_ab, const double* sigma_bb,
+                    double* energy_out);
+
+/* ---- the path in one call -------------------------------------------------------------- */
+/* mcpdft::mcpdft_energy (energy.cc:27-188) on the device-resident inputs: density -> Pi ->
+ * R/translate/XC -> quadrature (-> NCCL all-reduce when a communicator is attached). */
+int ordm_energy(ordm_ctx* ctx, int functional, double eclass, ordm_result* out);
+
+/* Same, from HOST buffers: the grid is streamed through the device in point batches with
+ * the H2D copies overlapped with compute; nothing but the RDMs has to be resident.  This is
+ * the end-to-end call a host-memory caller (arma::mat) makes.  ncore/nact/A1a/A1b/D2act as
+ * in ordm_set_active_space (ncore = 0 and nact = n for the plain dense case). */
+int ordm_energy_host(ordm_ctx* ctx, int functional, double eclass, size_t npts, int n, size_t ld,
+                     const double* w, const double* phi, const double* phi_x, const double* phi_y,
+                     const double* phi_z, size_t batch_points, ordm_result* out);
+
+/* ---- outputs --------------------------------------------------------------------------- */
+/* MCPDFT::get_rhoa ... get_tr_sigma_bb (mcpdft.h:64-110): copies npts doubles to the host.
+ * Needs ORDM_OPT_DIAGNOSTICS, except RHO / PI / W which always exist after their stage. */
+int ordm_get_vector(ordm_ctx* ctx, int which, double* host_out, size_t npts);
+/* raw device pointer of a per-point vector (NULL if not materialised) */
+void* ordm_device_vector(ordm_ctx* ctx, int which);
+
+/* ---- synthetic inputs of BASELINE.json's configs 3-5 (ordm_synth.h) ------------------- */
+/* Fill this context's phi (and grad phi if gga) and w on the device for global points
+ * [p0, p0+npts_local) of a grid of npts_total points. */
+int ordm_synth_fill_device(ordm_ctx* ctx, uint64_t seed, size_t npts_total, size_t p0,
+                           size_t npts_local, int n, int gga);
+/* Same values into host arrays (column-major, ld = npts_local); any pointer may be NULL. */
+int ordm_synth_fill_host(uint64_t seed, size_t npts_total, size_t p0, size_t npts_local, int n,
+                         double* w, double* phi, double* phi_x, double* phi_y, double* phi_z);
+/* N-representable ensemble-of-determinants active-space RDMs:
+ * A1a, A1b nact x nact; D2act (nact^2)x(nact^2); nelec_a/b active electrons per spin. */
+int ordm_synth_rdms(uint64_t seed, int nact, int nelec_a, int nelec_b, int ndet, double* A1a,
+                    double* A1b, double* D2act);
+
+/* ---- multi-GPU: one process per GPU, grid sharded by point ranges ---------------------- */
+/* NCCL is loaded lazily (dlopen libnccl.so.2).  Rank 0 makes the id, the launcher ships the
+ * 128 bytes to the other ranks (torch.distributed / MPI / a file), every rank attaches. */
+int ordm_comm_unique_id(char id_out[128]);
+int ordm_comm_attach(ordm_ctx* ctx, int nranks, int rank, const char id[128]);
+int ordm_comm_detach(ordm_ctx* ctx);
+/* contiguous shard [p0, p0+count) of rank `rank`: balanced in units of 64 points */
+void ordm_shard_range(size_t npts_total, int nranks, int rank, size_t* p0, size_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENRDM_B200_H */

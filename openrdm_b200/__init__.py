@@ -1,0 +1,253 @@
+"""openrdm_b200 -- B200-native MC-PDFT energy engine (OpenRDM's libmcpdft/libfunc hot path).
+
+The product is the C-ABI shared library ``libopenrdm_b200.so`` (include/openrdm_b200.h) built
+from ``csrc/`` (CUDA, sm_100a) and the C++ host mirror of OpenRDM's classes in ``host/``.
+This module is only the ctypes binding the Python-side harnesses (tests/, bench.py) use to
+call that C ABI; it adds no compute and has no fallback: if the library or a CUDA device is
+missing, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libopenrdm_b200.so")
+
+FUNC_SVWN, FUNC_PBE = 0, 1
+EX_LSDA, EC_VWN3, EX_PBE, EC_PBE = 0, 1, 2, 3
+OPT_DIAGNOSTICS, OPT_PI_GRADIENT = 1, 2
+
+VEC_NAMES = [
+    "rhoa", "rhob", "rho",
+    "rhoa_x", "rhoa_y", "rhoa_z", "rhob_x", "rhob_y", "rhob_z",
+    "sigma_aa", "sigma_ab", "sigma_bb",
+    "pi", "R", "tr_rhoa", "tr_rhob",
+    "tr_sigma_aa", "tr_sigma_ab", "tr_sigma_bb",
+    "pi_x", "pi_y", "pi_z", "w",
+]
+VEC_ID = {n: i for i, n in enumerate(VEC_NAMES)}
+
+
+class OrdmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"openrdm_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Result(C.Structure):
+    _fields_ = [(k, C.c_double) for k in (
+        "e_tot", "ex", "ec", "eclass", "n_tot", "n_a", "n_b", "trn_tot", "trn_a", "trn_b",
+        "ms_density", "ms_pi", "ms_xc", "ms_reduce", "ms_total")] + [
+        ("npts", C.c_uint64), ("gpu_launches", C.c_uint32), ("reserved", C.c_uint32)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+_lib = None
+
+
+def load(rebuild: bool = False) -> C.CDLL:
+    """Load (building first if the sources are newer) the C-ABI library."""
+    global _lib
+    if _lib is not None and not rebuild:
+        return _lib
+    if rebuild or not os.path.exists(LIB_PATH):
+        _build.build(force=rebuild)
+    lib = C.CDLL(LIB_PATH)
+    P, D, S, I = C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.c_int
+    lib.ordm_version.restype = C.c_char_p
+    lib.ordm_last_error.restype = C.c_char_p
+    lib.ordm_last_error.argtypes = [P]
+    lib.ordm_device_vector.restype = P
+    lib.ordm_device_vector.argtypes = [P, I]
+    lib.ordm_create.argtypes = [I, C.POINTER(P)]
+    lib.ordm_destroy.argtypes = [P]
+    lib.ordm_destroy.restype = None
+    lib.ordm_set_stream.argtypes = [P, P]
+    lib.ordm_set_options.argtypes = [P, C.c_uint]
+    lib.ordm_synchronize.argtypes = [P]
+    lib.ordm_host_alloc.argtypes = [S, C.POINTER(P)]
+    lib.ordm_host_free.argtypes = [P]
+    lib.ordm_set_grid.argtypes = [P, S, D]
+    lib.ordm_set_orbitals.argtypes = [P, S, I, S, D, D, D, D]
+    lib.ordm_set_rdm1.argtypes = [P, I, D, D]
+    lib.ordm_set_rdm2ab_dense.argtypes = [P, I, D]
+    lib.ordm_set_active_space.argtypes = [P, I, I, D, D, D]
+    for f in ("ordm_build_rho", "ordm_build_pi", "ordm_build_R", "ordm_translate", "ordm_comm_detach"):
+        getattr(lib, f).argtypes = [P]
+    lib.ordm_integrated_densities.argtypes = [P, D, D]
+    lib.ordm_functional.argtypes = [P, I, S, D, D, D, D, D, D]
+    lib.ordm_energy.argtypes = [P, I, C.c_double, C.POINTER(Result)]
+    lib.ordm_energy_host.argtypes = [P, I, C.c_double, S, I, S, D, D, D, D, D, S, C.POINTER(Result)]
+    lib.ordm_get_vector.argtypes = [P, I, D, S]
+    lib.ordm_synth_fill_device.argtypes = [P, C.c_uint64, S, S, S, I, I]
+    lib.ordm_synth_fill_host.argtypes = [C.c_uint64, S, S, S, I, D, D, D, D, D]
+    lib.ordm_synth_rdms.argtypes = [C.c_uint64, I, I, I, I, D, D, D]
+    lib.ordm_comm_unique_id.argtypes = [C.c_char_p]
+    lib.ordm_comm_attach.argtypes = [P, I, I, C.c_char_p]
+    lib.ordm_shard_range.argtypes = [S, I, I, C.POINTER(S), C.POINTER(S)]
+    lib.ordm_shard_range.restype = None
+    _lib = lib
+    return lib
+
+
+def _d(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else C.POINTER(C.c_double)()
+
+
+def _f(a):
+    return None if a is None else np.require(np.asarray(a, dtype=np.float64), requirements=["A", "F"])
+
+
+def shard_range(npts_total: int, nranks: int, rank: int):
+    p0, cnt = C.c_size_t(), C.c_size_t()
+    load().ordm_shard_range(npts_total, nranks, rank, C.byref(p0), C.byref(cnt))
+    return p0.value, cnt.value
+
+
+def synth_rdms(seed: int, nact: int, nelec_a: int, nelec_b: int, ndet: int = 8, want_d2: bool = True):
+    """Host-side synthetic active-space RDMs (no GPU needed)."""
+    A1a = np.zeros((nact, nact), order="F"); A1b = np.zeros((nact, nact), order="F")
+    D2 = np.zeros((nact * nact, nact * nact), order="F") if want_d2 else None
+    rc = load().ordm_synth_rdms(seed, nact, nelec_a, nelec_b, ndet, _d(A1a), _d(A1b), _d(D2))
+    if rc:
+        raise OrdmError(rc, load().ordm_last_error(None).decode())
+    return A1a, A1b, D2
+
+
+def synth_fill_host(seed: int, npts_total: int, p0: int, m: int, n: int, gga: bool):
+    """Host copy of the synthetic grid slice [p0, p0+m): returns w, phi, (phix, phiy, phiz) or None."""
+    w = np.zeros(m); phi = np.zeros((m, n), order="F")
+    g = [np.zeros((m, n), order="F") for _ in range(3)] if gga else [None] * 3
+    rc = load().ordm_synth_fill_host(seed, npts_total, p0, m, n, _d(w), _d(phi), _d(g[0]), _d(g[1]), _d(g[2]))
+    if rc:
+        raise OrdmError(rc, load().ordm_last_error(None).decode())
+    return w, phi, (g if gga else None)
+
+
+class Engine:
+    """One context = one GPU = one grid shard.  Thin wrapper over the C ABI."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        self.ctx = C.c_void_p()
+        rc = self.lib.ordm_create(device, C.byref(self.ctx))
+        if rc:
+            raise OrdmError(rc, self.lib.ordm_last_error(None).decode())
+        self.npts = 0
+
+    def _ck(self, rc):
+        if rc:
+            raise OrdmError(rc, self.lib.ordm_last_error(self.ctx).decode())
+
+    def close(self):
+        if self.ctx:
+            self.lib.ordm_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- inputs
+    def set_stream(self, cuda_stream_handle: int):
+        self._ck(self.lib.ordm_set_stream(self.ctx, C.c_void_p(cuda_stream_handle)))
+
+    def set_options(self, diagnostics=False, pi_gradient=False):
+        self._ck(self.lib.ordm_set_options(self.ctx, (OPT_DIAGNOSTICS if diagnostics else 0) | (OPT_PI_GRADIENT if pi_gradient else 0)))
+
+    def set_grid(self, w):
+        w = _f(w)
+        self.npts = int(w.shape[0])
+        self._ck(self.lib.ordm_set_grid(self.ctx, self.npts, _d(w)))
+
+    def set_orbitals(self, phi, grads=None):
+        phi = _f(phi)
+        npts, n = phi.shape
+        g = [_f(x) for x in grads] if grads is not None else [None] * 3
+        self._ck(self.lib.ordm_set_orbitals(self.ctx, npts, n, max(npts, 1), _d(phi), _d(g[0]), _d(g[1]), _d(g[2])))
+
+    def set_rdm1(self, D1a, D1b):
+        D1a, D1b = _f(D1a), _f(D1b)
+        self._ck(self.lib.ordm_set_rdm1(self.ctx, D1a.shape[0], _d(D1a), _d(D1b)))
+
+    def set_rdm2ab_dense(self, D2ab, n):
+        D2ab = _f(D2ab)
+        self._ck(self.lib.ordm_set_rdm2ab_dense(self.ctx, n, _d(D2ab)))
+
+    def set_active_space(self, ncore, A1a, A1b, D2act):
+        A1a, A1b, D2act = _f(A1a), _f(A1b), _f(D2act)
+        self._ck(self.lib.ordm_set_active_space(self.ctx, ncore, A1a.shape[0], _d(A1a), _d(A1b), _d(D2act)))
+
+    def synth_fill(self, seed, npts_total, p0, m, n, gga):
+        self._ck(self.lib.ordm_synth_fill_device(self.ctx, seed, npts_total, p0, m, n, int(gga)))
+        self.npts = m
+
+    # ---- stages
+    def build_rho(self): self._ck(self.lib.ordm_build_rho(self.ctx))
+    def build_pi(self): self._ck(self.lib.ordm_build_pi(self.ctx))
+    def build_R(self): self._ck(self.lib.ordm_build_R(self.ctx))
+    def translate(self): self._ck(self.lib.ordm_translate(self.ctx))
+
+    def integrated_densities(self):
+        n = (C.c_double * 3)(); t = (C.c_double * 3)()
+        self._ck(self.lib.ordm_integrated_densities(self.ctx, n, t))
+        return list(n), list(t)
+
+    def functional(self, term, ra, rb, saa=None, sab=None, sbb=None) -> float:
+        ra, rb, saa, sab, sbb = (_f(x) for x in (ra, rb, saa, sab, sbb))
+        e = C.c_double()
+        self._ck(self.lib.ordm_functional(self.ctx, term, ra.shape[0], _d(ra), _d(rb), _d(saa), _d(sab), _d(sbb), C.byref(e)))
+        return e.value
+
+    def energy(self, functional=FUNC_SVWN, eclass=0.0) -> dict:
+        r = Result()
+        self._ck(self.lib.ordm_energy(self.ctx, functional, eclass, C.byref(r)))
+        return r.asdict()
+
+    def energy_host(self, functional, eclass, w, phi, grads=None, batch_points=0, ld=None) -> dict:
+        """w, phi, grads: numpy arrays (ideally views of pinned memory, see host_empty)."""
+        npts, n = phi.shape
+        g = grads if grads is not None else [None] * 3
+        r = Result()
+        self._ck(self.lib.ordm_energy_host(self.ctx, functional, eclass, npts, n, ld or max(npts, 1), _d(w), _d(phi),
+                                           _d(g[0]), _d(g[1]), _d(g[2]), batch_points, C.byref(r)))
+        return r.asdict()
+
+    def get_vector(self, name) -> np.ndarray:
+        out = np.zeros(self.npts)
+        self._ck(self.lib.ordm_get_vector(self.ctx, VEC_ID[name], _d(out), self.npts))
+        return out
+
+    def synchronize(self): self._ck(self.lib.ordm_synchronize(self.ctx))
+
+    # ---- multi-GPU
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = load().ordm_comm_unique_id(buf)
+        if rc:
+            raise OrdmError(rc, load().ordm_last_error(None).decode())
+        return buf.raw
+
+    def comm_attach(self, nranks, rank, uid: bytes):
+        self._ck(self.lib.ordm_comm_attach(self.ctx, nranks, rank, C.c_char_p(uid) if False else C.create_string_buffer(uid, 128)))
+
+
+def host_empty(shape, order="F") -> np.ndarray:
+    """numpy array backed by page-locked host memory (ordm_host_alloc); freed with the process."""
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    rc = load().ordm_host_alloc(n * 8, C.byref(p))
+    if rc:
+        raise OrdmError(rc, load().ordm_last_error(None).decode())
+    buf = (C.c_double * n).from_address(p.value)
+    return np.frombuffer(buf, dtype=np.float64).reshape(shape, order=order)

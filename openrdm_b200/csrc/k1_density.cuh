@@ -1,0 +1,207 @@
+// k1_density.cuh -- K1: spin densities, their gradients and sigma on the grid.
+// Replaces MCPDFT::build_density_functions (mcpdft.cc:42-105) and build_density_gradients
+// (mcpdft.cc:107-176).
+//
+// HBM layout: phi, phi_x, phi_y, phi_z are column-major [n_occ][ld] FP64 (point index fastest,
+// exactly arma::mat(npts,nbfs)); one thread owns one grid point, so every load instruction of
+// a warp reads 256 contiguous bytes of one orbital column.  The kernel is a pure stream over
+// 8*n_occ*(1+3*GGA) bytes per point.
+//
+// Orbitals are [ncore | nact].  Core orbitals have D1a = D1b = 1 on the diagonal, so
+//     rho_c = sum phi_i^2,      grad rho_c = 2 sum phi_i grad phi_i          (closed form)
+// The active block uses the symmetrised 1-RDMs Ds = (D + D^T)/2 held in constant memory
+// (a DFMA reads its coefficient straight from the constant bank, no load instruction):
+//     T_s = Ds_s . phi_act(p),  rho_t,s = T_s . phi_act,  grad rho_t,s = 2 T_s . grad phi_act
+// which reproduces mcpdft.cc:83-84 and :148-153 for arbitrary, non-symmetric D1
+// (SURVEY.md Appendix B.2).  Also emitted for K2/K3: pi_core = rc^2 + rc*rtb + rta*rc
+// (Appendix B.3) and the total gradient grad rho = grad rho_a + grad rho_b (mcpdft.cc:381-383).
+#pragma once
+#include <cuda_runtime.h>
+#include "reduce.cuh"
+
+namespace k1 {
+
+constexpr int MAX_ACT = 32;      // active orbitals handled by the register-tiled kernel
+constexpr int THREADS = 128;
+
+__constant__ double c_Dsa[MAX_ACT * MAX_ACT];
+__constant__ double c_Dsb[MAX_ACT * MAX_ACT];
+
+struct Params {
+  const double* phi;   // [n][ld]
+  const double* phix;  // nullable when !GGA
+  const double* phiy;
+  const double* phiz;
+  const double* w;
+  size_t ld;
+  size_t npts;
+  int ncore, nact;
+  // outputs (each npts long, any may be null)
+  double* rho;      // total density
+  double* gx;       // total gradient
+  double* gy;
+  double* gz;
+  double* pi_core;  // closed-form core part of Pi (null when ncore == 0 => treated as 0)
+  double* rhoa;     // diagnostics
+  double* rhob;
+  double* grad[6];  // ax ay az bx by bz
+  double* saa;
+  double* sab;
+  double* sbb;
+  double* partial;  // [gridDim.x][3] : sum rho*w, rho_a*w, rho_b*w
+  // generic path only: symmetrised active 1-RDMs in global memory
+  const double* Dsa_g;
+  const double* Dsb_g;
+};
+
+__device__ __forceinline__ void st(double* p, size_t i, double v) {
+  if (p) p[i] = v;
+}
+
+// NP = nact rounded up to a multiple of 4 (coefficients beyond nact are zero-padded).
+template <int NP, bool GGA>
+__global__ void __launch_bounds__(THREADS) k1_density(const Params P) {
+  __shared__ double scratch[3 * 32];
+  double acc[3] = {0.0, 0.0, 0.0};
+  const size_t ld = P.ld;
+  for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS) {
+    // ---- core orbitals: closed form, 4 columns (16 independent loads when GGA) per trip ----
+    double rc = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+    int i = 0;
+    for (; i + 4 <= P.ncore; i += 4) {
+      double v[4], vx[4], vy[4], vz[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const size_t o = (size_t)(i + j) * ld + p;
+        v[j] = __ldg(P.phi + o);
+        if (GGA) { vx[j] = __ldg(P.phix + o); vy[j] = __ldg(P.phiy + o); vz[j] = __ldg(P.phiz + o); }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rc = fma(v[j], v[j], rc);
+        if (GGA) { cx = fma(v[j], vx[j], cx); cy = fma(v[j], vy[j], cy); cz = fma(v[j], vz[j], cz); }
+      }
+    }
+    for (; i < P.ncore; ++i) {
+      const size_t o = (size_t)i * ld + p;
+      const double v = __ldg(P.phi + o);
+      rc = fma(v, v, rc);
+      if (GGA) {
+        cx = fma(v, __ldg(P.phix + o), cx);
+        cy = fma(v, __ldg(P.phiy + o), cy);
+        cz = fma(v, __ldg(P.phiz + o), cz);
+      }
+    }
+    // ---- active orbitals: T = Ds . phi_act in registers ----
+    double f[NP];
+#pragma unroll
+    for (int t = 0; t < NP; ++t) f[t] = (t < P.nact) ? __ldg(P.phi + (size_t)(P.ncore + t) * ld + p) : 0.0;
+    double ra = 0.0, rb = 0.0, ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+#pragma unroll
+    for (int t = 0; t < NP; ++t) {
+      double Ta = 0.0, Tb = 0.0;
+#pragma unroll
+      for (int u = 0; u < NP; ++u) {
+        Ta = fma(c_Dsa[t * MAX_ACT + u], f[u], Ta);
+        Tb = fma(c_Dsb[t * MAX_ACT + u], f[u], Tb);
+      }
+      ra = fma(Ta, f[t], ra);
+      rb = fma(Tb, f[t], rb);
+      if (GGA) {
+        if (t < P.nact) {
+          const size_t o = (size_t)(P.ncore + t) * ld + p;
+          const double fx = __ldg(P.phix + o), fy = __ldg(P.phiy + o), fz = __ldg(P.phiz + o);
+          ax = fma(Ta, fx, ax); ay = fma(Ta, fy, ay); az = fma(Ta, fz, az);
+          bx = fma(Tb, fx, bx); by = fma(Tb, fy, by); bz = fma(Tb, fz, bz);
+        }
+      }
+    }
+    const double rhoa = rc + ra, rhob = rc + rb;
+    const double rho = rhoa + rhob;  // mcpdft.cc:89
+    st(P.rho, p, rho);
+    st(P.rhoa, p, rhoa);
+    st(P.rhob, p, rhob);
+    st(P.pi_core, p, rc * rc + rc * rb + ra * rc);
+    if (GGA) {
+      ax = 2.0 * (cx + ax); ay = 2.0 * (cy + ay); az = 2.0 * (cz + az);
+      bx = 2.0 * (cx + bx); by = 2.0 * (cy + by); bz = 2.0 * (cz + bz);
+      st(P.gx, p, ax + bx);  // mcpdft.cc:381-383
+      st(P.gy, p, ay + by);
+      st(P.gz, p, az + bz);
+      st(P.grad[0], p, ax); st(P.grad[1], p, ay); st(P.grad[2], p, az);
+      st(P.grad[3], p, bx); st(P.grad[4], p, by); st(P.grad[5], p, bz);
+      st(P.saa, p, (ax * ax) + (ay * ay) + (az * az));  // mcpdft.cc:162-164
+      st(P.sbb, p, (bx * bx) + (by * by) + (bz * bz));
+      st(P.sab, p, (ax * bx) + (ay * by) + (az * bz));
+    }
+    const double wp = __ldg(P.w + p);
+    acc[0] = fma(rhoa + rhob, wp, acc[0]);  // mcpdft.cc:91-93
+    acc[1] = fma(rhoa, wp, acc[1]);
+    acc[2] = fma(rhob, wp, acc[2]);
+  }
+  ordm::block_sum_store<3>(acc, scratch, P.partial + (size_t)blockIdx.x * 3);
+}
+
+// Generic path for nact > MAX_ACT: same math, coefficients from global memory (L1/L2
+// resident), active orbital values re-read through L1.  Correct for any size; not tuned.
+template <bool GGA>
+__global__ void __launch_bounds__(THREADS) k1_density_generic(const Params P) {
+  __shared__ double scratch[3 * 32];
+  double acc[3] = {0.0, 0.0, 0.0};
+  const size_t ld = P.ld;
+  const int na = P.nact;
+  for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS) {
+    double rc = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+    for (int i = 0; i < P.ncore; ++i) {
+      const size_t o = (size_t)i * ld + p;
+      const double v = __ldg(P.phi + o);
+      rc = fma(v, v, rc);
+      if (GGA) {
+        cx = fma(v, __ldg(P.phix + o), cx);
+        cy = fma(v, __ldg(P.phiy + o), cy);
+        cz = fma(v, __ldg(P.phiz + o), cz);
+      }
+    }
+    double ra = 0.0, rb = 0.0, ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+    const double* fa = P.phi + (size_t)P.ncore * ld + p;
+    for (int t = 0; t < na; ++t) {
+      double Ta = 0.0, Tb = 0.0;
+      for (int u = 0; u < na; ++u) {
+        const double fu = __ldg(fa + (size_t)u * ld);
+        Ta = fma(__ldg(P.Dsa_g + t * na + u), fu, Ta);
+        Tb = fma(__ldg(P.Dsb_g + t * na + u), fu, Tb);
+      }
+      const double ft = __ldg(fa + (size_t)t * ld);
+      ra = fma(Ta, ft, ra);
+      rb = fma(Tb, ft, rb);
+      if (GGA) {
+        const size_t o = (size_t)(P.ncore + t) * ld + p;
+        const double fx = __ldg(P.phix + o), fy = __ldg(P.phiy + o), fz = __ldg(P.phiz + o);
+        ax = fma(Ta, fx, ax); ay = fma(Ta, fy, ay); az = fma(Ta, fz, az);
+        bx = fma(Tb, fx, bx); by = fma(Tb, fy, by); bz = fma(Tb, fz, bz);
+      }
+    }
+    const double rhoa = rc + ra, rhob = rc + rb, rho = rhoa + rhob;
+    st(P.rho, p, rho);
+    st(P.rhoa, p, rhoa);
+    st(P.rhob, p, rhob);
+    st(P.pi_core, p, rc * rc + rc * rb + ra * rc);
+    if (GGA) {
+      ax = 2.0 * (cx + ax); ay = 2.0 * (cy + ay); az = 2.0 * (cz + az);
+      bx = 2.0 * (cx + bx); by = 2.0 * (cy + by); bz = 2.0 * (cz + bz);
+      st(P.gx, p, ax + bx); st(P.gy, p, ay + by); st(P.gz, p, az + bz);
+      st(P.grad[0], p, ax); st(P.grad[1], p, ay); st(P.grad[2], p, az);
+      st(P.grad[3], p, bx); st(P.grad[4], p, by); st(P.grad[5], p, bz);
+      st(P.saa, p, (ax * ax) + (ay * ay) + (az * az));
+      st(P.sbb, p, (bx * bx) + (by * by) + (bz * bz));
+      st(P.sab, p, (ax * bx) + (ay * by) + (az * bz));
+    }
+    const double wp = __ldg(P.w + p);
+    acc[0] = fma(rhoa + rhob, wp, acc[0]);
+    acc[1] = fma(rhoa, wp, acc[1]);
+    acc[2] = fma(rhob, wp, acc[2]);
+  }
+  ordm::block_sum_store<3>(acc, scratch, P.partial + (size_t)blockIdx.x * 3);
+}
+
+}  // namespace k1

@@ -1,0 +1,101 @@
+// k3_xc.cuh -- K3: R(r), density translation and the translated on-top functional, fused
+// into one elementwise pass with the weighted quadrature partial sums.
+// Replaces MCPDFT::build_R (mcpdft.cc:272-285), translate_density (294-344),
+// translate_density_gradients (346-416) and Functional::EX_LSDA+EC_VWN3 | EX_PBE+EC_PBE
+// (functional.cc:12-309) as dispatched by mcpdft_energy (energy.cc:110-122).
+//
+// Energy-only traffic: 24 B/point (rho, Pi, w) for tSVWN, 48 B/point (+ grad rho) for tPBE;
+// with diagnostics on, R, rho~a, rho~b (and sigma~aa/ab/bb) are also written (+8 B each).
+// No intermediate per-point vector is re-read: everything between the loads and the five
+// partial sums stays in registers.
+#pragma once
+#include <cuda_runtime.h>
+#include "reduce.cuh"
+#include "xc_math.cuh"
+
+namespace k3 {
+
+constexpr int THREADS = 256;
+
+struct Params {
+  const double* rho;
+  const double* pi;
+  const double* w;
+  const double* gx;  // total density gradient (GGA only)
+  const double* gy;
+  const double* gz;
+  size_t npts;
+  // optional diagnostics (null = not written)
+  double* R;
+  double* tra;
+  double* trb;
+  double* tsaa;
+  double* tsab;
+  double* tsbb;
+  double* partial;  // [gridDim.x][5] : trN, trNa, trNb, Ex, Ec
+};
+
+template <bool PBE>
+__global__ void __launch_bounds__(THREADS) k3_translate_xc(const Params P) {
+  __shared__ double scratch[5 * 32];
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS) {
+    const double rho = __ldg(P.rho + p), pi = __ldg(P.pi + p), w = __ldg(P.w + p);
+    double gx = 0.0, gy = 0.0, gz = 0.0;
+    if (PBE) { gx = __ldg(P.gx + p); gy = __ldg(P.gy + p); gz = __ldg(P.gz + p); }
+    const xc::Translated t = xc::translate_pt<PBE>(rho, pi, gx, gy, gz);
+    double ex, ec;
+    if (PBE) {
+      ex = xc::ex_pbe_pt(t.ra, t.rb, t.saa, t.sbb);
+      ec = xc::ec_pbe_pt(t.ra, t.rb, t.saa, t.sab, t.sbb);
+    } else {
+      ex = xc::ex_lsda_pt(t.ra, t.rb);
+      ec = xc::ec_vwn3_pt(t.ra, t.rb);
+    }
+    acc[0] = fma(t.ra + t.rb, w, acc[0]);  // mcpdft.cc:332-334
+    acc[1] = fma(t.ra, w, acc[1]);
+    acc[2] = fma(t.rb, w, acc[2]);
+    acc[3] = fma(ex, w, acc[3]);
+    acc[4] = fma(ec, w, acc[4]);
+    if (P.R) P.R[p] = t.R;
+    if (P.tra) P.tra[p] = t.ra;
+    if (P.trb) P.trb[p] = t.rb;
+    if (PBE) {
+      if (P.tsaa) P.tsaa[p] = t.saa;
+      if (P.tsab) P.tsab[p] = t.sab;
+      if (P.tsbb) P.tsbb[p] = t.sbb;
+    }
+  }
+  ordm::block_sum_store<5>(acc, scratch, P.partial + (size_t)blockIdx.x * 5);
+}
+
+// libfunc's four entry points on caller-provided vectors (functional.h:17-43):
+// one weighted sum per call, partial[blockIdx.x] = sum over this block's points.
+struct FuncParams {
+  const double* ra;
+  const double* rb;
+  const double* saa;
+  const double* sab;
+  const double* sbb;
+  const double* w;
+  size_t npts;
+  double* partial;  // [gridDim.x][1]
+};
+
+template <int TERM>
+__global__ void __launch_bounds__(THREADS) k3_functional(const FuncParams P) {
+  __shared__ double scratch[32];
+  double acc[1] = {0.0};
+  for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS) {
+    const double ra = __ldg(P.ra + p), rb = __ldg(P.rb + p);
+    double e;
+    if (TERM == 0) e = xc::ex_lsda_pt(ra, rb);
+    else if (TERM == 1) e = xc::ec_vwn3_pt(ra, rb);
+    else if (TERM == 2) e = xc::ex_pbe_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sbb + p));
+    else e = xc::ec_pbe_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sab + p), __ldg(P.sbb + p));
+    acc[0] = fma(e, __ldg(P.w + p), acc[0]);
+  }
+  ordm::block_sum_store<1>(acc, scratch, P.partial + blockIdx.x);
+}
+
+}  // namespace k3

@@ -1,0 +1,940 @@
+// ordm_api.cu -- the C ABI of include/openrdm_b200.h on top of the sm_100a kernels.
+//
+// Host orchestration of OpenRDM's MC-PDFT energy path (energy.cc:27-188):
+//   K1 k1_density  ->  K2 k2_ontop  ->  K3 k3_translate_xc  ->  K4 k4_finalize  (-> NCCL)
+// all on one CUDA stream per context.  There is no CPU implementation of any stage here:
+// without a CUDA device every compute entry point returns ORDM_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/openrdm_b200.h"
+#include "../../include/ordm_synth.h"
+#include "k1_density.cuh"
+#include "k2_ontop.cuh"
+#include "k3_xc.cuh"
+#include "rdm_pack.h"
+#include "reduce.cuh"
+#include "synth_rdm.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+constexpr size_t PT_ALIGN = 64;  // device leading dimensions are multiples of 64 points
+inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct GridView {  // one resident grid or one streamed batch
+  size_t npts = 0, ld = 0;
+  int n = 0;
+  bool gga = false;
+  const double *w = nullptr, *phi = nullptr, *phix = nullptr, *phiy = nullptr, *phiz = nullptr;
+  double* vec[ORDM_VEC_COUNT] = {};  // per-point outputs (null = not materialised)
+  double *gx = nullptr, *gy = nullptr, *gz = nullptr, *pi_core = nullptr;
+};
+
+// ---- NCCL through dlopen (no link-time dependency; absent NCCL only breaks comm_attach) ----
+struct IdBlob { char b[128]; };  // ncclUniqueId (nccl.h:37-38), passed by value
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, IdBlob, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+bool load_nccl(std::string& why) {
+  if (g_nccl.handle) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle) break;
+  }
+  if (!g_nccl.handle) { why = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.handle, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, IdBlob, int))dlsym(g_nccl.handle, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.handle, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.handle, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.handle, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    why = "libnccl is missing a required symbol";
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+struct ordm_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  bool own_stream = true;
+  unsigned opts = 0;
+  std::string err;
+
+  // resident grid
+  GridView g;
+  double *d_w = nullptr, *d_phi[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t cap_pts = 0;  // allocated ld
+  int cap_n = 0;
+  bool cap_gga = false;
+  size_t vec_cap = 0;
+  bool vec_diag = false;
+
+  // RDMs
+  int ncore = 0, nact = 0;
+  bool have_rdm1 = false, have_rdm2 = false, core_form = false;
+  std::vector<double> h_Dsa, h_Dsb;  // symmetrised, row-major stride k1::MAX_ACT (or nact when generic)
+  double *d_Dsa_g = nullptr, *d_Dsb_g = nullptr;
+  // K2 operands
+  int k2_npg = 0, k2_mt = 0;
+  k2::Params k2p{};
+  double* d_dfrag = nullptr;
+  uint16_t* d_pairs = nullptr;
+  size_t k2_smem = 0;
+  std::vector<double> h_Dt;  // folded Dt kept for repacking when the tile shape changes
+
+  // reductions
+  double *d_partial = nullptr, *d_res = nullptr, *h_res = nullptr;
+  size_t partial_cap = 0;
+  cudaEvent_t ev[6] = {};
+
+  // streamed (host-buffer) path
+  struct Stage {
+    double *w = nullptr, *phi[4] = {nullptr, nullptr, nullptr, nullptr};
+    double* vec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // rho pi gx gy gz pi_core
+    cudaEvent_t copied = nullptr, done = nullptr;
+  } stage[2];
+  size_t stage_pts = 0;
+  int stage_n = 0;
+  bool stage_gga = false;
+
+  // stage bookkeeping
+  bool rho_done = false, pi_done = false, xc_done = false;
+  double last_n[3] = {0, 0, 0}, last_trn[3] = {0, 0, 0};
+
+  // NCCL
+  void* comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+
+namespace {
+
+int fail(ordm_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define CU(ctx, call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(ctx, ORDM_ERR_CUDA, "CUDA error '%s' in %s (%s:%d)", cudaGetErrorString(e_), \
+                  #call, __FILE__, __LINE__);                                                  \
+  } while (0)
+
+#define CHECK_CTX(ctx) \
+  if (!(ctx)) return fail(nullptr, ORDM_ERR_INVALID, "null context")
+
+template <typename T>
+void dfree(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+int ensure_partials(ordm_ctx* c, size_t doubles) {
+  if (doubles <= c->partial_cap) return ORDM_OK;
+  dfree(c->d_partial);
+  CU(c, cudaMalloc(&c->d_partial, doubles * sizeof(double)));
+  c->partial_cap = doubles;
+  return ORDM_OK;
+}
+
+// (re)allocate the resident per-point vectors according to the option flags
+int ensure_vectors(ordm_ctx* c) {
+  const bool diag = (c->opts & ORDM_OPT_DIAGNOSTICS) != 0;
+  const bool pig = (c->opts & ORDM_OPT_PI_GRADIENT) != 0;
+  GridView& g = c->g;
+  if (c->vec_cap >= g.ld && c->vec_diag == diag && g.vec[ORDM_VEC_RHO] && (!pig || g.vec[ORDM_VEC_PI_X])) return ORDM_OK;
+  for (int i = 0; i < ORDM_VEC_COUNT; ++i)
+    if (i != ORDM_VEC_W) dfree(g.vec[i]);
+  dfree(g.gx); dfree(g.gy); dfree(g.gz); dfree(g.pi_core);
+  const size_t bytes = g.ld * sizeof(double);
+  auto al = [&](double*& p) -> cudaError_t { cudaError_t e = cudaMalloc(&p, bytes); if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, bytes, c->stream); return e; };
+  CU(c, al(g.vec[ORDM_VEC_RHO]));
+  CU(c, al(g.vec[ORDM_VEC_PI]));
+  CU(c, al(g.gx)); CU(c, al(g.gy)); CU(c, al(g.gz));
+  CU(c, al(g.pi_core));
+  if (diag) {
+    for (int i = 0; i < ORDM_VEC_COUNT; ++i) {
+      if (i == ORDM_VEC_W || i == ORDM_VEC_RHO || i == ORDM_VEC_PI) continue;
+      if (i >= ORDM_VEC_PI_X && i <= ORDM_VEC_PI_Z && !pig) continue;
+      CU(c, al(g.vec[i]));
+    }
+  } else if (pig) {
+    CU(c, al(g.vec[ORDM_VEC_PI_X])); CU(c, al(g.vec[ORDM_VEC_PI_Y])); CU(c, al(g.vec[ORDM_VEC_PI_Z]));
+  }
+  c->vec_cap = g.ld;
+  c->vec_diag = diag;
+  return ORDM_OK;
+}
+
+// ------------------------------------------------------------------ kernel launchers
+template <bool GGA>
+int launch_k1_np(ordm_ctx* c, const k1::Params& p, int grid) {
+  const int np = (int)round_up((size_t)std::max(c->nact, 1), 4);
+  switch (np) {
+#define K1CASE(N) case N: k1::k1_density<N, GGA><<<grid, k1::THREADS, 0, c->stream>>>(p); break;
+    K1CASE(4) K1CASE(8) K1CASE(12) K1CASE(16) K1CASE(20) K1CASE(24) K1CASE(28) K1CASE(32)
+#undef K1CASE
+    default: k1::k1_density_generic<GGA><<<grid, k1::THREADS, 0, c->stream>>>(p); break;
+  }
+  CU(c, cudaGetLastError());
+  return ORDM_OK;
+}
+
+int k1_grid(const ordm_ctx* c, size_t npts) {
+  const size_t want = (npts + k1::THREADS - 1) / k1::THREADS;
+  return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 16));
+}
+int k3_grid(const ordm_ctx* c, size_t npts) {
+  const size_t want = (npts + k3::THREADS - 1) / k3::THREADS;
+  return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 8));
+}
+
+int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches) {
+  if (c->nact <= k1::MAX_ACT) {
+    CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsa, c->h_Dsa.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsb, c->h_Dsb.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, c->stream));
+  }
+  k1::Params p{};
+  p.phi = v.phi; p.phix = v.phix; p.phiy = v.phiy; p.phiz = v.phiz; p.w = v.w;
+  p.ld = v.ld; p.npts = v.npts; p.ncore = c->ncore; p.nact = c->nact;
+  p.rho = v.vec[ORDM_VEC_RHO];
+  p.gx = v.gx; p.gy = v.gy; p.gz = v.gz;
+  p.pi_core = c->core_form ? v.pi_core : nullptr;
+  p.rhoa = v.vec[ORDM_VEC_RHOA]; p.rhob = v.vec[ORDM_VEC_RHOB];
+  for (int i = 0; i < 6; ++i) p.grad[i] = v.vec[ORDM_VEC_RHOA_X + i];
+  p.saa = v.vec[ORDM_VEC_SIGMA_AA]; p.sab = v.vec[ORDM_VEC_SIGMA_AB]; p.sbb = v.vec[ORDM_VEC_SIGMA_BB];
+  p.Dsa_g = c->d_Dsa_g; p.Dsb_g = c->d_Dsb_g;
+  const int grid = k1_grid(c, v.npts);
+  int rc = ensure_partials(c, (size_t)c->sm_count * 16 * 8);
+  if (rc) return rc;
+  p.partial = c->d_partial;
+  rc = v.gga ? launch_k1_np<true>(c, p, grid) : launch_k1_np<false>(c, p, grid);
+  if (rc) return rc;
+  ordm::k4_finalize<3><<<1, 256, 0, c->stream>>>(c->d_partial, grid, c->d_res, ordm::RES_N, accumulate);
+  CU(c, cudaGetLastError());
+  *launches += 2;
+  return ORDM_OK;
+}
+
+template <int NPG, int MT>
+int launch_k2(ordm_ctx* c, k2::Params p) {
+  constexpr int P = 8 * MT * NPG;
+  p.ntiles = (int)((p.npts + P - 1) / P);
+  const int grid = std::max(1, std::min(p.ntiles, c->sm_count));
+  static thread_local int attr_dev = -1;
+  static thread_local size_t attr_bytes = 0;
+  if (attr_dev != c->device || attr_bytes < c->k2_smem) {
+    CU(c, cudaFuncSetAttribute(k2::k2_ontop<NPG, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k2_smem));
+    attr_dev = c->device;
+    attr_bytes = c->k2_smem;
+  }
+  k2::k2_ontop<NPG, MT><<<grid, k2::THREADS, c->k2_smem, c->stream>>>(p);
+  CU(c, cudaGetLastError());
+  return ORDM_OK;
+}
+
+int run_k2(ordm_ctx* c, const GridView& v, int* launches) {
+  k2::Params p = c->k2p;
+  p.phi_act = v.phi + (size_t)c->ncore * v.ld;
+  p.ld = v.ld;
+  p.npts = v.npts;
+  p.pi_core = c->core_form ? v.pi_core : nullptr;
+  p.pi = v.vec[ORDM_VEC_PI];
+  int rc;
+  if (c->k2_npg == 2 && c->k2_mt == 4) rc = launch_k2<2, 4>(c, p);
+  else if (c->k2_npg == 1 && c->k2_mt == 4) rc = launch_k2<1, 4>(c, p);
+  else if (c->k2_npg == 1 && c->k2_mt == 2) rc = launch_k2<1, 2>(c, p);
+  else rc = launch_k2<1, 1>(c, p);
+  if (rc) return rc;
+  *launches += 1;
+  return ORDM_OK;
+}
+
+int run_k3(ordm_ctx* c, const GridView& v, int functional, int accumulate, int* launches) {
+  k3::Params p{};
+  p.rho = v.vec[ORDM_VEC_RHO]; p.pi = v.vec[ORDM_VEC_PI]; p.w = v.w;
+  p.gx = v.gga ? v.gx : nullptr; p.gy = v.gga ? v.gy : nullptr; p.gz = v.gga ? v.gz : nullptr;
+  p.npts = v.npts;
+  p.R = v.vec[ORDM_VEC_R]; p.tra = v.vec[ORDM_VEC_TR_RHOA]; p.trb = v.vec[ORDM_VEC_TR_RHOB];
+  p.tsaa = v.vec[ORDM_VEC_TR_SIGMA_AA]; p.tsab = v.vec[ORDM_VEC_TR_SIGMA_AB]; p.tsbb = v.vec[ORDM_VEC_TR_SIGMA_BB];
+  const int grid = k3_grid(c, v.npts);
+  int rc = ensure_partials(c, (size_t)c->sm_count * 16 * 8);
+  if (rc) return rc;
+  p.partial = c->d_partial;
+  // energy.cc:114-120: "SVWN" -> LSDA+VWN3, else PBE.  Without orbital gradients the
+  // translated sigma are zero vectors (energy.cc:63-65): PBE then runs with gx=gy=gz=0.
+  if (functional == ORDM_FUNC_SVWN) k3::k3_translate_xc<false><<<grid, k3::THREADS, 0, c->stream>>>(p);
+  else {
+    if (!v.gga) { p.gx = p.gy = p.gz = nullptr; }
+    k3::k3_translate_xc<true><<<grid, k3::THREADS, 0, c->stream>>>(p);
+  }
+  CU(c, cudaGetLastError());
+  ordm::k4_finalize<5><<<1, 256, 0, c->stream>>>(c->d_partial, grid, c->d_res, ordm::RES_TRN, accumulate);
+  CU(c, cudaGetLastError());
+  *launches += 2;
+  return ORDM_OK;
+}
+
+// choose the K2 tile shape that fits shared memory and (re)pack Dt' for its lane count
+int configure_k2(ordm_ctx* c) {
+  const int M = ordm::pair_count(c->nact);
+  const int nblk = (M + k2::BLK - 1) / k2::BLK, Mpad = nblk * k2::BLK;
+  struct Cand { int npg, mt; size_t bytes; } cand[4] = {
+      {2, 4, k2::Smem<64>::bytes(Mpad, c->nact)}, {1, 4, k2::Smem<32>::bytes(Mpad, c->nact)},
+      {1, 2, k2::Smem<16>::bytes(Mpad, c->nact)}, {1, 1, k2::Smem<8>::bytes(Mpad, c->nact)}};
+  int pick = -1;
+  for (int i = 0; i < 4; ++i)
+    if (cand[i].bytes <= (size_t)c->max_smem_optin) { pick = i; break; }
+  if (pick < 0)
+    return fail(c, ORDM_ERR_UNSUPPORTED, "on-top pair density: %d orbitals (M=%d pairs) exceed shared memory; use ordm_set_active_space with a smaller active block", c->nact, M);
+  c->k2_npg = cand[pick].npg;
+  c->k2_mt = cand[pick].mt;
+  c->k2_smem = cand[pick].bytes;
+  ordm::DfragLayout lay;
+  ordm::pack_dfrag(M, c->h_Dt, k2::WARPS / c->k2_npg, k2::PREFETCH, lay);
+  std::vector<uint16_t> tab;
+  ordm::pair_table(c->nact, Mpad, tab);
+  dfree(c->d_dfrag);
+  dfree(c->d_pairs);
+  CU(c, cudaMalloc(&c->d_dfrag, lay.data.size() * sizeof(double)));
+  CU(c, cudaMalloc(&c->d_pairs, tab.size() * sizeof(uint16_t)));
+  CU(c, cudaMemcpy(c->d_dfrag, lay.data.data(), lay.data.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(c->d_pairs, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  c->k2p = k2::Params{};
+  c->k2p.nact = c->nact; c->k2p.M = M; c->k2p.nblk = nblk; c->k2p.ntask = lay.ntask;
+  c->k2p.dfrag = c->d_dfrag; c->k2p.pairs = c->d_pairs;
+  for (int i = 0; i < k2::MAX_LANES; ++i) c->k2p.lane_ofs[i] = lay.lane_ofs[i];
+  return ORDM_OK;
+}
+
+int install_rdm1(ordm_ctx* c, int ncore, int nact, const double* A1a, const double* A1b) {
+  c->ncore = ncore;
+  c->nact = nact;
+  const int stride = (nact <= k1::MAX_ACT) ? k1::MAX_ACT : nact;
+  ordm::symmetrise_opdm(nact, A1a, stride, c->h_Dsa);
+  ordm::symmetrise_opdm(nact, A1b, stride, c->h_Dsb);
+  dfree(c->d_Dsa_g);
+  dfree(c->d_Dsb_g);
+  if (nact > k1::MAX_ACT) {
+    const size_t b = (size_t)nact * nact * sizeof(double);
+    CU(c, cudaMalloc(&c->d_Dsa_g, b));
+    CU(c, cudaMalloc(&c->d_Dsb_g, b));
+    CU(c, cudaMemcpy(c->d_Dsa_g, c->h_Dsa.data(), b, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->d_Dsb_g, c->h_Dsb.data(), b, cudaMemcpyHostToDevice));
+  }
+  c->have_rdm1 = true;
+  c->rho_done = c->pi_done = c->xc_done = false;
+  return ORDM_OK;
+}
+
+int check_inputs(ordm_ctx* c, bool need_rdm2) {
+  if (!c->g.w || !c->g.phi) return fail(c, ORDM_ERR_STATE, "grid/orbitals not set (ordm_set_grid, ordm_set_orbitals)");
+  if (!c->have_rdm1) return fail(c, ORDM_ERR_STATE, "1-RDMs not set (ordm_set_rdm1 / ordm_set_active_space)");
+  if (need_rdm2 && !c->have_rdm2) return fail(c, ORDM_ERR_STATE, "2-RDM not set (ordm_set_rdm2ab_dense / ordm_set_active_space)");
+  if (c->ncore + c->nact != c->g.n)
+    return fail(c, ORDM_ERR_STATE, "RDM dimension %d+%d does not match the %d orbital columns", c->ncore, c->nact, c->g.n);
+  return ORDM_OK;
+}
+
+int fetch_result(ordm_ctx* c, double eclass, ordm_result* out, uint64_t npts, int launches) {
+  CU(c, cudaMemcpyAsync(c->h_res, c->d_res, ordm::RES_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaEventRecord(c->ev[5], c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  const double* r = c->h_res;
+  std::memset(out, 0, sizeof(*out));
+  out->eclass = eclass;
+  out->ex = r[ordm::RES_EX];
+  out->ec = r[ordm::RES_EC];
+  out->e_tot = 0.0; out->e_tot += eclass; out->e_tot += out->ex; out->e_tot += out->ec;  // energy.cc:181-183
+  out->n_tot = r[ordm::RES_N]; out->n_a = r[ordm::RES_NA]; out->n_b = r[ordm::RES_NB];
+  out->trn_tot = r[ordm::RES_TRN]; out->trn_a = r[ordm::RES_TRNA]; out->trn_b = r[ordm::RES_TRNB];
+  out->npts = npts;
+  out->gpu_launches = (uint32_t)launches;
+  for (int i = 0; i < 3; ++i) { c->last_n[i] = r[ordm::RES_N + i]; c->last_trn[i] = r[ordm::RES_TRN + i]; }
+  return ORDM_OK;
+}
+
+// synthetic fill kernels ----------------------------------------------------------------
+__global__ void k_synth_phi(double* __restrict__ dst, size_t ld, size_t npts_local, size_t p0, size_t npts_total,
+                            int n, uint64_t comp_key, uint64_t env_key) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npts_local) return;
+  const double env = ordm_env_key(env_key, p0 + p);
+  for (int i = blockIdx.y; i < n; i += gridDim.y) dst[(size_t)i * ld + p] = ordm_synth_phi(comp_key, env, npts_total, p0 + p, (uint64_t)i);
+}
+__global__ void k_synth_w(double* __restrict__ dst, size_t npts_local, size_t p0, double inv_total, uint64_t w_key) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < npts_local) dst[p] = ordm_synth_w(w_key, inv_total, p0 + p);
+}
+
+int alloc_grid(ordm_ctx* c, size_t npts, int n, bool gga) {
+  const size_t ld = round_up(std::max<size_t>(npts, 1), PT_ALIGN);
+  if (ld > c->cap_pts || n > c->cap_n || (gga && !c->cap_gga) || !c->d_phi[0]) {
+    for (int k = 0; k < 4; ++k) dfree(c->d_phi[k]);
+    const size_t bytes = ld * (size_t)n * sizeof(double);
+    for (int k = 0; k < (gga ? 4 : 1); ++k) {
+      CU(c, cudaMalloc(&c->d_phi[k], bytes));
+      CU(c, cudaMemsetAsync(c->d_phi[k], 0, bytes, c->stream));
+    }
+    c->cap_pts = ld; c->cap_n = n; c->cap_gga = gga;
+  }
+  c->g.ld = c->cap_pts;
+  c->g.n = n;
+  c->g.gga = gga;
+  c->g.npts = npts;
+  c->g.phi = c->d_phi[0];
+  c->g.phix = gga ? c->d_phi[1] : nullptr;
+  c->g.phiy = gga ? c->d_phi[2] : nullptr;
+  c->g.phiz = gga ? c->d_phi[3] : nullptr;
+  c->rho_done = c->pi_done = c->xc_done = false;
+  return ORDM_OK;
+}
+
+int alloc_w(ordm_ctx* c, size_t npts) {
+  const size_t ld = round_up(std::max<size_t>(npts, 1), PT_ALIGN);
+  dfree(c->d_w);
+  CU(c, cudaMalloc(&c->d_w, ld * sizeof(double)));
+  CU(c, cudaMemsetAsync(c->d_w, 0, ld * sizeof(double), c->stream));
+  c->g.w = c->d_w;
+  c->g.vec[ORDM_VEC_W] = c->d_w;
+  c->rho_done = c->pi_done = c->xc_done = false;
+  return ORDM_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+//                                      C ABI
+// =========================================================================================
+extern "C" {
+
+const char* ordm_version(void) { return "openrdm_b200 0.1 (sm_100a)"; }
+
+int ordm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* ordm_last_error(const ordm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int ordm_create(int device, ordm_ctx** out) {
+  if (!out) return fail(nullptr, ORDM_ERR_INVALID, "null output pointer");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, ORDM_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, ORDM_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+  CU(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, ORDM_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+  ordm_ctx* c = new ordm_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  CU(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (auto& ev : c->ev) CU(c, cudaEventCreate(&ev));
+  CU(c, cudaMalloc(&c->d_res, 16 * sizeof(double)));
+  CU(c, cudaMemset(c->d_res, 0, 16 * sizeof(double)));
+  CU(c, cudaMallocHost(&c->h_res, 16 * sizeof(double)));
+  *out = c;
+  return ORDM_OK;
+}
+
+void ordm_destroy(ordm_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  for (int i = 0; i < ORDM_VEC_COUNT; ++i)
+    if (i != ORDM_VEC_W) dfree(c->g.vec[i]);
+  dfree(c->g.gx); dfree(c->g.gy); dfree(c->g.gz); dfree(c->g.pi_core);
+  dfree(c->d_w);
+  for (int k = 0; k < 4; ++k) dfree(c->d_phi[k]);
+  dfree(c->d_Dsa_g); dfree(c->d_Dsb_g); dfree(c->d_dfrag); dfree(c->d_pairs);
+  dfree(c->d_partial); dfree(c->d_res);
+  if (c->h_res) cudaFreeHost(c->h_res);
+  for (auto& s : c->stage) {
+    dfree(s.w);
+    for (auto& p : s.phi) dfree(p);
+    for (auto& p : s.vec) dfree(p);
+    if (s.copied) cudaEventDestroy(s.copied);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  for (auto& ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+int ordm_set_stream(ordm_ctx* c, void* s) {
+  CHECK_CTX(c);
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)s;
+  c->own_stream = false;
+  return ORDM_OK;
+}
+
+int ordm_set_options(ordm_ctx* c, unsigned flags) {
+  CHECK_CTX(c);
+  if (flags != c->opts) c->rho_done = c->pi_done = c->xc_done = false;
+  c->opts = flags;
+  return ORDM_OK;
+}
+
+int ordm_synchronize(ordm_ctx* c) {
+  CHECK_CTX(c);
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return ORDM_OK;
+}
+
+int ordm_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(nullptr, ORDM_ERR_INVALID, "null output pointer");
+  CU(nullptr, cudaMallocHost(out, bytes ? bytes : 1));
+  return ORDM_OK;
+}
+int ordm_host_free(void* p) {
+  if (p) CU(nullptr, cudaFreeHost(p));
+  return ORDM_OK;
+}
+
+// ---- inputs ------------------------------------------------------------------------------
+int ordm_set_grid(ordm_ctx* c, size_t npts, const double* w) {
+  CHECK_CTX(c);
+  if (npts && !w) return fail(c, ORDM_ERR_INVALID, "null weights");
+  CU(c, cudaSetDevice(c->device));
+  int rc = alloc_w(c, npts);
+  if (rc) return rc;
+  if (c->g.phi && c->g.npts != npts) { c->g.phi = nullptr; }  // orbitals must be re-set for a new grid size
+  c->g.npts = npts;
+  if (npts) CU(c, cudaMemcpyAsync(c->d_w, w, npts * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return ORDM_OK;
+}
+
+int ordm_set_orbitals(ordm_ctx* c, size_t npts, int n, size_t ld, const double* phi, const double* px, const double* py, const double* pz) {
+  CHECK_CTX(c);
+  if (n <= 0 || (npts && !phi) || ld < npts) return fail(c, ORDM_ERR_INVALID, "bad orbital matrix (n=%d, ld=%zu < npts=%zu or null)", n, ld, npts);
+  const bool gga = px || py || pz;
+  if (gga && !(px && py && pz)) return fail(c, ORDM_ERR_INVALID, "give all of phi_x, phi_y, phi_z or none");
+  if (c->g.w && c->g.npts != npts) return fail(c, ORDM_ERR_INVALID, "orbitals have %zu points but the grid has %zu", npts, c->g.npts);
+  CU(c, cudaSetDevice(c->device));
+  int rc = alloc_grid(c, npts, n, gga);
+  if (rc) return rc;
+  const double* src[4] = {phi, px, py, pz};
+  if (npts)
+    for (int k = 0; k < (gga ? 4 : 1); ++k)
+      CU(c, cudaMemcpy2DAsync(c->d_phi[k], c->g.ld * sizeof(double), src[k], ld * sizeof(double), npts * sizeof(double), (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return ORDM_OK;
+}
+
+int ordm_set_rdm1(ordm_ctx* c, int n, const double* D1a, const double* D1b) {
+  CHECK_CTX(c);
+  if (n <= 0 || !D1a || !D1b) return fail(c, ORDM_ERR_INVALID, "bad 1-RDM");
+  CU(c, cudaSetDevice(c->device));
+  if (c->core_form || c->nact != n) c->have_rdm2 = false;  // a dense D2 of another dimension is stale
+  c->core_form = false;
+  return install_rdm1(c, 0, n, D1a, D1b);
+}
+
+int ordm_set_rdm2ab_dense(ordm_ctx* c, int n, const double* D2ab) {
+  CHECK_CTX(c);
+  if (n <= 0 || !D2ab) return fail(c, ORDM_ERR_INVALID, "bad 2-RDM");
+  if (c->have_rdm1 && (c->core_form || c->nact != n))
+    return fail(c, ORDM_ERR_INVALID, "dense D2ab of %d orbitals does not match the 1-RDMs (%d+%d)", n, c->ncore, c->nact);
+  CU(c, cudaSetDevice(c->device));
+  if (!c->have_rdm1) { c->ncore = 0; c->nact = n; }
+  ordm::fold_tpdm(n, D2ab, c->h_Dt);
+  int rc = configure_k2(c);
+  if (rc) return rc;
+  c->have_rdm2 = true;
+  c->pi_done = c->xc_done = false;
+  return ORDM_OK;
+}
+
+int ordm_set_active_space(ordm_ctx* c, int ncore, int nact, const double* A1a, const double* A1b, const double* D2act) {
+  CHECK_CTX(c);
+  if (ncore < 0 || nact <= 0 || !A1a || !A1b) return fail(c, ORDM_ERR_INVALID, "bad active space (ncore=%d nact=%d)", ncore, nact);
+  CU(c, cudaSetDevice(c->device));
+  c->core_form = ncore > 0;
+  int rc = install_rdm1(c, ncore, nact, A1a, A1b);
+  if (rc) return rc;
+  if (D2act) {
+    ordm::fold_tpdm(nact, D2act, c->h_Dt);
+    rc = configure_k2(c);
+    if (rc) return rc;
+    c->have_rdm2 = true;
+  } else {
+    c->have_rdm2 = false;
+  }
+  return ORDM_OK;
+}
+
+// ---- stages -------------------------------------------------------------------------------
+int ordm_build_rho(ordm_ctx* c) {
+  CHECK_CTX(c);
+  CU(c, cudaSetDevice(c->device));
+  int rc = check_inputs(c, false);
+  if (rc) return rc;
+  if ((rc = ensure_vectors(c))) return rc;
+  int launches = 0;
+  if ((rc = run_k1(c, c->g, 0, &launches))) return rc;
+  CU(c, cudaMemcpyAsync(c->h_res, c->d_res, ordm::RES_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 3; ++i) c->last_n[i] = c->h_res[ordm::RES_N + i];
+  c->rho_done = true;
+  c->pi_done = c->xc_done = false;
+  return ORDM_OK;
+}
+
+int ordm_build_pi(ordm_ctx* c) {
+  CHECK_CTX(c);
+  CU(c, cudaSetDevice(c->device));
+  int rc = check_inputs(c, true);
+  if (rc) return rc;
+  if (c->opts & ORDM_OPT_PI_GRADIENT) return fail(c, ORDM_ERR_UNSUPPORTED, "ORDM_OPT_PI_GRADIENT is not implemented yet");
+  if (c->core_form && !c->rho_done) return fail(c, ORDM_ERR_STATE, "build_pi with core orbitals needs build_rho first (closed-form core terms)");
+  if ((rc = ensure_vectors(c))) return rc;
+  int launches = 0;
+  if ((rc = run_k2(c, c->g, &launches))) return rc;
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->pi_done = true;
+  c->xc_done = false;
+  return ORDM_OK;
+}
+
+static int staged_xc(ordm_ctx* c) {
+  if (!c->rho_done || !c->pi_done) return fail(c, ORDM_ERR_STATE, "build_R/translate need build_rho and build_pi first");
+  if (c->xc_done) return ORDM_OK;
+  int launches = 0;
+  int rc = run_k3(c, c->g, c->g.gga ? ORDM_FUNC_PBE : ORDM_FUNC_SVWN, 0, &launches);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(c->h_res, c->d_res, ordm::RES_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 3; ++i) c->last_trn[i] = c->h_res[ordm::RES_TRN + i];
+  c->xc_done = true;
+  return ORDM_OK;
+}
+
+int ordm_build_R(ordm_ctx* c) {
+  CHECK_CTX(c);
+  CU(c, cudaSetDevice(c->device));
+  return staged_xc(c);
+}
+int ordm_translate(ordm_ctx* c) {
+  CHECK_CTX(c);
+  CU(c, cudaSetDevice(c->device));
+  return staged_xc(c);
+}
+
+int ordm_integrated_densities(ordm_ctx* c, double n[3], double trn[3]) {
+  CHECK_CTX(c);
+  for (int i = 0; i < 3; ++i) {
+    if (n) n[i] = c->last_n[i];
+    if (trn) trn[i] = c->last_trn[i];
+  }
+  return ORDM_OK;
+}
+
+int ordm_functional(ordm_ctx* c, int term, size_t npts, const double* ra, const double* rb, const double* saa,
+                    const double* sab, const double* sbb, double* e_out) {
+  CHECK_CTX(c);
+  if (term < 0 || term > 3 || !e_out || (npts && (!ra || !rb))) return fail(c, ORDM_ERR_INVALID, "bad functional call");
+  if (!c->g.w || c->g.npts != npts) return fail(c, ORDM_ERR_STATE, "functional: set the %zu-point grid first (ordm_set_grid)", npts);
+  if ((term == ORDM_EX_PBE && (!saa || !sbb)) || (term == ORDM_EC_PBE && (!saa || !sab || !sbb)))
+    return fail(c, ORDM_ERR_INVALID, "functional: missing sigma vectors");
+  CU(c, cudaSetDevice(c->device));
+  const size_t bytes = std::max<size_t>(npts, 1) * sizeof(double);
+  double* d[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  const double* h[5] = {ra, rb, saa, sab, sbb};
+  int rc = ORDM_OK;
+  for (int i = 0; i < 5 && rc == ORDM_OK; ++i) {
+    if (!h[i]) continue;
+    if (cudaMalloc(&d[i], bytes) != cudaSuccess) { rc = fail(c, ORDM_ERR_CUDA, "out of device memory"); break; }
+    if (npts && cudaMemcpyAsync(d[i], h[i], npts * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = fail(c, ORDM_ERR_CUDA, "H2D copy failed");
+  }
+  if (rc == ORDM_OK) {
+    k3::FuncParams p{d[0], d[1], d[2], d[3], d[4], c->g.w, npts, nullptr};
+    const int grid = k3_grid(c, npts);
+    rc = ensure_partials(c, (size_t)c->sm_count * 16 * 8);
+    if (rc == ORDM_OK) {
+      p.partial = c->d_partial;
+      switch (term) {
+        case 0: k3::k3_functional<0><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
+        case 1: k3::k3_functional<1><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
+        case 2: k3::k3_functional<2><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
+        default: k3::k3_functional<3><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
+      }
+      ordm::k4_finalize<1><<<1, 256, 0, c->stream>>>(c->d_partial, grid, c->d_res, 8, 0);
+      cudaError_t e = cudaMemcpyAsync(c->h_res, c->d_res + 8, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess) rc = fail(c, ORDM_ERR_CUDA, "functional kernel failed: %s", cudaGetErrorString(e));
+      else *e_out = c->h_res[0];
+    }
+  }
+  cudaStreamSynchronize(c->stream);
+  for (auto& p : d) dfree(p);
+  return rc;
+}
+
+// ---- the path in one call -----------------------------------------------------------------
+int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
+  CHECK_CTX(c);
+  if (!out) return fail(c, ORDM_ERR_INVALID, "null result");
+  CU(c, cudaSetDevice(c->device));
+  int rc = check_inputs(c, true);
+  if (rc) return rc;
+  if (c->opts & ORDM_OPT_PI_GRADIENT) return fail(c, ORDM_ERR_UNSUPPORTED, "ORDM_OPT_PI_GRADIENT is not implemented yet");
+  if ((rc = ensure_vectors(c))) return rc;
+  int launches = 0;
+  CU(c, cudaEventRecord(c->ev[0], c->stream));
+  if ((rc = run_k1(c, c->g, 0, &launches))) return rc;
+  CU(c, cudaEventRecord(c->ev[1], c->stream));
+  if ((rc = run_k2(c, c->g, &launches))) return rc;
+  CU(c, cudaEventRecord(c->ev[2], c->stream));
+  if ((rc = run_k3(c, c->g, functional, 0, &launches))) return rc;
+  CU(c, cudaEventRecord(c->ev[3], c->stream));
+  if (c->comm) {
+    int nr = g_nccl.AllReduce(c->d_res, c->d_res, ordm::RES_COUNT, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream);
+    if (nr != 0) return fail(c, ORDM_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+    launches += 1;
+  }
+  CU(c, cudaEventRecord(c->ev[4], c->stream));
+  if ((rc = fetch_result(c, eclass, out, c->g.npts, launches))) return rc;
+  float ms;
+  CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); out->ms_density = ms;
+  CU(c, cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); out->ms_pi = ms;
+  CU(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); out->ms_xc = ms;
+  CU(c, cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); out->ms_reduce = ms;
+  CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[5])); out->ms_total = ms;
+  c->rho_done = c->pi_done = true;
+  c->xc_done = false;  // R/translated vectors belong to `functional`; staged getters recompute
+  if ((c->g.gga ? ORDM_FUNC_PBE : ORDM_FUNC_SVWN) == functional) c->xc_done = true;
+  return ORDM_OK;
+}
+
+int ordm_energy_host(ordm_ctx* c, int functional, double eclass, size_t npts, int n, size_t ld, const double* w,
+                     const double* phi, const double* px, const double* py, const double* pz, size_t batch,
+                     ordm_result* out) {
+  CHECK_CTX(c);
+  if (!out || !w || !phi || n <= 0 || ld < npts) return fail(c, ORDM_ERR_INVALID, "bad host buffers");
+  const bool gga = px || py || pz;
+  if (gga && !(px && py && pz)) return fail(c, ORDM_ERR_INVALID, "give all of phi_x, phi_y, phi_z or none");
+  if (!c->have_rdm1 || !c->have_rdm2) return fail(c, ORDM_ERR_STATE, "RDMs not set");
+  if (c->ncore + c->nact != n) return fail(c, ORDM_ERR_STATE, "RDM dimension %d+%d does not match n=%d", c->ncore, c->nact, n);
+  CU(c, cudaSetDevice(c->device));
+  if (batch == 0) batch = 1u << 18;
+  batch = round_up(std::min(batch, std::max<size_t>(npts, 1)), PT_ALIGN);
+  // (re)allocate the two staging sets
+  if (batch > c->stage_pts || n > c->stage_n || (gga && !c->stage_gga)) {
+    for (auto& s : c->stage) {
+      dfree(s.w);
+      for (auto& p : s.phi) dfree(p);
+      for (auto& p : s.vec) dfree(p);
+      CU(c, cudaMalloc(&s.w, batch * sizeof(double)));
+      for (int k = 0; k < (gga ? 4 : 1); ++k) {
+        CU(c, cudaMalloc(&s.phi[k], batch * (size_t)n * sizeof(double)));
+        CU(c, cudaMemset(s.phi[k], 0, batch * (size_t)n * sizeof(double)));
+      }
+      for (auto& p : s.vec) CU(c, cudaMalloc(&p, batch * sizeof(double)));
+      if (!s.copied) CU(c, cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+      if (!s.done) CU(c, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    c->stage_pts = batch; c->stage_n = n; c->stage_gga = gga;
+  }
+  int launches = 0;
+  CU(c, cudaMemsetAsync(c->d_res, 0, 16 * sizeof(double), c->stream));
+  CU(c, cudaEventRecord(c->ev[0], c->stream));
+  const double* src[4] = {phi, px, py, pz};
+  size_t ib = 0;
+  for (size_t p0 = 0; p0 < npts; p0 += batch, ++ib) {
+    ordm_ctx::Stage& s = c->stage[ib & 1];
+    const size_t m = std::min(batch, npts - p0);
+    if (ib >= 2) CU(c, cudaStreamWaitEvent(c->copy_stream, s.done, 0));  // staging set is free again
+    CU(c, cudaMemcpyAsync(s.w, w + p0, m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    for (int k = 0; k < (gga ? 4 : 1); ++k)
+      CU(c, cudaMemcpy2DAsync(s.phi[k], c->stage_pts * sizeof(double), src[k] + p0, ld * sizeof(double), m * sizeof(double), (size_t)n, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(c, cudaEventRecord(s.copied, c->copy_stream));
+    CU(c, cudaStreamWaitEvent(c->stream, s.copied, 0));
+    GridView v;
+    v.npts = m; v.ld = c->stage_pts; v.n = n; v.gga = gga;
+    v.w = s.w; v.phi = s.phi[0]; v.phix = s.phi[1]; v.phiy = s.phi[2]; v.phiz = s.phi[3];
+    v.vec[ORDM_VEC_RHO] = s.vec[0]; v.vec[ORDM_VEC_PI] = s.vec[1];
+    v.gx = s.vec[2]; v.gy = s.vec[3]; v.gz = s.vec[4]; v.pi_core = s.vec[5];
+    int rc;
+    if ((rc = run_k1(c, v, 1, &launches))) return rc;
+    if ((rc = run_k2(c, v, &launches))) return rc;
+    if ((rc = run_k3(c, v, functional, 1, &launches))) return rc;
+    CU(c, cudaEventRecord(s.done, c->stream));
+  }
+  CU(c, cudaEventRecord(c->ev[3], c->stream));
+  if (c->comm) {
+    int nr = g_nccl.AllReduce(c->d_res, c->d_res, ordm::RES_COUNT, 8, 0, c->comm, c->stream);
+    if (nr != 0) return fail(c, ORDM_ERR_NCCL, "ncclAllReduce failed");
+    launches += 1;
+  }
+  CU(c, cudaEventRecord(c->ev[4], c->stream));
+  int rc = fetch_result(c, eclass, out, npts, launches);
+  if (rc) return rc;
+  float ms;
+  CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[5])); out->ms_total = ms;
+  CU(c, cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); out->ms_reduce = ms;
+  return ORDM_OK;
+}
+
+// ---- outputs --------------------------------------------------------------------------------
+int ordm_get_vector(ordm_ctx* c, int which, double* host_out, size_t npts) {
+  CHECK_CTX(c);
+  if (which < 0 || which >= ORDM_VEC_COUNT || (npts && !host_out)) return fail(c, ORDM_ERR_INVALID, "bad vector request");
+  if (npts != c->g.npts) return fail(c, ORDM_ERR_INVALID, "vector length %zu != grid size %zu", npts, c->g.npts);
+  CU(c, cudaSetDevice(c->device));
+  const bool needs_xc = which == ORDM_VEC_R || (which >= ORDM_VEC_TR_RHOA && which <= ORDM_VEC_TR_SIGMA_BB);
+  if (needs_xc && !c->xc_done) {
+    int rc = staged_xc(c);
+    if (rc) return rc;
+  }
+  const double* src = c->g.vec[which];
+  if (!src) return fail(c, ORDM_ERR_STATE, "vector %d is not materialised (enable ORDM_OPT_DIAGNOSTICS%s before the build_* calls)", which,
+                        (which >= ORDM_VEC_RHOA_X && which <= ORDM_VEC_SIGMA_BB) || which >= ORDM_VEC_TR_SIGMA_AA ? "; gradients need phi_x/y/z" : "");
+  if (npts) CU(c, cudaMemcpyAsync(host_out, src, npts * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return ORDM_OK;
+}
+
+void* ordm_device_vector(ordm_ctx* c, int which) {
+  if (!c || which < 0 || which >= ORDM_VEC_COUNT) return nullptr;
+  return c->g.vec[which];
+}
+
+// ---- synthetic inputs -------------------------------------------------------------------------
+int ordm_synth_fill_device(ordm_ctx* c, uint64_t seed, size_t npts_total, size_t p0, size_t m, int n, int gga) {
+  CHECK_CTX(c);
+  if (n <= 0 || p0 + m > npts_total) return fail(c, ORDM_ERR_INVALID, "bad synthetic shard [%zu,%zu) of %zu", p0, p0 + m, npts_total);
+  CU(c, cudaSetDevice(c->device));
+  int rc = alloc_w(c, m);
+  if (rc) return rc;
+  if ((rc = alloc_grid(c, m, n, gga != 0))) return rc;
+  if (m) {
+    const uint64_t env_key = ordm_stream_key(seed, ORDM_STREAM_ENV);
+    dim3 grid((unsigned)((m + 255) / 256), (unsigned)std::min(n, 64));
+    for (int k = 0; k < (gga ? 4 : 1); ++k) {
+      k_synth_phi<<<grid, 256, 0, c->stream>>>(c->d_phi[k], c->g.ld, m, p0, npts_total, n, ordm_stream_key(seed, ORDM_STREAM_PHI + k), env_key);
+      CU(c, cudaGetLastError());
+    }
+    k_synth_w<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(c->d_w, m, p0, 1.0 / (double)npts_total, ordm_stream_key(seed, ORDM_STREAM_W));
+    CU(c, cudaGetLastError());
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  return ORDM_OK;
+}
+
+int ordm_synth_fill_host(uint64_t seed, size_t npts_total, size_t p0, size_t m, int n, double* w, double* phi, double* px, double* py, double* pz) {
+  if (p0 + m > npts_total || n <= 0) return fail(nullptr, ORDM_ERR_INVALID, "bad synthetic shard");
+  const uint64_t env_key = ordm_stream_key(seed, ORDM_STREAM_ENV), w_key = ordm_stream_key(seed, ORDM_STREAM_W);
+  const double inv = 1.0 / (double)npts_total;
+  double* dst[4] = {phi, px, py, pz};
+  if (w) for (size_t p = 0; p < m; ++p) w[p] = ordm_synth_w(w_key, inv, p0 + p);
+  for (int k = 0; k < 4; ++k) {
+    if (!dst[k]) continue;
+    const uint64_t key = ordm_stream_key(seed, ORDM_STREAM_PHI + k);
+    for (size_t p = 0; p < m; ++p) {
+      const double env = ordm_env_key(env_key, p0 + p);
+      for (int i = 0; i < n; ++i) dst[k][(size_t)i * m + p] = ordm_synth_phi(key, env, npts_total, p0 + p, (uint64_t)i);
+    }
+  }
+  return ORDM_OK;
+}
+
+int ordm_synth_rdms(uint64_t seed, int nact, int na, int nb, int ndet, double* A1a, double* A1b, double* D2act) {
+  if (nact <= 0 || na < 0 || nb < 0 || na > nact || nb > nact || ndet <= 0 || !A1a || !A1b)
+    return fail(nullptr, ORDM_ERR_INVALID, "bad synthetic RDM request");
+  ordm::synth_rdms(seed, nact, na, nb, ndet, A1a, A1b, D2act);
+  return ORDM_OK;
+}
+
+// ---- multi-GPU -----------------------------------------------------------------------------------
+int ordm_comm_unique_id(char id_out[128]) {
+  std::string why;
+  if (!load_nccl(why)) return fail(nullptr, ORDM_ERR_NCCL, "%s", why.c_str());
+  int nr = g_nccl.GetUniqueId(id_out);
+  if (nr != 0) return fail(nullptr, ORDM_ERR_NCCL, "ncclGetUniqueId failed (%d)", nr);
+  return ORDM_OK;
+}
+
+int ordm_comm_attach(ordm_ctx* c, int nranks, int rank, const char id[128]) {
+  CHECK_CTX(c);
+  if (nranks < 1 || rank < 0 || rank >= nranks || !id) return fail(c, ORDM_ERR_INVALID, "bad communicator geometry");
+  std::string why;
+  if (!load_nccl(why)) return fail(c, ORDM_ERR_NCCL, "%s", why.c_str());
+  CU(c, cudaSetDevice(c->device));
+  IdBlob blob;
+  std::memcpy(blob.b, id, 128);
+  int nr = g_nccl.CommInitRank(&c->comm, nranks, blob, rank);
+  if (nr != 0) { c->comm = nullptr; return fail(c, ORDM_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?"); }
+  c->nranks = nranks;
+  c->rank = rank;
+  return ORDM_OK;
+}
+
+int ordm_comm_detach(ordm_ctx* c) {
+  CHECK_CTX(c);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  c->comm = nullptr;
+  c->nranks = 1;
+  c->rank = 0;
+  return ORDM_OK;
+}
+
+void ordm_shard_range(size_t npts_total, int nranks, int rank, size_t* p0, size_t* count) {
+  if (nranks < 1) nranks = 1;
+  if (rank < 0) rank = 0;
+  if (rank >= nranks) rank = nranks - 1;
+  // balanced in units of 64 points (the K2 tile / TMA alignment); the last shard takes the ragged tail
+  const size_t units = (npts_total + PT_ALIGN - 1) / PT_ALIGN;
+  const size_t b = std::min(npts_total, PT_ALIGN * (units * (size_t)rank / (size_t)nranks));
+  const size_t e = std::min(npts_total, PT_ALIGN * (units * (size_t)(rank + 1) / (size_t)nranks));
+  if (p0) *p0 = b;
+  if (count) *count = e - b;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// xc_math.cuh -- per-grid-point exchange-correlation algebra of OpenRDM's libfunc, as FP64
+// device functions.  One function per reference entry point; each returns the *integrand*
+// (energy per unit volume, i.e. what the reference multiplies by W(p) and accumulates):
+//   ex_lsda_pt   Functional::EX_LSDA   /root/reference/src/libfunc/functional.cc:12-29
+//   ex_pbe_pt    Functional::EX_PBE    functional.cc:31-99
+//   ec_vwn3_pt   Functional::EC_VWN3   functional.cc:103-177
+//   ec_pbe_pt    Functional::EC_PBE    functional.cc:179-309
+// and translate_pt = MCPDFT::build_R + translate_density(+_gradients), mcpdft.cc:272-416.
+//
+// The branch structure (rho <= 1e-20, single-spin cases, sigma clamps, zeta/rs taken from the
+// un-swapped density in EC_PBE) is the reference's.  The algebra is re-associated for the GPU:
+// pow(x,4/3) -> x*cbrt(x), pow(x,2/3) -> cbrt(x)^2, shared sub-expressions are evaluated once
+// (the reference evaluates A(r,zeta) three times and t() five times per point,
+// functional.cc:268-271) and divisions are merged.  Every re-association is exact in real
+// arithmetic; rounding differences are O(1e-16) relative per point.
+#pragma once
+#include <math.h>
+
+namespace xc {
+
+constexpr double TOL = 1.0e-20;  // functional.cc:39,106,185 ; mcpdft.cc:295
+constexpr double PI = 3.14159265358979323846;
+constexpr double C_LSDA = 0.9305257363491;       // 2^(1/3) * (9/8)(2/3)(3/pi)^(1/3), functional.cc:15-16,23
+constexpr double THREE_PI2 = 29.608813203268074;  // 3 pi^2
+constexpr double FZ_DEN = 0.5198420997897464;     // 2*2^(1/3) - 2, functional.cc:126
+constexpr double PBE_BETA = 0.06672455060314922;  // functional.cc:37,208
+constexpr double PBE_GAMMA = 0.0310906908696549;  // functional.cc:209
+constexpr double PBE_KAPPA = 0.804;               // functional.cc:38
+constexpr double PBE_MU = 0.219514972764517;      // beta pi^2 / 3, functional.cc:37
+constexpr double D2FZ = 1.7099209341613656173;    // functional.cc:207
+
+// ---------------------------------------------------------------- translation
+struct Translated {
+  double R, zeta;
+  double ra, rb;           // translated spin densities, mcpdft.cc:326-330
+  double saa, sab, sbb;    // translated sigma, mcpdft.cc:407-409 (zero when !GGA, energy.cc:63-65)
+};
+
+template <bool GGA>
+__device__ __forceinline__ Translated translate_pt(double rho, double pi, double gx, double gy, double gz) {
+  Translated t;
+  t.R = 4.0 * pi / (rho * rho);  // mcpdft.cc:282 (unguarded; inf/NaN masked by the test below)
+  const bool live = !(rho < TOL) && !(pi < 0.0);  // mcpdft.cc:319
+  double z = 0.0;
+  if (live && (1.0 - t.R) > TOL) z = sqrt(1.0 - t.R);  // mcpdft.cc:321-325
+  t.zeta = z;
+  const double up = live ? (1.0 + z) : 0.0, dn = live ? (1.0 - z) : 0.0;
+  t.ra = up * (rho / 2.0);
+  t.rb = dn * (rho / 2.0);
+  if (GGA) {
+    const double ax = up * (gx / 2.0), ay = up * (gy / 2.0), az = up * (gz / 2.0);  // mcpdft.cc:391-398
+    const double bx = dn * (gx / 2.0), by = dn * (gy / 2.0), bz = dn * (gz / 2.0);
+    t.saa = (ax * ax) + (ay * ay) + (az * az);
+    t.sab = (ax * bx) + (ay * by) + (az * bz);
+    t.sbb = (bx * bx) + (by * by) + (bz * bz);
+  } else {
+    t.saa = t.sab = t.sbb = 0.0;
+  }
+  return t;
+}
+
+// ---------------------------------------------------------------- exchange
+__device__ __forceinline__ double ex_lsda_pt(double ra, double rb) {
+  // -(2^(1/3) Cx ra^(4/3) + 2^(1/3) Cx rb^(4/3)), no density threshold (functional.cc:22-27)
+  return -(C_LSDA * (ra * cbrt(ra)) + C_LSDA * (rb * cbrt(rb)));
+}
+
+// rho_s * eX(2 rho_s) * FX(S(2 rho_s, 4 sigma_ss))   (functional.cc:41-60,89-90)
+__device__ __forceinline__ double pbe_x_spin(double rs_, double sig) {
+  const double r2 = 2.0 * rs_;
+  const double kF = cbrt(THREE_PI2 * r2);
+  const double eX = -(3.0 * kF) / (4.0 * PI);
+  // s^2 = 4 sig / (2 kF r2)^2 = sig / (kF r2)^2 ;  FX = 1 + k - k^2 / (k + mu s^2)
+  const double d = (kF * r2) * (kF * r2);
+  const double FX = 1.0 + PBE_KAPPA - (PBE_KAPPA * PBE_KAPPA) * d / (PBE_KAPPA * d + PBE_MU * sig);
+  return rs_ * eX * FX;
+}
+
+__device__ __forceinline__ double ex_pbe_pt(double ra, double rb, double saa, double sbb) {
+  const double rho = ra + rb;
+  if (!(rho > TOL)) return 0.0;                              // functional.cc:74,94-96
+  if (ra < TOL) return pbe_x_spin(rb, fmax(0.0, sbb));       // functional.cc:75-81
+  if (rb < TOL) return pbe_x_spin(ra, fmax(0.0, saa));       // functional.cc:82-87
+  return pbe_x_spin(ra, saa) + pbe_x_spin(rb, sbb);          // functional.cc:88-93
+}
+
+// ---------------------------------------------------------------- correlation
+// f(zeta) = ((1+z)^(4/3) + (1-z)^(4/3) - 2) / (2 2^(1/3) - 2) from the two cube roots
+__device__ __forceinline__ double spin_f(double z, double cu, double cd) {
+  return ((1.0 + z) * cu + (1.0 - z) * cd - 2.0) / FZ_DEN;   // functional.cc:125-128
+}
+
+// VWN q(x) (functional.cc:137-142) with x = sqrt(rs), x^2 = rs; invQ = 1/sqrt(4d-c^2), Xp = X(p)
+__device__ __forceinline__ double vwn_q(double x, double rs, double A, double p, double c, double d,
+                                        double invQ, double Q, double Xp) {
+  const double Xx = rs + c * x + d;
+  const double at = atan(Q / (2.0 * x + c)) * invQ;
+  const double xm = x - p;
+  return A * (log(rs / Xx) + 2.0 * c * at - (c * p / Xp) * (log(xm * xm / Xx) + 2.0 * (c + 2.0 * p) * at));
+}
+
+__device__ __forceinline__ double ec_vwn3_pt(double ra, double rb) {
+  double rho = ra + rb;
+  if (!(rho > TOL)) return 0.0;                    // functional.cc:159,171-174
+  double zeta;
+  if (ra < TOL) { rho = rb; zeta = 1.0; }          // functional.cc:160-162
+  else if (rb < TOL) { rho = ra; zeta = 1.0; }     // functional.cc:163-165
+  else zeta = (ra - rb) / rho;                     // functional.cc:167
+  const double rs = cbrt(3.0 / (4.0 * PI * rho));  // functional.cc:121
+  const double x = sqrt(rs);
+  const double eP = vwn_q(x, rs, 0.03109070000, -0.409286, 13.0720, 42.7198, 22.271770159225095,
+                          0.0448998886415768, 37.537128437796);
+  const double eF = vwn_q(x, rs, 0.01554535000, -0.743294, 20.1231, 101.578, 0.8534715072594644,
+                          1.1716852777089715, 87.17310647903601);
+  const double fz = spin_f(zeta, cbrt(1.0 + zeta), cbrt(1.0 - zeta));
+  return rho * (eP + fz * (eF - eP));              // functional.cc:169-170
+}
+
+// PW92 G (functional.cc:237-241) with sr = sqrt(r); p = 1 for all three parameter sets
+__device__ __forceinline__ double pw92_G(double r, double sr, double T, double a1, double b1, double b2,
+                                         double b3, double b4) {
+  const double poly = T * (b1 * sr + b2 * r + b3 * (r * sr) + b4 * (r * r));
+  return -2.0 * T * (1.0 + a1 * r) * log(1.0 + 0.5 / poly);
+}
+
+__device__ __forceinline__ double ec_pbe_pt(double ra, double rb, double saa, double sab, double sbb) {
+  double rho = ra + rb;
+  if (!(rho > TOL)) return 0.0;                              // functional.cc:285,303-306
+  double zeta = (ra - rb) / rho;                             // functional.cc:279 (before the branches)
+  const double rs = cbrt(3.0 / (4.0 * PI * rho));            // functional.cc:280 (before the branches)
+  double sig;
+  if (ra < TOL) { rho = rb; sig = fmax(0.0, sbb); zeta = 1.0; }        // functional.cc:286-290
+  else if (rb < TOL) { rho = ra; sig = fmax(0.0, saa); zeta = 1.0; }   // functional.cc:291-295
+  else sig = fmax(0.0, saa) + fmax(0.0, sbb) + 2.0 * sab;              // functional.cc:296-300
+  // PW92 eps_c(rs, zeta), functional.cc:243-261
+  const double sr = sqrt(rs);
+  const double mAc = pw92_G(rs, sr, 0.0168869, 0.11125, 10.357, 3.6231, 0.88026, 0.49671);
+  const double eP = pw92_G(rs, sr, 0.0310907, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294);
+  const double eF = pw92_G(rs, sr, 0.01554535, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517);
+  const double cu = cbrt(1.0 + zeta), cd = cbrt(1.0 - zeta);
+  const double fz = spin_f(zeta, cu, cd);
+  const double z2 = zeta * zeta, z4 = z2 * z2;
+  const double ec = eP + ((-mAc) * fz * (1.0 - z4)) / D2FZ + (eF - eP) * fz * z4;
+  // H(rho, sigma, rs, zeta), functional.cc:210-233,263-271
+  const double fi = 0.5 * (cu * cu + cd * cd);
+  const double fi3 = fi * fi * fi;
+  const double kF = cbrt(THREE_PI2 * rho);
+  const double ks2 = 4.0 * kF / PI;
+  const double t2 = sig / (4.0 * ks2 * (fi * fi) * (rho * rho));
+  const double A = (PBE_BETA / PBE_GAMMA) / (exp(-ec / (fi3 * PBE_GAMMA)) - 1.0);
+  const double At2 = A * t2;
+  const double H = fi3 * PBE_GAMMA *
+                   log(1.0 + (PBE_BETA / PBE_GAMMA) * t2 * (1.0 + At2) / (1.0 + At2 + At2 * At2));
+  return rho * (H + ec);                                     // functional.cc:301-302
+}
+
+}  // namespace xc
