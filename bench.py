@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- MC-PDFT grid points/s (rho + Pi + translated XC + quadrature) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 3|4|5] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one evaluation of the whole hot path (mcpdft::mcpdft_energy, energy.cc:27-188) over
+the synthetic grid of the chosen BASELINE.json config, inputs resident in HBM.  With N ranks the
+fixed grid is sharded by contiguous point ranges (strong scaling), the RDMs are replicated and
+one NCCL all-reduce combines the eight scalars.  Prints ONE JSON line on rank 0.
+
+    value     grid points/s, device-resident inputs, CUDA events, max over ranks
+    e2e       same metric through ordm_energy_host(): inputs in pinned HOST memory, H2D streamed
+              inside the timed region, result scalars read back every step
+    roofline  the dominant kernel (K2, on-top pair density, FP64 tensor pipe) against the cuBLAS
+              DGEMM rate measured in this process; K1/K3 against MEASURED_PEAKS.json's HBM GB/s
+    cpu_baseline   OpenRDM's own compiled code (oracle/_ref) on a bounded sample, all host cores
+
+--impl reference times only the reference CPU arm (rank 0), same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MCPDFT grid points/sec (rho+Pi+tXC+quadrature)"
+UNIT = "grid points/s"
+
+# BASELINE.json configs 3-5 ("Config sizes")
+CONFIGS = {
+    3: dict(name="synthetic N2 cc-pVTZ (10e,8o), 500k-point grid, tPBE", npts=500_000, ncore=2, nact=8, nelec=5, functional="PBE", seed=3),
+    4: dict(name="synthetic Fe-porphyrin-like (20e,20o), def2-TZVP-size basis, 5M-point grid, tPBE", npts=5_000_000, ncore=83, nact=20, nelec=10, functional="PBE", seed=4),
+    5: dict(name="synthetic polyacene (26e,26o), 20M-point grid, tPBE", npts=20_000_000, ncore=73, nact=26, nelec=13, functional="PBE", seed=5),
+}
+
+
+def algorithmic(cfg):
+    """Per-point algorithmic work."""
+    n = cfg["ncore"] + cfg["nact"]
+    M = cfg["nact"] * (cfg["nact"] + 1) // 2
+    gga = cfg["functional"] == "PBE"
+    return dict(
+        M=M,
+        k2_flops=M * (M + 1) + 2 * M,            # symmetric packed contraction: each unordered (I,J) once + row dot
+        k2_flops_survey=2 * M * M + 2 * M,       # SURVEY.md 8(d) count for the unsymmetrised GEMM row
+        k1_bytes=8 * n * (4 if gga else 1) + 8 + 8 * (5 if gga else 2),   # phi(+grad phi) + w in; rho, grad rho, pi_core out
+        k3_bytes=48 if gga else 24,
+    )
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def dgemm_peak(torch, seconds=0.6):
+    """cuBLAS DGEMM 8192^3 in this process: the FP64-tensor roofline denominator."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        a @ b
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    reps = max(3, int(seconds * 1e3 / best))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        a @ b
+    e1.record(); torch.cuda.synchronize()
+    sus = e0.elapsed_time(e1) / reps
+    del a, b
+    torch.cuda.empty_cache()
+    f = 2.0 * n ** 3
+    return f / best * 1e-9, f / sus * 1e-9
+
+
+def cpu_reference_leg(cfg, sample_pts, threads, steps=1, warmup=0):
+    """OpenRDM's own compiled code (oracle/_ref) on a bounded sample of the same synthetic grid.
+    Returns (points/s as written, points/s necessary-work-only, description)."""
+    from oracle import oracle as O
+    import openrdm_b200 as ordm
+    if not O.have_ref():
+        return None
+    ref = O.Ref()
+    n = cfg["ncore"] + cfg["nact"]
+    gga = cfg["functional"] == "PBE"
+    A1a, A1b, D2 = ordm.synth_rdms(cfg["seed"], cfg["nact"], cfg["nelec"], cfg["nelec"], 8)
+    w, phi, grads = ordm.synth_fill_host(cfg["seed"], cfg["npts"], 0, sample_pts, n, gga)
+    times = []
+    for i in range(warmup + steps):
+        r = ref.energy_threads(threads, w, phi, cfg["ncore"], A1a, A1b, D2, cfg["functional"], grads, 0.0, with_pi_grad=True)
+        if i >= warmup:
+            times.append(r.seconds)
+    t_written = sum(times) / len(times)
+    r2 = ref.energy_threads(threads, w, phi, cfg["ncore"], A1a, A1b, D2, cfg["functional"], grads, 0.0, with_pi_grad=False)
+    return dict(as_written=sample_pts / t_written, necessary=sample_pts / r2.seconds, seconds=t_written, e_tot=r.scalars["e_tot"],
+                sample=f"first {sample_pts} points of the {cfg['npts']}-point grid, {threads} threads x contiguous slices, "
+                       f"reference kernels unmodified (build_rho on all {n} orbitals; build_ontop_pair_density(+_gradients as mcpdft_energy "
+                       f"does for GGA) on the {cfg['nact']} active orbitals; closed-form core terms added by the harness)")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--npts", type=int, default=0, help="override the grid size (debug)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = dict(CONFIGS[args.config])
+    if args.npts:
+        cfg["npts"] = args.npts
+    alg = algorithmic(cfg)
+    n = cfg["ncore"] + cfg["nact"]
+    gga = cfg["functional"] == "PBE"
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    cores = os.cpu_count() or 1
+    workload = {"workload": cfg["name"], "npts": cfg["npts"], "n_occ": n, "ncore": cfg["ncore"], "nact": cfg["nact"], "M_pairs": alg["M"],
+                "functional": "t" + cfg["functional"], "sharding": f"grid points, {world} contiguous shard(s), RDMs replicated",
+                "l2_policy": "inputs larger than L2 (no flush needed)" if cfg["npts"] * n * 8 > 2e8 else "inputs smaller than L2"}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = args.cpu_sample or (16384 if cfg["nact"] >= 20 else 131072)
+        sample = min(sample, cfg["npts"])
+        leg = cpu_reference_leg(cfg, sample, cores, steps=steps, warmup=min(warmup, 1))
+        if leg is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+            return 0
+        v = leg["as_written"]
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 1),
+            "ms_per_step": leg["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": leg["sample"],
+                             "value_necessary_work_only": leg["necessary"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import openrdm_b200 as ordm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    eng = ordm.Engine(local_rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    eng.set_stream(stream.cuda_stream)
+    A1a, A1b, D2 = ordm.synth_rdms(cfg["seed"], cfg["nact"], cfg["nelec"], cfg["nelec"], 8)
+    eng.set_options(diagnostics=False)
+    eng.set_active_space(cfg["ncore"], A1a, A1b, D2)
+    p0, cnt = ordm.shard_range(cfg["npts"], world, rank)
+    eng.synth_fill(cfg["seed"], cfg["npts"], p0, cnt, n, gga)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(ordm.Engine.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        eng.comm_attach(world, rank, bytes(uid.cpu().numpy().tobytes()))
+    fid = ordm.FUNC_PBE if gga else ordm.FUNC_SVWN
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing
+    for _ in range(warmup):
+        res = eng.energy(fid, 0.0)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_k = {"density": 0.0, "pi": 0.0, "xc": 0.0, "reduce": 0.0}
+    launches = 0
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(steps):
+            res = eng.energy(fid, 0.0)
+            for k in ms_k:
+                ms_k[k] += res["ms_" + k]
+            launches += res["gpu_launches"]
+        e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / steps
+    value = cfg["npts"] / (ms_step * 1e-3)
+    for k in ms_k:
+        ms_k[k] = max_over_ranks(ms_k[k] / steps)
+
+    # ---- end-to-end: pinned host buffers -> ordm_energy_host, H2D inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        w_h = ordm.host_empty((cnt,)); phi_h = ordm.host_empty((cnt, n))
+        g_h = [ordm.host_empty((cnt, n)) for _ in range(3)] if gga else None
+        # fill the pinned buffers from the device-resident copy (same bits as the timed inputs;
+        # the host generator would need minutes for 2e9 values)
+        w_h[:] = eng.get_vector("w")
+        eng.get_orbitals(phi_h, g_h)
+        e2e_steps = max(1, min(steps, 3))
+        eng.energy_host(fid, 0.0, w_h, phi_h, g_h)  # warm-up (allocates staging)
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(e2e_steps):
+                r2 = eng.energy_host(fid, 0.0, w_h, phi_h, g_h)
+            e1.record(stream)
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
+        wall_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+        ms_e2e = max(ms_e2e, wall_e2e)  # host-side call time (the copies are issued from the host) bounds it from below
+        h2d = 8 * cfg["npts"] * (n * (4 if gga else 1) + 1)
+        e2e = {"value": cfg["npts"] / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * 8 * world,
+               "ms_per_step": ms_e2e, "steps": e2e_steps, "e_tot_matches_resident": abs(r2["e_tot"] - res["e_tot"]) <= 1e-10 * max(1.0, abs(res["e_tot"]))}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- rooflines
+    peaks, peak_src = measured_peaks()
+    dg_burst, dg_sus = dgemm_peak(torch)
+    pts_rank = cfg["npts"] / world  # per-kernel times are per rank
+    k2_tf = alg["k2_flops"] * pts_rank / (ms_k["pi"] * 1e-3) * 1e-12
+    k1_gbs = alg["k1_bytes"] * pts_rank / (ms_k["density"] * 1e-3) * 1e-9
+    k3_gbs = alg["k3_bytes"] * pts_rank / (ms_k["xc"] * 1e-3) * 1e-9
+    roofline = {"kernel": "k2_ontop (Pi, DMMA.8x8x4)", "bound": "tensor", "achieved": k2_tf, "peak": dg_sus, "unit": "TFLOP/s", "frac": k2_tf / dg_sus,
+                "traffic": None, "peak_source": f"cuBLAS DGEMM 8192^3 measured in this process (sustained {dg_sus:.2f}, burst {dg_burst:.2f} TFLOP/s)",
+                "algorithmic_flops_per_point": alg["k2_flops"], "survey_flops_per_point": alg["k2_flops_survey"],
+                "achieved_survey_count": alg["k2_flops_survey"] * pts_rank / (ms_k["pi"] * 1e-3) * 1e-12,
+                "share_of_step": ms_k["pi"] / ms_step}
+    kernels = {
+        "k1_density": {"ms": ms_k["density"], "bound": "hbm", "achieved": k1_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": k1_gbs / peaks["hbm_gbs"], "bytes_per_point": alg["k1_bytes"]},
+        "k2_ontop": {"ms": ms_k["pi"]},
+        "k3_translate_xc": {"ms": ms_k["xc"], "bound": "hbm (FP64-ALU limited, DESIGN.md)", "achieved": k3_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": k3_gbs / peaks["hbm_gbs"], "bytes_per_point": alg["k3_bytes"]},
+        "k4_reduce_allreduce": {"ms": ms_k["reduce"]},
+        "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
+    }
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        sample = args.cpu_sample or (16384 if cfg["nact"] >= 20 else 131072)
+        leg = cpu_reference_leg(cfg, min(sample, cfg["npts"]), cores)
+        if leg:
+            cpu = {"value": leg["as_written"], "unit": UNIT, "cores": cores, "kind": "reference", "sample": leg["sample"],
+                   "value_necessary_work_only": leg["necessary"]}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+           "result": {k: res[k] for k in ("e_tot", "ex", "ec", "n_tot", "trn_tot")}}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -145,6 +145,9 @@ int ordm_energy_host(ordm_ctx* ctx, int functional, double eclass, size_t npts, 
 /* MCPDFT::get_rhoa ... get_tr_sigma_bb (mcpdft.h:64-110): copies npts doubles to the host.
  * Needs ORDM_OPT_DIAGNOSTICS, except RHO / PI / W which always exist after their stage. */
 int ordm_get_vector(ordm_ctx* ctx, int which, double* host_out, size_t npts);
+/* MCPDFT::get_phi / get_phi_x / _y / _z (mcpdft.h:72-75): component 0..3, column-major into
+ * host_out with leading dimension ld_host >= npts. */
+int ordm_get_orbitals(ordm_ctx* ctx, int component, double* host_out, size_t ld_host);
 /* raw device pointer of a per-point vector (NULL if not materialised) */
 void* ordm_device_vector(ordm_ctx* ctx, int which);
 

@@ -86,6 +86,7 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.ordm_energy.argtypes = [P, I, C.c_double, C.POINTER(Result)]
     lib.ordm_energy_host.argtypes = [P, I, C.c_double, S, I, S, D, D, D, D, D, S, C.POINTER(Result)]
     lib.ordm_get_vector.argtypes = [P, I, D, S]
+    lib.ordm_get_orbitals.argtypes = [P, I, D, S]
     lib.ordm_synth_fill_device.argtypes = [P, C.c_uint64, S, S, S, I, I]
     lib.ordm_synth_fill_host.argtypes = [C.c_uint64, S, S, S, I, D, D, D, D, D]
     lib.ordm_synth_rdms.argtypes = [C.c_uint64, I, I, I, I, D, D, D]
@@ -227,6 +228,11 @@ class Engine:
         self._ck(self.lib.ordm_get_vector(self.ctx, VEC_ID[name], _d(out), self.npts))
         return out
 
+    def get_orbitals(self, phi_out, grads_out=None):
+        """Copy the resident phi (and grad phi) into caller-provided F-ordered (npts, n) arrays."""
+        for comp, arr in enumerate([phi_out] + (list(grads_out) if grads_out is not None else [])):
+            self._ck(self.lib.ordm_get_orbitals(self.ctx, comp, _d(arr), max(arr.shape[0], 1)))
+
     def synchronize(self): self._ck(self.lib.ordm_synchronize(self.ctx))
 
     # ---- multi-GPU
@@ -239,7 +245,7 @@ class Engine:
         return buf.raw
 
     def comm_attach(self, nranks, rank, uid: bytes):
-        self._ck(self.lib.ordm_comm_attach(self.ctx, nranks, rank, C.c_char_p(uid) if False else C.create_string_buffer(uid, 128)))
+        self._ck(self.lib.ordm_comm_attach(self.ctx, nranks, rank, C.create_string_buffer(uid, 128)))
 
 
 def host_empty(shape, order="F") -> np.ndarray:

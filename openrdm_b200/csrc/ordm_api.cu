@@ -841,6 +841,18 @@ int ordm_get_vector(ordm_ctx* c, int which, double* host_out, size_t npts) {
   return ORDM_OK;
 }
 
+int ordm_get_orbitals(ordm_ctx* c, int comp, double* host_out, size_t ld_host) {
+  CHECK_CTX(c);
+  if (comp < 0 || comp > 3 || !host_out || ld_host < c->g.npts) return fail(c, ORDM_ERR_INVALID, "bad orbital request");
+  const double* src = comp == 0 ? c->g.phi : comp == 1 ? c->g.phix : comp == 2 ? c->g.phiy : c->g.phiz;
+  if (!src) return fail(c, ORDM_ERR_STATE, "orbital component %d is not set", comp);
+  CU(c, cudaSetDevice(c->device));
+  if (c->g.npts)
+    CU(c, cudaMemcpy2DAsync(host_out, ld_host * sizeof(double), src, c->g.ld * sizeof(double), c->g.npts * sizeof(double), (size_t)c->g.n, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return ORDM_OK;
+}
+
 void* ordm_device_vector(ordm_ctx* c, int which) {
   if (!c || which < 0 || which >= ORDM_VEC_COUNT) return nullptr;
   return c->g.vec[which];
