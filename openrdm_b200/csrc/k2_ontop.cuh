@@ -18,12 +18,17 @@
 //    mbarrier, one 8*P-byte copy per column; next tile prefetched during the math);
 //  * X lives in shared memory as [I][P+4] (the +4 pad makes the DMMA A-fragment loads
 //    bank-conflict free: lane -> (I0 + lane%4, p0 + lane/4));
-//  * the unit of work is a "task" = one 32x32 block (ib<=jb) of Dt' applied to a 32-point
-//    group: C(32x32) = X[:,ib] . Dt'[ib,jb] as 8 k-steps x 16 DMMA.8x8x4, followed by the
-//    fused epilogue  pi[p] += sum_j C[p,j] * X[p, jb*32+j]  on the accumulator fragments;
+//  * the unit of work is a "segment" = a run of row blocks ib0..ib0+n-1 of one 32-wide block
+//    column jb of Dt' applied to a 32-point group: C(32x32) += X[:,ib] . Dt'[ib,jb], 8 k-steps
+//    x 16 DMMA.8x8x4 per block, all blocks of the run accumulated in registers, followed by
+//    ONE fused epilogue  pi[p] += sum_j C[p,j] * X[p, jb*32+j]  on the accumulator fragments.
+//    The diagonal block only issues the sub-tiles that touch the upper triangle and a ragged
+//    last column only its live n-tiles (both compile-time patterns: the DMMA stream of a
+//    segment is branch-free).  Segments are balanced over the task lanes on the host;
 //  * Dt' is pre-packed on the host in DMMA B-fragment order, per task lane, so each k-step
 //    of B is one coalesced 1 KB read (2 x LDG.128 per thread) straight from L2 into
 //    registers, software-pipelined 3 k-steps ahead -- Dt' (<= 1 MB) stays L2-resident;
+//    A fragments are double-buffered one k-step ahead;
 //  * per-point results: quad shuffle reduction, then a fixed-order cross-warp sum in smem.
 #pragma once
 #include <cuda_runtime.h>
@@ -43,6 +48,11 @@ constexpr int RING = PREFETCH + 1;                  // register ring slots (powe
 static_assert((RING & (RING - 1)) == 0 && KSTEPS % RING == 0, "ring must tile the k-steps");
 constexpr int MAX_LANES = 8;
 
+struct SegDesc {  // same layout as ordm::SegDesc (rdm_pack.h)
+  uint16_t jb, ib0, nblk;
+  uint8_t has_diag, ntl;
+};
+
 struct Params {
   const double* phi_act;  // first active column, [nact][ld]
   size_t ld;
@@ -50,13 +60,14 @@ struct Params {
   int nact;
   int M;       // nact(nact+1)/2
   int nblk;    // ceil(M/32)
-  int ntask;   // nblk(nblk+1)/2
   int ntiles;  // ceil(npts/P)
-  const double* dfrag;            // packed Dt' (fragment order, per lane, zero-padded tail)
-  const uint16_t* pairs;          // [Mpad][2] : (t,u) of pair I, (0,0) beyond M
-  uint32_t lane_ofs[MAX_LANES];   // first task slot of each task lane in dfrag
-  const double* pi_core;          // nullable: closed-form core part added to the result
-  double* pi;                     // out, npts
+  const double* dfrag;              // packed Dt' (fragment order, per task lane, zero-padded tail)
+  const SegDesc* segs;              // segment descriptors, lane-major (+1 sentinel)
+  const uint16_t* pairs;            // [M][2]: (t,u), t<=u, of packed pair index I (row-major upper triangle)
+  uint32_t seg_ofs[MAX_LANES + 1];  // lane l owns segments [seg_ofs[l], seg_ofs[l+1])
+  uint32_t blk_ofs[MAX_LANES + 1];  // first 8 KB block slot of lane l in dfrag
+  const double* pi_core;            // nullable: closed-form core part added to the result
+  double* pi;                       // out, npts
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -98,33 +109,93 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 template <int P>
 struct Smem {
   static constexpr int PS = P + 4;  // X row stride
-  static __host__ __device__ size_t xs_doubles(int Mpad) { return (size_t)Mpad * PS; }
+  static __host__ __device__ size_t xs_doubles(int Mpad) { return (size_t)(Mpad + 4) * PS; }  // +4 rows: A prefetch overrun
   static __host__ __device__ size_t bytes(int Mpad, int nact) {
-    return sizeof(double) * (xs_doubles(Mpad) + (size_t)nact * P + (size_t)WARPS * P) + sizeof(uint16_t) * 2 * Mpad + 16;
+    return sizeof(double) * (xs_doubles(Mpad) + (size_t)nact * P + (size_t)WARPS * P) + 16 + sizeof(uint32_t) * Mpad;
   }
 };
 
+// One 32-row block of a segment: 8 k-steps; B ring prefetched PREFETCH k-steps ahead, A fragments
+// one k-step ahead (the row pointer simply runs on into the next block of the run).
+// NTL = live n-tiles of the block column, DIAG = diagonal block (static sub-tile pattern).
+template <int MT, int PS, int NTL, bool DIAG>
+__device__ __forceinline__ void kblock(double (&c)[MT][NTILE][2], double (&bq)[RING][NTILE], double (&a)[2][MT],
+                                       const double*& xa, const double*& bptr) {
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    {
+      const double2* src = reinterpret_cast<const double2*>(bptr + (ks + PREFETCH) * STEP_DOUBLES);
+      const double2 lo = __ldg(src), hi = __ldg(src + 1);
+      bq[(ks + PREFETCH) & (RING - 1)][0] = lo.x; bq[(ks + PREFETCH) & (RING - 1)][1] = lo.y;
+      bq[(ks + PREFETCH) & (RING - 1)][2] = hi.x; bq[(ks + PREFETCH) & (RING - 1)][3] = hi.y;
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m) a[(ks + 1) & 1][m] = xa[(size_t)((ks + 1) * 4) * PS + m * 8];
+#pragma unroll
+    for (int n = 0; n < NTL; ++n)
+      if (!DIAG || 4 * ks <= 8 * n + 7) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) dmma884(c[m][n][0], c[m][n][1], a[ks & 1][m], bq[ks & (RING - 1)][n]);
+      }
+  }
+  xa += (size_t)BLK * PS;
+  bptr += TASK_DOUBLES;
+}
+
+template <int MT, int PS, int NTL>
+__device__ __forceinline__ void run_segment(const SegDesc sd, double (&piacc)[MT], double (&bq)[RING][NTILE],
+                                            const double* xrow, int qcol, const double*& bptr) {
+  double c[MT][NTILE][2];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int n = 0; n < NTILE; ++n) c[m][n][0] = c[m][n][1] = 0.0;
+  const double* xa = xrow + (size_t)(sd.ib0 * BLK + qcol) * PS;
+  double a[2][MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) a[0][m] = xa[m * 8];
+  const int nfull = (int)sd.nblk - (int)sd.has_diag;
+  for (int b = 0; b < nfull; ++b) kblock<MT, PS, NTL, false>(c, bq, a, xa, bptr);
+  if (sd.has_diag) kblock<MT, PS, NTL, true>(c, bq, a, xa, bptr);
+  // fused epilogue: pi[p] += sum_j C[p][j] * X[jb*32 + j][p].  The C fragment of a lane is row
+  // qrow, DMMA columns 2*qcol+{0,1} = (host-permuted) J offsets qcol and qcol+4 of the n-tile.
+  const double* xe = xrow + (size_t)(sd.jb * BLK + qcol) * PS;
+#pragma unroll
+  for (int n = 0; n < NTL; ++n)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      piacc[m] = fma(c[m][n][0], xe[(size_t)(n * 8) * PS + m * 8], piacc[m]);
+      piacc[m] = fma(c[m][n][1], xe[(size_t)(n * 8 + 4) * PS + m * 8], piacc[m]);
+    }
+}
+
 // NPG point groups per tile (P = 8*MT*NPG points), MT DMMA m-tiles per warp.
-// warp w: point group w % NPG ... task lane w / NPG  (NL = WARPS/NPG task lanes).
+// warp w: point group w % NPG, task lane w / NPG  (NL = WARPS/NPG task lanes).
 template <int NPG, int MT>
 __global__ void __launch_bounds__(THREADS, 1) k2_ontop(const Params prm) {
   constexpr int P = 8 * MT * NPG;
   constexpr int PS = P + 4;
   constexpr int NL = WARPS / NPG;
+  constexpr int G = THREADS / P;  // pair rows covered per pass of the X build
+  constexpr int XU = 8;           // independent products in flight per thread
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int Mpad = prm.nblk * BLK;
   double* Xs = reinterpret_cast<double*>(smem_raw);
-  double* phis = Xs + (size_t)Mpad * PS;                 // [nact][P]
+  double* phis = Xs + (size_t)(Mpad + 4) * PS;           // [nact][P]
   double* red = phis + (size_t)prm.nact * P;             // [NL][P] cross-warp partials
   uint64_t* bar = reinterpret_cast<uint64_t*>(red + (size_t)WARPS * P);
-  uint16_t* pairs = reinterpret_cast<uint16_t*>(bar + 2);
+  uint32_t* pofs = reinterpret_cast<uint32_t*>(bar + 2);  // [M]: (t*P) | (u*P) << 16
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int pg = wid % NPG, tl = wid / NPG;
   const int qrow = lane >> 2, qcol = lane & 3;
-  const uint32_t tile_bytes = (uint32_t)(prm.nact * P * sizeof(double));
+  const int nact = prm.nact;
+  const uint32_t tile_bytes = (uint32_t)(nact * P * sizeof(double));
 
-  for (int i = tid; i < 2 * Mpad; i += THREADS) pairs[i] = prm.pairs[i];
+  // rows M..Mpad+3 of X never change: zero them once
+  for (int idx = prm.M * P + tid; idx < (Mpad + 4) * P; idx += THREADS) Xs[(size_t)(idx / P) * PS + (idx % P)] = 0.0;
+  for (int I = tid; I < prm.M; I += THREADS)
+    pofs[I] = (uint32_t)prm.pairs[2 * I] * P | ((uint32_t)prm.pairs[2 * I + 1] * P) << 16;
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -134,23 +205,30 @@ __global__ void __launch_bounds__(THREADS, 1) k2_ontop(const Params prm) {
   int tile = blockIdx.x;
   if (tid == 0 && tile < prm.ntiles) {
     mbar_expect_tx(bar, tile_bytes);
-    for (int t = 0; t < prm.nact; ++t)
+    for (int t = 0; t < nact; ++t)
       tma_bulk_g2s(phis + (size_t)t * P, prm.phi_act + (size_t)t * prm.ld + (size_t)tile * P, P * sizeof(double), bar);
   }
-  // number of tasks of this warp's lane: tasks tl, tl+NL, ...
-  const int my_tasks = (prm.ntask > tl) ? (prm.ntask - tl + NL - 1) / NL : 0;
-  const double* bbase = prm.dfrag + (size_t)prm.lane_ofs[tl] * TASK_DOUBLES + lane * NTILE;
+  const int seg0 = (int)prm.seg_ofs[tl], nseg = (int)prm.seg_ofs[tl + 1] - seg0;
+  const double* bbase = prm.dfrag + (size_t)prm.blk_ofs[tl] * TASK_DOUBLES + lane * NTILE;
+  const SegDesc* sdesc = prm.segs + seg0;
+  const int xp = tid % P, xg = tid / P;
 
   uint32_t parity = 0;
   for (; tile < prm.ntiles; tile += gridDim.x) {
     mbar_wait(bar, parity);
     parity ^= 1;
-    // ---- X[I][p] = phi_t[p] * phi_u[p] ----
-    for (int idx = tid; idx < Mpad * P; idx += THREADS) {
-      const int I = idx / P, p = idx % P;
-      const int t = pairs[2 * I], u = pairs[2 * I + 1];
-      const double v = (I < prm.M) ? phis[t * P + p] * phis[u * P + p] : 0.0;
-      Xs[(size_t)I * PS + p] = v;
+    // ---- X[I][p] = phi_t[p] * phi_u[p]: thread owns point xp and pair rows xg, xg+G, ...;
+    //      XU independent (table -> two phi loads -> product -> store) chains in flight ----
+    for (int I0 = xg; I0 < prm.M; I0 += G * XU) {
+      uint32_t po[XU];
+      double ft[XU], fu[XU];
+#pragma unroll
+      for (int j = 0; j < XU; ++j) po[j] = (I0 + j * G < prm.M) ? pofs[I0 + j * G] : 0u;
+#pragma unroll
+      for (int j = 0; j < XU; ++j) { ft[j] = phis[(po[j] & 0xffffu) + xp]; fu[j] = phis[(po[j] >> 16) + xp]; }
+#pragma unroll
+      for (int j = 0; j < XU; ++j)
+        if (I0 + j * G < prm.M) Xs[(size_t)(I0 + j * G) * PS + xp] = ft[j] * fu[j];
     }
     __syncthreads();
     // phis is free again: prefetch the next tile's columns while this one is contracted
@@ -158,11 +236,11 @@ __global__ void __launch_bounds__(THREADS, 1) k2_ontop(const Params prm) {
       const int nxt = tile + gridDim.x;
       if (tid == 0 && nxt < prm.ntiles) {
         mbar_expect_tx(bar, tile_bytes);
-        for (int t = 0; t < prm.nact; ++t)
+        for (int t = 0; t < nact; ++t)
           tma_bulk_g2s(phis + (size_t)t * P, prm.phi_act + (size_t)t * prm.ld + (size_t)nxt * P, P * sizeof(double), bar);
       }
     }
-    // ---- contraction over this warp's tasks ----
+    // ---- contraction over this warp's segments ----
     double piacc[MT];
 #pragma unroll
     for (int m = 0; m < MT; ++m) piacc[m] = 0.0;
@@ -175,48 +253,16 @@ __global__ void __launch_bounds__(THREADS, 1) k2_ontop(const Params prm) {
       const double2 hi = __ldg(reinterpret_cast<const double2*>(bptr + s * STEP_DOUBLES) + 1);
       bq[s][0] = lo.x; bq[s][1] = lo.y; bq[s][2] = hi.x; bq[s][3] = hi.y;
     }
-    int ib = 0, jb = 0;
-    {  // (ib,jb) of task index tl in the order jb outer, ib<=jb inner
-      int rem = tl;
-      while (rem > jb) { rem -= jb + 1; ++jb; }
-      ib = rem;
-    }
-    for (int task = 0; task < my_tasks; ++task) {
-      double c[MT][NTILE][2];
-#pragma unroll
-      for (int m = 0; m < MT; ++m)
-#pragma unroll
-        for (int n = 0; n < NTILE; ++n) c[m][n][0] = c[m][n][1] = 0.0;
-      const double* xa = xrow + (size_t)(ib * BLK + qcol) * PS;
-#pragma unroll
-      for (int ks = 0; ks < KSTEPS; ++ks) {
-        {  // prefetch B of k-step ks+PREFETCH (runs into the zero-padded tail at the very end)
-          const double2* src = reinterpret_cast<const double2*>(bptr + (ks + PREFETCH) * STEP_DOUBLES);
-          const double2 lo = __ldg(src), hi = __ldg(src + 1);
-          bq[(ks + PREFETCH) & (RING - 1)][0] = lo.x; bq[(ks + PREFETCH) & (RING - 1)][1] = lo.y;
-          bq[(ks + PREFETCH) & (RING - 1)][2] = hi.x; bq[(ks + PREFETCH) & (RING - 1)][3] = hi.y;
-        }
-        double a[MT];
-#pragma unroll
-        for (int m = 0; m < MT; ++m) a[m] = xa[(size_t)(ks * 4) * PS + m * 8];
-#pragma unroll
-        for (int m = 0; m < MT; ++m)
-#pragma unroll
-          for (int n = 0; n < NTILE; ++n) dmma884(c[m][n][0], c[m][n][1], a[m], bq[ks & (RING - 1)][n]);
+    SegDesc sd = sdesc[0];
+    for (int sg = 0; sg < nseg; ++sg) {
+      const SegDesc sd_next = sdesc[sg + 1];  // sentinel-terminated
+      switch (sd.ntl) {
+        case 4: run_segment<MT, PS, 4>(sd, piacc, bq, xrow, qcol, bptr); break;
+        case 3: run_segment<MT, PS, 3>(sd, piacc, bq, xrow, qcol, bptr); break;
+        case 2: run_segment<MT, PS, 2>(sd, piacc, bq, xrow, qcol, bptr); break;
+        default: run_segment<MT, PS, 1>(sd, piacc, bq, xrow, qcol, bptr); break;
       }
-      bptr += TASK_DOUBLES;
-      // fused epilogue: pi[p] += sum_j C[p][j] * X[jb*32 + j][p]; C fragment = rows qrow, cols 2*qcol+{0,1}
-      const double* xe = xrow + (size_t)(jb * BLK + 2 * qcol) * PS;
-#pragma unroll
-      for (int n = 0; n < NTILE; ++n)
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          piacc[m] = fma(c[m][n][0], xe[(size_t)(n * 8) * PS + m * 8], piacc[m]);
-          piacc[m] = fma(c[m][n][1], xe[(size_t)(n * 8 + 1) * PS + m * 8], piacc[m]);
-        }
-      // next task of this lane
-      ib += NL;
-      while (ib > jb) { ib -= jb + 1; ++jb; }
+      sd = sd_next;
     }
     // ---- reduce: 4 lanes of a quad hold the same rows ----
 #pragma unroll
@@ -237,8 +283,8 @@ __global__ void __launch_bounds__(THREADS, 1) k2_ontop(const Params prm) {
         prm.pi[gp] = s;
       }
     }
-    // the next iteration's X build must not start before `red` was consumed: the
-    // __syncthreads() after the X build orders it (red is only rewritten after that).
+    // `red` is only rewritten after the next tile's post-X-build __syncthreads(), which the
+    // readers above also have to pass: no extra barrier needed.
   }
 }
 

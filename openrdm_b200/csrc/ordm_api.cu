@@ -101,7 +101,9 @@ struct ordm_ctx {
   int k2_npg = 0, k2_mt = 0;
   k2::Params k2p{};
   double* d_dfrag = nullptr;
+  void* d_tasks = nullptr;
   uint16_t* d_pairs = nullptr;
+  uint64_t k2_dmma_per_mtile = 0;
   size_t k2_smem = 0;
   std::vector<double> h_Dt;  // folded Dt kept for repacking when the tile shape changes
 
@@ -322,18 +324,24 @@ int configure_k2(ordm_ctx* c) {
   c->k2_smem = cand[pick].bytes;
   ordm::DfragLayout lay;
   ordm::pack_dfrag(M, c->h_Dt, k2::WARPS / c->k2_npg, k2::PREFETCH, lay);
+  static_assert(sizeof(ordm::SegDesc) == sizeof(k2::SegDesc) && sizeof(ordm::SegDesc) == 8, "segment descriptor layout");
   std::vector<uint16_t> tab;
-  ordm::pair_table(c->nact, Mpad, tab);
+  ordm::pair_table(c->nact, tab);
   dfree(c->d_dfrag);
+  dfree(c->d_tasks);
   dfree(c->d_pairs);
-  CU(c, cudaMalloc(&c->d_dfrag, lay.data.size() * sizeof(double)));
   CU(c, cudaMalloc(&c->d_pairs, tab.size() * sizeof(uint16_t)));
-  CU(c, cudaMemcpy(c->d_dfrag, lay.data.data(), lay.data.size() * sizeof(double), cudaMemcpyHostToDevice));
   CU(c, cudaMemcpy(c->d_pairs, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  CU(c, cudaMalloc(&c->d_dfrag, lay.data.size() * sizeof(double)));
+  CU(c, cudaMalloc(&c->d_tasks, lay.segs.size() * sizeof(ordm::SegDesc)));
+  CU(c, cudaMemcpy(c->d_dfrag, lay.data.data(), lay.data.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(c->d_tasks, lay.segs.data(), lay.segs.size() * sizeof(ordm::SegDesc), cudaMemcpyHostToDevice));
   c->k2p = k2::Params{};
-  c->k2p.nact = c->nact; c->k2p.M = M; c->k2p.nblk = nblk; c->k2p.ntask = lay.ntask;
-  c->k2p.dfrag = c->d_dfrag; c->k2p.pairs = c->d_pairs;
-  for (int i = 0; i < k2::MAX_LANES; ++i) c->k2p.lane_ofs[i] = lay.lane_ofs[i];
+  c->k2p.nact = c->nact; c->k2p.M = M; c->k2p.nblk = nblk;
+  c->k2p.pairs = c->d_pairs;
+  c->k2p.dfrag = c->d_dfrag; c->k2p.segs = reinterpret_cast<const k2::SegDesc*>(c->d_tasks);
+  for (int i = 0; i <= k2::MAX_LANES; ++i) { c->k2p.seg_ofs[i] = lay.seg_ofs[i]; c->k2p.blk_ofs[i] = lay.blk_ofs[i]; }
+  c->k2_dmma_per_mtile = lay.subtiles;
   return ORDM_OK;
 }
 
@@ -486,7 +494,7 @@ void ordm_destroy(ordm_ctx* c) {
   dfree(c->g.gx); dfree(c->g.gy); dfree(c->g.gz); dfree(c->g.pi_core);
   dfree(c->d_w);
   for (int k = 0; k < 4; ++k) dfree(c->d_phi[k]);
-  dfree(c->d_Dsa_g); dfree(c->d_Dsb_g); dfree(c->d_dfrag); dfree(c->d_pairs);
+  dfree(c->d_Dsa_g); dfree(c->d_Dsb_g); dfree(c->d_dfrag); dfree(c->d_tasks); dfree(c->d_pairs);
   dfree(c->d_partial); dfree(c->d_res);
   if (c->h_res) cudaFreeHost(c->h_res);
   for (auto& s : c->stage) {

@@ -9,6 +9,7 @@
 //                doubled), laid out in DMMA.8x8x4 B-fragment order per task lane (k2_ontop.cuh).
 //  * symmetrise_opdm: Ds = (D + D^T)/2 for K1.
 #pragma once
+#include <algorithm>
 #include <cstddef>
 #include <cstdint>
 #include <vector>
@@ -23,13 +24,13 @@ inline int pair_index(int n, int t, int u) {
   return t * n - t * (t - 1) / 2 + (u - t);
 }
 
-inline void pair_table(int n, int Mpad, std::vector<uint16_t>& tab) {
-  tab.assign((size_t)2 * Mpad, 0);
-  int I = 0;
+// (t,u), t <= u, of every packed pair index, row-major upper triangle
+inline void pair_table(int n, std::vector<uint16_t>& tab) {
+  tab.clear();
   for (int t = 0; t < n; ++t)
-    for (int u = t; u < n; ++u, ++I) {
-      tab[2 * I] = (uint16_t)t;
-      tab[2 * I + 1] = (uint16_t)u;
+    for (int u = t; u < n; ++u) {
+      tab.push_back((uint16_t)t);
+      tab.push_back((uint16_t)u);
     }
 }
 
@@ -52,42 +53,137 @@ inline void fold_tpdm(int n, const double* D2, std::vector<double>& Dt) {
     }
 }
 
-struct DfragLayout {
-  int M = 0, nblk = 0, ntask = 0, nlanes = 0;
-  uint32_t lane_ofs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  std::vector<double> data;
+// ---- K2 work decomposition ------------------------------------------------------------------
+// Dt' (upper triangle of the symmetric Dt, strictly-upper part doubled) is cut into 32x32 blocks.
+// A *segment* is a run of consecutive row blocks ib0 .. ib0+nblk-1 of one block column jb: the
+// kernel accumulates C = X[:, rows] . Dt'[rows, jb] over the whole run in registers and applies
+// the epilogue pi += rowsum(C o X[:, jb]) once per segment.  The last block of a column is the
+// diagonal block (only sub-tiles touching the upper triangle are multiplied); the last column
+// may be ragged (ntl < 4 live 8-wide n-tiles).  Segments are distributed over the task lanes
+// by cost (LPT), columns being split into runs of at most S blocks with S chosen to minimise
+// the most loaded lane.
+struct SegDesc {
+  uint16_t jb, ib0, nblk;
+  uint8_t has_diag, ntl;
 };
 
-// blk = 32, 8 k-steps x (32 lanes x 4 n-tiles) doubles per task, `prefetch_steps` zero k-steps appended.
+struct DfragLayout {
+  int M = 0, nblk = 0, nlanes = 0, max_run = 0;
+  uint32_t seg_ofs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // lane l owns segments [seg_ofs[l], seg_ofs[l+1])
+  uint32_t blk_ofs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // first 8 KB block slot of lane l in `data`
+  std::vector<SegDesc> segs;                         // lane-major (+1 sentinel)
+  std::vector<double> data;
+  uint64_t subtiles = 0;        // live 4x8 sub-tiles per 8-point m-tile per grid tile (= DMMA.8x8x4 count)
+  uint64_t max_lane_cost = 0;   // most loaded lane, in sub-tiles (incl. epilogue estimate)
+};
+
+// DMMA n index c (0..7) of a C fragment <-> column offset inside the 8-wide n-tile.  A lane holds
+// C columns 2*(lane%4)+{0,1}; mapping them to offsets (lane%4) and (lane%4)+4 makes the epilogue's
+// X[J][p] reads of a half-warp hit 16 distinct 8-byte banks (row stride = 4 mod 16 doubles).
+inline int ncol_perm(int c) { return (c >> 1) + 4 * (c & 1); }
+
+inline bool diag_subtile_live(int ks, int nt) { return 4 * ks <= 8 * nt + 7; }
+
 inline void pack_dfrag(int M, const std::vector<double>& Dt, int nlanes, int prefetch_steps, DfragLayout& out) {
-  const int BLK = 32, KSTEPS = 8, NT = 4;
+  const int BLK = 32, KSTEPS = 8, NT = 4, EPI_COST = 3;
+  const int nb = (M + BLK - 1) / BLK;
   out.M = M;
-  out.nblk = (M + BLK - 1) / BLK;
-  out.ntask = out.nblk * (out.nblk + 1) / 2;
+  out.nblk = nb;
   out.nlanes = nlanes;
-  const size_t task_doubles = (size_t)KSTEPS * 32 * NT;
-  out.data.assign((size_t)out.ntask * task_doubles + (size_t)prefetch_steps * 32 * NT, 0.0);
-  uint32_t ofs = 0;
-  for (int l = 0; l < 8; ++l) {
-    out.lane_ofs[l] = ofs;
-    if (l < nlanes && out.ntask > l) ofs += (uint32_t)((out.ntask - l + nlanes - 1) / nlanes);
-  }
-  // enumerate tasks tau = (jb outer, ib <= jb inner)
-  int tau = 0;
-  for (int jb = 0; jb < out.nblk; ++jb)
-    for (int ib = 0; ib <= jb; ++ib, ++tau) {
-      const int lane_q = tau % nlanes, k_in_lane = tau / nlanes;
-      double* dst = out.data.data() + ((size_t)out.lane_ofs[lane_q] + k_in_lane) * task_doubles;
-      const double scale = (ib < jb) ? 2.0 : 1.0;
-      for (int ks = 0; ks < KSTEPS; ++ks)
-        for (int lane = 0; lane < 32; ++lane)
-          for (int nt = 0; nt < NT; ++nt) {
-            const int I = ib * BLK + ks * 4 + (lane & 3);
-            const int J = jb * BLK + nt * 8 + (lane >> 2);
-            const double v = (I < M && J < M) ? scale * Dt[(size_t)I * M + J] : 0.0;
-            dst[((size_t)ks * 32 + lane) * NT + nt] = v;
-          }
+  auto col_ntl = [&](int jb) { const int w = std::min(BLK, M - jb * BLK); return (w + 7) / 8; };
+  auto blk_cost = [&](int ib, int jb) {
+    const int ntl = col_ntl(jb);
+    int cst = 0;
+    for (int ks = 0; ks < KSTEPS; ++ks)
+      for (int nt = 0; nt < ntl; ++nt)
+        if (ib < jb || diag_subtile_live(ks, nt)) ++cst;
+    return cst;
+  };
+  struct Seg { int jb, ib0, n, cost; };
+  std::vector<Seg> best_segs;
+  std::vector<int> best_lane;
+  long best_obj = -1;
+  int best_S = 0;
+  for (int S = nb; S >= 1; --S) {
+    std::vector<Seg> segs;
+    for (int jb = 0; jb < nb; ++jb)
+      for (int ib0 = 0; ib0 <= jb; ib0 += S) {
+        Seg sg{jb, ib0, std::min(S, jb + 1 - ib0), EPI_COST};
+        for (int b = 0; b < sg.n; ++b) sg.cost += blk_cost(ib0 + b, jb);
+        segs.push_back(sg);
+      }
+    std::vector<int> order(segs.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    for (size_t i = 1; i < order.size(); ++i) {  // stable insertion sort, cost descending
+      int v = order[i];
+      size_t j = i;
+      while (j > 0 && segs[order[j - 1]].cost < segs[v].cost) { order[j] = order[j - 1]; --j; }
+      order[j] = v;
     }
+    std::vector<long> load(nlanes, 0);
+    std::vector<int> lane_of(segs.size(), 0);
+    for (int id : order) {
+      int b = 0;
+      for (int l = 1; l < nlanes; ++l)
+        if (load[l] < load[b]) b = l;
+      lane_of[id] = b;
+      load[b] += segs[id].cost;
+    }
+    long obj = 0;
+    for (long v : load) obj = std::max(obj, v);
+    if (best_obj < 0 || obj < best_obj) { best_obj = obj; best_segs = segs; best_lane = lane_of; best_S = S; }
+  }
+  out.max_run = best_S;
+  out.max_lane_cost = (uint64_t)best_obj;
+  // physical lane order: lanes l and l+nlanes/2 share an SM sub-partition -> pair heavy with light
+  std::vector<long> load(nlanes, 0);
+  for (size_t i = 0; i < best_segs.size(); ++i) load[best_lane[i]] += best_segs[i].cost;
+  std::vector<int> by_load(nlanes);
+  for (int l = 0; l < nlanes; ++l) by_load[l] = l;
+  for (int i = 1; i < nlanes; ++i) {
+    int v = by_load[i], j = i;
+    while (j > 0 && load[by_load[j - 1]] < load[v]) { by_load[j] = by_load[j - 1]; --j; }
+    by_load[j] = v;
+  }
+  std::vector<int> phys(nlanes);  // phys[logical] = physical lane
+  if (nlanes >= 2)
+    for (int k = 0; k < nlanes / 2; ++k) { phys[by_load[k]] = k; phys[by_load[nlanes - 1 - k]] = k + nlanes / 2; }
+  else phys[0] = 0;
+  size_t total_blocks = 0;
+  for (const Seg& sg : best_segs) total_blocks += sg.n;
+  const size_t task_doubles = (size_t)KSTEPS * 32 * NT;
+  out.data.assign(total_blocks * task_doubles + (size_t)prefetch_steps * 32 * NT, 0.0);
+  auto elem = [&](int I, int J) -> double {
+    if (I >= M || J >= M || I > J) return 0.0;
+    return (I < J ? 2.0 : 1.0) * Dt[(size_t)I * M + J];
+  };
+  out.segs.clear();
+  out.subtiles = 0;
+  uint32_t slot = 0;
+  for (int pl = 0; pl < nlanes; ++pl) {
+    out.seg_ofs[pl] = (uint32_t)out.segs.size();
+    out.blk_ofs[pl] = slot;
+    for (size_t i = 0; i < best_segs.size(); ++i) {
+      if (phys[best_lane[i]] != pl) continue;
+      const Seg& sg = best_segs[i];
+      const bool has_diag = (sg.ib0 + sg.n - 1 == sg.jb);
+      out.segs.push_back({(uint16_t)sg.jb, (uint16_t)sg.ib0, (uint16_t)sg.n, (uint8_t)has_diag, (uint8_t)col_ntl(sg.jb)});
+      out.subtiles += (uint64_t)(sg.cost - EPI_COST);
+      for (int b = 0; b < sg.n; ++b, ++slot) {
+        double* dst = out.data.data() + (size_t)slot * task_doubles;
+        const int ib = sg.ib0 + b;
+        for (int ks = 0; ks < KSTEPS; ++ks)
+          for (int lane = 0; lane < 32; ++lane)
+            for (int nt = 0; nt < NT; ++nt) {
+              const int I = ib * BLK + ks * 4 + (lane & 3);
+              const int J = sg.jb * BLK + nt * 8 + ncol_perm(lane >> 2);
+              dst[((size_t)ks * 32 + lane) * NT + nt] = elem(I, J);
+            }
+      }
+    }
+  }
+  for (int l = nlanes; l < 9; ++l) { out.seg_ofs[l] = (uint32_t)out.segs.size(); out.blk_ofs[l] = slot; }
+  out.segs.push_back({0, 0, 0, 0, 4});  // sentinel
 }
 
 // Ds = (D + D^T)/2, written row-major with row stride `stride` (zero padded).

@@ -9,7 +9,7 @@
 #define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("CUDA error %s at %d\n",cudaGetErrorString(e),__LINE__); exit(1);} }while(0)
 
 template<int NACC>
-__global__ void __launch_bounds__(256) dmma_rate(double* out, int iters) {
+__global__ void __launch_bounds__(384) dmma_rate(double* out, int iters) {
   double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
   double c[NACC][2];
 #pragma unroll
@@ -84,6 +84,21 @@ int main() {
       double flop = (double)grid * 256 * iters * 16.0 * 2.0;
       printf("DFMA NACC=16 ctas/SM=%d: %.3f ms  %.2f TFLOP/s\n", ctas, ms, flop / ms * 1e-9);
     }
+  }
+  // can ONE warp per SM sub-partition keep the DMMA pipe full?  (128-thread CTA, 1 CTA/SM)
+  for (int rep = 0; rep < 3; rep++) {
+    int iters = 20000;
+    cudaEventRecord(e0); dmma_rate<16><<<sms, 128>>>(out, iters); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1);
+    double flop = (double)sms * 4 * iters * 16.0 * 512.0;
+    printf("DMMA.8x8x4 NACC=16 ONE warp/SMSP: %.3f ms  %.2f TFLOP/s\n", ms, flop / ms * 1e-9);
+  }
+  for (int rep = 0; rep < 2; rep++) {
+    int iters = 20000;
+    cudaEventRecord(e0); dmma_rate<16><<<sms, 384>>>(out, iters); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1);
+    double flop = (double)sms * 12 * iters * 16.0 * 512.0;
+    printf("DMMA.8x8x4 NACC=16 THREE warps/SMSP: %.3f ms  %.2f TFLOP/s\n", ms, flop / ms * 1e-9);
   }
   // streaming read
   size_t bytes = (size_t)8 << 30;
