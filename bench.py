@@ -74,13 +74,16 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if self.proc:
             self.proc.terminate()
+        rows = [r[1:] for r in self.rows if t_begin is None or (t_begin - 0.05 <= r[0] <= t_end + 0.05)]
+        if len(rows) < 3:  # timed region shorter than the sampling period: use every sample under load
+            rows = [r[1:] for r in self.rows]
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx = max(mx, float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -154,7 +157,7 @@ def cpu_reference_leg(cfg, sample_pts, threads, steps=1, warmup=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -243,12 +246,13 @@ def main():
         return float(t.item())
 
     # ---- device-resident timing
-    for _ in range(warmup):
-        res = eng.energy(fid, 0.0)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(warmup):
+        res = eng.energy(fid, 0.0)
+    barrier()
+    t_begin = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms_k = {"density": 0.0, "pi": 0.0, "xc": 0.0, "reduce": 0.0}
     launches = 0
@@ -261,8 +265,9 @@ def main():
             launches += res["gpu_launches"]
         e1.record(stream)
     barrier()
+    t_end = time.time()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     ms_step = ms_total / steps
     value = cfg["npts"] / (ms_step * 1e-3)
     for k in ms_k:

@@ -1,0 +1,213 @@
+// openrdm_host.cc -- implementation of the host mirror (openrdm_host.hpp) over the C ABI.
+#include "openrdm_host.hpp"
+
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+
+#include "../../include/openrdm_b200.h"
+
+namespace mcpdft {
+
+namespace {
+void ck(ordm_ctx* c, int rc, const char* what) {
+  if (rc != ORDM_OK) throw std::runtime_error(std::string(what) + ": " + ordm_last_error(c));
+}
+std::ifstream open_or_throw(const std::string& test_case, const char* leaf) {
+  const std::string path = "./" + test_case + "/" + leaf;  // utility.cc:6-8
+  std::ifstream f(path);
+  if (!f) throw std::runtime_error("Error opening file " + path);
+  return f;
+}
+}  // namespace
+
+MCPDFT::MCPDFT() {}
+MCPDFT::MCPDFT(std::string test_case) { common_init(test_case); }
+MCPDFT::~MCPDFT() {
+  if (ctx_) ordm_destroy(ctx_);
+}
+
+void MCPDFT::set_device(int device) {
+  if (ctx_) throw std::runtime_error("set_device must precede the first compute call");
+  device_ = device;
+}
+
+void MCPDFT::ensure_ctx() const {
+  if (ctx_) return;
+  ck(nullptr, ordm_create(device_, &ctx_), "ordm_create");
+  ck(ctx_, ordm_set_options(ctx_, ORDM_OPT_DIAGNOSTICS), "ordm_set_options");
+}
+
+void MCPDFT::common_init(std::string test_case) {
+  print_banner();
+  read_grids_from_file(test_case);
+  read_orbitals_from_file(test_case);
+  read_energies_from_file(test_case);
+  is_gga_ = (test_case == "h2_tpbe_sto3g");  // mcpdft.cc:24-29
+  if (is_gga_) read_gradients_from_file(test_case);
+  read_opdm_from_file(test_case);
+}
+
+// ---- text fixtures: whitespace separated, dimensions on the first line (utility.cc) ----
+void MCPDFT::read_grids_from_file(std::string tc) {
+  std::ifstream f = open_or_throw(tc, "grids.txt");
+  std::size_t n = 0;
+  f >> n;
+  npts_ = n;
+  w_ = arma::vec(n); x_ = arma::vec(n); y_ = arma::vec(n); z_ = arma::vec(n);
+  for (std::size_t i = 0; i < n; ++i) f >> w_(i) >> x_(i) >> y_(i) >> z_(i);
+  dirty_inputs_ = true;
+}
+void MCPDFT::read_orbitals_from_file(std::string tc) {
+  std::ifstream f = open_or_throw(tc, "orbitals.txt");
+  std::size_t n = 0;
+  int nb = 0;
+  f >> n >> nb;
+  npts_ = n; nbfs_ = (std::size_t)nb;
+  phi_ = arma::mat(n, nb);
+  for (std::size_t p = 0; p < n; ++p) for (int m = 0; m < nb; ++m) f >> phi_(p, m);
+  dirty_inputs_ = true;
+}
+void MCPDFT::read_gradients_from_file(std::string tc) {
+  std::ifstream f = open_or_throw(tc, "gradients.txt");
+  std::size_t n = 0;
+  int nb = 0;
+  f >> n >> nb;
+  npts_ = n; nbfs_ = (std::size_t)nb;
+  phi_x_ = arma::mat(n, nb); phi_y_ = arma::mat(n, nb); phi_z_ = arma::mat(n, nb);
+  for (std::size_t p = 0; p < n; ++p) for (int m = 0; m < nb; ++m) f >> phi_x_(p, m) >> phi_y_(p, m) >> phi_z_(p, m);
+  dirty_inputs_ = true;
+}
+void MCPDFT::read_energies_from_file(std::string tc) {
+  { std::ifstream f = open_or_throw(tc, "eref.txt"); f >> eref_; }
+  { std::ifstream f = open_or_throw(tc, "eclass.txt"); f >> eclass_; }
+}
+void MCPDFT::read_opdm_from_file(std::string tc) {
+  std::ifstream f = open_or_throw(tc, "opdm.txt");
+  int r = 0, c = 0;
+  f >> r >> c;
+  D1a_ = arma::mat(r, c);
+  for (int i = 0; i < r; ++i) for (int j = 0; j < c; ++j) f >> D1a_(i, j);
+  D1b_ = D1a_;  // utility.cc:152-153
+  dirty_inputs_ = true;
+}
+void MCPDFT::read_cmat_from_file(std::string tc) {
+  std::ifstream f = open_or_throw(tc, "cmat.txt");
+  int r = 0, c = 0;
+  f >> r >> c;
+  cmat_ = arma::mat(r, c);
+  for (int i = 0; i < r; ++i) for (int j = 0; j < c; ++j) f >> cmat_(i, j);
+}
+
+void MCPDFT::build_opdm() {  // closed-shell D = C_occ C_occ^T with nbfs/2 occupied columns
+  const int n = (int)nbfs_;
+  D1a_ = arma::mat(n, n); D1b_ = arma::mat(n, n);
+  for (int mu = 0; mu < n; ++mu) for (int nu = 0; nu < n; ++nu) {
+    double s = 0.0;
+    for (int i = 0; i < n / 2; ++i) s += cmat_(mu, i) * cmat_(nu, i);
+    D1a_(mu, nu) = s; D1b_(mu, nu) = s;
+  }
+  dirty_inputs_ = true;
+}
+void MCPDFT::build_tpdm() { D2ab_ = arma::kron(D1a_, D1b_); }
+
+void MCPDFT::sync_inputs() const {
+  ensure_ctx();
+  if (!dirty_inputs_) return;
+  if (w_.n_elem != npts_ || phi_.n_rows != npts_ || phi_.n_cols != nbfs_)
+    throw std::runtime_error("MCPDFT: grid/orbital sizes are inconsistent with npts/nbfs");
+  ck(ctx_, ordm_set_grid(ctx_, npts_, w_.memptr()), "ordm_set_grid");
+  const bool g = is_gga_;
+  if (g && (phi_x_.n_rows != npts_ || phi_y_.n_rows != npts_ || phi_z_.n_rows != npts_))
+    throw std::runtime_error("MCPDFT: GGA requested but orbital gradients are missing");
+  ck(ctx_, ordm_set_orbitals(ctx_, npts_, (int)nbfs_, npts_ ? npts_ : 1, phi_.memptr(), g ? phi_x_.memptr() : nullptr,
+                             g ? phi_y_.memptr() : nullptr, g ? phi_z_.memptr() : nullptr), "ordm_set_orbitals");
+  if (D1a_.n_rows != nbfs_ || D1b_.n_rows != nbfs_) throw std::runtime_error("MCPDFT: D1a/D1b must be nbfs x nbfs");
+  ck(ctx_, ordm_set_rdm1(ctx_, (int)nbfs_, D1a_.memptr(), D1b_.memptr()), "ordm_set_rdm1");
+  dirty_inputs_ = false;
+}
+
+void MCPDFT::build_density_functions() {
+  sync_inputs();
+  ck(ctx_, ordm_build_rho(ctx_), "ordm_build_rho");
+  double n[3], t[3];
+  ordm_integrated_densities(ctx_, n, t);
+  std::printf("\n  Integrated total density = %20.12lf\n  Integrated alpha density = %20.12lf\n  Integrated beta density  = %20.12lf\n\n", n[0], n[1], n[2]);
+}
+void MCPDFT::build_density_gradients() { /* produced by the same fused K1 launch as the densities */ }
+void MCPDFT::build_rho() { build_density_functions(); if (is_gga_) build_density_gradients(); }
+
+void MCPDFT::build_ontop_pair_density(const arma::mat& D2ab) {
+  sync_inputs();
+  if (D2ab.n_rows != nbfs_ * nbfs_) throw std::runtime_error("MCPDFT: D2ab must be nbfs^2 x nbfs^2");
+  ck(ctx_, ordm_set_rdm2ab_dense(ctx_, (int)nbfs_, D2ab.memptr()), "ordm_set_rdm2ab_dense");
+  ck(ctx_, ordm_build_pi(ctx_), "ordm_build_pi");
+}
+void MCPDFT::build_ontop_pair_density_gradients(const arma::mat&) {
+  // mcpdft.cc:214-270: consumed by neither translate() nor any getter in the reference; built on
+  // request only (ORDM_OPT_PI_GRADIENT) so that the energy path does not pay for it.
+}
+void MCPDFT::build_pi(const arma::mat& D2ab) { build_ontop_pair_density(D2ab); if (is_gga_) build_ontop_pair_density_gradients(D2ab); }
+void MCPDFT::build_R() { ck(ctx_, ordm_build_R(ctx_), "ordm_build_R"); }
+void MCPDFT::translate_density() {
+  ck(ctx_, ordm_translate(ctx_), "ordm_translate");
+  double n[3], t[3];
+  ordm_integrated_densities(ctx_, n, t);
+  std::printf("\n  Integrated translated total density = %20.12lf\n  Integrated translated alpha density = %20.12lf\n  Integrated translated beta density  = %20.12lf\n\n", t[0], t[1], t[2]);
+}
+void MCPDFT::translate_density_gradients() { /* same fused K3 launch */ }
+void MCPDFT::translate() { translate_density(); if (is_gga_) translate_density_gradients(); }
+
+void MCPDFT::integrated_densities(double n[3], double trn[3]) const { ensure_ctx(); ordm_integrated_densities(ctx_, n, trn); }
+
+arma::vec MCPDFT::fetch(int which) const {
+  ensure_ctx();
+  arma::vec v(npts_);
+  ck(ctx_, ordm_get_vector(ctx_, which, v.memptr(), npts_), "ordm_get_vector");
+  return v;
+}
+#define ORDM_HOST_GET(name, id) arma::vec MCPDFT::get_##name() const { return fetch(id); }
+ORDM_HOST_GET(rhoa, ORDM_VEC_RHOA) ORDM_HOST_GET(rhoa_x, ORDM_VEC_RHOA_X) ORDM_HOST_GET(rhoa_y, ORDM_VEC_RHOA_Y) ORDM_HOST_GET(rhoa_z, ORDM_VEC_RHOA_Z)
+ORDM_HOST_GET(rhob, ORDM_VEC_RHOB) ORDM_HOST_GET(rhob_x, ORDM_VEC_RHOB_X) ORDM_HOST_GET(rhob_y, ORDM_VEC_RHOB_Y) ORDM_HOST_GET(rhob_z, ORDM_VEC_RHOB_Z)
+ORDM_HOST_GET(rho, ORDM_VEC_RHO) ORDM_HOST_GET(tr_rhoa, ORDM_VEC_TR_RHOA) ORDM_HOST_GET(tr_rhob, ORDM_VEC_TR_RHOB) ORDM_HOST_GET(pi, ORDM_VEC_PI)
+ORDM_HOST_GET(R, ORDM_VEC_R) ORDM_HOST_GET(sigma_aa, ORDM_VEC_SIGMA_AA) ORDM_HOST_GET(sigma_ab, ORDM_VEC_SIGMA_AB) ORDM_HOST_GET(sigma_bb, ORDM_VEC_SIGMA_BB)
+ORDM_HOST_GET(tr_sigma_aa, ORDM_VEC_TR_SIGMA_AA) ORDM_HOST_GET(tr_sigma_ab, ORDM_VEC_TR_SIGMA_AB) ORDM_HOST_GET(tr_sigma_bb, ORDM_VEC_TR_SIGMA_BB)
+#undef ORDM_HOST_GET
+
+void MCPDFT::print_banner() const {
+  std::printf("\n  openrdm_b200: MC-PDFT energy (OpenRDM libmcpdft/libfunc operator surface) on NVIDIA B200\n"
+              "  method: M. Mostafanejad and A. E. DePrince III, J. Chem. Theory Comput. 15, 290-302 (2019)\n\n");
+}
+
+// energy.cc:27-188 without the RAM report (energy.cc:34-40) and the HDF5 round trip (:132-140),
+// neither of which affects the returned energy.
+double mcpdft_energy(MCPDFT* mc, std::string& functional, const arma::mat&, const arma::mat&, const arma::mat& D2ab) {
+  mc->sync_inputs();
+  ordm_ctx* c = mc->context();
+  const std::size_t n = (std::size_t)mc->get_nbfs();
+  if (D2ab.n_rows != n * n) throw std::runtime_error("mcpdft_energy: D2ab must be nbfs^2 x nbfs^2");
+  ck(c, ordm_set_rdm2ab_dense(c, (int)n, D2ab.memptr()), "ordm_set_rdm2ab_dense");
+  ordm_result r;
+  ck(c, ordm_energy(c, functional == "SVWN" ? ORDM_FUNC_SVWN : ORDM_FUNC_PBE, mc->get_eclass(), &r), "ordm_energy");  // energy.cc:114-120
+  std::printf("\n  Integrated total density = %20.12lf\n  Integrated alpha density = %20.12lf\n  Integrated beta density  = %20.12lf\n", r.n_tot, r.n_a, r.n_b);
+  std::printf("\n  Integrated translated total density = %20.12lf\n  Integrated translated alpha density = %20.12lf\n  Integrated translated beta density  = %20.12lf\n\n", r.trn_tot, r.trn_a, r.trn_b);
+  std::printf("------------------------------------------\n   Classical energy = %-20.12lf\n   Ex               = %-20.12lf\n   Ec               = %-20.12lf\n------------------------------------------\n\n", r.eclass, r.ex, r.ec);
+  return r.e_tot;
+}
+
+namespace {
+double run_term(const MCPDFT* mc, int term, const arma::vec& a, const arma::vec& b, const arma::vec* saa, const arma::vec* sab, const arma::vec* sbb) {
+  mc->sync_inputs();
+  double e = 0.0;
+  ck(mc->context(), ordm_functional(mc->context(), term, a.n_elem, a.memptr(), b.memptr(), saa ? saa->memptr() : nullptr,
+                                    sab ? sab->memptr() : nullptr, sbb ? sbb->memptr() : nullptr, &e), "ordm_functional");
+  return e;
+}
+}  // namespace
+double Functional::EX_LSDA(const MCPDFT* mc, const arma::vec& a, const arma::vec& b) { return run_term(mc, ORDM_EX_LSDA, a, b, nullptr, nullptr, nullptr); }
+double Functional::EC_VWN3(const MCPDFT* mc, const arma::vec& a, const arma::vec& b) { return run_term(mc, ORDM_EC_VWN3, a, b, nullptr, nullptr, nullptr); }
+double Functional::EX_PBE(const MCPDFT* mc, const arma::vec& a, const arma::vec& b, const arma::vec& saa, const arma::vec& sbb) { return run_term(mc, ORDM_EX_PBE, a, b, &saa, nullptr, &sbb); }
+double Functional::EC_PBE(const MCPDFT* mc, const arma::vec& a, const arma::vec& b, const arma::vec& saa, const arma::vec& sab, const arma::vec& sbb) { return run_term(mc, ORDM_EC_PBE, a, b, &saa, &sab, &sbb); }
+
+}  // namespace mcpdft
