@@ -123,17 +123,25 @@ __device__ __forceinline__ void kblock(double (&c)[MT][NTILE][2], double (&bq)[R
                                        const double*& xa, const double*& bptr) {
 #pragma unroll
   for (int ks = 0; ks < KSTEPS; ++ks) {
+#ifndef K2_EXP_NOBLOAD  // (tools/k2lab experiment switches; never defined in the product build)
     {
       const double2* src = reinterpret_cast<const double2*>(bptr + (ks + PREFETCH) * STEP_DOUBLES);
       const double2 lo = __ldg(src), hi = __ldg(src + 1);
       bq[(ks + PREFETCH) & (RING - 1)][0] = lo.x; bq[(ks + PREFETCH) & (RING - 1)][1] = lo.y;
       bq[(ks + PREFETCH) & (RING - 1)][2] = hi.x; bq[(ks + PREFETCH) & (RING - 1)][3] = hi.y;
     }
+#endif
+#ifndef K2_EXP_NOALOAD
 #pragma unroll
     for (int m = 0; m < MT; ++m) a[(ks + 1) & 1][m] = xa[(size_t)((ks + 1) * 4) * PS + m * 8];
+#endif
 #pragma unroll
     for (int n = 0; n < NTL; ++n)
+#ifdef K2_EXP_NODIAGSKIP
+      {
+#else
       if (!DIAG || 4 * ks <= 8 * n + 7) {
+#endif
 #pragma unroll
         for (int m = 0; m < MT; ++m) dmma884(c[m][n][0], c[m][n][1], a[ks & 1][m], bq[ks & (RING - 1)][n]);
       }
@@ -160,6 +168,13 @@ __device__ __forceinline__ void run_segment(const SegDesc sd, double (&piacc)[MT
   // fused epilogue: pi[p] += sum_j C[p][j] * X[jb*32 + j][p].  The C fragment of a lane is row
   // qrow, DMMA columns 2*qcol+{0,1} = (host-permuted) J offsets qcol and qcol+4 of the n-tile.
   const double* xe = xrow + (size_t)(sd.jb * BLK + qcol) * PS;
+#ifdef K2_EXP_NOEPI
+#pragma unroll
+  for (int n = 0; n < NTL; ++n)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) piacc[m] += c[m][n][0] + c[m][n][1];
+  (void)xe;
+#else
 #pragma unroll
   for (int n = 0; n < NTL; ++n)
 #pragma unroll
@@ -167,6 +182,7 @@ __device__ __forceinline__ void run_segment(const SegDesc sd, double (&piacc)[MT
       piacc[m] = fma(c[m][n][0], xe[(size_t)(n * 8) * PS + m * 8], piacc[m]);
       piacc[m] = fma(c[m][n][1], xe[(size_t)(n * 8 + 4) * PS + m * 8], piacc[m]);
     }
+#endif
 }
 
 // NPG point groups per tile (P = 8*MT*NPG points), MT DMMA m-tiles per warp.
@@ -285,6 +301,186 @@ __global__ void __launch_bounds__(THREADS, 1) k2_ontop(const Params prm) {
     }
     // `red` is only rewritten after the next tile's post-X-build __syncthreads(), which the
     // readers above also have to pass: no extra barrier needed.
+  }
+}
+
+// =============================================================================================
+// Warp-specialised variant (used whenever two X buffers fit shared memory: nact <= 26).
+//
+// 12 warps = 3 warpgroups.  Warpgroup 0 ("builders", registers trimmed with setmaxnreg) owns
+// everything that is not a DMMA: TMA loads of the phi tile, the X = phi_t*phi_u build into a
+// double-buffered X, the final fixed-order cross-lane sum and the store of Pi.  Warpgroups 1-2
+// (8 "MMA" warps, registers raised with setmaxnreg) only stream segments: each warp is one task
+// lane over all 32 points of the tile.  Builders and MMA warps hand X buffers back and forth
+// through mbarriers (full[b]: X[b] ready; done[b]: all 8 lanes finished with X[b], partials in
+// red[b]), so the X build of tile k+1 and the epilogue/store of tile k-1 overlap the DMMA stream
+// of tile k and no CTA-wide barrier is left in the steady state.
+// =============================================================================================
+#ifdef K2_EXP_TRACE
+__device__ long long g_trace[12][64][4];  // [warp][tile][event] clock64 stamps of block 0
+#define K2_TRACE(ev) do { if (blockIdx.x == 0 && lane == 0 && k < 64) g_trace[wid][k][ev] = clock64(); } while (0)
+#else
+#define K2_TRACE(ev) do { } while (0)
+#endif
+constexpr int WS_THREADS = 384;
+constexpr int WS_P = 32;         // points per tile
+constexpr int WS_PS = WS_P + 4;  // X row stride
+constexpr int WS_BUILDERS = 128;
+
+struct WsSmem {
+  static __host__ __device__ size_t x_doubles(int Mpad) { return (size_t)(Mpad + 4) * WS_PS; }
+  static __host__ __device__ size_t bytes(int Mpad, int nact) {
+    return sizeof(double) * (2 * x_doubles(Mpad) + 2 * (size_t)nact * WS_P + 2 * (size_t)WARPS * WS_P) + 64 + sizeof(uint32_t) * Mpad;
+  }
+};
+
+template <int NREG> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NREG)); }
+template <int NREG> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NREG)); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1) k2_ontop_ws(const Params prm) {
+  constexpr int P = WS_P, PS = WS_PS, MT = 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int Mpad = prm.nblk * BLK;
+  const int nact = prm.nact;
+  double* Xs0 = reinterpret_cast<double*>(smem_raw);
+  const size_t xsz = WsSmem::x_doubles(Mpad);
+  double* phis0 = Xs0 + 2 * xsz;                         // [2][nact][P]
+  double* red0 = phis0 + 2 * (size_t)nact * P;           // [2][8 lanes][P]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red0 + 2 * (size_t)WARPS * P);
+  uint64_t* full = bars;      // [2] builders -> MMA   (count WS_BUILDERS/32 = 4 warp arrivals)
+  uint64_t* done = bars + 2;  // [2] MMA -> builders   (count 8 warp arrivals)
+  uint64_t* tma = bars + 4;   // [2] phi tile landed   (count 1 + tx bytes)
+  uint32_t* pofs = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t tile_bytes = (uint32_t)(nact * P * sizeof(double));
+  const int ntiles = prm.ntiles;
+  // tiles of this CTA: blockIdx.x + k*gridDim.x, k = 0..nmine-1
+  const int nmine = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  for (int I = tid; I < prm.M; I += WS_THREADS)
+    pofs[I] = (uint32_t)prm.pairs[2 * I] * P | ((uint32_t)prm.pairs[2 * I + 1] * P) << 16;
+  for (int b = 0; b < 2; ++b)  // rows M..Mpad+3 of both X buffers stay zero for the whole launch
+    for (int idx = prm.M * P + tid; idx < (Mpad + 4) * P; idx += WS_THREADS) Xs0[b * xsz + (size_t)(idx / P) * PS + (idx % P)] = 0.0;
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) { mbar_init(&full[b], WS_BUILDERS / 32); mbar_init(&done[b], WARPS); mbar_init(&tma[b], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // Builders are the HIGHEST warp ids: the SM sub-partition arbiter favours higher warp ids, and
+  // the builders' few FP64 multiplies share the FP64/DMMA pipe with the MMA warps' DMMA stream --
+  // as low-priority warps they were starved (X build 13k clk per tile instead of ~2k).
+  if (wid >= WARPS) {
+    // ================================ builders ================================
+    reg_dec<56>();
+    const int btid = tid - WARPS * 32;  // 0..127 within the builder warpgroup
+    auto issue_tma = [&](int k) {  // phi tile of my k-th tile into phis[k&1]
+      const int b = k & 1;
+      const size_t t0 = (size_t)(blockIdx.x + (size_t)k * gridDim.x) * P;
+      mbar_expect_tx(&tma[b], tile_bytes);
+      for (int t = 0; t < nact; ++t)
+        tma_bulk_g2s(phis0 + ((size_t)b * nact + t) * P, prm.phi_act + (size_t)t * prm.ld + t0, P * sizeof(double), &tma[b]);
+    };
+    auto flush_tile = [&](int k) {  // fixed-order sum of the 8 lanes' partials of tile k, store Pi
+      const int b = k & 1;
+      mbar_wait(&done[b], (uint32_t)((k >> 1) & 1));
+      if (btid < P) {
+        const double* r = red0 + (size_t)b * WARPS * P + btid;
+        double s = 0.0;
+#pragma unroll
+        for (int l = 0; l < WARPS; ++l) s += r[(size_t)l * P];
+        const size_t gp = (size_t)(blockIdx.x + (size_t)k * gridDim.x) * P + btid;
+        if (gp < prm.npts) {
+          if (prm.pi_core) s += prm.pi_core[gp];
+          prm.pi[gp] = s;
+        }
+      }
+    };
+    if (btid == 0) { if (nmine > 0) issue_tma(0); if (nmine > 1) issue_tma(1); }
+    const int xp = btid % P, xg = btid / P;
+    constexpr int G = WS_BUILDERS / P, XU = 8;
+    for (int k = 0; k < nmine; ++k) {
+      const int b = k & 1;
+      K2_TRACE(0);
+      if (k >= 2) flush_tile(k - 2);  // also proves X[b] and red[b] are free again
+      K2_TRACE(1);
+      mbar_wait(&tma[b], (uint32_t)((k >> 1) & 1));
+      K2_TRACE(2);
+      double* Xs = Xs0 + (size_t)b * xsz;
+      const double* phis = phis0 + (size_t)b * nact * P;
+      for (int I0 = xg; I0 < prm.M; I0 += G * XU) {
+        uint32_t po[XU];
+        double ft[XU], fu[XU];
+#pragma unroll
+        for (int j = 0; j < XU; ++j) po[j] = (I0 + j * G < prm.M) ? pofs[I0 + j * G] : 0u;
+#pragma unroll
+        for (int j = 0; j < XU; ++j) { ft[j] = phis[(po[j] & 0xffffu) + xp]; fu[j] = phis[(po[j] >> 16) + xp]; }
+#pragma unroll
+        for (int j = 0; j < XU; ++j)
+          if (I0 + j * G < prm.M) Xs[(size_t)(I0 + j * G) * PS + xp] = ft[j] * fu[j];
+      }
+      __syncwarp();
+      K2_TRACE(3);
+      if (lane == 0) mbar_arrive(&full[b]);
+      // phis[b] may be refilled once every builder warp has read it
+      asm volatile("bar.sync 1, %0;" ::"n"(WS_BUILDERS) : "memory");
+      if (btid == 0 && k + 2 < nmine) issue_tma(k + 2);
+    }
+    if (nmine >= 2) flush_tile(nmine - 2);
+    if (nmine >= 1) flush_tile(nmine - 1);
+  } else {
+    // ================================ MMA warps ================================
+    reg_inc<224>();
+    const int tl = wid;  // task lane 0..7
+    const int qrow = lane >> 2, qcol = lane & 3;
+    const int seg0 = (int)prm.seg_ofs[tl], nseg = (int)prm.seg_ofs[tl + 1] - seg0;
+    const double* bbase = prm.dfrag + (size_t)prm.blk_ofs[tl] * TASK_DOUBLES + lane * NTILE;
+    const SegDesc* sdesc = prm.segs + seg0;
+    for (int k = 0; k < nmine; ++k) {
+      const int b = k & 1;
+      const double* bptr = bbase;
+      double bq[RING][NTILE];
+#pragma unroll
+      for (int s = 0; s < PREFETCH; ++s) {  // B does not depend on the tile: fetch before waiting for X
+        const double2 lo = __ldg(reinterpret_cast<const double2*>(bptr + s * STEP_DOUBLES));
+        const double2 hi = __ldg(reinterpret_cast<const double2*>(bptr + s * STEP_DOUBLES) + 1);
+        bq[s][0] = lo.x; bq[s][1] = lo.y; bq[s][2] = hi.x; bq[s][3] = hi.y;
+      }
+      SegDesc sd = sdesc[0];
+      K2_TRACE(0);
+      mbar_wait(&full[b], (uint32_t)((k >> 1) & 1));
+      K2_TRACE(1);
+      const double* xrow = Xs0 + (size_t)b * xsz + qrow;
+      double piacc[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) piacc[m] = 0.0;
+      for (int sg = 0; sg < nseg; ++sg) {
+        const SegDesc sd_next = sdesc[sg + 1];
+        switch (sd.ntl) {
+          case 4: run_segment<MT, PS, 4>(sd, piacc, bq, xrow, qcol, bptr); break;
+          case 3: run_segment<MT, PS, 3>(sd, piacc, bq, xrow, qcol, bptr); break;
+          case 2: run_segment<MT, PS, 2>(sd, piacc, bq, xrow, qcol, bptr); break;
+          default: run_segment<MT, PS, 1>(sd, piacc, bq, xrow, qcol, bptr); break;
+        }
+        sd = sd_next;
+      }
+      K2_TRACE(2);
+      double* red = red0 + ((size_t)b * WARPS + tl) * P;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        double v = piacc[m];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (qcol == 0) red[m * 8 + qrow] = v;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&done[b]);
+      K2_TRACE(3);
+    }
   }
 }
 

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -102,6 +103,7 @@ struct ordm_ctx {
   k2::Params k2p{};
   double* d_dfrag = nullptr;
   void* d_tasks = nullptr;
+  bool k2_ws = false, k2_force_plain = false;
   uint16_t* d_pairs = nullptr;
   uint64_t k2_dmma_per_mtile = 0;
   size_t k2_smem = 0;
@@ -273,7 +275,19 @@ int run_k2(ordm_ctx* c, const GridView& v, int* launches) {
   p.pi_core = c->core_form ? v.pi_core : nullptr;
   p.pi = v.vec[ORDM_VEC_PI];
   int rc;
-  if (c->k2_npg == 2 && c->k2_mt == 4) rc = launch_k2<2, 4>(c, p);
+  if (c->k2_ws) {
+    p.ntiles = (int)((p.npts + k2::WS_P - 1) / k2::WS_P);
+    const int grid = std::max(1, std::min(p.ntiles, c->sm_count));
+    static thread_local int ws_dev = -1;
+    static thread_local size_t ws_bytes = 0;
+    if (ws_dev != c->device || ws_bytes < c->k2_smem) {
+      CU(c, cudaFuncSetAttribute(k2::k2_ontop_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k2_smem));
+      ws_dev = c->device; ws_bytes = c->k2_smem;
+    }
+    k2::k2_ontop_ws<<<grid, k2::WS_THREADS, c->k2_smem, c->stream>>>(p);
+    CU(c, cudaGetLastError());
+    rc = ORDM_OK;
+  } else if (c->k2_npg == 2 && c->k2_mt == 4) rc = launch_k2<2, 4>(c, p);
   else if (c->k2_npg == 1 && c->k2_mt == 4) rc = launch_k2<1, 4>(c, p);
   else if (c->k2_npg == 1 && c->k2_mt == 2) rc = launch_k2<1, 2>(c, p);
   else rc = launch_k2<1, 1>(c, p);
@@ -317,6 +331,8 @@ int configure_k2(ordm_ctx* c) {
   int pick = -1;
   for (int i = 0; i < 4; ++i)
     if (cand[i].bytes <= (size_t)c->max_smem_optin) { pick = i; break; }
+  c->k2_ws = !c->k2_force_plain && k2::WsSmem::bytes(Mpad, c->nact) <= (size_t)c->max_smem_optin;
+  if (c->k2_ws) { cand[1].bytes = k2::WsSmem::bytes(Mpad, c->nact); pick = 1; }  // 32-point tiles, 8 task lanes
   if (pick < 0)
     return fail(c, ORDM_ERR_UNSUPPORTED, "on-top pair density: %d orbitals (M=%d pairs) exceed shared memory; use ordm_set_active_space with a smaller active block", c->nact, M);
   c->k2_npg = cand[pick].npg;
@@ -472,6 +488,7 @@ int ordm_create(int device, ordm_ctx** out) {
     return fail(nullptr, ORDM_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
   ordm_ctx* c = new ordm_ctx();
   c->device = device;
+  if (const char* e = getenv("ORDM_K2_PLAIN")) c->k2_force_plain = (e[0] == '1');  // test hook: single-buffer K2
   c->sm_count = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   CU(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
