@@ -52,20 +52,24 @@ struct Params {
   // generic path only: symmetrised active 1-RDMs in global memory
   const double* Dsa_g;
   const double* Dsb_g;
+  // core partial sums produced by k1_core (rc = sum phi_i^2, c{x,y,z} = sum phi_i d phi_i); when
+  // core_rc is set the kernels below skip their own core loop and read these instead
+  double* core_rc;
+  double* core_cx;
+  double* core_cy;
+  double* core_cz;
 };
 
-__device__ __forceinline__ void st(double* p, size_t i, double v) {
-  if (p) p[i] = v;
-}
-
-// NP = nact rounded up to a multiple of 4 (coefficients beyond nact are zero-padded).
-template <int NP, bool GGA>
-__global__ void __launch_bounds__(THREADS) k1_density(const Params P) {
-  __shared__ double scratch[3 * 32];
-  double acc[3] = {0.0, 0.0, 0.0};
+// K1a: the core-orbital stream.  80 % of K1's bytes for config 4 are core columns whose
+// contribution is a plain sum of squares / products; running them in their own light-weight
+// kernel (about 40 registers, 16 independent 8-byte loads in flight per thread, full occupancy)
+// keeps that part of the stream at HBM speed instead of at the occupancy of the
+// register-heavy active-space kernel.
+constexpr int CORE_THREADS = 256;
+template <bool GGA>
+__global__ void __launch_bounds__(CORE_THREADS) k1_core(const Params P) {
   const size_t ld = P.ld;
-  for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS) {
-    // ---- core orbitals: closed form, 4 columns (16 independent loads when GGA) per trip ----
+  for (size_t p = (size_t)blockIdx.x * CORE_THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * CORE_THREADS) {
     double rc = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
     int i = 0;
     for (; i + 4 <= P.ncore; i += 4) {
@@ -92,27 +96,75 @@ __global__ void __launch_bounds__(THREADS) k1_density(const Params P) {
         cz = fma(v, __ldg(P.phiz + o), cz);
       }
     }
+    P.core_rc[p] = rc;
+    if (GGA) { P.core_cx[p] = cx; P.core_cy[p] = cy; P.core_cz[p] = cz; }
+  }
+}
+
+__device__ __forceinline__ void st(double* p, size_t i, double v) {
+  if (p) p[i] = v;
+}
+
+// NP = nact rounded up to a multiple of 4 (coefficients beyond nact are zero-padded).
+template <int NP, bool GGA>
+__global__ void __launch_bounds__(THREADS) k1_density(const Params P) {
+  __shared__ double scratch[3 * 32];
+  double acc[3] = {0.0, 0.0, 0.0};
+  const size_t ld = P.ld;
+  for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS) {
+    // ---- core orbitals: closed form (from k1_core's partials when those were produced) ----
+    double rc = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+    if (P.core_rc) {
+      rc = P.core_rc[p];
+      if (GGA) { cx = P.core_cx[p]; cy = P.core_cy[p]; cz = P.core_cz[p]; }
+    } else {
+      for (int i = 0; i < P.ncore; ++i) {
+        const size_t o = (size_t)i * ld + p;
+        const double v = __ldg(P.phi + o);
+        rc = fma(v, v, rc);
+        if (GGA) {
+          cx = fma(v, __ldg(P.phix + o), cx);
+          cy = fma(v, __ldg(P.phiy + o), cy);
+          cz = fma(v, __ldg(P.phiz + o), cz);
+        }
+      }
+    }
     // ---- active orbitals: T = Ds . phi_act in registers ----
     double f[NP];
 #pragma unroll
     for (int t = 0; t < NP; ++t) f[t] = (t < P.nact) ? __ldg(P.phi + (size_t)(P.ncore + t) * ld + p) : 0.0;
     double ra = 0.0, rb = 0.0, ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+    // four rows of T at a time: 8 independent FMA chains (a single row pair leaves the FP64
+    // pipe latency-bound at this kernel's occupancy)
 #pragma unroll
-    for (int t = 0; t < NP; ++t) {
-      double Ta = 0.0, Tb = 0.0;
+    for (int t0 = 0; t0 < NP; t0 += 4) {
+      double Ta[4] = {0.0, 0.0, 0.0, 0.0}, Tb[4] = {0.0, 0.0, 0.0, 0.0};
+      double fx[4], fy[4], fz[4];
+      if (GGA) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool live = (t0 + j) < P.nact;
+          const size_t o = (size_t)(P.ncore + (live ? t0 + j : 0)) * ld + p;
+          fx[j] = live ? __ldg(P.phix + o) : 0.0;
+          fy[j] = live ? __ldg(P.phiy + o) : 0.0;
+          fz[j] = live ? __ldg(P.phiz + o) : 0.0;
+        }
+      }
 #pragma unroll
       for (int u = 0; u < NP; ++u) {
-        Ta = fma(c_Dsa[t * MAX_ACT + u], f[u], Ta);
-        Tb = fma(c_Dsb[t * MAX_ACT + u], f[u], Tb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          Ta[j] = fma(c_Dsa[(t0 + j) * MAX_ACT + u], f[u], Ta[j]);
+          Tb[j] = fma(c_Dsb[(t0 + j) * MAX_ACT + u], f[u], Tb[j]);
+        }
       }
-      ra = fma(Ta, f[t], ra);
-      rb = fma(Tb, f[t], rb);
-      if (GGA) {
-        if (t < P.nact) {
-          const size_t o = (size_t)(P.ncore + t) * ld + p;
-          const double fx = __ldg(P.phix + o), fy = __ldg(P.phiy + o), fz = __ldg(P.phiz + o);
-          ax = fma(Ta, fx, ax); ay = fma(Ta, fy, ay); az = fma(Ta, fz, az);
-          bx = fma(Tb, fx, bx); by = fma(Tb, fy, by); bz = fma(Tb, fz, bz);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ra = fma(Ta[j], f[t0 + j], ra);
+        rb = fma(Tb[j], f[t0 + j], rb);
+        if (GGA) {
+          ax = fma(Ta[j], fx[j], ax); ay = fma(Ta[j], fy[j], ay); az = fma(Ta[j], fz[j], az);
+          bx = fma(Tb[j], fx[j], bx); by = fma(Tb[j], fy[j], by); bz = fma(Tb[j], fz[j], bz);
         }
       }
     }
@@ -152,14 +204,19 @@ __global__ void __launch_bounds__(THREADS) k1_density_generic(const Params P) {
   const int na = P.nact;
   for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS) {
     double rc = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
-    for (int i = 0; i < P.ncore; ++i) {
-      const size_t o = (size_t)i * ld + p;
-      const double v = __ldg(P.phi + o);
-      rc = fma(v, v, rc);
-      if (GGA) {
-        cx = fma(v, __ldg(P.phix + o), cx);
-        cy = fma(v, __ldg(P.phiy + o), cy);
-        cz = fma(v, __ldg(P.phiz + o), cz);
+    if (P.core_rc) {
+      rc = P.core_rc[p];
+      if (GGA) { cx = P.core_cx[p]; cy = P.core_cy[p]; cz = P.core_cz[p]; }
+    } else {
+      for (int i = 0; i < P.ncore; ++i) {
+        const size_t o = (size_t)i * ld + p;
+        const double v = __ldg(P.phi + o);
+        rc = fma(v, v, rc);
+        if (GGA) {
+          cx = fma(v, __ldg(P.phix + o), cx);
+          cy = fma(v, __ldg(P.phiy + o), cy);
+          cz = fma(v, __ldg(P.phiz + o), cz);
+        }
       }
     }
     double ra = 0.0, rb = 0.0, ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;

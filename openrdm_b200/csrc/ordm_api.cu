@@ -39,6 +39,7 @@ struct GridView {  // one resident grid or one streamed batch
   const double *w = nullptr, *phi = nullptr, *phix = nullptr, *phiy = nullptr, *phiz = nullptr;
   double* vec[ORDM_VEC_COUNT] = {};  // per-point outputs (null = not materialised)
   double *gx = nullptr, *gy = nullptr, *gz = nullptr, *pi_core = nullptr;
+  double* core[4] = {nullptr, nullptr, nullptr, nullptr};  // k1_core partials rc, cx, cy, cz
 };
 
 // ---- NCCL through dlopen (no link-time dependency; absent NCCL only breaks comm_attach) ----
@@ -104,6 +105,7 @@ struct ordm_ctx {
   double* d_dfrag = nullptr;
   void* d_tasks = nullptr;
   bool k2_ws = false, k2_force_plain = false;
+  bool k1_split = false;  // two-kernel K1 (k1_core + active) measured slower than the fused kernel; kept as a test hook
   uint16_t* d_pairs = nullptr;
   uint64_t k2_dmma_per_mtile = 0;
   size_t k2_smem = 0;
@@ -117,7 +119,7 @@ struct ordm_ctx {
   // streamed (host-buffer) path
   struct Stage {
     double *w = nullptr, *phi[4] = {nullptr, nullptr, nullptr, nullptr};
-    double* vec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // rho pi gx gy gz pi_core
+    double* vec[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // rho pi gx gy gz pi_core + k1_core partials
     cudaEvent_t copied = nullptr, done = nullptr;
   } stage[2];
   size_t stage_pts = 0;
@@ -180,12 +182,14 @@ int ensure_vectors(ordm_ctx* c) {
   for (int i = 0; i < ORDM_VEC_COUNT; ++i)
     if (i != ORDM_VEC_W) dfree(g.vec[i]);
   dfree(g.gx); dfree(g.gy); dfree(g.gz); dfree(g.pi_core);
+  for (auto& q : g.core) dfree(q);
   const size_t bytes = g.ld * sizeof(double);
   auto al = [&](double*& p) -> cudaError_t { cudaError_t e = cudaMalloc(&p, bytes); if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, bytes, c->stream); return e; };
   CU(c, al(g.vec[ORDM_VEC_RHO]));
   CU(c, al(g.vec[ORDM_VEC_PI]));
   CU(c, al(g.gx)); CU(c, al(g.gy)); CU(c, al(g.gz));
   CU(c, al(g.pi_core));
+  for (auto& q : g.core) CU(c, al(q));
   if (diag) {
     for (int i = 0; i < ORDM_VEC_COUNT; ++i) {
       if (i == ORDM_VEC_W || i == ORDM_VEC_RHO || i == ORDM_VEC_PI) continue;
@@ -238,6 +242,15 @@ int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches) {
   for (int i = 0; i < 6; ++i) p.grad[i] = v.vec[ORDM_VEC_RHOA_X + i];
   p.saa = v.vec[ORDM_VEC_SIGMA_AA]; p.sab = v.vec[ORDM_VEC_SIGMA_AB]; p.sbb = v.vec[ORDM_VEC_SIGMA_BB];
   p.Dsa_g = c->d_Dsa_g; p.Dsb_g = c->d_Dsb_g;
+  if (c->k1_split && c->ncore >= 8 && v.core[0]) {  // K1a: stream the core columns at full occupancy first
+    p.core_rc = v.core[0]; p.core_cx = v.core[1]; p.core_cy = v.core[2]; p.core_cz = v.core[3];
+    const size_t want = (v.npts + k1::CORE_THREADS - 1) / k1::CORE_THREADS;
+    const int cgrid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 8));
+    if (v.gga) k1::k1_core<true><<<cgrid, k1::CORE_THREADS, 0, c->stream>>>(p);
+    else k1::k1_core<false><<<cgrid, k1::CORE_THREADS, 0, c->stream>>>(p);
+    CU(c, cudaGetLastError());
+    *launches += 1;
+  }
   const int grid = k1_grid(c, v.npts);
   int rc = ensure_partials(c, (size_t)c->sm_count * 16 * 8);
   if (rc) return rc;
@@ -489,6 +502,7 @@ int ordm_create(int device, ordm_ctx** out) {
   ordm_ctx* c = new ordm_ctx();
   c->device = device;
   if (const char* e = getenv("ORDM_K2_PLAIN")) c->k2_force_plain = (e[0] == '1');  // test hook: single-buffer K2
+  if (const char* e = getenv("ORDM_K1_SPLIT")) c->k1_split = (e[0] == '1');         // test hook: two-kernel K1
   c->sm_count = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   CU(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -509,6 +523,7 @@ void ordm_destroy(ordm_ctx* c) {
   for (int i = 0; i < ORDM_VEC_COUNT; ++i)
     if (i != ORDM_VEC_W) dfree(c->g.vec[i]);
   dfree(c->g.gx); dfree(c->g.gy); dfree(c->g.gz); dfree(c->g.pi_core);
+  for (auto& q : c->g.core) dfree(q);
   dfree(c->d_w);
   for (int k = 0; k < 4; ++k) dfree(c->d_phi[k]);
   dfree(c->d_Dsa_g); dfree(c->d_Dsb_g); dfree(c->d_dfrag); dfree(c->d_tasks); dfree(c->d_pairs);
@@ -826,6 +841,7 @@ int ordm_energy_host(ordm_ctx* c, int functional, double eclass, size_t npts, in
     v.w = s.w; v.phi = s.phi[0]; v.phix = s.phi[1]; v.phiy = s.phi[2]; v.phiz = s.phi[3];
     v.vec[ORDM_VEC_RHO] = s.vec[0]; v.vec[ORDM_VEC_PI] = s.vec[1];
     v.gx = s.vec[2]; v.gy = s.vec[3]; v.gz = s.vec[4]; v.pi_core = s.vec[5];
+    for (int q = 0; q < 4; ++q) v.core[q] = s.vec[6 + q];
     int rc;
     if ((rc = run_k1(c, v, 1, &launches))) return rc;
     if ((rc = run_k2(c, v, &launches))) return rc;
