@@ -311,8 +311,16 @@ def main():
     k2_tf = alg["k2_flops"] * pts_rank / (ms_k["pi"] * 1e-3) * 1e-12
     k1_gbs = alg["k1_bytes"] * pts_rank / (ms_k["density"] * 1e-3) * 1e-9
     k3_gbs = alg["k3_bytes"] * pts_rank / (ms_k["xc"] * 1e-3) * 1e-9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f)
+        if args.config == 4 and world == 1 and not args.npts:
+            traffic = tr["config4_n1"]["k2_ontop"]
+    except Exception:
+        pass
     roofline = {"kernel": "k2_ontop (Pi, DMMA.8x8x4)", "bound": "tensor", "achieved": k2_tf, "peak": dg_sus, "unit": "TFLOP/s", "frac": k2_tf / dg_sus,
-                "traffic": None, "peak_source": f"cuBLAS DGEMM 8192^3 measured in this process (sustained {dg_sus:.2f}, burst {dg_burst:.2f} TFLOP/s)",
+                "traffic": traffic, "peak_source": f"cuBLAS DGEMM 8192^3 measured in this process (sustained {dg_sus:.2f}, burst {dg_burst:.2f} TFLOP/s)",
                 "algorithmic_flops_per_point": alg["k2_flops"], "survey_flops_per_point": alg["k2_flops_survey"],
                 "achieved_survey_count": alg["k2_flops_survey"] * pts_rank / (ms_k["pi"] * 1e-3) * 1e-12,
                 "share_of_step": ms_k["pi"] / ms_step}
