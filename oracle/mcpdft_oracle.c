@@ -39,6 +39,10 @@ typedef struct {
   double trn_tot, trn_a, trn_b; /* "Integrated translated ... density", mcpdft.cc:339-343 */
 } orc_result;
 
+/* 0 = MCPDFT::translate (what mcpdft_energy calls), 1 = MCPDFT::fully_translate */
+static int g_fully_translated = 0;
+void orc_set_translation(int fully) { g_fully_translated = fully; }
+
 /* order of the optional per-point output vectors (orc_energy*'s `vecs` argument) */
 enum {
   ORC_RHOA, ORC_RHOB, ORC_RHO,
@@ -222,6 +226,81 @@ void orc_translate_gradients(size_t npts, const double* rho, const double* pi, c
   }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Fully-translated scheme.   mcpdft.cc:418-606 (not called by mcpdft_energy; reached through
+ * MCPDFT::fully_translate()).  zeta(R): sqrt(1-R) for R < R0 = 0.9, the quintic
+ * A dR^5 + B dR^4 + C dR^3 (dR = R - R1, R1 = 1.15) on [R0, R1], 0 above (mcpdft.cc:460-468).
+ * The reference's gradient routine reads pi_y_, which its own build_pi never stores
+ * (mcpdft.cc:268); the intended math (all three components) is restated here.
+ * ---------------------------------------------------------------------------------------- */
+#define FT_R0 0.9
+#define FT_R1 1.15
+#define FT_A (-475.60656009)
+#define FT_B (-379.47331922)
+#define FT_C (-85.38149682)
+
+void orc_fully_translate(size_t npts, const double* rho, const double* pi, const double* R,
+                         const double* w, double* tra, double* trb, double* sums) {
+  double acc_a = 0, acc_b = 0, acc_t = 0;
+  for (size_t p = 0; p < npts; ++p) {
+    double zeta = 0.0;
+    const double dR = R[p] - FT_R1; /* mcpdft.cc:457 */
+    if (!(rho[p] < ORC_TOL) && !(pi[p] < 0.0)) {
+      const double r = R[p];
+      if (((1.0 - r) > ORC_TOL) && (r < FT_R0)) zeta = sqrt(1.0 - r);
+      else if (!(r < FT_R0) && !(r > FT_R1)) zeta = FT_A * pow(dR, 5.0) + FT_B * pow(dR, 4.0) + FT_C * pow(dR, 3.0);
+      else if (r > FT_R1) zeta = 0.0;
+      tra[p] = (1.0 + zeta) * (rho[p] / 2.0);
+      trb[p] = (1.0 - zeta) * (rho[p] / 2.0);
+    } else {
+      tra[p] = 0.0;
+      trb[p] = 0.0;
+    }
+    if (w) {
+      acc_a += tra[p] * w[p];
+      acc_b += trb[p] * w[p];
+      acc_t += (trb[p] + tra[p]) * w[p]; /* mcpdft.cc:475-477 */
+    }
+  }
+  if (sums) { sums[0] = acc_t; sums[1] = acc_a; sums[2] = acc_b; }
+}
+
+/* mcpdft.cc:490-606.  g[0..5] = spin-density gradients, pg[0..2] = grad Pi. */
+void orc_fully_translate_gradients(size_t npts, const double* rho, const double* pi, const double* R,
+                                   double* const* g, double* const* pg, double* tsaa, double* tsab, double* tsbb) {
+  for (size_t p = 0; p < npts; ++p) {
+    double ta[3] = {0, 0, 0}, tb[3] = {0, 0, 0};
+    const double r0 = rho[p];
+    const double dR = R[p] - FT_R1;
+    if (!(r0 < ORC_TOL) && !(pi[p] < 0.0)) {
+      const double r = R[p];
+      for (int c = 0; c < 3; ++c) {
+        const double rx = g[c][p] + g[3 + c][p]; /* mcpdft.cc:531-533 */
+        const double px = pg[c][p];
+        if (((1.0 - r) > ORC_TOL) && (r < FT_R0)) { /* mcpdft.cc:541-548 */
+          const double zeta = sqrt(1.0 - r);
+          ta[c] = (1.0 + zeta) * (rx / 2.0) + (r * rx) / (2.0 * zeta) - px / (r0 * zeta);
+          tb[c] = (1.0 - zeta) * (rx / 2.0) - (r * rx) / (2.0 * zeta) + px / (r0 * zeta);
+        } else if (!(r < FT_R0) && !(r > FT_R1)) { /* mcpdft.cc:549-581 */
+          const double zeta = FT_A * pow(dR, 5.0) + FT_B * pow(dR, 4.0) + FT_C * pow(dR, 3.0);
+          ta[c] = (1.0 + zeta) * (rx / 2.0) + (FT_A * pow(dR, 4.0)) * ((10.0 * px / r0) - (5.0 * r * rx)) +
+                  (FT_B * pow(dR, 3.0)) * ((8.0 * px / r0) - (4.0 * r * rx)) +
+                  (FT_C * pow(dR, 2.0)) * ((6.0 * px / r0) - (3.0 * r * rx));
+          tb[c] = (1.0 - zeta) * (rx / 2.0) + (FT_A * pow(dR, 4.0)) * (-(10.0 * px / r0) + (5.0 * r * rx)) +
+                  (FT_B * pow(dR, 3.0)) * (-(8.0 * px / r0) + (4.0 * r * rx)) +
+                  (FT_C * pow(dR, 2.0)) * (-(6.0 * px / r0) + (3.0 * r * rx));
+        } else if (r > FT_R1) { /* mcpdft.cc:582-590 */
+          ta[c] = (1.0 + 0.0) * (rx / 2.0);
+          tb[c] = (1.0 - 0.0) * (rx / 2.0);
+        }
+      }
+    }
+    tsaa[p] = (ta[0] * ta[0]) + (ta[1] * ta[1]) + (ta[2] * ta[2]); /* mcpdft.cc:599-601 */
+    tsab[p] = (ta[0] * tb[0]) + (ta[1] * tb[1]) + (ta[2] * tb[2]);
+    tsbb[p] = (tb[0] * tb[0]) + (tb[1] * tb[1]) + (tb[2] * tb[2]);
+  }
+}
+
 /* ==========================================================================================
  *                                libfunc: exchange
  * ======================================================================================== */
@@ -380,13 +459,19 @@ static double* pick(double** vecs, int id, size_t npts, double** owned, int* now
 static void orc_finish(size_t npts, int is_gga, int functional_is_svwn, const double* w,
                        double eclass, double** v, orc_result* out) {
   double tsum[3];
+  double* g[6] = {v[ORC_RHOA_X], v[ORC_RHOA_Y], v[ORC_RHOA_Z], v[ORC_RHOB_X], v[ORC_RHOB_Y], v[ORC_RHOB_Z]};
   orc_R(npts, v[ORC_PI], v[ORC_RHO], v[ORC_R]);
-  orc_translate(npts, v[ORC_RHO], v[ORC_PI], v[ORC_R], w, v[ORC_TR_RHOA], v[ORC_TR_RHOB], tsum);
-  if (is_gga) {
-    double* g[6] = {v[ORC_RHOA_X], v[ORC_RHOA_Y], v[ORC_RHOA_Z], v[ORC_RHOB_X], v[ORC_RHOB_Y], v[ORC_RHOB_Z]};
-    orc_translate_gradients(npts, v[ORC_RHO], v[ORC_PI], v[ORC_R], g, v[ORC_TR_SIGMA_AA],
-                            v[ORC_TR_SIGMA_AB], v[ORC_TR_SIGMA_BB]);
-  } /* else tr_sigma stay zero (energy.cc:63-65) */
+  if (g_fully_translated) { /* MCPDFT::fully_translate, mcpdft.cc:418-423 */
+    orc_fully_translate(npts, v[ORC_RHO], v[ORC_PI], v[ORC_R], w, v[ORC_TR_RHOA], v[ORC_TR_RHOB], tsum);
+    if (is_gga)
+      orc_fully_translate_gradients(npts, v[ORC_RHO], v[ORC_PI], v[ORC_R], g, &v[ORC_PI_X], v[ORC_TR_SIGMA_AA],
+                                    v[ORC_TR_SIGMA_AB], v[ORC_TR_SIGMA_BB]);
+  } else {
+    orc_translate(npts, v[ORC_RHO], v[ORC_PI], v[ORC_R], w, v[ORC_TR_RHOA], v[ORC_TR_RHOB], tsum);
+    if (is_gga)
+      orc_translate_gradients(npts, v[ORC_RHO], v[ORC_PI], v[ORC_R], g, v[ORC_TR_SIGMA_AA],
+                              v[ORC_TR_SIGMA_AB], v[ORC_TR_SIGMA_BB]);
+  } /* without gradients tr_sigma stay zero (energy.cc:63-65) */
   double ex, ec;
   if (functional_is_svwn) {
     ex = orc_ex_lsda(npts, v[ORC_TR_RHOA], v[ORC_TR_RHOB], w);
@@ -421,6 +506,7 @@ int orc_energy(size_t npts, int n, int is_gga, int functional_is_svwn, const dou
   double* owned[ORC_NVEC];
   int nowned = 0;
   double* v[ORC_NVEC];
+  if (g_fully_translated && is_gga) with_pi_grad = 1; /* the ft gradients consume grad Pi */
   for (int i = 0; i < ORC_NVEC; ++i) v[i] = pick(vecs, i, npts, owned, &nowned);
   double s[3];
   orc_density(npts, n, phi, D1a, D1b, w, v[ORC_RHOA], v[ORC_RHOB], v[ORC_RHO], s); /* energy.cc:49 */
@@ -456,6 +542,7 @@ int orc_energy_coreactive(size_t npts, int ncore, int nact, int is_gga, int func
   double* owned[ORC_NVEC + 16];
   int nowned = 0;
   double* v[ORC_NVEC];
+  if (g_fully_translated && is_gga) with_pi_grad = 1;
   for (int i = 0; i < ORC_NVEC; ++i) v[i] = pick(vecs, i, npts, owned, &nowned);
   const size_t off = (size_t)ncore * npts;
   const double *pa = phi + off, *pax = phix ? phix + off : 0, *pay = phiy ? phiy + off : 0,

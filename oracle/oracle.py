@@ -128,6 +128,10 @@ class Port:
                                        C.byref(res), tbl)
         return Outcome(res.asdict(), _vecs_dict(arrs, is_gga))
 
+    def set_translation(self, fully: bool):
+        """False: MCPDFT::translate (mcpdft_energy's choice); True: MCPDFT::fully_translate."""
+        self.lib.orc_set_translation(int(bool(fully)))
+
     def functional(self, which, w, ra, rb, saa=None, sab=None, sbb=None) -> float:
         """which in {'EX_LSDA','EC_VWN3','EX_PBE','EC_PBE'} on caller-provided vectors."""
         w, ra, rb = _f64(w), _f64(ra), _f64(rb)
@@ -168,6 +172,9 @@ class Ref:
         self.lib = C.CDLL(REF_SO)
         self.lib.ref_functional.restype = C.c_double
         self.lib.ref_energy_threads.restype = C.c_double
+
+    def set_translation(self, fully: bool):
+        self.lib.ref_set_translation(int(bool(fully)))
 
     def energy_as_written(self, w, phi, D1a, D1b, D2ab, functional="SVWN", grads=None, eclass=0.0,
                           want_vecs=True, quiet=True) -> Outcome:

@@ -161,6 +161,14 @@ static void integrate(const mcpdft::MCPDFT& mc, size_t npts, orc_result* out) {
   out->trn_tot = t0; out->trn_a = t1; out->trn_b = t2;
 }
 
+// Translation used by ref_energy_staged: 0 = MCPDFT::translate (what mcpdft_energy calls),
+// 1 = MCPDFT::fully_translate (mcpdft.cc:418-606).  The fully-translated gradient routine reads
+// pi_y_, which the reference's build_pi never stores (mcpdft.cc:268 writes pi_y into the pi_z
+// slot); the harness obtains d(Pi)/dy from the reference's own routine by running it once more
+// with the y-derivatives of the orbitals in the x slot, and installs it with set_pi_y().
+static int g_fully_translated = 0;
+void ref_set_translation(int fully) { g_fully_translated = fully; }
+
 // functional: "SVWN" or anything else (= PBE), as energy.cc:114-120.
 // Runs mcpdft::mcpdft_energy() exactly as tests/main.cc:38 does (for GGA that includes the
 // grad-Pi stage whose output never reaches the energy).
@@ -227,9 +235,20 @@ int ref_energy_staged(size_t npts, int ncore, int nact, int is_gga, const char* 
   if (is_gga) { t0 = now_s(); mc.build_density_gradients(); t.t_grad_rho = now_s() - t0; }
 
   arma::mat d2 = to_mat(D2act, (size_t)nact * nact, (size_t)nact * nact);
+  const bool ft = g_fully_translated != 0;
+  if (ft && is_gga) with_pi_grad = 1;
+  arma::vec piy_act(npts, arma::fill::zeros);
+  if (ft && is_gga) {  // d(Pi_act)/dy through the reference's x-slot (see ref_set_translation)
+    const size_t off = (size_t)ncore * npts;
+    mcpdft::MCPDFT tmp;
+    fill_mc(tmp, npts, nact, 1, w, phi + off, phiy + off, phiy + off, phiy + off, A1a, A1b, 0.0);
+    tmp.build_ontop_pair_density_gradients(d2);
+    piy_act = tmp.pi_x_;
+  }
   if (ncore == 0) {
     t0 = now_s(); mc.build_ontop_pair_density(d2); t.t_pi = now_s() - t0;
     if (is_gga && with_pi_grad) { t0 = now_s(); mc.build_ontop_pair_density_gradients(d2); t.t_grad_pi = now_s() - t0; }
+    if (ft && is_gga) mc.set_pi_y(piy_act);
   } else {
     const size_t off = (size_t)ncore * npts;
     mcpdft::MCPDFT act;  // the reference's kernels on the active columns only
@@ -248,10 +267,27 @@ int ref_energy_staged(size_t npts, int ncore, int nact, int is_gga, const char* 
     }
     mc.set_pi(pi);
     t.t_pi += now_s() - t0;
+    if (is_gga && with_pi_grad) {  // core terms of grad Pi: 2 rc drc + drc (rta+rtb) + rc (drta + drtb) + dPi_act
+      act.build_density_gradients();
+      arma::vec gax[3] = {act.get_rhoa_x(), act.get_rhoa_y(), act.get_rhoa_z()};
+      arma::vec gbx[3] = {act.get_rhob_x(), act.get_rhob_y(), act.get_rhob_z()};
+      arma::vec pg[3] = {act.pi_x_, piy_act, act.pi_z_};
+      const double* gphi[3] = {phix, phiy, phiz};
+      for (size_t p = 0; p < npts; ++p) {
+        double rc = 0.0, dc[3] = {0, 0, 0};
+        for (int i = 0; i < ncore; ++i) {
+          const size_t o = p + (size_t)i * npts;
+          rc += phi[o] * phi[o];
+          for (int c = 0; c < 3; ++c) dc[c] += gphi[c][o] * phi[o] + phi[o] * gphi[c][o];
+        }
+        for (int c = 0; c < 3; ++c) pg[c](p) += 2.0 * rc * dc[c] + dc[c] * (rta(p) + rtb(p)) + rc * (gax[c](p) + gbx[c](p));
+      }
+      mc.set_pi_x(pg[0]); mc.set_pi_y(pg[1]); mc.set_pi_z(pg[2]);
+    }
   }
   t0 = now_s();
   mc.build_R();
-  mc.translate();
+  if (ft) mc.fully_translate(); else mc.translate();
   t.t_R_translate = now_s() - t0;
 
   mcpdft::Functional fn;
