@@ -63,7 +63,14 @@ enum ordm_vector {
 /* option bits for ordm_set_options */
 enum {
   ORDM_OPT_DIAGNOSTICS = 1, /* keep every per-point vector (getters work); off = energy-only mode */
-  ORDM_OPT_PI_GRADIENT = 2  /* also build grad Pi (mcpdft.cc:214-270); never enters the energy */
+  ORDM_OPT_PI_GRADIENT = 2, /* also build grad Pi (MCPDFT::build_ontop_pair_density_gradients,
+                               mcpdft.cc:214-270; needs phi_x/y/z).  mcpdft_energy runs that stage for
+                               every GGA case although translate() never reads its result; here it is
+                               on request, and all three components are stored (the reference drops
+                               pi_y, mcpdft.cc:268) */
+  ORDM_OPT_FULLY_TRANSLATED = 4 /* ordm_energy / ordm_energy_host use MCPDFT::fully_translate
+                               (mcpdft.cc:418-606) instead of MCPDFT::translate; with orbital gradients
+                               this implies ORDM_OPT_PI_GRADIENT (the ft gradients consume grad Pi) */
 };
 
 /* What mcpdft_energy returns or prints: energy.cc:175-183, mcpdft.cc:100-104,339-343. */
@@ -118,6 +125,9 @@ int ordm_build_rho(ordm_ctx* ctx);   /* MCPDFT::build_rho,  mcpdft.cc:35-40  */
 int ordm_build_pi(ordm_ctx* ctx);    /* MCPDFT::build_pi,   mcpdft.cc:178-183 (D2ab from set_rdm2ab_*) */
 int ordm_build_R(ordm_ctx* ctx);     /* MCPDFT::build_R,    mcpdft.cc:272-285 */
 int ordm_translate(ordm_ctx* ctx);   /* MCPDFT::translate,  mcpdft.cc:287-292 */
+/* MCPDFT::fully_translate, mcpdft.cc:418-423 (after build_rho, build_pi with ORDM_OPT_PI_GRADIENT
+ * when the orbitals carry gradients, build_R) */
+int ordm_fully_translate(ordm_ctx* ctx);
 /* the integrated densities the reference prints after build_rho / translate */
 int ordm_integrated_densities(ordm_ctx* ctx, double out_n[3], double out_trn[3]);
 

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(PKG, "libopenrdm_b200.so")
 
 FUNC_SVWN, FUNC_PBE = 0, 1
 EX_LSDA, EC_VWN3, EX_PBE, EC_PBE = 0, 1, 2, 3
-OPT_DIAGNOSTICS, OPT_PI_GRADIENT = 1, 2
+OPT_DIAGNOSTICS, OPT_PI_GRADIENT, OPT_FULLY_TRANSLATED = 1, 2, 4
 
 VEC_NAMES = [
     "rhoa", "rhob", "rho",
@@ -79,7 +79,7 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.ordm_set_rdm1.argtypes = [P, I, D, D]
     lib.ordm_set_rdm2ab_dense.argtypes = [P, I, D]
     lib.ordm_set_active_space.argtypes = [P, I, I, D, D, D]
-    for f in ("ordm_build_rho", "ordm_build_pi", "ordm_build_R", "ordm_translate", "ordm_comm_detach"):
+    for f in ("ordm_build_rho", "ordm_build_pi", "ordm_build_R", "ordm_translate", "ordm_fully_translate", "ordm_comm_detach"):
         getattr(lib, f).argtypes = [P]
     lib.ordm_integrated_densities.argtypes = [P, D, D]
     lib.ordm_functional.argtypes = [P, I, S, D, D, D, D, D, D]
@@ -162,8 +162,9 @@ class Engine:
     def set_stream(self, cuda_stream_handle: int):
         self._ck(self.lib.ordm_set_stream(self.ctx, C.c_void_p(cuda_stream_handle)))
 
-    def set_options(self, diagnostics=False, pi_gradient=False):
-        self._ck(self.lib.ordm_set_options(self.ctx, (OPT_DIAGNOSTICS if diagnostics else 0) | (OPT_PI_GRADIENT if pi_gradient else 0)))
+    def set_options(self, diagnostics=False, pi_gradient=False, fully_translated=False):
+        self._ck(self.lib.ordm_set_options(self.ctx, (OPT_DIAGNOSTICS if diagnostics else 0) | (OPT_PI_GRADIENT if pi_gradient else 0)
+                                           | (OPT_FULLY_TRANSLATED if fully_translated else 0)))
 
     def set_grid(self, w):
         w = _f(w)
@@ -197,6 +198,7 @@ class Engine:
     def build_pi(self): self._ck(self.lib.ordm_build_pi(self.ctx))
     def build_R(self): self._ck(self.lib.ordm_build_R(self.ctx))
     def translate(self): self._ck(self.lib.ordm_translate(self.ctx))
+    def fully_translate(self): self._ck(self.lib.ordm_fully_translate(self.ctx))
 
     def integrated_densities(self):
         n = (C.c_double * 3)(); t = (C.c_double * 3)()

@@ -42,6 +42,7 @@ struct Params {
   double* gy;
   double* gz;
   double* pi_core;  // closed-form core part of Pi (null when ncore == 0 => treated as 0)
+  double* pcg[3];   // closed-form core part of grad Pi (null unless grad Pi is requested with core orbitals)
   double* rhoa;     // diagnostics
   double* rhob;
   double* grad[6];  // ax ay az bx by bz
@@ -175,6 +176,12 @@ __global__ void __launch_bounds__(THREADS) k1_density(const Params P) {
     st(P.rhob, p, rhob);
     st(P.pi_core, p, rc * rc + rc * rb + ra * rc);
     if (GGA) {
+      if (P.pcg[0]) {  // grad(rc^2 + rc (rta + rtb)) with grad rc = 2 c, grad rt = 2 (T . grad phi)
+        const double rt = ra + rb;
+        P.pcg[0][p] = 2.0 * rc * (2.0 * cx) + (2.0 * cx) * rt + rc * (2.0 * ax + 2.0 * bx);
+        P.pcg[1][p] = 2.0 * rc * (2.0 * cy) + (2.0 * cy) * rt + rc * (2.0 * ay + 2.0 * by);
+        P.pcg[2][p] = 2.0 * rc * (2.0 * cz) + (2.0 * cz) * rt + rc * (2.0 * az + 2.0 * bz);
+      }
       ax = 2.0 * (cx + ax); ay = 2.0 * (cy + ay); az = 2.0 * (cz + az);
       bx = 2.0 * (cx + bx); by = 2.0 * (cy + by); bz = 2.0 * (cz + bz);
       st(P.gx, p, ax + bx);  // mcpdft.cc:381-383
@@ -244,6 +251,12 @@ __global__ void __launch_bounds__(THREADS) k1_density_generic(const Params P) {
     st(P.rhob, p, rhob);
     st(P.pi_core, p, rc * rc + rc * rb + ra * rc);
     if (GGA) {
+      if (P.pcg[0]) {
+        const double rt = ra + rb;
+        P.pcg[0][p] = 2.0 * rc * (2.0 * cx) + (2.0 * cx) * rt + rc * (2.0 * ax + 2.0 * bx);
+        P.pcg[1][p] = 2.0 * rc * (2.0 * cy) + (2.0 * cy) * rt + rc * (2.0 * ay + 2.0 * by);
+        P.pcg[2][p] = 2.0 * rc * (2.0 * cz) + (2.0 * cz) * rt + rc * (2.0 * az + 2.0 * bz);
+      }
       ax = 2.0 * (cx + ax); ay = 2.0 * (cy + ay); az = 2.0 * (cz + az);
       bx = 2.0 * (cx + bx); by = 2.0 * (cy + by); bz = 2.0 * (cz + bz);
       st(P.gx, p, ax + bx); st(P.gy, p, ay + by); st(P.gz, p, az + bz);

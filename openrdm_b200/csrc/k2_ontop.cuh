@@ -68,6 +68,11 @@ struct Params {
   uint32_t blk_ofs[MAX_LANES + 1];  // first 8 KB block slot of lane l in dfrag
   const double* pi_core;            // nullable: closed-form core part added to the result
   double* pi;                       // out, npts
+  // grad-Pi variant only (k2_ontop_ws<true, *>): active columns of grad phi, closed-form core
+  // parts of grad Pi (nullable) and the three outputs
+  const double* dphi_act[3];
+  const double* pi_core_g[3];
+  double* pi_g[3];
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -150,9 +155,10 @@ __device__ __forceinline__ void kblock(double (&c)[MT][NTILE][2], double (&bq)[R
   bptr += TASK_DOUBLES;
 }
 
-template <int MT, int PS, int NTL>
-__device__ __forceinline__ void run_segment(const SegDesc sd, double (&piacc)[MT], double (&bq)[RING][NTILE],
-                                            const double* xrow, int qcol, const double*& bptr) {
+template <int MT, int PS, int NTL, bool GRAD = false>
+__device__ __forceinline__ void run_segment(const SegDesc sd, double (&piacc)[GRAD ? 4 : 1][MT], double (&bq)[RING][NTILE],
+                                            const double* xrow, int qcol, const double*& bptr,
+                                            const double* ph = nullptr, const uint32_t* pofs = nullptr, int cstride = 0) {
   double c[MT][NTILE][2];
 #pragma unroll
   for (int m = 0; m < MT; ++m)
@@ -172,16 +178,43 @@ __device__ __forceinline__ void run_segment(const SegDesc sd, double (&piacc)[MT
 #pragma unroll
   for (int n = 0; n < NTL; ++n)
 #pragma unroll
-    for (int m = 0; m < MT; ++m) piacc[m] += c[m][n][0] + c[m][n][1];
+    for (int m = 0; m < MT; ++m) piacc[0][m] += c[m][n][0] + c[m][n][1];
   (void)xe;
 #else
+  if (!GRAD) {
 #pragma unroll
-  for (int n = 0; n < NTL; ++n)
+    for (int n = 0; n < NTL; ++n)
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      piacc[m] = fma(c[m][n][0], xe[(size_t)(n * 8) * PS + m * 8], piacc[m]);
-      piacc[m] = fma(c[m][n][1], xe[(size_t)(n * 8 + 4) * PS + m * 8], piacc[m]);
-    }
+      for (int m = 0; m < MT; ++m) {
+        piacc[0][m] = fma(c[m][n][0], xe[(size_t)(n * 8) * PS + m * 8], piacc[0][m]);
+        piacc[0][m] = fma(c[m][n][1], xe[(size_t)(n * 8 + 4) * PS + m * 8], piacc[0][m]);
+      }
+  } else {
+    // C = Y[:, jb] (full Dt).  Pi += Y o X and d_c Pi += Y o d_c X with
+    // d_c X(p, J=(t,u)) = d_c phi_t phi_u + phi_t d_c phi_u formed on the fly from the phi /
+    // grad phi tiles (ph: [4][nact][P], component stride cstride); the factor 2 of
+    // grad Pi = 2 rowsum(dX o Y) is applied once at the store.
+    (void)xe;
+#pragma unroll
+    for (int n = 0; n < NTL; ++n)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t po = pofs[sd.jb * BLK + n * 8 + 4 * h + qcol];
+        const double* ft = ph + (po & 0xffffu);
+        const double* fu = ph + (po >> 16);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const double cc = c[m][n][h];
+          const double a = ft[m * 8], b = fu[m * 8];
+          piacc[0][m] = fma(cc, a * b, piacc[0][m]);
+#pragma unroll
+          for (int d = 1; d < 4; ++d) {
+            const double da = ft[d * cstride + m * 8], db = fu[d * cstride + m * 8];
+            piacc[GRAD ? d : 0][m] = fma(cc, fma(da, b, a * db), piacc[GRAD ? d : 0][m]);
+          }
+        }
+      }
+  }
 #endif
 }
 
@@ -257,9 +290,9 @@ __global__ void __launch_bounds__(THREADS, 1) k2_ontop(const Params prm) {
       }
     }
     // ---- contraction over this warp's segments ----
-    double piacc[MT];
+    double piacc[1][MT];
 #pragma unroll
-    for (int m = 0; m < MT; ++m) piacc[m] = 0.0;
+    for (int m = 0; m < MT; ++m) piacc[0][m] = 0.0;
     const double* xrow = Xs + pg * (8 * MT) + qrow;  // + I*PS + m*8
     const double* bptr = bbase;
     double bq[RING][NTILE];
@@ -283,7 +316,7 @@ __global__ void __launch_bounds__(THREADS, 1) k2_ontop(const Params prm) {
     // ---- reduce: 4 lanes of a quad hold the same rows ----
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-      double v = piacc[m];
+      double v = piacc[0][m];
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       if (qcol == 0) red[(size_t)tl * P + pg * (8 * MT) + m * 8 + qrow] = v;
@@ -305,16 +338,23 @@ __global__ void __launch_bounds__(THREADS, 1) k2_ontop(const Params prm) {
 }
 
 // =============================================================================================
-// Warp-specialised variant (used whenever two X buffers fit shared memory: nact <= 26).
+// Warp-specialised variant (used whenever its X buffers fit shared memory).
 //
-// 12 warps = 3 warpgroups.  Warpgroup 0 ("builders", registers trimmed with setmaxnreg) owns
+// 12 warps = 3 warpgroups.  Warpgroup 2 ("builders", registers trimmed with setmaxnreg) owns
 // everything that is not a DMMA: TMA loads of the phi tile, the X = phi_t*phi_u build into a
-// double-buffered X, the final fixed-order cross-lane sum and the store of Pi.  Warpgroups 1-2
+// (double-)buffered X, the final fixed-order cross-lane sum and the store of Pi.  Warpgroups 0-1
 // (8 "MMA" warps, registers raised with setmaxnreg) only stream segments: each warp is one task
 // lane over all 32 points of the tile.  Builders and MMA warps hand X buffers back and forth
 // through mbarriers (full[b]: X[b] ready; done[b]: all 8 lanes finished with X[b], partials in
 // red[b]), so the X build of tile k+1 and the epilogue/store of tile k-1 overlap the DMMA stream
 // of tile k and no CTA-wide barrier is left in the steady state.
+//
+// GRAD = true additionally produces grad Pi (MCPDFT::build_ontop_pair_density_gradients,
+// mcpdft.cc:214-270) from the same product Y = X . Dt:  d_c Pi = 2 rowsum(d_c X o Y)
+// (SURVEY.md App. B.1).  That needs Y itself, so the whole symmetric Dt is streamed (2 M^2
+// flops per point instead of M(M+1)); the grad phi tiles arrive by TMA next to phi and d_c X is
+// formed on the fly in the segment epilogue.  NBUF = 1 (single X buffer) is the fallback when
+// two do not fit shared memory.
 // =============================================================================================
 #ifdef K2_EXP_TRACE
 __device__ long long g_trace[12][64][4];  // [warp][tile][event] clock64 stamps of block 0
@@ -329,8 +369,10 @@ constexpr int WS_BUILDERS = 128;
 
 struct WsSmem {
   static __host__ __device__ size_t x_doubles(int Mpad) { return (size_t)(Mpad + 4) * WS_PS; }
-  static __host__ __device__ size_t bytes(int Mpad, int nact) {
-    return sizeof(double) * (2 * x_doubles(Mpad) + 2 * (size_t)nact * WS_P + 2 * (size_t)WARPS * WS_P) + 64 + sizeof(uint32_t) * Mpad;
+  static __host__ __device__ size_t bytes(int Mpad, int nact, bool grad = false, int nbuf = 2) {
+    const size_t nc = grad ? 4 : 1;
+    return sizeof(double) * ((size_t)nbuf * x_doubles(Mpad) + (size_t)nbuf * nc * nact * WS_P + (size_t)nbuf * nc * WARPS * WS_P) + 64 +
+           sizeof(uint32_t) * Mpad;
   }
 };
 
@@ -340,33 +382,36 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+template <bool GRAD, int NBUF>
 __global__ void __launch_bounds__(WS_THREADS, 1) k2_ontop_ws(const Params prm) {
   constexpr int P = WS_P, PS = WS_PS, MT = 4;
+  constexpr int NC = GRAD ? 4 : 1;  // phi (+ grad phi) components staged per tile; result rows per point
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int Mpad = prm.nblk * BLK;
   const int nact = prm.nact;
   double* Xs0 = reinterpret_cast<double*>(smem_raw);
   const size_t xsz = WsSmem::x_doubles(Mpad);
-  double* phis0 = Xs0 + 2 * xsz;                         // [2][nact][P]
-  double* red0 = phis0 + 2 * (size_t)nact * P;           // [2][8 lanes][P]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red0 + 2 * (size_t)WARPS * P);
+  double* phis0 = Xs0 + NBUF * xsz;                               // [NBUF][NC][nact][P]
+  double* red0 = phis0 + (size_t)NBUF * NC * nact * P;            // [NBUF][8 lanes][NC][P]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red0 + (size_t)NBUF * NC * WARPS * P);
   uint64_t* full = bars;      // [2] builders -> MMA   (count WS_BUILDERS/32 = 4 warp arrivals)
   uint64_t* done = bars + 2;  // [2] MMA -> builders   (count 8 warp arrivals)
   uint64_t* tma = bars + 4;   // [2] phi tile landed   (count 1 + tx bytes)
-  uint32_t* pofs = reinterpret_cast<uint32_t*>(bars + 8);
+  uint32_t* pofs = reinterpret_cast<uint32_t*>(bars + 8);  // [Mpad]: (t*P) | (u*P) << 16, 0 beyond M
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint32_t tile_bytes = (uint32_t)(nact * P * sizeof(double));
+  const int cstride = nact * P;  // component stride inside a phi tile buffer
+  const uint32_t tile_bytes = (uint32_t)(NC * nact * P * sizeof(double));
   const int ntiles = prm.ntiles;
   // tiles of this CTA: blockIdx.x + k*gridDim.x, k = 0..nmine-1
   const int nmine = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  for (int I = tid; I < prm.M; I += WS_THREADS)
-    pofs[I] = (uint32_t)prm.pairs[2 * I] * P | ((uint32_t)prm.pairs[2 * I + 1] * P) << 16;
-  for (int b = 0; b < 2; ++b)  // rows M..Mpad+3 of both X buffers stay zero for the whole launch
+  for (int I = tid; I < Mpad; I += WS_THREADS)
+    pofs[I] = I < prm.M ? ((uint32_t)prm.pairs[2 * I] * P | ((uint32_t)prm.pairs[2 * I + 1] * P) << 16) : 0u;
+  for (int b = 0; b < NBUF; ++b)  // rows M..Mpad+3 of the X buffers stay zero for the whole launch
     for (int idx = prm.M * P + tid; idx < (Mpad + 4) * P; idx += WS_THREADS) Xs0[b * xsz + (size_t)(idx / P) * PS + (idx % P)] = 0.0;
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) { mbar_init(&full[b], WS_BUILDERS / 32); mbar_init(&done[b], WARPS); mbar_init(&tma[b], 1); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(&full[b], WS_BUILDERS / 32); mbar_init(&done[b], WARPS); mbar_init(&tma[b], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -378,40 +423,60 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k2_ontop_ws(const Params prm) {
     // ================================ builders ================================
     reg_dec<56>();
     const int btid = tid - WARPS * 32;  // 0..127 within the builder warpgroup
-    auto issue_tma = [&](int k) {  // phi tile of my k-th tile into phis[k&1]
-      const int b = k & 1;
+    auto issue_tma = [&](int k) {  // phi (+ grad phi) tile of my k-th tile into phis[k % NBUF]
+      const int b = k % NBUF;
       const size_t t0 = (size_t)(blockIdx.x + (size_t)k * gridDim.x) * P;
       mbar_expect_tx(&tma[b], tile_bytes);
-      for (int t = 0; t < nact; ++t)
-        tma_bulk_g2s(phis0 + ((size_t)b * nact + t) * P, prm.phi_act + (size_t)t * prm.ld + t0, P * sizeof(double), &tma[b]);
-    };
-    auto flush_tile = [&](int k) {  // fixed-order sum of the 8 lanes' partials of tile k, store Pi
-      const int b = k & 1;
-      mbar_wait(&done[b], (uint32_t)((k >> 1) & 1));
-      if (btid < P) {
-        const double* r = red0 + (size_t)b * WARPS * P + btid;
-        double s = 0.0;
+      double* dst = phis0 + (size_t)b * NC * cstride;
+      for (int t = 0; t < nact; ++t) {
+        tma_bulk_g2s(dst + (size_t)t * P, prm.phi_act + (size_t)t * prm.ld + t0, P * sizeof(double), &tma[b]);
+        if (GRAD) {
 #pragma unroll
-        for (int l = 0; l < WARPS; ++l) s += r[(size_t)l * P];
-        const size_t gp = (size_t)(blockIdx.x + (size_t)k * gridDim.x) * P + btid;
-        if (gp < prm.npts) {
-          if (prm.pi_core) s += prm.pi_core[gp];
-          prm.pi[gp] = s;
+          for (int d = 0; d < 3; ++d)
+            tma_bulk_g2s(dst + (size_t)(d + 1) * cstride + (size_t)t * P, prm.dphi_act[d] + (size_t)t * prm.ld + t0, P * sizeof(double), &tma[b]);
         }
       }
     };
-    if (btid == 0) { if (nmine > 0) issue_tma(0); if (nmine > 1) issue_tma(1); }
+    auto flush_tile = [&](int k) {  // fixed-order sum of the 8 lanes' partials of tile k, store Pi
+      const int b = k % NBUF;
+      mbar_wait(&done[b], (uint32_t)((k / NBUF) & 1));
+      if (btid < NC * P) {
+        const int comp = btid / P, pt = btid % P;
+        const double* r = red0 + (size_t)b * NC * WARPS * P + (size_t)comp * P + pt;
+        double s = 0.0;
+#pragma unroll
+        for (int l = 0; l < WARPS; ++l) s += r[(size_t)l * NC * P];
+        const size_t gp = (size_t)(blockIdx.x + (size_t)k * gridDim.x) * P + pt;
+        if (gp < prm.npts) {
+          if (comp == 0) {
+            if (prm.pi_core) s += prm.pi_core[gp];
+            prm.pi[gp] = s;
+          } else {
+            s *= 2.0;
+            if (prm.pi_core_g[comp - 1]) s += prm.pi_core_g[comp - 1][gp];
+            prm.pi_g[comp - 1][gp] = s;
+          }
+        }
+      }
+    };
+    // plain: the phi tile is only read by the X build, so the next-but-one tile is requested as
+    // soon as the builders are through with it.  GRAD: the MMA warps' epilogue reads the tile too,
+    // so phis[b] is refilled only after done[b] (inside the loop, right after flush_tile).
+    if (btid == 0) { if (nmine > 0) issue_tma(0); if (NBUF > 1 && nmine > 1) issue_tma(1); }
     const int xp = btid % P, xg = btid / P;
     constexpr int G = WS_BUILDERS / P, XU = 8;
     for (int k = 0; k < nmine; ++k) {
-      const int b = k & 1;
+      const int b = k % NBUF;
       K2_TRACE(0);
-      if (k >= 2) flush_tile(k - 2);  // also proves X[b] and red[b] are free again
+      if (k >= NBUF) {
+        flush_tile(k - NBUF);  // also proves X[b] and red[b] (GRAD: phis[b]) are free again
+        if (GRAD && btid == 0) issue_tma(k);
+      }
       K2_TRACE(1);
-      mbar_wait(&tma[b], (uint32_t)((k >> 1) & 1));
+      mbar_wait(&tma[b], (uint32_t)((k / NBUF) & 1));
       K2_TRACE(2);
       double* Xs = Xs0 + (size_t)b * xsz;
-      const double* phis = phis0 + (size_t)b * nact * P;
+      const double* phis = phis0 + (size_t)b * NC * cstride;
       for (int I0 = xg; I0 < prm.M; I0 += G * XU) {
         uint32_t po[XU];
         double ft[XU], fu[XU];
@@ -426,12 +491,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k2_ontop_ws(const Params prm) {
       __syncwarp();
       K2_TRACE(3);
       if (lane == 0) mbar_arrive(&full[b]);
-      // phis[b] may be refilled once every builder warp has read it
-      asm volatile("bar.sync 1, %0;" ::"n"(WS_BUILDERS) : "memory");
-      if (btid == 0 && k + 2 < nmine) issue_tma(k + 2);
+      if (!GRAD) {
+        // phis[b] may be refilled once every builder warp has read it
+        asm volatile("bar.sync 1, %0;" ::"n"(WS_BUILDERS) : "memory");
+        if (btid == 0 && k + NBUF < nmine) issue_tma(k + NBUF);
+      }
     }
-    if (nmine >= 2) flush_tile(nmine - 2);
-    if (nmine >= 1) flush_tile(nmine - 1);
+    for (int k = (nmine > NBUF ? nmine - NBUF : 0); k < nmine; ++k) flush_tile(k);
   } else {
     // ================================ MMA warps ================================
     reg_inc<224>();
@@ -441,7 +507,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k2_ontop_ws(const Params prm) {
     const double* bbase = prm.dfrag + (size_t)prm.blk_ofs[tl] * TASK_DOUBLES + lane * NTILE;
     const SegDesc* sdesc = prm.segs + seg0;
     for (int k = 0; k < nmine; ++k) {
-      const int b = k & 1;
+      const int b = k % NBUF;
       const double* bptr = bbase;
       double bq[RING][NTILE];
 #pragma unroll
@@ -452,31 +518,36 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k2_ontop_ws(const Params prm) {
       }
       SegDesc sd = sdesc[0];
       K2_TRACE(0);
-      mbar_wait(&full[b], (uint32_t)((k >> 1) & 1));
+      mbar_wait(&full[b], (uint32_t)((k / NBUF) & 1));
       K2_TRACE(1);
       const double* xrow = Xs0 + (size_t)b * xsz + qrow;
-      double piacc[MT];
+      const double* ph = phis0 + (size_t)b * NC * cstride + qrow;
+      double piacc[NC][MT];
 #pragma unroll
-      for (int m = 0; m < MT; ++m) piacc[m] = 0.0;
+      for (int d = 0; d < NC; ++d)
+#pragma unroll
+        for (int m = 0; m < MT; ++m) piacc[d][m] = 0.0;
       for (int sg = 0; sg < nseg; ++sg) {
         const SegDesc sd_next = sdesc[sg + 1];
         switch (sd.ntl) {
-          case 4: run_segment<MT, PS, 4>(sd, piacc, bq, xrow, qcol, bptr); break;
-          case 3: run_segment<MT, PS, 3>(sd, piacc, bq, xrow, qcol, bptr); break;
-          case 2: run_segment<MT, PS, 2>(sd, piacc, bq, xrow, qcol, bptr); break;
-          default: run_segment<MT, PS, 1>(sd, piacc, bq, xrow, qcol, bptr); break;
+          case 4: run_segment<MT, PS, 4, GRAD>(sd, piacc, bq, xrow, qcol, bptr, ph, pofs, cstride); break;
+          case 3: run_segment<MT, PS, 3, GRAD>(sd, piacc, bq, xrow, qcol, bptr, ph, pofs, cstride); break;
+          case 2: run_segment<MT, PS, 2, GRAD>(sd, piacc, bq, xrow, qcol, bptr, ph, pofs, cstride); break;
+          default: run_segment<MT, PS, 1, GRAD>(sd, piacc, bq, xrow, qcol, bptr, ph, pofs, cstride); break;
         }
         sd = sd_next;
       }
       K2_TRACE(2);
-      double* red = red0 + ((size_t)b * WARPS + tl) * P;
+      double* red = red0 + ((size_t)b * WARPS + tl) * NC * P;
 #pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        double v = piacc[m];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        if (qcol == 0) red[m * 8 + qrow] = v;
-      }
+      for (int d = 0; d < NC; ++d)
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          double v = piacc[d][m];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          if (qcol == 0) red[d * P + m * 8 + qrow] = v;
+        }
       __syncwarp();
       if (lane == 0) mbar_arrive(&done[b]);
       K2_TRACE(3);

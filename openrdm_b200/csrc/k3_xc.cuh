@@ -24,6 +24,9 @@ struct Params {
   const double* gx;  // total density gradient (GGA only)
   const double* gy;
   const double* gz;
+  const double* px;  // grad Pi (fully-translated GGA only)
+  const double* py;
+  const double* pz;
   size_t npts;
   // optional diagnostics (null = not written)
   double* R;
@@ -35,15 +38,24 @@ struct Params {
   double* partial;  // [gridDim.x][5] : trN, trNa, trNb, Ex, Ec
 };
 
-template <bool PBE>
+// PBE: tPBE (EX_PBE + EC_PBE on translated densities and sigma) else tSVWN.
+// FT:  MCPDFT::fully_translate (mcpdft.cc:418-606) instead of MCPDFT::translate.
+template <bool PBE, bool FT = false>
 __global__ void __launch_bounds__(THREADS) k3_translate_xc(const Params P) {
   __shared__ double scratch[5 * 32];
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS) {
     const double rho = __ldg(P.rho + p), pi = __ldg(P.pi + p), w = __ldg(P.w + p);
     double gx = 0.0, gy = 0.0, gz = 0.0;
-    if (PBE) { gx = __ldg(P.gx + p); gy = __ldg(P.gy + p); gz = __ldg(P.gz + p); }
-    const xc::Translated t = xc::translate_pt<PBE>(rho, pi, gx, gy, gz);
+    if (PBE && P.gx) { gx = __ldg(P.gx + p); gy = __ldg(P.gy + p); gz = __ldg(P.gz + p); }
+    xc::Translated t;
+    if (FT) {
+      double px = 0.0, py = 0.0, pz = 0.0;
+      if (PBE && P.px) { px = __ldg(P.px + p); py = __ldg(P.py + p); pz = __ldg(P.pz + p); }
+      t = xc::fully_translate_pt<PBE>(rho, pi, gx, gy, gz, px, py, pz);
+    } else {
+      t = xc::translate_pt<PBE>(rho, pi, gx, gy, gz);
+    }
     double ex, ec;
     if (PBE) {
       ex = xc::ex_pbe_pt(t.ra, t.rb, t.saa, t.sbb);

@@ -39,6 +39,7 @@ struct GridView {  // one resident grid or one streamed batch
   const double *w = nullptr, *phi = nullptr, *phix = nullptr, *phiy = nullptr, *phiz = nullptr;
   double* vec[ORDM_VEC_COUNT] = {};  // per-point outputs (null = not materialised)
   double *gx = nullptr, *gy = nullptr, *gz = nullptr, *pi_core = nullptr;
+  double* pcg[3] = {nullptr, nullptr, nullptr};  // closed-form core part of grad Pi
   double* core[4] = {nullptr, nullptr, nullptr, nullptr};  // k1_core partials rc, cx, cy, cz
 };
 
@@ -107,6 +108,13 @@ struct ordm_ctx {
   bool k2_ws = false, k2_force_plain = false;
   bool k1_split = false;  // two-kernel K1 (k1_core + active) measured slower than the fused kernel; kept as a test hook
   uint16_t* d_pairs = nullptr;
+  // grad-Pi variant of K2: the whole symmetric Dt in fragment order (built on first use)
+  k2::Params k2gp{};
+  double* d_dfrag_full = nullptr;
+  void* d_tasks_full = nullptr;
+  int k2g_nbuf = 0;
+  size_t k2g_smem = 0;
+  bool k2g_ready = false;
   uint64_t k2_dmma_per_mtile = 0;
   size_t k2_smem = 0;
   std::vector<double> h_Dt;  // folded Dt kept for repacking when the tile shape changes
@@ -119,7 +127,7 @@ struct ordm_ctx {
   // streamed (host-buffer) path
   struct Stage {
     double *w = nullptr, *phi[4] = {nullptr, nullptr, nullptr, nullptr};
-    double* vec[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // rho pi gx gy gz pi_core + k1_core partials
+    double* vec[16] = {};  // rho pi gx gy gz pi_core + k1_core partials (4) + grad Pi (3) + its core part (3)
     cudaEvent_t copied = nullptr, done = nullptr;
   } stage[2];
   size_t stage_pts = 0;
@@ -127,7 +135,7 @@ struct ordm_ctx {
   bool stage_gga = false;
 
   // stage bookkeeping
-  bool rho_done = false, pi_done = false, xc_done = false;
+  bool rho_done = false, pi_done = false, xc_done = false, xc_ft = false, pig_done = false;
   double last_n[3] = {0, 0, 0}, last_trn[3] = {0, 0, 0};
 
   // NCCL
@@ -165,6 +173,11 @@ void dfree(T*& p) {
   p = nullptr;
 }
 
+// grad Pi is built when asked for, or when the fully-translated GGA gradients need it
+bool want_pig(const ordm_ctx* c, bool gga) {
+  return gga && (c->opts & (ORDM_OPT_PI_GRADIENT | ORDM_OPT_FULLY_TRANSLATED)) != 0;
+}
+
 int ensure_partials(ordm_ctx* c, size_t doubles) {
   if (doubles <= c->partial_cap) return ORDM_OK;
   dfree(c->d_partial);
@@ -176,13 +189,14 @@ int ensure_partials(ordm_ctx* c, size_t doubles) {
 // (re)allocate the resident per-point vectors according to the option flags
 int ensure_vectors(ordm_ctx* c) {
   const bool diag = (c->opts & ORDM_OPT_DIAGNOSTICS) != 0;
-  const bool pig = (c->opts & ORDM_OPT_PI_GRADIENT) != 0;
+  const bool pig = want_pig(c, c->g.gga);
   GridView& g = c->g;
   if (c->vec_cap >= g.ld && c->vec_diag == diag && g.vec[ORDM_VEC_RHO] && (!pig || g.vec[ORDM_VEC_PI_X])) return ORDM_OK;
   for (int i = 0; i < ORDM_VEC_COUNT; ++i)
     if (i != ORDM_VEC_W) dfree(g.vec[i]);
   dfree(g.gx); dfree(g.gy); dfree(g.gz); dfree(g.pi_core);
   for (auto& q : g.core) dfree(q);
+  for (auto& q : g.pcg) dfree(q);
   const size_t bytes = g.ld * sizeof(double);
   auto al = [&](double*& p) -> cudaError_t { cudaError_t e = cudaMalloc(&p, bytes); if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, bytes, c->stream); return e; };
   CU(c, al(g.vec[ORDM_VEC_RHO]));
@@ -199,6 +213,8 @@ int ensure_vectors(ordm_ctx* c) {
   } else if (pig) {
     CU(c, al(g.vec[ORDM_VEC_PI_X])); CU(c, al(g.vec[ORDM_VEC_PI_Y])); CU(c, al(g.vec[ORDM_VEC_PI_Z]));
   }
+  if (pig)
+    for (auto& q : g.pcg) CU(c, al(q));
   c->vec_cap = g.ld;
   c->vec_diag = diag;
   return ORDM_OK;
@@ -238,6 +254,7 @@ int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches) {
   p.rho = v.vec[ORDM_VEC_RHO];
   p.gx = v.gx; p.gy = v.gy; p.gz = v.gz;
   p.pi_core = c->core_form ? v.pi_core : nullptr;
+  for (int i = 0; i < 3; ++i) p.pcg[i] = (c->core_form && v.gga && want_pig(c, v.gga)) ? v.pcg[i] : nullptr;
   p.rhoa = v.vec[ORDM_VEC_RHOA]; p.rhob = v.vec[ORDM_VEC_RHOB];
   for (int i = 0; i < 6; ++i) p.grad[i] = v.vec[ORDM_VEC_RHOA_X + i];
   p.saa = v.vec[ORDM_VEC_SIGMA_AA]; p.sab = v.vec[ORDM_VEC_SIGMA_AB]; p.sbb = v.vec[ORDM_VEC_SIGMA_BB];
@@ -280,7 +297,48 @@ int launch_k2(ordm_ctx* c, k2::Params p) {
   return ORDM_OK;
 }
 
+template <int NBUF>
+int launch_k2_grad(ordm_ctx* c, const k2::Params& p, int grid) {
+  static thread_local int dev = -1;
+  static thread_local size_t bytes = 0;
+  if (dev != c->device || bytes < c->k2g_smem) {
+    CU(c, cudaFuncSetAttribute(k2::k2_ontop_ws<true, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k2g_smem));
+    dev = c->device; bytes = c->k2g_smem;
+  }
+  k2::k2_ontop_ws<true, NBUF><<<grid, k2::WS_THREADS, c->k2g_smem, c->stream>>>(p);
+  CU(c, cudaGetLastError());
+  return ORDM_OK;
+}
+
+int configure_k2_grad(ordm_ctx* c);
+
+// Pi and grad Pi in one pass (full Dt): MCPDFT::build_pi for a GGA case, mcpdft.cc:178-183
+int run_k2_grad(ordm_ctx* c, const GridView& v, int* launches) {
+  int rc = configure_k2_grad(c);
+  if (rc) return rc;
+  k2::Params p = c->k2gp;
+  p.phi_act = v.phi + (size_t)c->ncore * v.ld;
+  p.dphi_act[0] = v.phix + (size_t)c->ncore * v.ld;
+  p.dphi_act[1] = v.phiy + (size_t)c->ncore * v.ld;
+  p.dphi_act[2] = v.phiz + (size_t)c->ncore * v.ld;
+  p.ld = v.ld;
+  p.npts = v.npts;
+  p.pi_core = c->core_form ? v.pi_core : nullptr;
+  p.pi = v.vec[ORDM_VEC_PI];
+  for (int i = 0; i < 3; ++i) {
+    p.pi_core_g[i] = c->core_form ? v.pcg[i] : nullptr;
+    p.pi_g[i] = v.vec[ORDM_VEC_PI_X + i];
+  }
+  p.ntiles = (int)((p.npts + k2::WS_P - 1) / k2::WS_P);
+  const int grid = std::max(1, std::min(p.ntiles, c->sm_count));
+  rc = c->k2g_nbuf == 2 ? launch_k2_grad<2>(c, p, grid) : launch_k2_grad<1>(c, p, grid);
+  if (rc) return rc;
+  *launches += 1;
+  return ORDM_OK;
+}
+
 int run_k2(ordm_ctx* c, const GridView& v, int* launches) {
+  if (want_pig(c, v.gga)) return run_k2_grad(c, v, launches);
   k2::Params p = c->k2p;
   p.phi_act = v.phi + (size_t)c->ncore * v.ld;
   p.ld = v.ld;
@@ -294,10 +352,10 @@ int run_k2(ordm_ctx* c, const GridView& v, int* launches) {
     static thread_local int ws_dev = -1;
     static thread_local size_t ws_bytes = 0;
     if (ws_dev != c->device || ws_bytes < c->k2_smem) {
-      CU(c, cudaFuncSetAttribute(k2::k2_ontop_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k2_smem));
+      CU(c, cudaFuncSetAttribute(k2::k2_ontop_ws<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k2_smem));
       ws_dev = c->device; ws_bytes = c->k2_smem;
     }
-    k2::k2_ontop_ws<<<grid, k2::WS_THREADS, c->k2_smem, c->stream>>>(p);
+    k2::k2_ontop_ws<false, 2><<<grid, k2::WS_THREADS, c->k2_smem, c->stream>>>(p);
     CU(c, cudaGetLastError());
     rc = ORDM_OK;
   } else if (c->k2_npg == 2 && c->k2_mt == 4) rc = launch_k2<2, 4>(c, p);
@@ -309,7 +367,7 @@ int run_k2(ordm_ctx* c, const GridView& v, int* launches) {
   return ORDM_OK;
 }
 
-int run_k3(ordm_ctx* c, const GridView& v, int functional, int accumulate, int* launches) {
+int run_k3(ordm_ctx* c, const GridView& v, int functional, bool ft, int accumulate, int* launches) {
   k3::Params p{};
   p.rho = v.vec[ORDM_VEC_RHO]; p.pi = v.vec[ORDM_VEC_PI]; p.w = v.w;
   p.gx = v.gga ? v.gx : nullptr; p.gy = v.gga ? v.gy : nullptr; p.gz = v.gga ? v.gz : nullptr;
@@ -322,10 +380,17 @@ int run_k3(ordm_ctx* c, const GridView& v, int functional, int accumulate, int* 
   p.partial = c->d_partial;
   // energy.cc:114-120: "SVWN" -> LSDA+VWN3, else PBE.  Without orbital gradients the
   // translated sigma are zero vectors (energy.cc:63-65): PBE then runs with gx=gy=gz=0.
-  if (functional == ORDM_FUNC_SVWN) k3::k3_translate_xc<false><<<grid, k3::THREADS, 0, c->stream>>>(p);
-  else {
+  if (functional == ORDM_FUNC_SVWN) {
+    if (ft) k3::k3_translate_xc<false, true><<<grid, k3::THREADS, 0, c->stream>>>(p);
+    else k3::k3_translate_xc<false, false><<<grid, k3::THREADS, 0, c->stream>>>(p);
+  } else {
     if (!v.gga) { p.gx = p.gy = p.gz = nullptr; }
-    k3::k3_translate_xc<true><<<grid, k3::THREADS, 0, c->stream>>>(p);
+    if (ft) {
+      if (v.gga) { p.px = v.vec[ORDM_VEC_PI_X]; p.py = v.vec[ORDM_VEC_PI_Y]; p.pz = v.vec[ORDM_VEC_PI_Z]; }
+      k3::k3_translate_xc<true, true><<<grid, k3::THREADS, 0, c->stream>>>(p);
+    } else {
+      k3::k3_translate_xc<true, false><<<grid, k3::THREADS, 0, c->stream>>>(p);
+    }
   }
   CU(c, cudaGetLastError());
   ordm::k4_finalize<5><<<1, 256, 0, c->stream>>>(c->d_partial, grid, c->d_res, ordm::RES_TRN, accumulate);
@@ -371,6 +436,34 @@ int configure_k2(ordm_ctx* c) {
   c->k2p.dfrag = c->d_dfrag; c->k2p.segs = reinterpret_cast<const k2::SegDesc*>(c->d_tasks);
   for (int i = 0; i <= k2::MAX_LANES; ++i) { c->k2p.seg_ofs[i] = lay.seg_ofs[i]; c->k2p.blk_ofs[i] = lay.blk_ofs[i]; }
   c->k2_dmma_per_mtile = lay.subtiles;
+  c->k2g_ready = false;  // the grad-Pi packing follows the same Dt: rebuilt on next use
+  return ORDM_OK;
+}
+
+int configure_k2_grad(ordm_ctx* c) {
+  if (c->k2g_ready) return ORDM_OK;
+  const int M = ordm::pair_count(c->nact);
+  const int nblk = (M + k2::BLK - 1) / k2::BLK, Mpad = nblk * k2::BLK;
+  c->k2g_nbuf = 0;
+  for (int nbuf = 2; nbuf >= 1; --nbuf)
+    if (k2::WsSmem::bytes(Mpad, c->nact, true, nbuf) <= (size_t)c->max_smem_optin) { c->k2g_nbuf = nbuf; break; }
+  if (!c->k2g_nbuf)
+    return fail(c, ORDM_ERR_UNSUPPORTED, "grad Pi: %d active orbitals (M=%d pairs) exceed shared memory", c->nact, M);
+  c->k2g_smem = k2::WsSmem::bytes(Mpad, c->nact, true, c->k2g_nbuf);
+  ordm::DfragLayout lay;
+  ordm::pack_dfrag(M, c->h_Dt, k2::WARPS, k2::PREFETCH, lay, /*full=*/true);
+  dfree(c->d_dfrag_full);
+  dfree(c->d_tasks_full);
+  CU(c, cudaMalloc(&c->d_dfrag_full, lay.data.size() * sizeof(double)));
+  CU(c, cudaMalloc(&c->d_tasks_full, lay.segs.size() * sizeof(ordm::SegDesc)));
+  CU(c, cudaMemcpy(c->d_dfrag_full, lay.data.data(), lay.data.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(c->d_tasks_full, lay.segs.data(), lay.segs.size() * sizeof(ordm::SegDesc), cudaMemcpyHostToDevice));
+  c->k2gp = k2::Params{};
+  c->k2gp.nact = c->nact; c->k2gp.M = M; c->k2gp.nblk = nblk;
+  c->k2gp.pairs = c->d_pairs;
+  c->k2gp.dfrag = c->d_dfrag_full; c->k2gp.segs = reinterpret_cast<const k2::SegDesc*>(c->d_tasks_full);
+  for (int i = 0; i <= k2::MAX_LANES; ++i) { c->k2gp.seg_ofs[i] = lay.seg_ofs[i]; c->k2gp.blk_ofs[i] = lay.blk_ofs[i]; }
+  c->k2g_ready = true;
   return ORDM_OK;
 }
 
@@ -524,6 +617,8 @@ void ordm_destroy(ordm_ctx* c) {
     if (i != ORDM_VEC_W) dfree(c->g.vec[i]);
   dfree(c->g.gx); dfree(c->g.gy); dfree(c->g.gz); dfree(c->g.pi_core);
   for (auto& q : c->g.core) dfree(q);
+  for (auto& q : c->g.pcg) dfree(q);
+  dfree(c->d_dfrag_full); dfree(c->d_tasks_full);
   dfree(c->d_w);
   for (int k = 0; k < 4; ++k) dfree(c->d_phi[k]);
   dfree(c->d_Dsa_g); dfree(c->d_Dsb_g); dfree(c->d_dfrag); dfree(c->d_tasks); dfree(c->d_pairs);
@@ -672,39 +767,50 @@ int ordm_build_pi(ordm_ctx* c) {
   CU(c, cudaSetDevice(c->device));
   int rc = check_inputs(c, true);
   if (rc) return rc;
-  if (c->opts & ORDM_OPT_PI_GRADIENT) return fail(c, ORDM_ERR_UNSUPPORTED, "ORDM_OPT_PI_GRADIENT is not implemented yet");
+  if ((c->opts & ORDM_OPT_PI_GRADIENT) && !c->g.gga)
+    return fail(c, ORDM_ERR_STATE, "ORDM_OPT_PI_GRADIENT needs the orbital gradients (phi_x, phi_y, phi_z)");
   if (c->core_form && !c->rho_done) return fail(c, ORDM_ERR_STATE, "build_pi with core orbitals needs build_rho first (closed-form core terms)");
   if ((rc = ensure_vectors(c))) return rc;
   int launches = 0;
   if ((rc = run_k2(c, c->g, &launches))) return rc;
   CU(c, cudaStreamSynchronize(c->stream));
   c->pi_done = true;
+  c->pig_done = want_pig(c, c->g.gga);
   c->xc_done = false;
   return ORDM_OK;
 }
 
-static int staged_xc(ordm_ctx* c) {
+static int staged_xc(ordm_ctx* c, bool ft) {
   if (!c->rho_done || !c->pi_done) return fail(c, ORDM_ERR_STATE, "build_R/translate need build_rho and build_pi first");
-  if (c->xc_done) return ORDM_OK;
+  if (ft && c->g.gga && !c->pig_done)
+    return fail(c, ORDM_ERR_STATE, "fully_translate with orbital gradients needs grad Pi: set ORDM_OPT_PI_GRADIENT (or ORDM_OPT_FULLY_TRANSLATED) before build_pi");
+  if (c->xc_done && c->xc_ft == ft) return ORDM_OK;
   int launches = 0;
-  int rc = run_k3(c, c->g, c->g.gga ? ORDM_FUNC_PBE : ORDM_FUNC_SVWN, 0, &launches);
+  int rc = run_k3(c, c->g, c->g.gga ? ORDM_FUNC_PBE : ORDM_FUNC_SVWN, ft, 0, &launches);
   if (rc) return rc;
   CU(c, cudaMemcpyAsync(c->h_res, c->d_res, ordm::RES_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < 3; ++i) c->last_trn[i] = c->h_res[ordm::RES_TRN + i];
   c->xc_done = true;
+  c->xc_ft = ft;
   return ORDM_OK;
 }
 
-int ordm_build_R(ordm_ctx* c) {
+int ordm_build_R(ordm_ctx* c) {  // R is the same vector under both translations
   CHECK_CTX(c);
   CU(c, cudaSetDevice(c->device));
-  return staged_xc(c);
+  if (c->xc_done) return ORDM_OK;
+  return staged_xc(c, (c->opts & ORDM_OPT_FULLY_TRANSLATED) != 0 && (!c->g.gga || c->pig_done));
 }
 int ordm_translate(ordm_ctx* c) {
   CHECK_CTX(c);
   CU(c, cudaSetDevice(c->device));
-  return staged_xc(c);
+  return staged_xc(c, false);
+}
+int ordm_fully_translate(ordm_ctx* c) {
+  CHECK_CTX(c);
+  CU(c, cudaSetDevice(c->device));
+  return staged_xc(c, true);
 }
 
 int ordm_integrated_densities(ordm_ctx* c, double n[3], double trn[3]) {
@@ -764,15 +870,17 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   CU(c, cudaSetDevice(c->device));
   int rc = check_inputs(c, true);
   if (rc) return rc;
-  if (c->opts & ORDM_OPT_PI_GRADIENT) return fail(c, ORDM_ERR_UNSUPPORTED, "ORDM_OPT_PI_GRADIENT is not implemented yet");
+  if ((c->opts & ORDM_OPT_PI_GRADIENT) && !c->g.gga)
+    return fail(c, ORDM_ERR_STATE, "ORDM_OPT_PI_GRADIENT needs the orbital gradients (phi_x, phi_y, phi_z)");
   if ((rc = ensure_vectors(c))) return rc;
+  const bool ft = (c->opts & ORDM_OPT_FULLY_TRANSLATED) != 0;
   int launches = 0;
   CU(c, cudaEventRecord(c->ev[0], c->stream));
   if ((rc = run_k1(c, c->g, 0, &launches))) return rc;
   CU(c, cudaEventRecord(c->ev[1], c->stream));
   if ((rc = run_k2(c, c->g, &launches))) return rc;
   CU(c, cudaEventRecord(c->ev[2], c->stream));
-  if ((rc = run_k3(c, c->g, functional, 0, &launches))) return rc;
+  if ((rc = run_k3(c, c->g, functional, ft, 0, &launches))) return rc;
   CU(c, cudaEventRecord(c->ev[3], c->stream));
   if (c->comm) {
     int nr = g_nccl.AllReduce(c->d_res, c->d_res, ordm::RES_COUNT, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream);
@@ -788,8 +896,9 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   CU(c, cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); out->ms_reduce = ms;
   CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[5])); out->ms_total = ms;
   c->rho_done = c->pi_done = true;
+  c->pig_done = want_pig(c, c->g.gga);
   c->xc_done = false;  // R/translated vectors belong to `functional`; staged getters recompute
-  if ((c->g.gga ? ORDM_FUNC_PBE : ORDM_FUNC_SVWN) == functional) c->xc_done = true;
+  if ((c->g.gga ? ORDM_FUNC_PBE : ORDM_FUNC_SVWN) == functional) { c->xc_done = true; c->xc_ft = ft; }
   return ORDM_OK;
 }
 
@@ -842,10 +951,11 @@ int ordm_energy_host(ordm_ctx* c, int functional, double eclass, size_t npts, in
     v.vec[ORDM_VEC_RHO] = s.vec[0]; v.vec[ORDM_VEC_PI] = s.vec[1];
     v.gx = s.vec[2]; v.gy = s.vec[3]; v.gz = s.vec[4]; v.pi_core = s.vec[5];
     for (int q = 0; q < 4; ++q) v.core[q] = s.vec[6 + q];
+    for (int q = 0; q < 3; ++q) { v.vec[ORDM_VEC_PI_X + q] = s.vec[10 + q]; v.pcg[q] = s.vec[13 + q]; }
     int rc;
     if ((rc = run_k1(c, v, 1, &launches))) return rc;
     if ((rc = run_k2(c, v, &launches))) return rc;
-    if ((rc = run_k3(c, v, functional, 1, &launches))) return rc;
+    if ((rc = run_k3(c, v, functional, (c->opts & ORDM_OPT_FULLY_TRANSLATED) != 0, 1, &launches))) return rc;
     CU(c, cudaEventRecord(s.done, c->stream));
   }
   CU(c, cudaEventRecord(c->ev[3], c->stream));
@@ -871,7 +981,7 @@ int ordm_get_vector(ordm_ctx* c, int which, double* host_out, size_t npts) {
   CU(c, cudaSetDevice(c->device));
   const bool needs_xc = which == ORDM_VEC_R || (which >= ORDM_VEC_TR_RHOA && which <= ORDM_VEC_TR_SIGMA_BB);
   if (needs_xc && !c->xc_done) {
-    int rc = staged_xc(c);
+    int rc = staged_xc(c, (c->opts & ORDM_OPT_FULLY_TRANSLATED) != 0);
     if (rc) return rc;
   }
   const double* src = c->g.vec[which];

@@ -84,7 +84,11 @@ inline int ncol_perm(int c) { return (c >> 1) + 4 * (c & 1); }
 
 inline bool diag_subtile_live(int ks, int nt) { return 4 * ks <= 8 * nt + 7; }
 
-inline void pack_dfrag(int M, const std::vector<double>& Dt, int nlanes, int prefetch_steps, DfragLayout& out) {
+// full = true packs the whole symmetric Dt (every block, nothing doubled, no diagonal pattern):
+// the grad-Pi kernel needs Y = X . Dt itself (grad Pi = 2 rowsum(dX o Y)),
+// not only the quadratic form.
+inline void pack_dfrag(int M, const std::vector<double>& Dt, int nlanes, int prefetch_steps, DfragLayout& out,
+                       bool full = false) {
   const int BLK = 32, KSTEPS = 8, NT = 4, EPI_COST = 3;
   const int nb = (M + BLK - 1) / BLK;
   out.M = M;
@@ -96,7 +100,7 @@ inline void pack_dfrag(int M, const std::vector<double>& Dt, int nlanes, int pre
     int cst = 0;
     for (int ks = 0; ks < KSTEPS; ++ks)
       for (int nt = 0; nt < ntl; ++nt)
-        if (ib < jb || diag_subtile_live(ks, nt)) ++cst;
+        if (full || ib < jb || diag_subtile_live(ks, nt)) ++cst;
     return cst;
   };
   struct Seg { int jb, ib0, n, cost; };
@@ -107,8 +111,8 @@ inline void pack_dfrag(int M, const std::vector<double>& Dt, int nlanes, int pre
   for (int S = nb; S >= 1; --S) {
     std::vector<Seg> segs;
     for (int jb = 0; jb < nb; ++jb)
-      for (int ib0 = 0; ib0 <= jb; ib0 += S) {
-        Seg sg{jb, ib0, std::min(S, jb + 1 - ib0), EPI_COST};
+      for (int ib0 = 0; ib0 <= (full ? nb - 1 : jb); ib0 += S) {
+        Seg sg{jb, ib0, std::min(S, (full ? nb : jb + 1) - ib0), full ? 4 * EPI_COST : EPI_COST};
         for (int b = 0; b < sg.n; ++b) sg.cost += blk_cost(ib0 + b, jb);
         segs.push_back(sg);
       }
@@ -154,8 +158,8 @@ inline void pack_dfrag(int M, const std::vector<double>& Dt, int nlanes, int pre
   const size_t task_doubles = (size_t)KSTEPS * 32 * NT;
   out.data.assign(total_blocks * task_doubles + (size_t)prefetch_steps * 32 * NT, 0.0);
   auto elem = [&](int I, int J) -> double {
-    if (I >= M || J >= M || I > J) return 0.0;
-    return (I < J ? 2.0 : 1.0) * Dt[(size_t)I * M + J];
+    if (I >= M || J >= M || (!full && I > J)) return 0.0;
+    return ((!full && I < J) ? 2.0 : 1.0) * Dt[(size_t)I * M + J];
   };
   out.segs.clear();
   out.subtiles = 0;
@@ -166,9 +170,9 @@ inline void pack_dfrag(int M, const std::vector<double>& Dt, int nlanes, int pre
     for (size_t i = 0; i < best_segs.size(); ++i) {
       if (phys[best_lane[i]] != pl) continue;
       const Seg& sg = best_segs[i];
-      const bool has_diag = (sg.ib0 + sg.n - 1 == sg.jb);
+      const bool has_diag = !full && (sg.ib0 + sg.n - 1 == sg.jb);
       out.segs.push_back({(uint16_t)sg.jb, (uint16_t)sg.ib0, (uint16_t)sg.n, (uint8_t)has_diag, (uint8_t)col_ntl(sg.jb)});
-      out.subtiles += (uint64_t)(sg.cost - EPI_COST);
+      out.subtiles += (uint64_t)(sg.cost - (full ? 4 * EPI_COST : EPI_COST));
       for (int b = 0; b < sg.n; ++b, ++slot) {
         double* dst = out.data.data() + (size_t)slot * task_doubles;
         const int ib = sg.ib0 + b;

@@ -59,6 +59,61 @@ __device__ __forceinline__ Translated translate_pt(double rho, double pi, double
   return t;
 }
 
+// Fully-translated scheme, MCPDFT::fully_translate_density(+_gradients), mcpdft.cc:425-606:
+// zeta(R) = sqrt(1-R) for R < R0, the quintic A dR^5 + B dR^4 + C dR^3 (dR = R - R1) on [R0, R1],
+// 0 above R1; the translated gradients carry the derivative of zeta through grad R (px,py,pz =
+// grad Pi).  pow(dR, k) of the reference becomes repeated multiplication.
+constexpr double FT_R0 = 0.9, FT_R1 = 1.15;                                         // mcpdft.cc:427-428
+constexpr double FT_A = -475.60656009, FT_B = -379.47331922, FT_C = -85.38149682;   // mcpdft.cc:429-431
+
+template <bool GGA>
+__device__ __forceinline__ Translated fully_translate_pt(double rho, double pi, double gx, double gy, double gz,
+                                                         double px, double py, double pz) {
+  Translated t;
+  t.R = 4.0 * pi / (rho * rho);
+  const bool live = !(rho < TOL) && !(pi < 0.0);  // mcpdft.cc:458
+  const double R = t.R, dR = R - FT_R1;
+  const double d2 = dR * dR, d3 = d2 * dR, d4 = d2 * d2, d5 = d4 * dR;
+  const bool lo = live && ((1.0 - R) > TOL) && (R < FT_R0);    // mcpdft.cc:460
+  const bool mid = live && !lo && !(R < FT_R0) && !(R > FT_R1);  // mcpdft.cc:462
+  const bool hi = live && !lo && !mid && (R > FT_R1);            // mcpdft.cc:464
+  double z = 0.0;
+  if (lo) z = sqrt(1.0 - R);
+  else if (mid) z = FT_A * d5 + FT_B * d4 + FT_C * d3;
+  t.zeta = z;
+  t.ra = live ? (1.0 + z) * (rho / 2.0) : 0.0;  // mcpdft.cc:467-468
+  t.rb = live ? (1.0 - z) * (rho / 2.0) : 0.0;
+  t.saa = t.sab = t.sbb = 0.0;
+  if (GGA) {
+    const double g[3] = {gx, gy, gz}, q[3] = {px, py, pz};
+    double a[3] = {0.0, 0.0, 0.0}, b[3] = {0.0, 0.0, 0.0};
+    if (lo) {  // mcpdft.cc:541-548
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double u = (R * g[c]) / (2.0 * z) - q[c] / (rho * z);
+        a[c] = (1.0 + z) * (g[c] / 2.0) + u;
+        b[c] = (1.0 - z) * (g[c] / 2.0) - u;
+      }
+    } else if (mid) {  // mcpdft.cc:549-581
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double qr = q[c] / rho, rg = R * g[c];
+        const double u = (FT_A * d4) * ((10.0 * qr) - (5.0 * rg)) + (FT_B * d3) * ((8.0 * qr) - (4.0 * rg)) +
+                         (FT_C * d2) * ((6.0 * qr) - (3.0 * rg));
+        a[c] = (1.0 + z) * (g[c] / 2.0) + u;
+        b[c] = (1.0 - z) * (g[c] / 2.0) - u;
+      }
+    } else if (hi) {  // mcpdft.cc:582-590
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { a[c] = g[c] / 2.0; b[c] = g[c] / 2.0; }
+    }
+    t.saa = (a[0] * a[0]) + (a[1] * a[1]) + (a[2] * a[2]);  // mcpdft.cc:599-601
+    t.sab = (a[0] * b[0]) + (a[1] * b[1]) + (a[2] * b[2]);
+    t.sbb = (b[0] * b[0]) + (b[1] * b[1]) + (b[2] * b[2]);
+  }
+  return t;
+}
+
 // ---------------------------------------------------------------- exchange
 __device__ __forceinline__ double ex_lsda_pt(double ra, double rb) {
   // -(2^(1/3) Cx ra^(4/3) + 2^(1/3) Cx rb^(4/3)), no density threshold (functional.cc:22-27)

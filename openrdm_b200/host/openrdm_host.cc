@@ -36,7 +36,17 @@ void MCPDFT::set_device(int device) {
 void MCPDFT::ensure_ctx() const {
   if (ctx_) return;
   ck(nullptr, ordm_create(device_, &ctx_), "ordm_create");
-  ck(ctx_, ordm_set_options(ctx_, ORDM_OPT_DIAGNOSTICS), "ordm_set_options");
+  ck(ctx_, ordm_set_options(ctx_, is_gga_ ? opts_ : (opts_ & ~(unsigned)ORDM_OPT_PI_GRADIENT)), "ordm_set_options");
+}
+
+void MCPDFT::set_pi_gradient(bool on) {
+  opts_ = on ? (opts_ | ORDM_OPT_PI_GRADIENT) : (opts_ & ~(unsigned)ORDM_OPT_PI_GRADIENT);
+  if (ctx_) ck(ctx_, ordm_set_options(ctx_, is_gga_ ? opts_ : (opts_ & ~(unsigned)ORDM_OPT_PI_GRADIENT)), "ordm_set_options");
+}
+
+void MCPDFT::set_fully_translated(bool ft) {
+  opts_ = ft ? (opts_ | ORDM_OPT_FULLY_TRANSLATED) : (opts_ & ~(unsigned)ORDM_OPT_FULLY_TRANSLATED);
+  if (ctx_) ck(ctx_, ordm_set_options(ctx_, is_gga_ ? opts_ : (opts_ & ~(unsigned)ORDM_OPT_PI_GRADIENT)), "ordm_set_options");
 }
 
 void MCPDFT::common_init(std::string test_case) {
@@ -115,6 +125,7 @@ void MCPDFT::build_tpdm() { D2ab_ = arma::kron(D1a_, D1b_); }
 void MCPDFT::sync_inputs() const {
   ensure_ctx();
   if (!dirty_inputs_) return;
+  ck(ctx_, ordm_set_options(ctx_, is_gga_ ? opts_ : (opts_ & ~(unsigned)ORDM_OPT_PI_GRADIENT)), "ordm_set_options");
   if (w_.n_elem != npts_ || phi_.n_rows != npts_ || phi_.n_cols != nbfs_)
     throw std::runtime_error("MCPDFT: grid/orbital sizes are inconsistent with npts/nbfs");
   ck(ctx_, ordm_set_grid(ctx_, npts_, w_.memptr()), "ordm_set_grid");
@@ -145,8 +156,8 @@ void MCPDFT::build_ontop_pair_density(const arma::mat& D2ab) {
   ck(ctx_, ordm_build_pi(ctx_), "ordm_build_pi");
 }
 void MCPDFT::build_ontop_pair_density_gradients(const arma::mat&) {
-  // mcpdft.cc:214-270: consumed by neither translate() nor any getter in the reference; built on
-  // request only (ORDM_OPT_PI_GRADIENT) so that the energy path does not pay for it.
+  // mcpdft.cc:214-270: with set_pi_gradient(true) / set_fully_translated(true) grad Pi comes out of
+  // the same K2 launch as Pi (build_ontop_pair_density above); nothing is left to do here.
 }
 void MCPDFT::build_pi(const arma::mat& D2ab) { build_ontop_pair_density(D2ab); if (is_gga_) build_ontop_pair_density_gradients(D2ab); }
 void MCPDFT::build_R() { ck(ctx_, ordm_build_R(ctx_), "ordm_build_R"); }
@@ -158,6 +169,14 @@ void MCPDFT::translate_density() {
 }
 void MCPDFT::translate_density_gradients() { /* same fused K3 launch */ }
 void MCPDFT::translate() { translate_density(); if (is_gga_) translate_density_gradients(); }
+void MCPDFT::fully_translate_density() {
+  ck(ctx_, ordm_fully_translate(ctx_), "ordm_fully_translate");
+  double n[3], t[3];
+  ordm_integrated_densities(ctx_, n, t);
+  std::printf("\n      Integrated fully translated total density = %20.12lf\n      Integrated fully translated alpha density = %20.12lf\n      Integrated fully translated beta density  = %20.12lf\n\n", t[0], t[1], t[2]);
+}
+void MCPDFT::fully_translate_density_gradients() { /* same fused K3 launch */ }
+void MCPDFT::fully_translate() { fully_translate_density(); if (is_gga_) fully_translate_density_gradients(); }
 
 void MCPDFT::integrated_densities(double n[3], double trn[3]) const { ensure_ctx(); ordm_integrated_densities(ctx_, n, trn); }
 
@@ -172,6 +191,7 @@ ORDM_HOST_GET(rhoa, ORDM_VEC_RHOA) ORDM_HOST_GET(rhoa_x, ORDM_VEC_RHOA_X) ORDM_H
 ORDM_HOST_GET(rhob, ORDM_VEC_RHOB) ORDM_HOST_GET(rhob_x, ORDM_VEC_RHOB_X) ORDM_HOST_GET(rhob_y, ORDM_VEC_RHOB_Y) ORDM_HOST_GET(rhob_z, ORDM_VEC_RHOB_Z)
 ORDM_HOST_GET(rho, ORDM_VEC_RHO) ORDM_HOST_GET(tr_rhoa, ORDM_VEC_TR_RHOA) ORDM_HOST_GET(tr_rhob, ORDM_VEC_TR_RHOB) ORDM_HOST_GET(pi, ORDM_VEC_PI)
 ORDM_HOST_GET(R, ORDM_VEC_R) ORDM_HOST_GET(sigma_aa, ORDM_VEC_SIGMA_AA) ORDM_HOST_GET(sigma_ab, ORDM_VEC_SIGMA_AB) ORDM_HOST_GET(sigma_bb, ORDM_VEC_SIGMA_BB)
+ORDM_HOST_GET(pi_x, ORDM_VEC_PI_X) ORDM_HOST_GET(pi_y, ORDM_VEC_PI_Y) ORDM_HOST_GET(pi_z, ORDM_VEC_PI_Z)
 ORDM_HOST_GET(tr_sigma_aa, ORDM_VEC_TR_SIGMA_AA) ORDM_HOST_GET(tr_sigma_ab, ORDM_VEC_TR_SIGMA_AB) ORDM_HOST_GET(tr_sigma_bb, ORDM_VEC_TR_SIGMA_BB)
 #undef ORDM_HOST_GET
 

@@ -37,6 +37,9 @@ class MCPDFT {
   void translate();                          // mcpdft.cc:287-292
   void translate_density();                  // mcpdft.cc:294-344
   void translate_density_gradients();        // mcpdft.cc:346-416
+  void fully_translate();                    // mcpdft.cc:418-423
+  void fully_translate_density();            // mcpdft.cc:425-488
+  void fully_translate_density_gradients();  // mcpdft.cc:490-606
 
   // ---- accessors (mcpdft.h:63-164); getters return copies, setters copy in, as the reference
   bool is_gga() const { return is_gga_; }
@@ -63,11 +66,20 @@ class MCPDFT {
   ORDM_HOST_OUTPUT(rho) ORDM_HOST_OUTPUT(tr_rhoa) ORDM_HOST_OUTPUT(tr_rhob) ORDM_HOST_OUTPUT(pi) ORDM_HOST_OUTPUT(R)
   ORDM_HOST_OUTPUT(sigma_aa) ORDM_HOST_OUTPUT(sigma_ab) ORDM_HOST_OUTPUT(sigma_bb)
   ORDM_HOST_OUTPUT(tr_sigma_aa) ORDM_HOST_OUTPUT(tr_sigma_ab) ORDM_HOST_OUTPUT(tr_sigma_bb)
+  // the reference has setters but no getters for grad Pi (mcpdft.h:139-141) and never stores pi_y
+  // (mcpdft.cc:268); here all three components are retrievable
+  ORDM_HOST_OUTPUT(pi_x) ORDM_HOST_OUTPUT(pi_y) ORDM_HOST_OUTPUT(pi_z)
 #undef ORDM_HOST_OUTPUT
   void print_banner() const;
 
   // ---- extensions (no reference counterpart) ----
   void set_gga(bool gga) { is_gga_ = gga; dirty_inputs_ = true; }   // the reference keys GGA on the directory name
+  // mcpdft_energy() uses fully_translate() instead of translate() (the reference hard-wires translate(), energy.cc:58)
+  void set_fully_translated(bool ft);
+  // build grad Pi in build_pi()/mcpdft_energy() for GGA cases.  The reference always runs that stage
+  // (mcpdft.cc:181-183) but nothing can observe its result (no getters, unused by translate()), so
+  // it is off by default here; fully_translate() switches it on by itself.
+  void set_pi_gradient(bool on);
   void set_device(int device);                                     // before the first compute call; default 0
   void integrated_densities(double n[3], double trn[3]) const;     // what mcpdft.cc:100-104,339-343 print
   ordm_ctx* context() const { return ctx_; }
@@ -92,6 +104,7 @@ class MCPDFT {
   mutable ordm_ctx* ctx_ = nullptr;
   mutable bool dirty_inputs_ = true;
   int device_ = 0;
+  unsigned opts_ = 1u;  // ORDM_OPT_DIAGNOSTICS
 };
 
 // energy.h:14-18.  As in the reference, the densities come from mc's own D1a/D1b members

@@ -199,3 +199,93 @@ def test_full_size_properties(engine, port, ordm, cfg):
     got = engine.energy(FN["PBE"], 0.0)
     check_scalars(got, want.scalars)
     check_vectors(engine.get_vector, want.vecs, True)
+
+
+@pytest.mark.parametrize("ncore,nact,npts,kind", [(0, 3, 500, "ensemble"), (0, 5, 1000, "nonsym"), (2, 4, 333, "ensemble"),
+                                                  (3, 8, 2049, "ensemble"), (0, 1, 64, "ensemble")])
+def test_pi_gradient_vs_oracle(engine, port, ncore, nact, npts, kind):
+    """MCPDFT::build_ontop_pair_density_gradients (mcpdft.cc:214-270): all three components (the
+    reference drops pi_y, mcpdft.cc:268), with and without closed-form core orbitals; Pi itself comes
+    from the same full-Dt launch and must still match."""
+    rng = np.random.default_rng(77 + 10 * ncore + nact)
+    phi, grads, w, A1a, A1b, D2 = random_case(rng, nact, npts, kind)
+    if ncore:
+        phic = np.asfortranarray(rng.uniform(-0.4, 0.4, (npts, ncore)))
+        gc = [np.asfortranarray(rng.uniform(-0.4, 0.4, (npts, ncore))) for _ in range(3)]
+        phi = np.asfortranarray(np.hstack([phic, phi]))
+        grads = [np.asfortranarray(np.hstack([a, b])) for a, b in zip(gc, grads)]
+    want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, "PBE", grads, eclass=0.0, with_pi_grad=True)
+    engine.set_options(diagnostics=True, pi_gradient=True)
+    engine.set_grid(w); engine.set_orbitals(phi, grads); engine.set_active_space(ncore, A1a, A1b, D2)
+    got = engine.energy(FN["PBE"], 0.0)
+    check_scalars(got, want.scalars)
+    check_vectors(engine.get_vector, want.vecs, True)
+    one_call = {}
+    for k in ("pi_x", "pi_y", "pi_z"):
+        a, b = engine.get_vector(k), want.vecs[k]
+        err = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+        assert err.max() <= 1e-12, (k, err.max())
+        one_call[k] = a
+    # staged: build_rho, build_pi give the same vectors
+    engine.build_rho(); engine.build_pi()
+    for k, a in one_call.items():
+        assert np.array_equal(engine.get_vector(k), a), k
+    # without the option the vectors are not materialised and the engine says so
+    engine.set_options(diagnostics=True)
+    engine.energy(FN["PBE"], 0.0)
+    with pytest.raises(Exception):
+        engine.get_vector("pi_x")
+
+
+@pytest.mark.parametrize("ncore,nact,npts,kind,fn", [(0, 3, 800, "ensemble", "PBE"), (0, 4, 1000, "nonsym", "PBE"),
+                                                     (2, 5, 1500, "ensemble", "PBE"), (0, 3, 800, "ensemble", "SVWN"),
+                                                     (1, 2, 300, "polarised", "PBE")])
+def test_fully_translated_vs_oracle(engine, port, ncore, nact, npts, kind, fn):
+    """MCPDFT::fully_translate (mcpdft.cc:418-606): zeta(R) on all three branches, ft gradients from
+    grad Pi; one-call path (ORDM_OPT_FULLY_TRANSLATED) and the staged ordm_fully_translate."""
+    rng = np.random.default_rng(900 + 10 * ncore + nact)
+    phi, grads, w, A1a, A1b, D2 = random_case(rng, nact, npts, kind)
+    if ncore:
+        phic = np.asfortranarray(rng.uniform(-0.3, 0.3, (npts, ncore)))
+        gc = [np.asfortranarray(rng.uniform(-0.3, 0.3, (npts, ncore))) for _ in range(3)]
+        phi = np.asfortranarray(np.hstack([phic, phi]))
+        grads = [np.asfortranarray(np.hstack([a, b])) for a, b in zip(gc, grads)]
+    gga = fn == "PBE"
+    port.set_translation(True)
+    try:
+        want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, fn, grads if gga else None, eclass=0.125, with_pi_grad=True)
+    finally:
+        port.set_translation(False)
+    engine.set_options(diagnostics=True, fully_translated=True)
+    engine.set_grid(w); engine.set_orbitals(phi, grads if gga else None); engine.set_active_space(ncore, A1a, A1b, D2)
+    got = engine.energy(FN[fn], 0.125)
+    check_scalars(got, want.scalars)
+    rho = want.vecs["rho"]
+    # strict vectors + R as usual; the ft spin densities carry the same zeta noise as the t ones
+    # below R0, and the ft sigma additionally divide by zeta there (mcpdft.cc:543): compare those
+    # where zeta is well away from 0
+    check_ft = {k: v for k, v in want.vecs.items()}
+    from helpers import STRICT, PT_TOL
+    for k in STRICT + (["pi_x", "pi_y", "pi_z"] if gga else []):
+        if k in check_ft and (gga or not ("_x" in k or "_y" in k or "_z" in k or "sigma" in k)):
+            a, b = engine.get_vector(k), check_ft[k]
+            err = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+            assert err.max(initial=0.0) <= PT_TOL, (k, err.max())
+    for k in ("tr_rhoa", "tr_rhob"):
+        a, b = engine.get_vector(k), want.vecs[k]
+        assert (np.abs(a - b) <= 1e-7 * np.abs(rho) + 1e-300).all(), k
+    if gga:
+        R = want.vecs["R"]
+        ok = np.isfinite(R) & ((R < 0.89) | (R > 0.91)) & (rho > 1e-6)
+        for k in ("tr_sigma_aa", "tr_sigma_ab", "tr_sigma_bb"):
+            a, b = engine.get_vector(k)[ok], want.vecs[k][ok]
+            assert np.allclose(a, b, rtol=1e-8, atol=1e-12), (k, np.abs(a - b).max())
+    # staged flow: build_rho, build_pi, build_R, fully_translate
+    engine.build_rho(); engine.build_pi(); engine.build_R(); engine.fully_translate()
+    _, tt = engine.integrated_densities()
+    assert abs(tt[0] - want.scalars["trn_tot"]) < 1e-10
+    # and translate() afterwards switches the translated vectors back to the t scheme
+    engine.translate()
+    base = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, fn, grads if gga else None, eclass=0.125)
+    a, b = engine.get_vector("tr_rhoa"), base.vecs["tr_rhoa"]
+    assert (np.abs(a - b) <= 1e-7 * np.abs(rho) + 1e-300).all()
