@@ -82,7 +82,8 @@ typedef struct {
   double ms_density, ms_pi, ms_xc, ms_reduce, ms_total;
   uint64_t npts;          /* points this context (shard) processed */
   uint32_t gpu_launches;  /* kernels launched by that call */
-  uint32_t reserved;
+  uint32_t overlapped;    /* 1: the density kernel ran underneath the on-top kernel (ms_density and
+                             ms_pi overlap in time); 0: stages ran back to back */
 } ordm_result;
 
 /* ---- lifecycle ----------------------------------------------------------------------- */

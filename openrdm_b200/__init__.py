@@ -43,10 +43,10 @@ class Result(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         "e_tot", "ex", "ec", "eclass", "n_tot", "n_a", "n_b", "trn_tot", "trn_a", "trn_b",
         "ms_density", "ms_pi", "ms_xc", "ms_reduce", "ms_total")] + [
-        ("npts", C.c_uint64), ("gpu_launches", C.c_uint32), ("reserved", C.c_uint32)]
+        ("npts", C.c_uint64), ("gpu_launches", C.c_uint32), ("overlapped", C.c_uint32)]
 
     def asdict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ }
 
 
 _lib = None

@@ -12,7 +12,9 @@
 // The active block uses the symmetrised 1-RDMs Ds = (D + D^T)/2 held in constant memory
 // (a DFMA reads its coefficient straight from the constant bank, no load instruction):
 //     T_s = Ds_s . phi_act(p),  rho_t,s = T_s . phi_act,  grad rho_t,s = 2 T_s . grad phi_act
-// which reproduces mcpdft.cc:83-84 and :148-153 for arbitrary, non-symmetric D1
+// Orbital values are loaded with ld.global.cs (evict-first): they are read exactly once here, and
+// when K1 runs underneath K2 they must not push K2's L2-resident Dt fragments out.
+// The T-form reproduces mcpdft.cc:83-84 and :148-153 for arbitrary, non-symmetric D1
 // (SURVEY.md Appendix B.2).  Also emitted for K2/K3: pi_core = rc^2 + rc*rtb + rta*rc
 // (Appendix B.3) and the total gradient grad rho = grad rho_a + grad rho_b (mcpdft.cc:381-383).
 #pragma once
@@ -78,8 +80,8 @@ __global__ void __launch_bounds__(CORE_THREADS) k1_core(const Params P) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const size_t o = (size_t)(i + j) * ld + p;
-        v[j] = __ldg(P.phi + o);
-        if (GGA) { vx[j] = __ldg(P.phix + o); vy[j] = __ldg(P.phiy + o); vz[j] = __ldg(P.phiz + o); }
+        v[j] = __ldcs(P.phi + o);
+        if (GGA) { vx[j] = __ldcs(P.phix + o); vy[j] = __ldcs(P.phiy + o); vz[j] = __ldcs(P.phiz + o); }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -89,12 +91,12 @@ __global__ void __launch_bounds__(CORE_THREADS) k1_core(const Params P) {
     }
     for (; i < P.ncore; ++i) {
       const size_t o = (size_t)i * ld + p;
-      const double v = __ldg(P.phi + o);
+      const double v = __ldcs(P.phi + o);
       rc = fma(v, v, rc);
       if (GGA) {
-        cx = fma(v, __ldg(P.phix + o), cx);
-        cy = fma(v, __ldg(P.phiy + o), cy);
-        cz = fma(v, __ldg(P.phiz + o), cz);
+        cx = fma(v, __ldcs(P.phix + o), cx);
+        cy = fma(v, __ldcs(P.phiy + o), cy);
+        cz = fma(v, __ldcs(P.phiz + o), cz);
       }
     }
     P.core_rc[p] = rc;
@@ -121,19 +123,19 @@ __global__ void __launch_bounds__(THREADS) k1_density(const Params P) {
     } else {
       for (int i = 0; i < P.ncore; ++i) {
         const size_t o = (size_t)i * ld + p;
-        const double v = __ldg(P.phi + o);
+        const double v = __ldcs(P.phi + o);
         rc = fma(v, v, rc);
         if (GGA) {
-          cx = fma(v, __ldg(P.phix + o), cx);
-          cy = fma(v, __ldg(P.phiy + o), cy);
-          cz = fma(v, __ldg(P.phiz + o), cz);
+          cx = fma(v, __ldcs(P.phix + o), cx);
+          cy = fma(v, __ldcs(P.phiy + o), cy);
+          cz = fma(v, __ldcs(P.phiz + o), cz);
         }
       }
     }
     // ---- active orbitals: T = Ds . phi_act in registers ----
     double f[NP];
 #pragma unroll
-    for (int t = 0; t < NP; ++t) f[t] = (t < P.nact) ? __ldg(P.phi + (size_t)(P.ncore + t) * ld + p) : 0.0;
+    for (int t = 0; t < NP; ++t) f[t] = (t < P.nact) ? __ldcs(P.phi + (size_t)(P.ncore + t) * ld + p) : 0.0;
     double ra = 0.0, rb = 0.0, ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
     // four rows of T at a time: 8 independent FMA chains (a single row pair leaves the FP64
     // pipe latency-bound at this kernel's occupancy)
@@ -146,9 +148,9 @@ __global__ void __launch_bounds__(THREADS) k1_density(const Params P) {
         for (int j = 0; j < 4; ++j) {
           const bool live = (t0 + j) < P.nact;
           const size_t o = (size_t)(P.ncore + (live ? t0 + j : 0)) * ld + p;
-          fx[j] = live ? __ldg(P.phix + o) : 0.0;
-          fy[j] = live ? __ldg(P.phiy + o) : 0.0;
-          fz[j] = live ? __ldg(P.phiz + o) : 0.0;
+          fx[j] = live ? __ldcs(P.phix + o) : 0.0;
+          fy[j] = live ? __ldcs(P.phiy + o) : 0.0;
+          fz[j] = live ? __ldcs(P.phiz + o) : 0.0;
         }
       }
 #pragma unroll
@@ -217,12 +219,12 @@ __global__ void __launch_bounds__(THREADS) k1_density_generic(const Params P) {
     } else {
       for (int i = 0; i < P.ncore; ++i) {
         const size_t o = (size_t)i * ld + p;
-        const double v = __ldg(P.phi + o);
+        const double v = __ldcs(P.phi + o);
         rc = fma(v, v, rc);
         if (GGA) {
-          cx = fma(v, __ldg(P.phix + o), cx);
-          cy = fma(v, __ldg(P.phiy + o), cy);
-          cz = fma(v, __ldg(P.phiz + o), cz);
+          cx = fma(v, __ldcs(P.phix + o), cx);
+          cy = fma(v, __ldcs(P.phiy + o), cy);
+          cz = fma(v, __ldcs(P.phiz + o), cz);
         }
       }
     }
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(THREADS) k1_density_generic(const Params P) {
       rb = fma(Tb, ft, rb);
       if (GGA) {
         const size_t o = (size_t)(P.ncore + t) * ld + p;
-        const double fx = __ldg(P.phix + o), fy = __ldg(P.phiy + o), fz = __ldg(P.phiz + o);
+        const double fx = __ldcs(P.phix + o), fy = __ldcs(P.phiy + o), fz = __ldcs(P.phiz + o);
         ax = fma(Ta, fx, ax); ay = fma(Ta, fy, ay); az = fma(Ta, fz, az);
         bx = fma(Tb, fx, bx); by = fma(Tb, fy, by); bz = fma(Tb, fz, bz);
       }

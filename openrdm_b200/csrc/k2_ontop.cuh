@@ -382,8 +382,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <bool GRAD, int NBUF>
-__global__ void __launch_bounds__(WS_THREADS, 1) k2_ontop_ws(const Params prm) {
+// LEAN = true trims the register footprint of the CTA to 384 x 128 = 48 K registers (launch cap 128
+// per thread via the 512-thread launch bound; builders 56, MMA warps 160 -- the DMMA stream needs no
+// more) so that one 128-thread x 128-register CTA of the density kernel K1 stays co-resident on
+// every SM: the HBM-bound K1 then streams underneath the tensor-bound K2 (ordm_api.cu, ordm_energy).
+template <bool GRAD, int NBUF, bool LEAN = false>
+__global__ void __launch_bounds__(LEAN ? 512 : WS_THREADS, 1) k2_ontop_ws(const Params prm) {
   constexpr int P = WS_P, PS = WS_PS, MT = 4;
   constexpr int NC = GRAD ? 4 : 1;  // phi (+ grad phi) components staged per tile; result rows per point
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k2_ontop_ws(const Params prm) {
     for (int k = (nmine > NBUF ? nmine - NBUF : 0); k < nmine; ++k) flush_tile(k);
   } else {
     // ================================ MMA warps ================================
-    reg_inc<224>();
+    reg_inc<LEAN ? 160 : 224>();
     const int tl = wid;  // task lane 0..7
     const int qrow = lane >> 2, qcol = lane & 3;
     const int seg0 = (int)prm.seg_ofs[tl], nseg = (int)prm.seg_ofs[tl + 1] - seg0;

@@ -20,6 +20,8 @@ constexpr int THREADS = 256;
 struct Params {
   const double* rho;
   const double* pi;
+  const double* pi_core;  // nullable: closed-form core part still to be added to pi (overlapped K1 || K2 mode)
+  double* pi_out;         // nullable: where the completed Pi is written back in that mode
   const double* w;
   const double* gx;  // total density gradient (GGA only)
   const double* gy;
@@ -45,7 +47,12 @@ __global__ void __launch_bounds__(THREADS) k3_translate_xc(const Params P) {
   __shared__ double scratch[5 * 32];
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS) {
-    const double rho = __ldg(P.rho + p), pi = __ldg(P.pi + p), w = __ldg(P.w + p);
+    const double rho = __ldg(P.rho + p), w = __ldg(P.w + p);
+    double pi = P.pi[p];
+    if (P.pi_core) {  // same association as K2's own store: (sum over lanes) + core part
+      pi += __ldg(P.pi_core + p);
+      if (P.pi_out) P.pi_out[p] = pi;
+    }
     double gx = 0.0, gy = 0.0, gz = 0.0;
     if (PBE && P.gx) { gx = __ldg(P.gx + p); gy = __ldg(P.gy + p); gz = __ldg(P.gz + p); }
     xc::Translated t;

@@ -82,6 +82,9 @@ struct ordm_ctx {
   int sm_count = 148;
   int max_smem_optin = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t side_stream = nullptr;  // K1 runs here underneath K2 (ordm_energy, overlapped mode)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_k1[2] = {nullptr, nullptr};
+  bool serial_stages = false;          // ORDM_SERIAL_STAGES=1: K1 -> K2 -> K3 back to back on one stream
   bool own_stream = true;
   unsigned opts = 0;
   std::string err;
@@ -222,13 +225,13 @@ int ensure_vectors(ordm_ctx* c) {
 
 // ------------------------------------------------------------------ kernel launchers
 template <bool GGA>
-int launch_k1_np(ordm_ctx* c, const k1::Params& p, int grid) {
+int launch_k1_np(ordm_ctx* c, const k1::Params& p, int grid, cudaStream_t st) {
   const int np = (int)round_up((size_t)std::max(c->nact, 1), 4);
   switch (np) {
-#define K1CASE(N) case N: k1::k1_density<N, GGA><<<grid, k1::THREADS, 0, c->stream>>>(p); break;
+#define K1CASE(N) case N: k1::k1_density<N, GGA><<<grid, k1::THREADS, 0, st>>>(p); break;
     K1CASE(4) K1CASE(8) K1CASE(12) K1CASE(16) K1CASE(20) K1CASE(24) K1CASE(28) K1CASE(32)
 #undef K1CASE
-    default: k1::k1_density_generic<GGA><<<grid, k1::THREADS, 0, c->stream>>>(p); break;
+    default: k1::k1_density_generic<GGA><<<grid, k1::THREADS, 0, st>>>(p); break;
   }
   CU(c, cudaGetLastError());
   return ORDM_OK;
@@ -243,10 +246,11 @@ int k3_grid(const ordm_ctx* c, size_t npts) {
   return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 8));
 }
 
-int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches) {
+int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaStream_t st = nullptr) {
+  if (!st) st = c->stream;
   if (c->nact <= k1::MAX_ACT) {
-    CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsa, c->h_Dsa.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsb, c->h_Dsb.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsa, c->h_Dsa.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsb, c->h_Dsb.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, st));
   }
   k1::Params p{};
   p.phi = v.phi; p.phix = v.phix; p.phiy = v.phiy; p.phiz = v.phiz; p.w = v.w;
@@ -263,8 +267,8 @@ int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches) {
     p.core_rc = v.core[0]; p.core_cx = v.core[1]; p.core_cy = v.core[2]; p.core_cz = v.core[3];
     const size_t want = (v.npts + k1::CORE_THREADS - 1) / k1::CORE_THREADS;
     const int cgrid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 8));
-    if (v.gga) k1::k1_core<true><<<cgrid, k1::CORE_THREADS, 0, c->stream>>>(p);
-    else k1::k1_core<false><<<cgrid, k1::CORE_THREADS, 0, c->stream>>>(p);
+    if (v.gga) k1::k1_core<true><<<cgrid, k1::CORE_THREADS, 0, st>>>(p);
+    else k1::k1_core<false><<<cgrid, k1::CORE_THREADS, 0, st>>>(p);
     CU(c, cudaGetLastError());
     *launches += 1;
   }
@@ -272,9 +276,9 @@ int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches) {
   int rc = ensure_partials(c, (size_t)c->sm_count * 16 * 8);
   if (rc) return rc;
   p.partial = c->d_partial;
-  rc = v.gga ? launch_k1_np<true>(c, p, grid) : launch_k1_np<false>(c, p, grid);
+  rc = v.gga ? launch_k1_np<true>(c, p, grid, st) : launch_k1_np<false>(c, p, grid, st);
   if (rc) return rc;
-  ordm::k4_finalize<3><<<1, 256, 0, c->stream>>>(c->d_partial, grid, c->d_res, ordm::RES_N, accumulate);
+  ordm::k4_finalize<3><<<1, 256, 0, st>>>(c->d_partial, grid, c->d_res, ordm::RES_N, accumulate);
   CU(c, cudaGetLastError());
   *launches += 2;
   return ORDM_OK;
@@ -337,16 +341,30 @@ int run_k2_grad(ordm_ctx* c, const GridView& v, int* launches) {
   return ORDM_OK;
 }
 
-int run_k2(ordm_ctx* c, const GridView& v, int* launches) {
+// lean = the register-trimmed WS kernel without the pi_core add (K1 is still running underneath;
+// K3 completes Pi)
+int run_k2(ordm_ctx* c, const GridView& v, int* launches, bool lean = false) {
   if (want_pig(c, v.gga)) return run_k2_grad(c, v, launches);
   k2::Params p = c->k2p;
   p.phi_act = v.phi + (size_t)c->ncore * v.ld;
   p.ld = v.ld;
   p.npts = v.npts;
-  p.pi_core = c->core_form ? v.pi_core : nullptr;
+  p.pi_core = (c->core_form && !lean) ? v.pi_core : nullptr;
   p.pi = v.vec[ORDM_VEC_PI];
   int rc;
-  if (c->k2_ws) {
+  if (c->k2_ws && lean) {
+    p.ntiles = (int)((p.npts + k2::WS_P - 1) / k2::WS_P);
+    const int grid = std::max(1, std::min(p.ntiles, c->sm_count));
+    static thread_local int ln_dev = -1;
+    static thread_local size_t ln_bytes = 0;
+    if (ln_dev != c->device || ln_bytes < c->k2_smem) {
+      CU(c, cudaFuncSetAttribute(k2::k2_ontop_ws<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k2_smem));
+      ln_dev = c->device; ln_bytes = c->k2_smem;
+    }
+    k2::k2_ontop_ws<false, 2, true><<<grid, k2::WS_THREADS, c->k2_smem, c->stream>>>(p);
+    CU(c, cudaGetLastError());
+    rc = ORDM_OK;
+  } else if (c->k2_ws) {
     p.ntiles = (int)((p.npts + k2::WS_P - 1) / k2::WS_P);
     const int grid = std::max(1, std::min(p.ntiles, c->sm_count));
     static thread_local int ws_dev = -1;
@@ -367,9 +385,10 @@ int run_k2(ordm_ctx* c, const GridView& v, int* launches) {
   return ORDM_OK;
 }
 
-int run_k3(ordm_ctx* c, const GridView& v, int functional, bool ft, int accumulate, int* launches) {
+int run_k3(ordm_ctx* c, const GridView& v, int functional, bool ft, int accumulate, int* launches, bool add_core = false) {
   k3::Params p{};
   p.rho = v.vec[ORDM_VEC_RHO]; p.pi = v.vec[ORDM_VEC_PI]; p.w = v.w;
+  if (add_core && c->core_form) { p.pi_core = v.pi_core; p.pi_out = v.vec[ORDM_VEC_PI]; }
   p.gx = v.gga ? v.gx : nullptr; p.gy = v.gga ? v.gy : nullptr; p.gz = v.gga ? v.gz : nullptr;
   p.npts = v.npts;
   p.R = v.vec[ORDM_VEC_R]; p.tra = v.vec[ORDM_VEC_TR_RHOA]; p.trb = v.vec[ORDM_VEC_TR_RHOB];
@@ -600,6 +619,11 @@ int ordm_create(int device, ordm_ctx** out) {
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   CU(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU(c, cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+  CU(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CU(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  for (auto& ev : c->ev_k1) CU(c, cudaEventCreate(&ev));
+  if (const char* e = getenv("ORDM_SERIAL_STAGES")) c->serial_stages = (e[0] == '1');  // per-kernel timing / test hook
   for (auto& ev : c->ev) CU(c, cudaEventCreate(&ev));
   CU(c, cudaMalloc(&c->d_res, 16 * sizeof(double)));
   CU(c, cudaMemset(c->d_res, 0, 16 * sizeof(double)));
@@ -635,6 +659,11 @@ void ordm_destroy(ordm_ctx* c) {
     if (ev) cudaEventDestroy(ev);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  for (auto& ev : c->ev_k1)
+    if (ev) cudaEventDestroy(ev);
   delete c;
 }
 
@@ -650,7 +679,7 @@ int ordm_set_stream(ordm_ctx* c, void* s) {
 
 int ordm_set_options(ordm_ctx* c, unsigned flags) {
   CHECK_CTX(c);
-  if (flags != c->opts) c->rho_done = c->pi_done = c->xc_done = false;
+  if (flags != c->opts) c->rho_done = c->pi_done = c->xc_done = c->pig_done = false;
   c->opts = flags;
   return ORDM_OK;
 }
@@ -875,12 +904,30 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   if ((rc = ensure_vectors(c))) return rc;
   const bool ft = (c->opts & ORDM_OPT_FULLY_TRANSLATED) != 0;
   int launches = 0;
+  // Overlapped mode (default): the tensor-bound K2 is launched first with a trimmed register
+  // footprint, and the HBM-bound K1 streams underneath it on a second stream (one K1 CTA stays
+  // co-resident per SM); K3 joins both and completes Pi = Pi_act + Pi_core.
+  const bool overlap = !c->serial_stages && c->k2_ws && !want_pig(c, c->g.gga);
   CU(c, cudaEventRecord(c->ev[0], c->stream));
-  if ((rc = run_k1(c, c->g, 0, &launches))) return rc;
-  CU(c, cudaEventRecord(c->ev[1], c->stream));
-  if ((rc = run_k2(c, c->g, &launches))) return rc;
-  CU(c, cudaEventRecord(c->ev[2], c->stream));
-  if ((rc = run_k3(c, c->g, functional, ft, 0, &launches))) return rc;
+  if (overlap) {
+    CU(c, cudaEventRecord(c->ev_fork, c->stream));
+    CU(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+    if ((rc = run_k2(c, c->g, &launches, /*lean=*/true))) return rc;
+    CU(c, cudaEventRecord(c->ev[2], c->stream));
+    CU(c, cudaEventRecord(c->ev_k1[0], c->side_stream));
+    if ((rc = run_k1(c, c->g, 0, &launches, c->side_stream))) return rc;
+    CU(c, cudaEventRecord(c->ev_k1[1], c->side_stream));
+    CU(c, cudaEventRecord(c->ev_join, c->side_stream));
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    CU(c, cudaEventRecord(c->ev[1], c->stream));  // = both K1 and K2 done
+    if ((rc = run_k3(c, c->g, functional, ft, 0, &launches, /*add_core=*/true))) return rc;
+  } else {
+    if ((rc = run_k1(c, c->g, 0, &launches))) return rc;
+    CU(c, cudaEventRecord(c->ev[1], c->stream));
+    if ((rc = run_k2(c, c->g, &launches))) return rc;
+    CU(c, cudaEventRecord(c->ev[2], c->stream));
+    if ((rc = run_k3(c, c->g, functional, ft, 0, &launches))) return rc;
+  }
   CU(c, cudaEventRecord(c->ev[3], c->stream));
   if (c->comm) {
     int nr = g_nccl.AllReduce(c->d_res, c->d_res, ordm::RES_COUNT, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream);
@@ -890,9 +937,16 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   CU(c, cudaEventRecord(c->ev[4], c->stream));
   if ((rc = fetch_result(c, eclass, out, c->g.npts, launches))) return rc;
   float ms;
-  CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); out->ms_density = ms;
-  CU(c, cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); out->ms_pi = ms;
-  CU(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); out->ms_xc = ms;
+  if (overlap) {  // K1 and K2 ran concurrently: each is timed on its own stream
+    CU(c, cudaEventElapsedTime(&ms, c->ev_k1[0], c->ev_k1[1])); out->ms_density = ms;
+    CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[2])); out->ms_pi = ms;
+    CU(c, cudaEventElapsedTime(&ms, c->ev[1], c->ev[3])); out->ms_xc = ms;
+    out->overlapped = 1;
+  } else {
+    CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); out->ms_density = ms;
+    CU(c, cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); out->ms_pi = ms;
+    CU(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); out->ms_xc = ms;
+  }
   CU(c, cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); out->ms_reduce = ms;
   CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[5])); out->ms_total = ms;
   c->rho_done = c->pi_done = true;
@@ -985,8 +1039,9 @@ int ordm_get_vector(ordm_ctx* c, int which, double* host_out, size_t npts) {
     if (rc) return rc;
   }
   const double* src = c->g.vec[which];
+  if (which >= ORDM_VEC_PI_X && which <= ORDM_VEC_PI_Z && !c->pig_done) src = nullptr;  // stale or never built
   if (!src) return fail(c, ORDM_ERR_STATE, "vector %d is not materialised (enable ORDM_OPT_DIAGNOSTICS%s before the build_* calls)", which,
-                        (which >= ORDM_VEC_RHOA_X && which <= ORDM_VEC_SIGMA_BB) || which >= ORDM_VEC_TR_SIGMA_AA ? "; gradients need phi_x/y/z" : "");
+                        which >= ORDM_VEC_PI_X && which <= ORDM_VEC_PI_Z ? " and ORDM_OPT_PI_GRADIENT" : (which >= ORDM_VEC_RHOA_X && which <= ORDM_VEC_SIGMA_BB) || which >= ORDM_VEC_TR_SIGMA_AA ? "; gradients need phi_x/y/z" : "");
   if (npts) CU(c, cudaMemcpyAsync(host_out, src, npts * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return ORDM_OK;
