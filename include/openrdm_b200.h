@@ -68,9 +68,12 @@ enum {
                                every GGA case although translate() never reads its result; here it is
                                on request, and all three components are stored (the reference drops
                                pi_y, mcpdft.cc:268) */
-  ORDM_OPT_FULLY_TRANSLATED = 4 /* ordm_energy / ordm_energy_host use MCPDFT::fully_translate
+  ORDM_OPT_FULLY_TRANSLATED = 4, /* ordm_energy / ordm_energy_host use MCPDFT::fully_translate
                                (mcpdft.cc:418-606) instead of MCPDFT::translate; with orbital gradients
                                this implies ORDM_OPT_PI_GRADIENT (the ft gradients consume grad Pi) */
+  ORDM_OPT_SERIAL_STAGES = 8 /* ordm_energy runs density -> on-top -> XC back to back on one stream
+                               (per-kernel timing); default: the HBM-bound density kernel streams
+                               underneath the tensor-bound on-top kernel */
 };
 
 /* What mcpdft_energy returns or prints: energy.cc:175-183, mcpdft.cc:100-104,339-343. */

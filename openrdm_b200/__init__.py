@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(PKG, "libopenrdm_b200.so")
 
 FUNC_SVWN, FUNC_PBE = 0, 1
 EX_LSDA, EC_VWN3, EX_PBE, EC_PBE = 0, 1, 2, 3
-OPT_DIAGNOSTICS, OPT_PI_GRADIENT, OPT_FULLY_TRANSLATED = 1, 2, 4
+OPT_DIAGNOSTICS, OPT_PI_GRADIENT, OPT_FULLY_TRANSLATED, OPT_SERIAL_STAGES = 1, 2, 4, 8
 
 VEC_NAMES = [
     "rhoa", "rhob", "rho",
@@ -162,9 +162,9 @@ class Engine:
     def set_stream(self, cuda_stream_handle: int):
         self._ck(self.lib.ordm_set_stream(self.ctx, C.c_void_p(cuda_stream_handle)))
 
-    def set_options(self, diagnostics=False, pi_gradient=False, fully_translated=False):
+    def set_options(self, diagnostics=False, pi_gradient=False, fully_translated=False, serial_stages=False):
         self._ck(self.lib.ordm_set_options(self.ctx, (OPT_DIAGNOSTICS if diagnostics else 0) | (OPT_PI_GRADIENT if pi_gradient else 0)
-                                           | (OPT_FULLY_TRANSLATED if fully_translated else 0)))
+                                           | (OPT_FULLY_TRANSLATED if fully_translated else 0) | (OPT_SERIAL_STAGES if serial_stages else 0)))
 
     def set_grid(self, w):
         w = _f(w)

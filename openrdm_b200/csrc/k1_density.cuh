@@ -108,98 +108,104 @@ __device__ __forceinline__ void st(double* p, size_t i, double v) {
   if (p) p[i] = v;
 }
 
-// NP = nact rounded up to a multiple of 4 (coefficients beyond nact are zero-padded).
+// One grid point of K1.  NP = nact rounded up to a multiple of 4 (coefficients beyond nact are
+// zero-padded).  acc += (rho, rho_a, rho_b) * w.  Shared by the stand-alone kernel below and by the
+// density warps of the fused K1+K2 kernel (k2_ontop.cuh).
+template <int NP, bool GGA>
+__device__ __forceinline__ void density_point(const Params& P, const size_t p, double (&acc)[3]) {
+  const size_t ld = P.ld;
+  // ---- core orbitals: closed form (from k1_core's partials when those were produced) ----
+  double rc = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+  if (P.core_rc) {
+    rc = P.core_rc[p];
+    if (GGA) { cx = P.core_cx[p]; cy = P.core_cy[p]; cz = P.core_cz[p]; }
+  } else {
+    for (int i = 0; i < P.ncore; ++i) {
+      const size_t o = (size_t)i * ld + p;
+      const double v = __ldcs(P.phi + o);
+      rc = fma(v, v, rc);
+      if (GGA) {
+        cx = fma(v, __ldcs(P.phix + o), cx);
+        cy = fma(v, __ldcs(P.phiy + o), cy);
+        cz = fma(v, __ldcs(P.phiz + o), cz);
+      }
+    }
+  }
+  // ---- active orbitals: T = Ds . phi_act in registers ----
+  double f[NP];
+#pragma unroll
+  for (int t = 0; t < NP; ++t) f[t] = (t < P.nact) ? __ldcs(P.phi + (size_t)(P.ncore + t) * ld + p) : 0.0;
+  double ra = 0.0, rb = 0.0, ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+  // four rows of T at a time: 8 independent FMA chains (a single row pair leaves the FP64
+  // pipe latency-bound at this kernel's occupancy)
+#pragma unroll
+  for (int t0 = 0; t0 < NP; t0 += 4) {
+    double Ta[4] = {0.0, 0.0, 0.0, 0.0}, Tb[4] = {0.0, 0.0, 0.0, 0.0};
+    double fx[4], fy[4], fz[4];
+    if (GGA) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool live = (t0 + j) < P.nact;
+        const size_t o = (size_t)(P.ncore + (live ? t0 + j : 0)) * ld + p;
+        fx[j] = live ? __ldcs(P.phix + o) : 0.0;
+        fy[j] = live ? __ldcs(P.phiy + o) : 0.0;
+        fz[j] = live ? __ldcs(P.phiz + o) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NP; ++u) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        Ta[j] = fma(c_Dsa[(t0 + j) * MAX_ACT + u], f[u], Ta[j]);
+        Tb[j] = fma(c_Dsb[(t0 + j) * MAX_ACT + u], f[u], Tb[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ra = fma(Ta[j], f[t0 + j], ra);
+      rb = fma(Tb[j], f[t0 + j], rb);
+      if (GGA) {
+        ax = fma(Ta[j], fx[j], ax); ay = fma(Ta[j], fy[j], ay); az = fma(Ta[j], fz[j], az);
+        bx = fma(Tb[j], fx[j], bx); by = fma(Tb[j], fy[j], by); bz = fma(Tb[j], fz[j], bz);
+      }
+    }
+  }
+  const double rhoa = rc + ra, rhob = rc + rb;
+  const double rho = rhoa + rhob;  // mcpdft.cc:89
+  st(P.rho, p, rho);
+  st(P.rhoa, p, rhoa);
+  st(P.rhob, p, rhob);
+  st(P.pi_core, p, rc * rc + rc * rb + ra * rc);
+  if (GGA) {
+    if (P.pcg[0]) {  // grad(rc^2 + rc (rta + rtb)) with grad rc = 2 c, grad rt = 2 (T . grad phi)
+      const double rt = ra + rb;
+      P.pcg[0][p] = 2.0 * rc * (2.0 * cx) + (2.0 * cx) * rt + rc * (2.0 * ax + 2.0 * bx);
+      P.pcg[1][p] = 2.0 * rc * (2.0 * cy) + (2.0 * cy) * rt + rc * (2.0 * ay + 2.0 * by);
+      P.pcg[2][p] = 2.0 * rc * (2.0 * cz) + (2.0 * cz) * rt + rc * (2.0 * az + 2.0 * bz);
+    }
+    ax = 2.0 * (cx + ax); ay = 2.0 * (cy + ay); az = 2.0 * (cz + az);
+    bx = 2.0 * (cx + bx); by = 2.0 * (cy + by); bz = 2.0 * (cz + bz);
+    st(P.gx, p, ax + bx);  // mcpdft.cc:381-383
+    st(P.gy, p, ay + by);
+    st(P.gz, p, az + bz);
+    st(P.grad[0], p, ax); st(P.grad[1], p, ay); st(P.grad[2], p, az);
+    st(P.grad[3], p, bx); st(P.grad[4], p, by); st(P.grad[5], p, bz);
+    st(P.saa, p, (ax * ax) + (ay * ay) + (az * az));  // mcpdft.cc:162-164
+    st(P.sbb, p, (bx * bx) + (by * by) + (bz * bz));
+    st(P.sab, p, (ax * bx) + (ay * by) + (az * bz));
+  }
+  const double wp = __ldg(P.w + p);
+  acc[0] = fma(rhoa + rhob, wp, acc[0]);  // mcpdft.cc:91-93
+  acc[1] = fma(rhoa, wp, acc[1]);
+  acc[2] = fma(rhob, wp, acc[2]);
+}
+
 template <int NP, bool GGA>
 __global__ void __launch_bounds__(THREADS) k1_density(const Params P) {
   __shared__ double scratch[3 * 32];
   double acc[3] = {0.0, 0.0, 0.0};
-  const size_t ld = P.ld;
-  for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS) {
-    // ---- core orbitals: closed form (from k1_core's partials when those were produced) ----
-    double rc = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
-    if (P.core_rc) {
-      rc = P.core_rc[p];
-      if (GGA) { cx = P.core_cx[p]; cy = P.core_cy[p]; cz = P.core_cz[p]; }
-    } else {
-      for (int i = 0; i < P.ncore; ++i) {
-        const size_t o = (size_t)i * ld + p;
-        const double v = __ldcs(P.phi + o);
-        rc = fma(v, v, rc);
-        if (GGA) {
-          cx = fma(v, __ldcs(P.phix + o), cx);
-          cy = fma(v, __ldcs(P.phiy + o), cy);
-          cz = fma(v, __ldcs(P.phiz + o), cz);
-        }
-      }
-    }
-    // ---- active orbitals: T = Ds . phi_act in registers ----
-    double f[NP];
-#pragma unroll
-    for (int t = 0; t < NP; ++t) f[t] = (t < P.nact) ? __ldcs(P.phi + (size_t)(P.ncore + t) * ld + p) : 0.0;
-    double ra = 0.0, rb = 0.0, ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
-    // four rows of T at a time: 8 independent FMA chains (a single row pair leaves the FP64
-    // pipe latency-bound at this kernel's occupancy)
-#pragma unroll
-    for (int t0 = 0; t0 < NP; t0 += 4) {
-      double Ta[4] = {0.0, 0.0, 0.0, 0.0}, Tb[4] = {0.0, 0.0, 0.0, 0.0};
-      double fx[4], fy[4], fz[4];
-      if (GGA) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool live = (t0 + j) < P.nact;
-          const size_t o = (size_t)(P.ncore + (live ? t0 + j : 0)) * ld + p;
-          fx[j] = live ? __ldcs(P.phix + o) : 0.0;
-          fy[j] = live ? __ldcs(P.phiy + o) : 0.0;
-          fz[j] = live ? __ldcs(P.phiz + o) : 0.0;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < NP; ++u) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          Ta[j] = fma(c_Dsa[(t0 + j) * MAX_ACT + u], f[u], Ta[j]);
-          Tb[j] = fma(c_Dsb[(t0 + j) * MAX_ACT + u], f[u], Tb[j]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        ra = fma(Ta[j], f[t0 + j], ra);
-        rb = fma(Tb[j], f[t0 + j], rb);
-        if (GGA) {
-          ax = fma(Ta[j], fx[j], ax); ay = fma(Ta[j], fy[j], ay); az = fma(Ta[j], fz[j], az);
-          bx = fma(Tb[j], fx[j], bx); by = fma(Tb[j], fy[j], by); bz = fma(Tb[j], fz[j], bz);
-        }
-      }
-    }
-    const double rhoa = rc + ra, rhob = rc + rb;
-    const double rho = rhoa + rhob;  // mcpdft.cc:89
-    st(P.rho, p, rho);
-    st(P.rhoa, p, rhoa);
-    st(P.rhob, p, rhob);
-    st(P.pi_core, p, rc * rc + rc * rb + ra * rc);
-    if (GGA) {
-      if (P.pcg[0]) {  // grad(rc^2 + rc (rta + rtb)) with grad rc = 2 c, grad rt = 2 (T . grad phi)
-        const double rt = ra + rb;
-        P.pcg[0][p] = 2.0 * rc * (2.0 * cx) + (2.0 * cx) * rt + rc * (2.0 * ax + 2.0 * bx);
-        P.pcg[1][p] = 2.0 * rc * (2.0 * cy) + (2.0 * cy) * rt + rc * (2.0 * ay + 2.0 * by);
-        P.pcg[2][p] = 2.0 * rc * (2.0 * cz) + (2.0 * cz) * rt + rc * (2.0 * az + 2.0 * bz);
-      }
-      ax = 2.0 * (cx + ax); ay = 2.0 * (cy + ay); az = 2.0 * (cz + az);
-      bx = 2.0 * (cx + bx); by = 2.0 * (cy + by); bz = 2.0 * (cz + bz);
-      st(P.gx, p, ax + bx);  // mcpdft.cc:381-383
-      st(P.gy, p, ay + by);
-      st(P.gz, p, az + bz);
-      st(P.grad[0], p, ax); st(P.grad[1], p, ay); st(P.grad[2], p, az);
-      st(P.grad[3], p, bx); st(P.grad[4], p, by); st(P.grad[5], p, bz);
-      st(P.saa, p, (ax * ax) + (ay * ay) + (az * az));  // mcpdft.cc:162-164
-      st(P.sbb, p, (bx * bx) + (by * by) + (bz * bz));
-      st(P.sab, p, (ax * bx) + (ay * by) + (az * bz));
-    }
-    const double wp = __ldg(P.w + p);
-    acc[0] = fma(rhoa + rhob, wp, acc[0]);  // mcpdft.cc:91-93
-    acc[1] = fma(rhoa, wp, acc[1]);
-    acc[2] = fma(rhob, wp, acc[2]);
-  }
+  for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS)
+    density_point<NP, GGA>(P, p, acc);
   ordm::block_sum_store<3>(acc, scratch, P.partial + (size_t)blockIdx.x * 3);
 }
 

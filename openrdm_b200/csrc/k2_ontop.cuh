@@ -382,12 +382,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// LEAN = true trims the register footprint of the CTA to 384 x 128 = 48 K registers (launch cap 128
-// per thread via the 512-thread launch bound; builders 56, MMA warps 160 -- the DMMA stream needs no
-// more) so that one 128-thread x 128-register CTA of the density kernel K1 stays co-resident on
-// every SM: the HBM-bound K1 then streams underneath the tensor-bound K2 (ordm_api.cu, ordm_energy).
-template <bool GRAD, int NBUF, bool LEAN = false>
-__global__ void __launch_bounds__(LEAN ? 512 : WS_THREADS, 1) k2_ontop_ws(const Params prm) {
+// The CTA body, warps 0..11.  MMA_REGS = register budget of the MMA warps (224 when the CTA owns
+// the whole register file, 160 in the fused K1+K2 kernel, which the DMMA stream does not exceed).
+// Threads beyond WS_THREADS (the density warps of the fused kernel) only take part in the prologue
+// barrier and return.
+template <bool GRAD, int NBUF, int MMA_REGS, int BW0 = WARPS>  // BW0 = first builder warp (lab: 12 puts the builders last)
+__device__ __forceinline__ void ws_cta(const Params& prm) {
   constexpr int P = WS_P, PS = WS_PS, MT = 4;
   constexpr int NC = GRAD ? 4 : 1;  // phi (+ grad phi) components staged per tile; result rows per point
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -410,15 +410,18 @@ __global__ void __launch_bounds__(LEAN ? 512 : WS_THREADS, 1) k2_ontop_ws(const 
   // tiles of this CTA: blockIdx.x + k*gridDim.x, k = 0..nmine-1
   const int nmine = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  for (int I = tid; I < Mpad; I += WS_THREADS)
-    pofs[I] = I < prm.M ? ((uint32_t)prm.pairs[2 * I] * P | ((uint32_t)prm.pairs[2 * I + 1] * P) << 16) : 0u;
-  for (int b = 0; b < NBUF; ++b)  // rows M..Mpad+3 of the X buffers stay zero for the whole launch
-    for (int idx = prm.M * P + tid; idx < (Mpad + 4) * P; idx += WS_THREADS) Xs0[b * xsz + (size_t)(idx / P) * PS + (idx % P)] = 0.0;
+  if (tid < WS_THREADS) {
+    for (int I = tid; I < Mpad; I += WS_THREADS)
+      pofs[I] = I < prm.M ? ((uint32_t)prm.pairs[2 * I] * P | ((uint32_t)prm.pairs[2 * I + 1] * P) << 16) : 0u;
+    for (int b = 0; b < NBUF; ++b)  // rows M..Mpad+3 of the X buffers stay zero for the whole launch
+      for (int idx = prm.M * P + tid; idx < (Mpad + 4) * P; idx += WS_THREADS) Xs0[b * xsz + (size_t)(idx / P) * PS + (idx % P)] = 0.0;
+  }
   if (tid == 0) {
     for (int b = 0; b < NBUF; ++b) { mbar_init(&full[b], WS_BUILDERS / 32); mbar_init(&done[b], WARPS); mbar_init(&tma[b], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (BW0 == WARPS ? tid >= WS_THREADS : (wid >= WARPS && wid < BW0)) return;
 
   // Builders are the HIGHEST warp ids: the SM sub-partition arbiter favours higher warp ids, and
   // the builders' few FP64 multiplies share the FP64/DMMA pipe with the MMA warps' DMMA stream --
@@ -426,7 +429,7 @@ __global__ void __launch_bounds__(LEAN ? 512 : WS_THREADS, 1) k2_ontop_ws(const 
   if (wid >= WARPS) {
     // ================================ builders ================================
     reg_dec<56>();
-    const int btid = tid - WARPS * 32;  // 0..127 within the builder warpgroup
+    const int btid = tid - BW0 * 32;  // 0..127 within the builder warpgroup
     auto issue_tma = [&](int k) {  // phi (+ grad phi) tile of my k-th tile into phis[k % NBUF]
       const int b = k % NBUF;
       const size_t t0 = (size_t)(blockIdx.x + (size_t)k * gridDim.x) * P;
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(LEAN ? 512 : WS_THREADS, 1) k2_ontop_ws(const 
     for (int k = (nmine > NBUF ? nmine - NBUF : 0); k < nmine; ++k) flush_tile(k);
   } else {
     // ================================ MMA warps ================================
-    reg_inc<LEAN ? 160 : 224>();
+    reg_inc<MMA_REGS>();
     const int tl = wid;  // task lane 0..7
     const int qrow = lane >> 2, qcol = lane & 3;
     const int seg0 = (int)prm.seg_ofs[tl], nseg = (int)prm.seg_ofs[tl + 1] - seg0;
@@ -557,6 +560,14 @@ __global__ void __launch_bounds__(LEAN ? 512 : WS_THREADS, 1) k2_ontop_ws(const 
       K2_TRACE(3);
     }
   }
+}
+
+// LEAN = true trims the register footprint of the CTA to 384 x 128 = 48 K registers (launch cap 128
+// per thread via the 512-thread launch bound; builders 56, MMA warps 160) so that one 128-thread
+// CTA of another kernel can stay co-resident on the SM.
+template <bool GRAD, int NBUF, bool LEAN = false>
+__global__ void __launch_bounds__(LEAN ? 512 : WS_THREADS, 1) k2_ontop_ws(const Params prm) {
+  ws_cta<GRAD, NBUF, LEAN ? 160 : 224>(prm);
 }
 
 }  // namespace k2

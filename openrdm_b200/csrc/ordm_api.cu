@@ -679,7 +679,7 @@ int ordm_set_stream(ordm_ctx* c, void* s) {
 
 int ordm_set_options(ordm_ctx* c, unsigned flags) {
   CHECK_CTX(c);
-  if (flags != c->opts) c->rho_done = c->pi_done = c->xc_done = c->pig_done = false;
+  if ((flags ^ c->opts) & ~(unsigned)ORDM_OPT_SERIAL_STAGES) c->rho_done = c->pi_done = c->xc_done = c->pig_done = false;
   c->opts = flags;
   return ORDM_OK;
 }
@@ -907,7 +907,7 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   // Overlapped mode (default): the tensor-bound K2 is launched first with a trimmed register
   // footprint, and the HBM-bound K1 streams underneath it on a second stream (one K1 CTA stays
   // co-resident per SM); K3 joins both and completes Pi = Pi_act + Pi_core.
-  const bool overlap = !c->serial_stages && c->k2_ws && !want_pig(c, c->g.gga);
+  const bool overlap = !c->serial_stages && !(c->opts & ORDM_OPT_SERIAL_STAGES) && c->k2_ws && !want_pig(c, c->g.gga);
   CU(c, cudaEventRecord(c->ev[0], c->stream));
   if (overlap) {
     CU(c, cudaEventRecord(c->ev_fork, c->stream));

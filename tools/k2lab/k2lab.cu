@@ -4,6 +4,9 @@
 #include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
+#ifndef K2LAB_LEAN
+#define K2LAB_LEAN false
+#endif
 #include "../../openrdm_b200/csrc/k2_ontop.cuh"
 #include "../../openrdm_b200/csrc/rdm_pack.h"
 #define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("CUDA error %s at %d\n",cudaGetErrorString(e),__LINE__); exit(1);} }while(0)
@@ -32,9 +35,9 @@ int main(int argc, char** argv) {
     int Mpad = lay.nblk * 32; float ms = 0;
     if (ws) {
       size_t sm = k2::WsSmem::bytes(Mpad, nact);
-      CK(cudaFuncSetAttribute(k2::k2_ontop_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      CK(cudaFuncSetAttribute(k2::k2_ontop_ws<false, 2, K2LAB_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       p.ntiles = (int)((npts + 31) / 32);
-      for (int r = 0; r < 4; ++r) { cudaEventRecord(e0); k2::k2_ontop_ws<<<148, k2::WS_THREADS, sm>>>(p); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1); }
+      for (int r = 0; r < 4; ++r) { cudaEventRecord(e0); k2::k2_ontop_ws<false, 2, K2LAB_LEAN><<<148, k2::WS_THREADS, sm>>>(p); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1); }
     } else {
       size_t sm = k2::Smem<64>::bytes(Mpad, nact);
       CK(cudaFuncSetAttribute(k2::k2_ontop<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
