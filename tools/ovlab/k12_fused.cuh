@@ -18,8 +18,8 @@
 // core part to K2's active-space Pi.  Per-CTA partial sums of the integrated densities go to
 // dp.partial[blockIdx.x][3] in a fixed order.
 #pragma once
-#include "k1_density.cuh"
-#include "k2_ontop.cuh"
+#include "../../openrdm_b200/csrc/k1_density.cuh"
+#include "../../openrdm_b200/csrc/k2_ontop.cuh"
 
 namespace k12 {
 

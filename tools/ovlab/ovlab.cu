@@ -8,7 +8,7 @@
 #include <cuda_runtime.h>
 #include "../../openrdm_b200/csrc/k1_density.cuh"
 #include "../../openrdm_b200/csrc/k2_ontop.cuh"
-#include "../../openrdm_b200/csrc/k12_fused.cuh"
+#include "k12_fused.cuh"
 #include "../../openrdm_b200/csrc/rdm_pack.h"
 #define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("CUDA error %s at %d\n",cudaGetErrorString(e),__LINE__); exit(1);} }while(0)
 
