@@ -57,6 +57,27 @@ __global__ void __launch_bounds__(128) core_fma(const k1::Params P) {
   }
 }
 
+template <int UNR, int MINB>
+__global__ void __launch_bounds__(128, MINB) core_fma_light(const k1::Params P) {
+  const size_t ld = P.ld;
+  for (size_t p = (size_t)blockIdx.x * 128 + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * 128) {
+    double rc = 0, cx = 0, cy = 0, cz = 0;
+    const int n = P.ncore + P.nact;
+    int i = 0;
+    for (; i + UNR <= n; i += UNR) {
+      double v[UNR][4];
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+        const size_t o = (size_t)(i + j) * ld + p;
+        v[j][0] = __ldcs(P.phi + o); v[j][1] = __ldcs(P.phix + o); v[j][2] = __ldcs(P.phiy + o); v[j][3] = __ldcs(P.phiz + o);
+      }
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) { rc = fma(v[j][0], v[j][0], rc); cx = fma(v[j][0], v[j][1], cx); cy = fma(v[j][0], v[j][2], cy); cz = fma(v[j][0], v[j][3], cz); }
+    }
+    P.rho[p] = rc; P.gx[p] = cx; P.gy[p] = cy; P.gz[p] = cz;
+  }
+}
+
 int main(int argc, char** argv) {
   const int ncore = 83, nact = 20, n = ncore + nact;
   size_t npts = argc > 1 ? atol(argv[1]) : 5000000;
@@ -105,10 +126,20 @@ int main(int argc, char** argv) {
       case 3: core_fma<4><<<g1, 128, 0, s>>>(p1); break;
       case 4: core_fma<8><<<g1, 128, 0, s>>>(p1); break;
       case 5: stream_only<16><<<g1, 128, 0, s>>>(p1); break;
+      case 6: core_fma_light<2, 12><<<g1, 128, 0, s>>>(p1); break;   // <= 40 regs: 3 CTAs next to K2
+      case 7: core_fma_light<1, 16><<<g1, 128, 0, s>>>(p1); break;   // <= 32 regs: 4 CTAs next to K2
+      case 8: core_fma_light<2, 8><<<g1, 128, 0, s>>>(p1); break;    // <= 64 regs: 2 CTAs next to K2
     }
   };
-  const char* names[] = {"k1_density<20,gga>", "stream_only<4>", "stream_only<8>", "core_fma<4>", "core_fma<8>", "stream_only<16>"};
-  for (int variant = 0; variant < 6; ++variant) {
+  // a K1 launched BEFORE K2 must leave the SM's shared-memory carve-out large enough for K2's 147 KB
+  CK(cudaFuncSetAttribute(k1::k1_density<20, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CK(cudaFuncSetAttribute(stream_only<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CK(cudaFuncSetAttribute(stream_only<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CK(cudaFuncSetAttribute(stream_only<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CK(cudaFuncSetAttribute(core_fma<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CK(cudaFuncSetAttribute(core_fma<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  const char* names[] = {"k1_density<20,gga>", "stream_only<4>", "stream_only<8>", "core_fma<4>", "core_fma<8>", "stream_only<16>", "core_fma_light<2,12>", "core_fma_light<1,16>", "core_fma_light<2,8>"};
+  for (int variant = (argc > 4 ? atoi(argv[4]) : 0); variant < 9; ++variant) {
     float alone = 0, tk2 = 0, tk1 = 0, span = 0;
     for (int r = 0; r < 3; ++r) { cudaEventRecord(b0, sb); launch_k1(variant, sb); cudaEventRecord(b1, sb); CK(cudaEventSynchronize(b1)); cudaEventElapsedTime(&alone, b0, b1); }
     for (int r = 0; r < 3; ++r) {
