@@ -337,7 +337,7 @@ def main():
     k3_gbs = alg["k3_bytes"] * pts_rank / (ms_k["xc"] * 1e-3) * 1e-9
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01c_traffic.json")) as f:
             tr = json.load(f)
         if args.config == 4 and world == 1 and not args.npts:
             traffic = tr["config4_n1"]["k2_ontop"]
