@@ -124,6 +124,27 @@ int ordm_set_rdm2ab_dense(ordm_ctx* ctx, int n, const double* D2ab);
 int ordm_set_active_space(ordm_ctx* ctx, int ncore, int nact, const double* A1a, const double* A1b,
                           const double* D2act);
 
+/* Sparse ingestion of the active-space RDMs -- what production callers
+ * hand over instead of dense matrices:
+ *   upper_packed = 0  Psi4 plugin lists  struct opdm {i,j,val} / struct tpdm {i,j,k,l,val}
+ *                     (src/libpsi4/mcpdft_solver.h:71-83): each element contributes val * phi_i phi_j
+ *                     (* phi_k phi_l) once, as BuildRhoFast / BuildPiFast do (mcpdft_solver.cc:1867-2061,
+ *                     1578-1735);
+ *   upper_packed = 1  PySCF exporter COO groups /SP_SYMM_D1/ACT_D1{a,b}_MO/{VAL,ROW_IDX,COL_IDX} and
+ *                     /SP_SYMM_D2/ACT_D2ab_MO/{VAL,DIM1_IDX..DIM4_IDX} (src/libpyscf/libpyscf.py:246-463):
+ *                     only i <= j (and k <= l) of the symmetric arrays is stored, values unscaled.
+ * Indices are active-space local (0..nact-1); ncore doubly-occupied orbitals precede them, as in
+ * ordm_set_active_space.  Cost O(nnz): the dense (nact^2)^2 matrix is never formed. */
+int ordm_set_active_space_sparse(ordm_ctx* ctx, int ncore, int nact,
+                                 size_t nnz1a, const int* i1a, const int* j1a, const double* v1a,
+                                 size_t nnz1b, const int* i1b, const int* j1b, const double* v1b,
+                                 size_t nnz2, const int* i2, const int* j2, const int* k2, const int* l2,
+                                 const double* v2, int upper_packed);
+/* Host-only helper: the same 2-RDM list expanded to the dense (n^2)x(n^2) reference convention
+ * (mcpdft.cc:204) that ordm_set_rdm2ab_dense / mcpdft_energy take.  D2ab_out is overwritten. */
+int ordm_rdm2ab_sparse_to_dense(int n, size_t nnz, const int* i2, const int* j2, const int* k2, const int* l2,
+                                const double* v2, int upper_packed, double* D2ab_out);
+
 /* ---- stages = the public methods of mcpdft::MCPDFT ------------------------------------ */
 int ordm_build_rho(ordm_ctx* ctx);   /* MCPDFT::build_rho,  mcpdft.cc:35-40  */
 int ordm_build_pi(ordm_ctx* ctx);    /* MCPDFT::build_pi,   mcpdft.cc:178-183 (D2ab from set_rdm2ab_*) */

@@ -79,6 +79,9 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.ordm_set_rdm1.argtypes = [P, I, D, D]
     lib.ordm_set_rdm2ab_dense.argtypes = [P, I, D]
     lib.ordm_set_active_space.argtypes = [P, I, I, D, D, D]
+    IP = C.POINTER(C.c_int)
+    lib.ordm_set_active_space_sparse.argtypes = [P, I, I, S, IP, IP, D, S, IP, IP, D, S, IP, IP, IP, IP, D, I]
+    lib.ordm_rdm2ab_sparse_to_dense.argtypes = [I, S, IP, IP, IP, IP, D, I, D]
     for f in ("ordm_build_rho", "ordm_build_pi", "ordm_build_R", "ordm_translate", "ordm_fully_translate", "ordm_comm_detach"):
         getattr(lib, f).argtypes = [P]
     lib.ordm_integrated_densities.argtypes = [P, D, D]
@@ -120,6 +123,17 @@ def synth_rdms(seed: int, nact: int, nelec_a: int, nelec_b: int, ndet: int = 8, 
     if rc:
         raise OrdmError(rc, load().ordm_last_error(None).decode())
     return A1a, A1b, D2
+
+
+def rdm2ab_sparse_to_dense(n: int, d2, upper_packed=False) -> np.ndarray:
+    """(i, j, k, l, val) list -> dense (n^2, n^2) matrix in the reference convention (host only)."""
+    t = [np.ascontiguousarray(x, dtype=np.int32) for x in d2[:4]] + [np.ascontiguousarray(d2[4], dtype=np.float64)]
+    out = np.zeros((n * n, n * n), order="F")
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    rc = load().ordm_rdm2ab_sparse_to_dense(n, len(t[4]), ip(t[0]), ip(t[1]), ip(t[2]), ip(t[3]), _d(t[4]), int(upper_packed), _d(out))
+    if rc:
+        raise OrdmError(rc, load().ordm_last_error(None).decode())
+    return out
 
 
 def synth_fill_host(seed: int, npts_total: int, p0: int, m: int, n: int, gga: bool):
@@ -188,6 +202,17 @@ class Engine:
     def set_active_space(self, ncore, A1a, A1b, D2act):
         A1a, A1b, D2act = _f(A1a), _f(A1b), _f(D2act)
         self._ck(self.lib.ordm_set_active_space(self.ctx, ncore, A1a.shape[0], _d(A1a), _d(A1b), _d(D2act)))
+
+    def set_active_space_sparse(self, ncore, nact, d1a, d1b, d2, upper_packed=False):
+        """d1a/d1b = (i, j, val) arrays, d2 = (i, j, k, l, val) arrays; see ordm_set_active_space_sparse."""
+        def ints(a): return np.ascontiguousarray(a, dtype=np.int32)
+        def ip(a): return a.ctypes.data_as(C.POINTER(C.c_int))
+        a = [ints(x) for x in d1a[:2]] + [np.ascontiguousarray(d1a[2], dtype=np.float64)]
+        b = [ints(x) for x in d1b[:2]] + [np.ascontiguousarray(d1b[2], dtype=np.float64)]
+        t = [ints(x) for x in d2[:4]] + [np.ascontiguousarray(d2[4], dtype=np.float64)]
+        self._ck(self.lib.ordm_set_active_space_sparse(self.ctx, ncore, nact, len(a[2]), ip(a[0]), ip(a[1]), _d(a[2]),
+                                                       len(b[2]), ip(b[0]), ip(b[1]), _d(b[2]),
+                                                       len(t[4]), ip(t[0]), ip(t[1]), ip(t[2]), ip(t[3]), _d(t[4]), int(upper_packed)))
 
     def synth_fill(self, seed, npts_total, p0, m, n, gga):
         self._ck(self.lib.ordm_synth_fill_device(self.ctx, seed, npts_total, p0, m, n, int(gga)))

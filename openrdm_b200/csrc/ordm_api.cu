@@ -774,6 +774,38 @@ int ordm_set_active_space(ordm_ctx* c, int ncore, int nact, const double* A1a, c
   return ORDM_OK;
 }
 
+int ordm_set_active_space_sparse(ordm_ctx* c, int ncore, int nact, size_t nnz1a, const int* i1a, const int* j1a, const double* v1a,
+                                 size_t nnz1b, const int* i1b, const int* j1b, const double* v1b, size_t nnz2, const int* i2,
+                                 const int* j2, const int* k2, const int* l2, const double* v2, int upper_packed) {
+  CHECK_CTX(c);
+  if (ncore < 0 || nact <= 0) return fail(c, ORDM_ERR_INVALID, "bad active space (ncore=%d nact=%d)", ncore, nact);
+  if ((nnz1a && !(i1a && j1a && v1a)) || (nnz1b && !(i1b && j1b && v1b)) || (nnz2 && !(i2 && j2 && k2 && l2 && v2)))
+    return fail(c, ORDM_ERR_INVALID, "null sparse RDM arrays");
+  CU(c, cudaSetDevice(c->device));
+  std::vector<double> A1a, A1b;
+  if (!ordm::sparse_opdm_to_dense(nact, nnz1a, i1a, j1a, v1a, upper_packed != 0, A1a) ||
+      !ordm::sparse_opdm_to_dense(nact, nnz1b, i1b, j1b, v1b, upper_packed != 0, A1b))
+    return fail(c, ORDM_ERR_INVALID, "sparse 1-RDM: index out of range [0,%d)%s", nact, upper_packed ? " or below the diagonal of an upper-packed list" : "");
+  std::vector<double> Dt;
+  if (!ordm::fold_tpdm_sparse(nact, nnz2, i2, j2, k2, l2, v2, upper_packed != 0, Dt))
+    return fail(c, ORDM_ERR_INVALID, "sparse 2-RDM: index out of range [0,%d)%s", nact, upper_packed ? " or not i<=j, k<=l in an upper-packed list" : "");
+  c->core_form = ncore > 0;
+  int rc = install_rdm1(c, ncore, nact, A1a.data(), A1b.data());
+  if (rc) return rc;
+  c->h_Dt.swap(Dt);
+  if ((rc = configure_k2(c))) return rc;
+  c->have_rdm2 = true;
+  return ORDM_OK;
+}
+
+int ordm_rdm2ab_sparse_to_dense(int n, size_t nnz, const int* i2, const int* j2, const int* k2, const int* l2, const double* v2,
+                                int upper_packed, double* D2) {
+  if (n <= 0 || !D2 || (nnz && !(i2 && j2 && k2 && l2 && v2))) return fail(nullptr, ORDM_ERR_INVALID, "bad sparse 2-RDM");
+  if (!ordm::sparse_tpdm_to_dense(n, nnz, i2, j2, k2, l2, v2, upper_packed != 0, D2))
+    return fail(nullptr, ORDM_ERR_INVALID, "sparse 2-RDM: index out of range [0,%d)%s", n, upper_packed ? " or not i<=j, k<=l in an upper-packed list" : "");
+  return ORDM_OK;
+}
+
 // ---- stages -------------------------------------------------------------------------------
 int ordm_build_rho(ordm_ctx* c) {
   CHECK_CTX(c);

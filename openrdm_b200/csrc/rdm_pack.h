@@ -53,6 +53,66 @@ inline void fold_tpdm(int n, const double* D2, std::vector<double>& Dt) {
     }
 }
 
+// ---- sparse ingestion -------------------------------------------
+// What production callers hand over instead of the dense (n^2)x(n^2) matrix:
+//  * Psi4 plugin:  struct opdm {i,j,val} / struct tpdm {i,j,k,l,val} lists (mcpdft_solver.h:71-83),
+//    consumed as rho += phi_i phi_j val (BuildRhoFast, mcpdft_solver.cc:1867-2061) and
+//    Pi += phi_i phi_j phi_k phi_l val (BuildPiFast, :1578-1735): every stored element counts once.
+//  * PySCF exporter: COO groups /SP_SYMM_D{1,2}/... holding only i <= j (and k <= l) of the symmetric
+//    arrays, values unscaled (libpyscf.py:246-463): an off-diagonal element stands for both
+//    orderings.  `upper_packed` selects that convention.
+// Both land directly in the packed pair matrix Dt / the small dense 1-RDM: O(nnz), the dense
+// (n^2)^2 matrix is never formed.
+inline bool sparse_opdm_to_dense(int n, size_t nnz, const int* ii, const int* jj, const double* val, bool upper_packed,
+                                 std::vector<double>& D) {  // D: n x n column-major
+  D.assign((size_t)n * n, 0.0);
+  for (size_t e = 0; e < nnz; ++e) {
+    const int i = ii[e], j = jj[e];
+    if (i < 0 || j < 0 || i >= n || j >= n || (upper_packed && i > j)) return false;
+    D[(size_t)i + (size_t)j * n] += val[e];
+    if (upper_packed && i != j) D[(size_t)j + (size_t)i * n] += val[e];
+  }
+  return true;
+}
+
+inline bool fold_tpdm_sparse(int n, size_t nnz, const int* ii, const int* jj, const int* kk, const int* ll, const double* val,
+                             bool upper_packed, std::vector<double>& Dt) {
+  const int M = pair_count(n);
+  Dt.assign((size_t)M * M, 0.0);
+  for (size_t e = 0; e < nnz; ++e) {
+    const int i = ii[e], j = jj[e], k = kk[e], l = ll[e];
+    if (i < 0 || j < 0 || k < 0 || l < 0 || i >= n || j >= n || k >= n || l >= n) return false;
+    if (upper_packed && (i > j || k > l)) return false;
+    double v = val[e];
+    if (upper_packed) v *= ((i != j) ? 2.0 : 1.0) * ((k != l) ? 2.0 : 1.0);
+    Dt[(size_t)pair_index(n, i, j) * M + pair_index(n, k, l)] += v;
+  }
+  for (int I = 0; I < M; ++I)
+    for (int J = I + 1; J < M; ++J) {
+      const double s = 0.5 * (Dt[(size_t)I * M + J] + Dt[(size_t)J * M + I]);
+      Dt[(size_t)I * M + J] = Dt[(size_t)J * M + I] = s;
+    }
+  return true;
+}
+
+// the same list expanded into the reference's dense convention (element (j*n+i, l*n+k) multiplies
+// phi_i phi_j phi_k phi_l, mcpdft.cc:204) -- for callers that still want the dense matrix, and for tests
+inline bool sparse_tpdm_to_dense(int n, size_t nnz, const int* ii, const int* jj, const int* kk, const int* ll, const double* val,
+                                 bool upper_packed, double* D2) {  // D2: (n*n) x (n*n) column-major, zeroed here
+  const size_t n2 = (size_t)n * n;
+  for (size_t e = 0; e < n2 * n2; ++e) D2[e] = 0.0;
+  for (size_t e = 0; e < nnz; ++e) {
+    const int i = ii[e], j = jj[e], k = kk[e], l = ll[e];
+    if (i < 0 || j < 0 || k < 0 || l < 0 || i >= n || j >= n || k >= n || l >= n) return false;
+    if (upper_packed && (i > j || k > l)) return false;
+    const int ij[2][2] = {{i, j}, {j, i}}, kl[2][2] = {{k, l}, {l, k}};
+    for (int a = 0; a < ((upper_packed && i != j) ? 2 : 1); ++a)
+      for (int b = 0; b < ((upper_packed && k != l) ? 2 : 1); ++b)
+        D2[((size_t)ij[a][1] * n + ij[a][0]) + ((size_t)kl[b][1] * n + kl[b][0]) * n2] += val[e];
+  }
+  return true;
+}
+
 // ---- K2 work decomposition ------------------------------------------------------------------
 // Dt' (upper triangle of the symmetric Dt, strictly-upper part doubled) is cut into 32x32 blocks.
 // A *segment* is a run of consecutive row blocks ib0 .. ib0+nblk-1 of one block column jb: the
