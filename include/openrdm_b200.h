@@ -112,6 +112,16 @@ int ordm_set_grid(ordm_ctx* ctx, size_t npts, const double* w);
 /* MCPDFT::set_nbfs + set_phi/_x/_y/_z (mcpdft.h:113,118-121).  phi_x/y/z NULL = LDA only. */
 int ordm_set_orbitals(ordm_ctx* ctx, size_t npts, int n, size_t ld, const double* phi,
                       const double* phi_x, const double* phi_y, const double* phi_z);
+/* AO -> MO transform of the orbital values on the device, the step
+ * directly in front of the path: TransformPhiMatrixAOMO (src/libpsi4/mcpdft_solver.cc:619-635, two
+ * F_DGEMMs per irrep) / mo_values = np.matmul(ao_values, C_mo) (src/libpyscf/libpyscf.py:608).
+ * ao, ao_x, ao_y, ao_z: npts x nao column-major host arrays (leading dimension ld; gradients NULL =
+ * LDA); C: nao x nmo column-major MO coefficients.  The AO values are streamed through the device in
+ * point batches (H2D overlapped with the FP64 GEMM, cuBLAS DGEMM = DMMA on sm_100a) and
+ * phi = ao . C (and its gradients) become the context's resident orbitals, exactly as if
+ * ordm_set_orbitals had been called with the transformed matrices. */
+int ordm_set_orbitals_ao(ordm_ctx* ctx, size_t npts, int nao, size_t ld, const double* ao, const double* ao_x,
+                         const double* ao_y, const double* ao_z, int nmo, const double* C);
 /* MCPDFT::set_D1a + set_D1b (mcpdft.h:125-126).  n x n, not assumed symmetric (mcpdft.cc:148). */
 int ordm_set_rdm1(ordm_ctx* ctx, int n, const double* D1a, const double* D1b);
 /* the D2ab argument of mcpdft_energy / build_pi (energy.h:14-18, mcpdft.h:35); dense

@@ -76,6 +76,7 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.ordm_host_free.argtypes = [P]
     lib.ordm_set_grid.argtypes = [P, S, D]
     lib.ordm_set_orbitals.argtypes = [P, S, I, S, D, D, D, D]
+    lib.ordm_set_orbitals_ao.argtypes = [P, S, I, S, D, D, D, D, I, D]
     lib.ordm_set_rdm1.argtypes = [P, I, D, D]
     lib.ordm_set_rdm2ab_dense.argtypes = [P, I, D]
     lib.ordm_set_active_space.argtypes = [P, I, I, D, D, D]
@@ -190,6 +191,13 @@ class Engine:
         npts, n = phi.shape
         g = [_f(x) for x in grads] if grads is not None else [None] * 3
         self._ck(self.lib.ordm_set_orbitals(self.ctx, npts, n, max(npts, 1), _d(phi), _d(g[0]), _d(g[1]), _d(g[2])))
+
+    def set_orbitals_ao(self, ao, C, ao_grads=None):
+        """AO values (npts, nao) [+ gradients] and MO coefficients (nao, nmo): phi = ao @ C on the device."""
+        ao, Cm = _f(ao), _f(C)
+        npts, nao = ao.shape
+        g = [_f(x) for x in ao_grads] if ao_grads is not None else [None] * 3
+        self._ck(self.lib.ordm_set_orbitals_ao(self.ctx, npts, nao, max(npts, 1), _d(ao), _d(g[0]), _d(g[1]), _d(g[2]), Cm.shape[1], _d(Cm)))
 
     def set_rdm1(self, D1a, D1b):
         D1a, D1b = _f(D1a), _f(D1b)

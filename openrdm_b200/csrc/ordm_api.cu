@@ -75,6 +75,33 @@ bool load_nccl(std::string& why) {
   return true;
 }
 
+// ---- cuBLAS through dlopen (plain library DGEMM for the AO -> MO transform only) ----
+struct CublasApi {
+  void* handle = nullptr;
+  int (*Create)(void**) = nullptr;
+  int (*Destroy)(void*) = nullptr;
+  int (*SetStream)(void*, cudaStream_t) = nullptr;
+  int (*Dgemm)(void*, int, int, int, int, int, const double*, const double*, int, const double*, int, const double*, double*, int) = nullptr;
+};
+CublasApi g_cublas;
+
+bool load_cublas(std::string& why) {
+  if (g_cublas.handle) return true;
+  const char* names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so"};
+  for (const char* nm : names) {
+    g_cublas.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_cublas.handle) break;
+  }
+  if (!g_cublas.handle) { why = std::string("dlopen libcublas.so.12 failed: ") + dlerror(); return false; }
+  g_cublas.Create = (int (*)(void**))dlsym(g_cublas.handle, "cublasCreate_v2");
+  g_cublas.Destroy = (int (*)(void*))dlsym(g_cublas.handle, "cublasDestroy_v2");
+  g_cublas.SetStream = (int (*)(void*, cudaStream_t))dlsym(g_cublas.handle, "cublasSetStream_v2");
+  g_cublas.Dgemm = (int (*)(void*, int, int, int, int, int, const double*, const double*, int, const double*, int, const double*, double*, int))
+      dlsym(g_cublas.handle, "cublasDgemm_v2");
+  if (!g_cublas.Create || !g_cublas.Destroy || !g_cublas.SetStream || !g_cublas.Dgemm) { why = "libcublas is missing a required symbol"; return false; }
+  return true;
+}
+
 }  // namespace
 
 struct ordm_ctx {
@@ -140,6 +167,9 @@ struct ordm_ctx {
   // stage bookkeeping
   bool rho_done = false, pi_done = false, xc_done = false, xc_ft = false, pig_done = false;
   double last_n[3] = {0, 0, 0}, last_trn[3] = {0, 0, 0};
+
+  // cuBLAS handle (AO -> MO transform), created on first use
+  void* cublas = nullptr;
 
   // NCCL
   void* comm = nullptr;
@@ -637,6 +667,7 @@ void ordm_destroy(ordm_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  if (c->cublas && g_cublas.Destroy) g_cublas.Destroy(c->cublas);
   for (int i = 0; i < ORDM_VEC_COUNT; ++i)
     if (i != ORDM_VEC_W) dfree(c->g.vec[i]);
   dfree(c->g.gx); dfree(c->g.gy); dfree(c->g.gz); dfree(c->g.pi_core);
@@ -729,6 +760,65 @@ int ordm_set_orbitals(ordm_ctx* c, size_t npts, int n, size_t ld, const double* 
     for (int k = 0; k < (gga ? 4 : 1); ++k)
       CU(c, cudaMemcpy2DAsync(c->d_phi[k], c->g.ld * sizeof(double), src[k], ld * sizeof(double), npts * sizeof(double), (size_t)n, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  return ORDM_OK;
+}
+
+int ordm_set_orbitals_ao(ordm_ctx* c, size_t npts, int nao, size_t ld, const double* ao, const double* ax, const double* ay,
+                         const double* az, int nmo, const double* C) {
+  CHECK_CTX(c);
+  if (nao <= 0 || nmo <= 0 || !C || (npts && !ao) || ld < npts) return fail(c, ORDM_ERR_INVALID, "bad AO matrix / MO coefficients (nao=%d nmo=%d ld=%zu npts=%zu)", nao, nmo, ld, npts);
+  const bool gga = ax || ay || az;
+  if (gga && !(ax && ay && az)) return fail(c, ORDM_ERR_INVALID, "give all of ao_x, ao_y, ao_z or none");
+  if (c->g.w && c->g.npts != npts) return fail(c, ORDM_ERR_INVALID, "orbitals have %zu points but the grid has %zu", npts, c->g.npts);
+  CU(c, cudaSetDevice(c->device));
+  std::string why;
+  if (!load_cublas(why)) return fail(c, ORDM_ERR_CUDA, "%s", why.c_str());
+  if (!c->cublas && g_cublas.Create(&c->cublas) != 0) { c->cublas = nullptr; return fail(c, ORDM_ERR_CUDA, "cublasCreate failed"); }
+  if (g_cublas.SetStream(c->cublas, c->stream) != 0) return fail(c, ORDM_ERR_CUDA, "cublasSetStream failed");
+  int rc = alloc_grid(c, npts, nmo, gga);
+  if (rc) return rc;
+  if (!npts) return ORDM_OK;
+  // point batches: two staging buffers of [nao][batch] doubles (<= 256 MB each)
+  size_t batch = std::max<size_t>(PT_ALIGN, ((size_t)1 << 25) / (size_t)nao / PT_ALIGN * PT_ALIGN);
+  batch = std::min(batch, round_up(npts, PT_ALIGN));
+  double *d_C = nullptr, *d_stage[2] = {nullptr, nullptr};
+  cudaEvent_t copied[2] = {nullptr, nullptr}, used[2] = {nullptr, nullptr};
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamSynchronize(c->stream);
+    dfree(d_C);
+    for (int b = 0; b < 2; ++b) { dfree(d_stage[b]); if (copied[b]) cudaEventDestroy(copied[b]); if (used[b]) cudaEventDestroy(used[b]); }
+  };
+#define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(c, ORDM_ERR_CUDA, "CUDA error '%s' in %s", cudaGetErrorString(e_), #call); } } while (0)
+  CUX(cudaMalloc(&d_C, (size_t)nao * nmo * sizeof(double)));
+  CUX(cudaMemcpyAsync(d_C, C, (size_t)nao * nmo * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  for (int b = 0; b < 2; ++b) {
+    CUX(cudaMalloc(&d_stage[b], batch * (size_t)nao * sizeof(double)));
+    CUX(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    CUX(cudaEventCreateWithFlags(&used[b], cudaEventDisableTiming));
+  }
+  const double one = 1.0, zero = 0.0;
+  const double* src[4] = {ao, ax, ay, az};
+  size_t it = 0;
+  for (int k = 0; k < (gga ? 4 : 1); ++k)
+    for (size_t p0 = 0; p0 < npts; p0 += batch, ++it) {
+      const int b = (int)(it & 1);
+      const size_t m = std::min(batch, npts - p0);
+      if (it >= 2) CUX(cudaStreamWaitEvent(c->copy_stream, used[b], 0));
+      CUX(cudaMemcpy2DAsync(d_stage[b], batch * sizeof(double), src[k] + p0, ld * sizeof(double), m * sizeof(double), (size_t)nao,
+                            cudaMemcpyHostToDevice, c->copy_stream));
+      CUX(cudaEventRecord(copied[b], c->copy_stream));
+      CUX(cudaStreamWaitEvent(c->stream, copied[b], 0));
+      // phi[p0:p0+m, 0:nmo] = stage[0:m, 0:nao] . C   (all column-major)
+      if (g_cublas.Dgemm(c->cublas, 0, 0, (int)m, nmo, nao, &one, d_stage[b], (int)batch, d_C, nao, &zero, c->d_phi[k] + p0, (int)c->g.ld) != 0) {
+        cleanup();
+        return fail(c, ORDM_ERR_CUDA, "cublasDgemm failed in the AO -> MO transform");
+      }
+      CUX(cudaEventRecord(used[b], c->stream));
+    }
+  CUX(cudaStreamSynchronize(c->stream));
+#undef CUX
+  cleanup();
   return ORDM_OK;
 }
 

@@ -289,3 +289,29 @@ def test_fully_translated_vs_oracle(engine, port, ncore, nact, npts, kind, fn):
     base = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, fn, grads if gga else None, eclass=0.125)
     a, b = engine.get_vector("tr_rhoa"), base.vecs["tr_rhoa"]
     assert (np.abs(a - b) <= 1e-7 * np.abs(rho) + 1e-300).all()
+
+
+@pytest.mark.parametrize("npts,nao,nmo,gga", [(1000, 13, 5, True), (4097, 40, 9, True), (300, 7, 7, False)])
+def test_ao_to_mo_transform_on_device(engine, port, npts, nao, nmo, gga):
+    """SURVEY 8f rank 2: phi = ao . C on the device (TransformPhiMatrixAOMO, mcpdft_solver.cc:619-635;
+    libpyscf.py:608) feeding the same path: against numpy's matmul + the oracle."""
+    rng = np.random.default_rng(nao * 100 + nmo)
+    ao = np.asfortranarray(rng.uniform(-0.5, 0.5, (npts, nao)))
+    ag = [np.asfortranarray(rng.uniform(-0.5, 0.5, (npts, nao))) for _ in range(3)] if gga else None
+    C, _ = np.linalg.qr(rng.normal(size=(nao, nao)))
+    C = np.asfortranarray(C[:, :nmo])
+    phi = np.asfortranarray(ao @ C)
+    grads = [np.asfortranarray(a @ C) for a in ag] if gga else None
+    _, _, w, D1a, D1b, D2 = random_case(rng, nmo, npts, "ensemble")
+    fn = "PBE" if gga else "SVWN"
+    want = port.energy(w, phi, D1a, D1b, D2, fn, grads, eclass=0.0)
+    engine.set_options(diagnostics=True)
+    engine.set_grid(w)
+    engine.set_orbitals_ao(ao, C, ag)
+    engine.set_rdm1(D1a, D1b); engine.set_rdm2ab_dense(D2, nmo)
+    got = engine.energy(FN[fn], 0.0)
+    check_scalars(got, want.scalars)
+    check_vectors(engine.get_vector, want.vecs, gga)
+    back = np.zeros((npts, nmo), order="F")
+    engine.get_orbitals(back)
+    assert np.abs(back - phi).max() <= 1e-13
