@@ -443,6 +443,134 @@ double orc_ec_pbe(size_t npts, const double* ra, const double* rb, const double*
 }
 
 /* ==========================================================================================
+ *      Psi4 plugin functionals: src/libpsi4/lsda_gga_functionals.cc
+ *      as dispatched by mcpdft_solver.cc:742-787 ("REVPBE", "BLYP", "BOP").
+ * ======================================================================================== */
+
+/* EX_PBE_I, lsda_gga_functionals.cc:317-398: the same spin-scaled PBE exchange as libfunc's EX_PBE
+ * with KAPPA = 1.245 for "REVPBE" (:323); here sigma IS clamped only in the single-spin branches,
+ * exactly as libfunc (:372-389). */
+static double pbe_FX_k(double s, double kappa) {
+  const double delta = 0.06672455060314922, mu = (1.0 / 3.0) * delta * M_PI * M_PI;
+  return 1.0 + kappa - kappa * pow(1.0 + (mu * pow(s, 2.0)) / kappa, -1.0);
+}
+double orc_ex_pbe_kappa(size_t npts, const double* ra, const double* rb, const double* saa, const double* sbb,
+                        const double* w, double kappa) {
+  double e = 0.0;
+  for (size_t p = 0; p < npts; ++p) {
+    const double a = ra[p], b = rb[p];
+    double rho = a + b;
+    if (rho > ORC_TOL) {
+      if (a < ORC_TOL) {
+        rho = b;
+        const double sg = fmax(0.0, sbb[p]);
+        const double zk = pbe_eX(2.0 * rho) * pbe_FX_k(pbe_S(2.0 * rho, 4.0 * sg), kappa);
+        e += rho * zk * w[p];
+      } else if (b < ORC_TOL) {
+        rho = a;
+        const double sg = fmax(0.0, saa[p]);
+        const double zk = pbe_eX(2.0 * rho) * pbe_FX_k(pbe_S(2.0 * rho, 4.0 * sg), kappa);
+        e += rho * zk * w[p];
+      } else {
+        const double za = a * pbe_eX(2.0 * a) * pbe_FX_k(pbe_S(2.0 * a, 4.0 * saa[p]), kappa);
+        const double zb = b * pbe_eX(2.0 * b) * pbe_FX_k(pbe_S(2.0 * b, 4.0 * sbb[p]), kappa);
+        const double zk = za + zb;
+        e += zk * w[p];
+      }
+    }
+  }
+  return e;
+}
+
+/* EX_B88_I, lsda_gga_functionals.cc:207-273.  Note the reference clamps sigma into a local it then
+ * does not use: X = sqrt(sigma_ss[p]) / rho_s^(4/3) reads the unclamped array (:237,245,253-254). */
+double orc_ex_b88(size_t npts, const double* ra, const double* rb, const double* saa, const double* sbb, const double* w) {
+  const double Cx = 0.73855876638202240586, beta = 0.0042;
+  const double c = pow(2.0, 1.0 / 3.0) * Cx;
+  double e = 0.0;
+  for (size_t p = 0; p < npts; ++p) {
+    double rhoa = ra[p], rhob = rb[p];
+    const double rho = rhoa + rhob;
+    double a43 = 0.0, b43 = 0.0, Xa = 0.0, Xb = 0.0, Xa2 = 0.0, Xb2 = 0.0;
+    if (rho > ORC_TOL) {
+      if (rhoa < ORC_TOL) {
+        b43 = pow(rhob, 4.0 / 3.0);
+        Xb = sqrt(sbb[p]) / b43;
+        Xb2 = Xb * Xb;
+      } else if (rhob < ORC_TOL) {
+        a43 = pow(rhoa, 4.0 / 3.0);
+        Xa = sqrt(saa[p]) / a43;
+        Xa2 = Xa * Xa;
+      } else {
+        a43 = pow(rhoa, 4.0 / 3.0);
+        b43 = pow(rhob, 4.0 / 3.0);
+        Xa = sqrt(saa[p]) / a43;
+        Xb = sqrt(sbb[p]) / b43;
+        Xa2 = Xa * Xa;
+        Xb2 = Xb * Xb;
+      }
+      e += -a43 * (c + (beta * Xa2) / (1.0 + 6.0 * beta * Xa * asinh(Xa))) * w[p];
+      e += -b43 * (c + (beta * Xb2) / (1.0 + 6.0 * beta * Xb * asinh(Xb))) * w[p];
+    }
+  }
+  return e;
+}
+
+/* EC_LYP_I, lsda_gga_functionals.cc:764-829: zero unless both spin densities exceed the threshold. */
+double orc_ec_lyp(size_t npts, const double* ra, const double* rb, const double* saa, const double* sab,
+                  const double* sbb, const double* w) {
+  const double A = 0.04918, B = 0.132, C = 0.2533, Dd = 0.349;
+  double e = 0.0;
+  for (size_t p = 0; p < npts; ++p) {
+    const double rhoa = ra[p], rhob = rb[p], rho = rhoa + rhob;
+    double sigmaaa = saa[p], sigmabb = sbb[p];
+    const double sigmaab = sab[p];
+    const double sigma = sigmaaa + sigmabb + 2.0 * sigmaab; /* from the UNclamped values (:787) */
+    if (rho > ORC_TOL && !(rhoa < ORC_TOL) && !(rhob < ORC_TOL)) {
+      sigmabb = fmax(0.0, sigmabb);
+      sigmaaa = fmax(0.0, sigmaaa);
+      const double rho_2 = pow(rho, 2.0), rho_a_2 = pow(rhoa, 2.0), rho_b_2 = pow(rhob, 2.0);
+      const double rho_m13 = pow(rho, -1.0 / 3.0);
+      const double rho_a_83 = pow(rhoa, 8.0 / 3.0), rho_b_83 = pow(rhob, 8.0 / 3.0);
+      const double f = pow(1.0 + Dd * rho_m13, -1.0);
+      const double omega = exp(-C * rho_m13) * f * pow(rho, -11.0 / 3.0);
+      const double delta = (C + Dd * f) * rho_m13;
+      const double zk =
+          -4.0 * A * rhoa * rhob * f / rho -
+          A * B * omega *
+              (rhoa * rhob *
+                   (36.462398978764777098 * (rho_a_83 + rho_b_83) + (2.6111111111111111111 - 0.38888888888888888889 * delta) * sigma -
+                    (2.5 - 0.055555555555555555556 * delta) * (sigmaaa + sigmabb) -
+                    0.11111111111111111111 * (delta - 11.0) * ((rhoa * sigmaaa + rhob * sigmabb) / rho)) -
+               0.66666666666666666667 * rho_2 * sigma + (0.66666666666666666667 * rho_2 - rho_a_2) * sigmabb +
+               (0.66666666666666666667 * rho_2 - rho_b_2) * sigmaaa);
+      e += zk * w[p];
+    }
+  }
+  return e;
+}
+
+/* EC_B88_OP, lsda_gga_functionals.cc:478-518: no density threshold at all -- a point with
+ * rho_a = 0 or rho_b = 0 gives 0/0 = NaN in the reference, and so it does here. */
+static double b88op_K(double X, double X2) {
+  const double beta = 0.0042;
+  return 3.0 * pow(3.0 / (4.0 * M_PI), 1.0 / 3.0) + 2.0 * (beta * X2) / (1.0 + 6.0 * beta * X * asinh(X));
+}
+double orc_ec_b88_op(size_t npts, const double* ra, const double* rb, const double* saa, const double* sbb, const double* w) {
+  double e = 0.0;
+  for (size_t p = 0; p < npts; ++p) {
+    const double rhoa = ra[p], rhob = rb[p];
+    const double a43 = pow(rhoa, 4.0 / 3.0), b43 = pow(rhob, 4.0 / 3.0);
+    const double a13 = pow(rhoa, 1.0 / 3.0), b13 = pow(rhob, 1.0 / 3.0);
+    const double Xa = sqrt(saa[p]) / a43, Xb = sqrt(sbb[p]) / b43;
+    const double Ka = b88op_K(Xa, Xa * Xa), Kb = b88op_K(Xb, Xb * Xb);
+    const double Bab = 2.3670 * (a13 * b13 * Ka * Kb) / (a13 * Ka + b13 * Kb);
+    e += -rhoa * rhob * ((1.5214 * Bab + 0.5764) / (pow(Bab, 4.0) + 1.1284 * pow(Bab, 3.0) + 0.3183 * pow(Bab, 2.0))) * w[p];
+  }
+  return e;
+}
+
+/* ==========================================================================================
  *                 mcpdft_energy: orchestration.   energy.cc:27-188
  * ======================================================================================== */
 
@@ -473,13 +601,29 @@ static void orc_finish(size_t npts, int is_gga, int functional_is_svwn, const do
                               v[ORC_TR_SIGMA_AB], v[ORC_TR_SIGMA_BB]);
   } /* without gradients tr_sigma stay zero (energy.cc:63-65) */
   double ex, ec;
-  if (functional_is_svwn) {
-    ex = orc_ex_lsda(npts, v[ORC_TR_RHOA], v[ORC_TR_RHOB], w);
-    ec = orc_ec_vwn3(npts, v[ORC_TR_RHOA], v[ORC_TR_RHOB], w);
-  } else {
-    ex = orc_ex_pbe(npts, v[ORC_TR_RHOA], v[ORC_TR_RHOB], v[ORC_TR_SIGMA_AA], v[ORC_TR_SIGMA_BB], w);
-    ec = orc_ec_pbe(npts, v[ORC_TR_RHOA], v[ORC_TR_RHOB], v[ORC_TR_SIGMA_AA], v[ORC_TR_SIGMA_AB],
-                    v[ORC_TR_SIGMA_BB], w);
+  /* `functional_is_svwn` doubles as the functional id: 1 SVWN, 0 PBE (energy.cc:114-120), and the
+   * Psi4 plugin's extra choices (mcpdft_solver.cc:742-787): 2 REVPBE, 3 BLYP, 4 BOP */
+  double *tra = v[ORC_TR_RHOA], *trb = v[ORC_TR_RHOB], *taa = v[ORC_TR_SIGMA_AA], *tab = v[ORC_TR_SIGMA_AB], *tbb = v[ORC_TR_SIGMA_BB];
+  switch (functional_is_svwn) {
+    case 1:
+      ex = orc_ex_lsda(npts, tra, trb, w);
+      ec = orc_ec_vwn3(npts, tra, trb, w);
+      break;
+    case 2: /* EX_PBE_I (kappa 1.245) + EC_PBE_I (== libfunc's EC_PBE, lsda_gga_functionals.cc:1096-1249) */
+      ex = orc_ex_pbe_kappa(npts, tra, trb, taa, tbb, w, 1.245);
+      ec = orc_ec_pbe(npts, tra, trb, taa, tab, tbb, w);
+      break;
+    case 3:
+      ex = orc_ex_b88(npts, tra, trb, taa, tbb, w);
+      ec = orc_ec_lyp(npts, tra, trb, taa, tab, tbb, w);
+      break;
+    case 4:
+      ex = orc_ex_b88(npts, tra, trb, taa, tbb, w);
+      ec = orc_ec_b88_op(npts, tra, trb, taa, tbb, w);
+      break;
+    default:
+      ex = orc_ex_pbe(npts, tra, trb, taa, tbb, w);
+      ec = orc_ec_pbe(npts, tra, trb, taa, tab, tbb, w);
   }
   out->ex = ex;
   out->ec = ec;

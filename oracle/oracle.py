@@ -21,6 +21,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "_build", "libmcpdft_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libopenrdm_ref.so")
+REF_PSI4_SO = os.path.join(HERE, "_ref", "libopenrdm_ref_psi4.so")
+# functional ids of the C port's drivers: 1 SVWN, 0 PBE (energy.cc:114-120: anything but "SVWN" is PBE),
+# plus the Psi4 plugin's REVPBE / BLYP / BOP (mcpdft_solver.cc:742-787)
+FUNC_ID = {"SVWN": 1, "PBE": 0, "REVPBE": 2, "BLYP": 3, "BOP": 4}
 
 VEC_NAMES = [
     "rhoa", "rhob", "rho",
@@ -98,6 +102,8 @@ class Port:
         self.lib.orc_ec_vwn3.restype = C.c_double
         self.lib.orc_ex_pbe.restype = C.c_double
         self.lib.orc_ec_pbe.restype = C.c_double
+        for f in ("orc_ex_pbe_kappa", "orc_ex_b88", "orc_ec_lyp", "orc_ec_b88_op"):
+            getattr(self.lib, f).restype = C.c_double
 
     def energy(self, w, phi, D1a, D1b, D2ab, functional="SVWN", grads=None, eclass=0.0,
                with_pi_grad=False, want_vecs=True) -> Outcome:
@@ -108,7 +114,7 @@ class Port:
         w, D1a, D1b, D2ab = _f64(w), _f64(D1a), _f64(D1b), _f64(D2ab)
         arrs, tbl = _vec_table(npts, want_vecs)
         res = OrcResult()
-        self.lib.orc_energy(C.c_size_t(npts), n, int(is_gga), int(functional == "SVWN"), _ptr(w), _ptr(phi),
+        self.lib.orc_energy(C.c_size_t(npts), n, int(is_gga), FUNC_ID.get(functional, 0), _ptr(w), _ptr(phi),
                             _ptr(gx), _ptr(gy), _ptr(gz), _ptr(D1a), _ptr(D1b), _ptr(D2ab),
                             C.c_double(eclass), int(with_pi_grad), C.byref(res), tbl)
         return Outcome(res.asdict(), _vecs_dict(arrs, is_gga))
@@ -122,7 +128,7 @@ class Port:
         w, A1a, A1b, D2act = _f64(w), _f64(A1a), _f64(A1b), _f64(D2act)
         arrs, tbl = _vec_table(npts, want_vecs)
         res = OrcResult()
-        self.lib.orc_energy_coreactive(C.c_size_t(npts), ncore, nact, int(is_gga), int(functional == "SVWN"),
+        self.lib.orc_energy_coreactive(C.c_size_t(npts), ncore, nact, int(is_gga), FUNC_ID.get(functional, 0),
                                        _ptr(w), _ptr(phi), _ptr(gx), _ptr(gy), _ptr(gz), _ptr(A1a),
                                        _ptr(A1b), _ptr(D2act), C.c_double(eclass), int(with_pi_grad),
                                        C.byref(res), tbl)
@@ -145,6 +151,14 @@ class Port:
             return self.lib.orc_ex_pbe(n, _ptr(ra), _ptr(rb), _ptr(saa), _ptr(sbb), _ptr(w))
         if which == "EC_PBE":
             return self.lib.orc_ec_pbe(n, _ptr(ra), _ptr(rb), _ptr(saa), _ptr(sab), _ptr(sbb), _ptr(w))
+        if which in ("EX_PBE_I", "EX_REVPBE"):
+            return self.lib.orc_ex_pbe_kappa(n, _ptr(ra), _ptr(rb), _ptr(saa), _ptr(sbb), _ptr(w), C.c_double(1.245 if which == "EX_REVPBE" else 0.804))
+        if which == "EX_B88":
+            return self.lib.orc_ex_b88(n, _ptr(ra), _ptr(rb), _ptr(saa), _ptr(sbb), _ptr(w))
+        if which == "EC_LYP":
+            return self.lib.orc_ec_lyp(n, _ptr(ra), _ptr(rb), _ptr(saa), _ptr(sab), _ptr(sbb), _ptr(w))
+        if which == "EC_B88_OP":
+            return self.lib.orc_ec_b88_op(n, _ptr(ra), _ptr(rb), _ptr(saa), _ptr(sbb), _ptr(w))
         raise ValueError(which)
 
     def kron_tpdm(self, D1a, D1b):
@@ -157,6 +171,32 @@ class Port:
 
 def have_ref() -> bool:
     return os.path.exists(REF_SO)
+
+
+def have_ref_psi4() -> bool:
+    return os.path.exists(REF_PSI4_SO)
+
+
+class RefPsi4:
+    """The Psi4 plugin's own functional routines (src/libpsi4/lsda_gga_functionals.cc, compiled
+    unmodified against stand-in Psi4 headers: oracle/shim_psi4, oracle/ref_psi4_harness.cc)."""
+
+    ID = {"EX_LSDA": 0, "EC_VWN3": 1, "EX_PBE_I": 2, "EC_PBE_I": 3, "EX_REVPBE": 4, "EX_B88": 5, "EC_LYP": 6, "EC_B88_OP": 7}
+
+    def __init__(self):
+        if not have_ref_psi4():
+            build(ref=True)
+        if not have_ref_psi4():
+            raise FileNotFoundError(REF_PSI4_SO)
+        self.lib = C.CDLL(REF_PSI4_SO)
+        self.lib.ref_psi4_functional.restype = C.c_double
+
+    def functional(self, which, w, ra, rb, saa=None, sab=None, sbb=None) -> float:
+        w, ra, rb = _f64(w), _f64(ra), _f64(rb)
+        z = np.zeros_like(w)
+        saa, sab, sbb = (_f64(s) if s is not None else z for s in (saa, sab, sbb))
+        return self.lib.ref_psi4_functional(self.ID[which], C.c_size_t(w.shape[0]), _ptr(w), _ptr(ra), _ptr(rb),
+                                            _ptr(saa), _ptr(sab), _ptr(sbb))
 
 
 class Ref:

@@ -54,3 +54,16 @@ def golden_small():
 @pytest.fixture(scope="session")
 def golden_h2():
     return np.load(os.path.join(ROOT, "tests", "golden", "h2_sto3g.npz"))
+
+
+@pytest.fixture(scope="session")
+def ref_psi4():
+    from oracle import oracle as O
+    if not O.have_ref_psi4():
+        try:
+            O.build(ref=True)
+        except Exception:
+            pass
+    if not O.have_ref_psi4():
+        pytest.skip("oracle/_ref/libopenrdm_ref_psi4.so not built (needs /root/reference)")
+    return O.RefPsi4()

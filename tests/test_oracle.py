@@ -169,3 +169,53 @@ def test_fully_translated_port_vs_compiled_reference(port, ref, ncore, nact, kin
                 assert np.allclose(a.vecs[k][fin], v[fin], rtol=1e-12, atol=1e-300), (fn, k, np.abs(a.vecs[k][fin] - v[fin]).max())
     finally:
         port.set_translation(False); ref.set_translation(False)
+
+
+def _functional_inputs(m=3000, seed=17, positive=False):
+    rng = np.random.default_rng(seed)
+    ra = rng.random(m) * 10.0 ** rng.integers(-12 if positive else -24, 2, m)
+    rb = rng.random(m) * 10.0 ** rng.integers(-12 if positive else -24, 2, m)
+    if not positive:
+        ra[:50] = 0.0; rb[50:100] = 0.0; ra[100:110] = 0.0; rb[100:110] = 0.0
+    saa, sbb = rng.random(m) * ra ** 2 * 4, rng.random(m) * rb ** 2 * 4
+    sab = np.sqrt(saa * sbb) * rng.uniform(-1, 1, m)
+    w = rng.random(m)
+    return w, ra, rb, saa, sab, sbb
+
+
+def test_psi4_plugin_functionals_port_vs_compiled_reference(port, ref_psi4):
+    """the Psi4 plugin's EX_PBE_I (PBE and revPBE), EX_B88_I, EC_LYP_I, EC_B88_OP
+    (src/libpsi4/lsda_gga_functionals.cc, compiled unmodified) against the C restatement, including
+    the single-spin and rho <= tol branches; and the plugin's PBE pair against libfunc's."""
+    w, ra, rb, saa, sab, sbb = _functional_inputs()
+    for term in ("EX_PBE_I", "EX_REVPBE", "EX_B88", "EC_LYP"):
+        a, b = port.functional(term, w, ra, rb, saa, sab, sbb), ref_psi4.functional(term, w, ra, rb, saa, sab, sbb)
+        assert np.isfinite(b) and abs(a - b) <= 1e-13 * max(1, abs(b)), (term, a, b)
+    # the plugin's PBE exchange / correlation are the libfunc ones
+    assert abs(port.functional("EX_PBE", w, ra, rb, saa, sab, sbb) - ref_psi4.functional("EX_PBE_I", w, ra, rb, saa, sab, sbb)) <= 1e-13
+    assert abs(port.functional("EC_PBE", w, ra, rb, saa, sab, sbb) - ref_psi4.functional("EC_PBE_I", w, ra, rb, saa, sab, sbb)) <= 1e-13
+    assert abs(port.functional("EX_LSDA", w, ra, rb) - ref_psi4.functional("EX_LSDA", w, ra, rb)) <= 1e-13
+    # B88-OP has no density threshold: NaN in the reference as soon as one spin density is zero ...
+    assert np.isnan(ref_psi4.functional("EC_B88_OP", w, ra, rb, saa, sab, sbb)) and np.isnan(port.functional("EC_B88_OP", w, ra, rb, saa, sab, sbb))
+    # ... and finite, and identical, on strictly positive densities
+    w, ra, rb, saa, sab, sbb = _functional_inputs(positive=True)
+    a, b = port.functional("EC_B88_OP", w, ra, rb, saa, sab, sbb), ref_psi4.functional("EC_B88_OP", w, ra, rb, saa, sab, sbb)
+    assert np.isfinite(b) and abs(a - b) <= 1e-13 * max(1, abs(b)), (a, b)
+
+
+@pytest.mark.parametrize("fn", ["REVPBE", "BLYP", "BOP"])
+def test_psi4_plugin_functionals_energy_path(port, ref_psi4, fn):
+    """The port's energy driver with the plugin's functional choices == translated vectors fed to the
+    compiled plugin routines (mcpdft_solver.cc:742-787 dispatch)."""
+    rng = np.random.default_rng(5)
+    phi, grads, w, D1a, D1b, D2 = random_case(rng, 3, 400, "ensemble")
+    if fn == "BOP":  # keep every point live (B88-OP is NaN on zero spin densities)
+        phi = np.asfortranarray(np.abs(phi) + 0.05)
+    r = port.energy(w, phi, D1a, D1b, D2, fn, grads, eclass=0.0)
+    v = r.vecs
+    args = (w, v["tr_rhoa"], v["tr_rhob"], v["tr_sigma_aa"], v["tr_sigma_ab"], v["tr_sigma_bb"])
+    pair = {"REVPBE": ("EX_REVPBE", "EC_PBE_I"), "BLYP": ("EX_B88", "EC_LYP"), "BOP": ("EX_B88", "EC_B88_OP")}[fn]
+    ex, ec = ref_psi4.functional(pair[0], *args), ref_psi4.functional(pair[1], *args)
+    if fn == "BOP" and not np.isfinite(ec):
+        pytest.skip("translated beta density hit zero")
+    assert abs(r.scalars["ex"] - ex) <= 1e-13 * max(1, abs(ex)) and abs(r.scalars["ec"] - ec) <= 1e-13 * max(1, abs(ec))
