@@ -40,11 +40,17 @@ enum ordm_status {
   ORDM_ERR_UNSUPPORTED = 5
 };
 
-/* energy.cc:114-120 dispatches on the string "SVWN"; every other string means PBE. */
-enum ordm_functional { ORDM_FUNC_SVWN = 0, ORDM_FUNC_PBE = 1 };
+/* energy.cc:114-120 dispatches on the string "SVWN"; every other string means PBE.  REVPBE, BLYP
+ * and BOP are the Psi4 plugin's further choices (MCPDFT_FUNCTIONAL, src/libpsi4/mcpdft_solver.cc:742-787):
+ * EX_PBE_I(kappa = 1.245) + EC_PBE_I, EX_B88_I + EC_LYP_I, EX_B88_I + EC_B88_OP. */
+enum ordm_functional { ORDM_FUNC_SVWN = 0, ORDM_FUNC_PBE = 1, ORDM_FUNC_REVPBE = 2, ORDM_FUNC_BLYP = 3, ORDM_FUNC_BOP = 4 };
 
-/* The four libfunc entry points (functional.h:17-43). */
-enum ordm_xc_term { ORDM_EX_LSDA = 0, ORDM_EC_VWN3 = 1, ORDM_EX_PBE = 2, ORDM_EC_PBE = 3 };
+/* 0-3: the four libfunc entry points (functional.h:17-43).  4-7: the plugin's routines
+ * (src/libpsi4/lsda_gga_functionals.cc: EX_PBE_I with kappa = 1.245 :317-398, EX_B88_I :207-273,
+ * EC_LYP_I :764-829, EC_B88_OP :478-518 -- the last has no density threshold in the reference and is
+ * NaN wherever a spin density is zero; so it is here). */
+enum ordm_xc_term { ORDM_EX_LSDA = 0, ORDM_EC_VWN3 = 1, ORDM_EX_PBE = 2, ORDM_EC_PBE = 3,
+                    ORDM_EX_REVPBE = 4, ORDM_EX_B88 = 5, ORDM_EC_LYP = 6, ORDM_EC_B88_OP = 7 };
 
 /* Per-point vectors held by the engine = the arma::vec members of mcpdft::MCPDFT
  * (mcpdft.h:216-305) that the path reads or writes. */

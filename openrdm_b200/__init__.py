@@ -18,8 +18,9 @@ from . import build as _build
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libopenrdm_b200.so")
 
-FUNC_SVWN, FUNC_PBE = 0, 1
-EX_LSDA, EC_VWN3, EX_PBE, EC_PBE = 0, 1, 2, 3
+FUNC_SVWN, FUNC_PBE, FUNC_REVPBE, FUNC_BLYP, FUNC_BOP = 0, 1, 2, 3, 4
+FUNC_ID = {"SVWN": 0, "PBE": 1, "REVPBE": 2, "BLYP": 3, "BOP": 4}
+EX_LSDA, EC_VWN3, EX_PBE, EC_PBE, EX_REVPBE, EX_B88, EC_LYP, EC_B88_OP = range(8)
 OPT_DIAGNOSTICS, OPT_PI_GRADIENT, OPT_FULLY_TRANSLATED, OPT_SERIAL_STAGES = 1, 2, 4, 8
 
 VEC_NAMES = [

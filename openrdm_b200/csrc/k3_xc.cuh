@@ -40,10 +40,12 @@ struct Params {
   double* partial;  // [gridDim.x][5] : trN, trNa, trNb, Ex, Ec
 };
 
-// PBE: tPBE (EX_PBE + EC_PBE on translated densities and sigma) else tSVWN.
-// FT:  MCPDFT::fully_translate (mcpdft.cc:418-606) instead of MCPDFT::translate.
-template <bool PBE, bool FT = false>
+// FUNC: 0 tSVWN, 1 tPBE (the two libfunc choices, energy.cc:114-120), 2 trevPBE, 3 tBLYP, 4 tBOP
+//       (the Psi4 plugin's, mcpdft_solver.cc:742-787).  Everything but SVWN consumes sigma.
+// FT:   MCPDFT::fully_translate (mcpdft.cc:418-606) instead of MCPDFT::translate.
+template <int FUNC, bool FT = false>
 __global__ void __launch_bounds__(THREADS) k3_translate_xc(const Params P) {
+  constexpr bool GGA = FUNC != 0;
   __shared__ double scratch[5 * 32];
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS) {
@@ -54,19 +56,28 @@ __global__ void __launch_bounds__(THREADS) k3_translate_xc(const Params P) {
       if (P.pi_out) P.pi_out[p] = pi;
     }
     double gx = 0.0, gy = 0.0, gz = 0.0;
-    if (PBE && P.gx) { gx = __ldg(P.gx + p); gy = __ldg(P.gy + p); gz = __ldg(P.gz + p); }
+    if (GGA && P.gx) { gx = __ldg(P.gx + p); gy = __ldg(P.gy + p); gz = __ldg(P.gz + p); }
     xc::Translated t;
     if (FT) {
       double px = 0.0, py = 0.0, pz = 0.0;
-      if (PBE && P.px) { px = __ldg(P.px + p); py = __ldg(P.py + p); pz = __ldg(P.pz + p); }
-      t = xc::fully_translate_pt<PBE>(rho, pi, gx, gy, gz, px, py, pz);
+      if (GGA && P.px) { px = __ldg(P.px + p); py = __ldg(P.py + p); pz = __ldg(P.pz + p); }
+      t = xc::fully_translate_pt<GGA>(rho, pi, gx, gy, gz, px, py, pz);
     } else {
-      t = xc::translate_pt<PBE>(rho, pi, gx, gy, gz);
+      t = xc::translate_pt<GGA>(rho, pi, gx, gy, gz);
     }
     double ex, ec;
-    if (PBE) {
+    if (FUNC == 1) {
       ex = xc::ex_pbe_pt(t.ra, t.rb, t.saa, t.sbb);
       ec = xc::ec_pbe_pt(t.ra, t.rb, t.saa, t.sab, t.sbb);
+    } else if (FUNC == 2) {
+      ex = xc::ex_pbe_pt(t.ra, t.rb, t.saa, t.sbb, xc::REVPBE_KAPPA);
+      ec = xc::ec_pbe_pt(t.ra, t.rb, t.saa, t.sab, t.sbb);
+    } else if (FUNC == 3) {
+      ex = xc::ex_b88_pt(t.ra, t.rb, t.saa, t.sbb);
+      ec = xc::ec_lyp_pt(t.ra, t.rb, t.saa, t.sab, t.sbb);
+    } else if (FUNC == 4) {
+      ex = xc::ex_b88_pt(t.ra, t.rb, t.saa, t.sbb);
+      ec = xc::ec_b88_op_pt(t.ra, t.rb, t.saa, t.sbb);
     } else {
       ex = xc::ex_lsda_pt(t.ra, t.rb);
       ec = xc::ec_vwn3_pt(t.ra, t.rb);
@@ -79,7 +90,7 @@ __global__ void __launch_bounds__(THREADS) k3_translate_xc(const Params P) {
     if (P.R) P.R[p] = t.R;
     if (P.tra) P.tra[p] = t.ra;
     if (P.trb) P.trb[p] = t.rb;
-    if (PBE) {
+    if (GGA) {
       if (P.tsaa) P.tsaa[p] = t.saa;
       if (P.tsab) P.tsab[p] = t.sab;
       if (P.tsbb) P.tsbb[p] = t.sbb;
@@ -88,7 +99,7 @@ __global__ void __launch_bounds__(THREADS) k3_translate_xc(const Params P) {
   ordm::block_sum_store<5>(acc, scratch, P.partial + (size_t)blockIdx.x * 5);
 }
 
-// libfunc's four entry points on caller-provided vectors (functional.h:17-43):
+// libfunc's four entry points (functional.h:17-43) and the Psi4 plugin's four (ordm_xc_term 4-7) on caller-provided vectors:
 // one weighted sum per call, partial[blockIdx.x] = sum over this block's points.
 struct FuncParams {
   const double* ra;
@@ -111,7 +122,11 @@ __global__ void __launch_bounds__(THREADS) k3_functional(const FuncParams P) {
     if (TERM == 0) e = xc::ex_lsda_pt(ra, rb);
     else if (TERM == 1) e = xc::ec_vwn3_pt(ra, rb);
     else if (TERM == 2) e = xc::ex_pbe_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sbb + p));
-    else e = xc::ec_pbe_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sab + p), __ldg(P.sbb + p));
+    else if (TERM == 3) e = xc::ec_pbe_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sab + p), __ldg(P.sbb + p));
+    else if (TERM == 4) e = xc::ex_pbe_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sbb + p), xc::REVPBE_KAPPA);
+    else if (TERM == 5) e = xc::ex_b88_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sbb + p));
+    else if (TERM == 6) e = xc::ec_lyp_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sab + p), __ldg(P.sbb + p));
+    else e = xc::ec_b88_op_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sbb + p));
     acc[0] = fma(e, __ldg(P.w + p), acc[0]);
   }
   ordm::block_sum_store<1>(acc, scratch, P.partial + blockIdx.x);

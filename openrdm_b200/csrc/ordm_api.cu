@@ -429,18 +429,20 @@ int run_k3(ordm_ctx* c, const GridView& v, int functional, bool ft, int accumula
   p.partial = c->d_partial;
   // energy.cc:114-120: "SVWN" -> LSDA+VWN3, else PBE.  Without orbital gradients the
   // translated sigma are zero vectors (energy.cc:63-65): PBE then runs with gx=gy=gz=0.
-  if (functional == ORDM_FUNC_SVWN) {
-    if (ft) k3::k3_translate_xc<false, true><<<grid, k3::THREADS, 0, c->stream>>>(p);
-    else k3::k3_translate_xc<false, false><<<grid, k3::THREADS, 0, c->stream>>>(p);
-  } else {
+  if (functional != ORDM_FUNC_SVWN) {
     if (!v.gga) { p.gx = p.gy = p.gz = nullptr; }
-    if (ft) {
-      if (v.gga) { p.px = v.vec[ORDM_VEC_PI_X]; p.py = v.vec[ORDM_VEC_PI_Y]; p.pz = v.vec[ORDM_VEC_PI_Z]; }
-      k3::k3_translate_xc<true, true><<<grid, k3::THREADS, 0, c->stream>>>(p);
-    } else {
-      k3::k3_translate_xc<true, false><<<grid, k3::THREADS, 0, c->stream>>>(p);
-    }
+    if (ft && v.gga) { p.px = v.vec[ORDM_VEC_PI_X]; p.py = v.vec[ORDM_VEC_PI_Y]; p.pz = v.vec[ORDM_VEC_PI_Z]; }
   }
+#define K3CASE(F)                                                                           \
+  case F:                                                                                   \
+    if (ft) k3::k3_translate_xc<F, true><<<grid, k3::THREADS, 0, c->stream>>>(p);            \
+    else k3::k3_translate_xc<F, false><<<grid, k3::THREADS, 0, c->stream>>>(p);              \
+    break;
+  switch (functional) {
+    K3CASE(0) K3CASE(1) K3CASE(2) K3CASE(3) K3CASE(4)
+    default: return fail(c, ORDM_ERR_INVALID, "unknown functional id %d", functional);
+  }
+#undef K3CASE
   CU(c, cudaGetLastError());
   ordm::k4_finalize<5><<<1, 256, 0, c->stream>>>(c->d_partial, grid, c->d_res, ordm::RES_TRN, accumulate);
   CU(c, cudaGetLastError());
@@ -976,9 +978,11 @@ int ordm_integrated_densities(ordm_ctx* c, double n[3], double trn[3]) {
 int ordm_functional(ordm_ctx* c, int term, size_t npts, const double* ra, const double* rb, const double* saa,
                     const double* sab, const double* sbb, double* e_out) {
   CHECK_CTX(c);
-  if (term < 0 || term > 3 || !e_out || (npts && (!ra || !rb))) return fail(c, ORDM_ERR_INVALID, "bad functional call");
+  if (term < 0 || term > 7 || !e_out || (npts && (!ra || !rb))) return fail(c, ORDM_ERR_INVALID, "bad functional call");
   if (!c->g.w || c->g.npts != npts) return fail(c, ORDM_ERR_STATE, "functional: set the %zu-point grid first (ordm_set_grid)", npts);
-  if ((term == ORDM_EX_PBE && (!saa || !sbb)) || (term == ORDM_EC_PBE && (!saa || !sab || !sbb)))
+  const bool needs_ss = term == ORDM_EX_PBE || term == ORDM_EX_REVPBE || term == ORDM_EX_B88 || term == ORDM_EC_B88_OP;
+  const bool needs_all = term == ORDM_EC_PBE || term == ORDM_EC_LYP;
+  if ((needs_ss && (!saa || !sbb)) || (needs_all && (!saa || !sab || !sbb)))
     return fail(c, ORDM_ERR_INVALID, "functional: missing sigma vectors");
   CU(c, cudaSetDevice(c->device));
   const size_t bytes = std::max<size_t>(npts, 1) * sizeof(double);
@@ -1000,7 +1004,11 @@ int ordm_functional(ordm_ctx* c, int term, size_t npts, const double* ra, const 
         case 0: k3::k3_functional<0><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
         case 1: k3::k3_functional<1><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
         case 2: k3::k3_functional<2><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
-        default: k3::k3_functional<3><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
+        case 3: k3::k3_functional<3><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
+        case 4: k3::k3_functional<4><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
+        case 5: k3::k3_functional<5><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
+        case 6: k3::k3_functional<6><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
+        default: k3::k3_functional<7><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
       }
       ordm::k4_finalize<1><<<1, 256, 0, c->stream>>>(c->d_partial, grid, c->d_res, 8, 0);
       cudaError_t e = cudaMemcpyAsync(c->h_res, c->d_res + 8, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
@@ -1077,7 +1085,7 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   c->rho_done = c->pi_done = true;
   c->pig_done = want_pig(c, c->g.gga);
   c->xc_done = false;  // R/translated vectors belong to `functional`; staged getters recompute
-  if ((c->g.gga ? ORDM_FUNC_PBE : ORDM_FUNC_SVWN) == functional) { c->xc_done = true; c->xc_ft = ft; }
+  if ((functional != ORDM_FUNC_SVWN) == c->g.gga) { c->xc_done = true; c->xc_ft = ft; }  // R / translated vectors do not depend on which GGA
   return ORDM_OK;
 }
 

@@ -121,22 +121,82 @@ __device__ __forceinline__ double ex_lsda_pt(double ra, double rb) {
 }
 
 // rho_s * eX(2 rho_s) * FX(S(2 rho_s, 4 sigma_ss))   (functional.cc:41-60,89-90)
-__device__ __forceinline__ double pbe_x_spin(double rs_, double sig) {
+// kappa = 0.804 (PBE) or 1.245 (revPBE: the Psi4 plugin's EX_PBE_I, lsda_gga_functionals.cc:323)
+__device__ __forceinline__ double pbe_x_spin(double rs_, double sig, double kappa) {
   const double r2 = 2.0 * rs_;
   const double kF = cbrt(THREE_PI2 * r2);
   const double eX = -(3.0 * kF) / (4.0 * PI);
   // s^2 = 4 sig / (2 kF r2)^2 = sig / (kF r2)^2 ;  FX = 1 + k - k^2 / (k + mu s^2)
   const double d = (kF * r2) * (kF * r2);
-  const double FX = 1.0 + PBE_KAPPA - (PBE_KAPPA * PBE_KAPPA) * d / (PBE_KAPPA * d + PBE_MU * sig);
+  const double FX = 1.0 + kappa - (kappa * kappa) * d / (kappa * d + PBE_MU * sig);
   return rs_ * eX * FX;
 }
 
-__device__ __forceinline__ double ex_pbe_pt(double ra, double rb, double saa, double sbb) {
+__device__ __forceinline__ double ex_pbe_pt(double ra, double rb, double saa, double sbb, double kappa = PBE_KAPPA) {
   const double rho = ra + rb;
-  if (!(rho > TOL)) return 0.0;                              // functional.cc:74,94-96
-  if (ra < TOL) return pbe_x_spin(rb, fmax(0.0, sbb));       // functional.cc:75-81
-  if (rb < TOL) return pbe_x_spin(ra, fmax(0.0, saa));       // functional.cc:82-87
-  return pbe_x_spin(ra, saa) + pbe_x_spin(rb, sbb);          // functional.cc:88-93
+  if (!(rho > TOL)) return 0.0;                                     // functional.cc:74,94-96
+  if (ra < TOL) return pbe_x_spin(rb, fmax(0.0, sbb), kappa);       // functional.cc:75-81
+  if (rb < TOL) return pbe_x_spin(ra, fmax(0.0, saa), kappa);       // functional.cc:82-87
+  return pbe_x_spin(ra, saa, kappa) + pbe_x_spin(rb, sbb, kappa);   // functional.cc:88-93
+}
+
+// ---- the Psi4 plugin's further functionals (src/libpsi4/lsda_gga_functionals.cc) ----
+constexpr double REVPBE_KAPPA = 1.245;                 // lsda_gga_functionals.cc:323
+constexpr double B88_BETA = 0.0042;                    // :212
+constexpr double B88_C = 0.9305257363491001;           // 2^(1/3) * 0.73855876638202240586, :211,213
+
+// -rho_s^(4/3) (c + beta X^2 / (1 + 6 beta X asinh X)),  X = sqrt(sigma_ss) / rho_s^(4/3)
+__device__ __forceinline__ double b88_x_spin(double r, double sig) {
+  const double r43 = r * cbrt(r);
+  const double X = sqrt(sig) / r43;  // the reference reads the UNclamped sigma here (:237,245,253-254)
+  return -r43 * (B88_C + (B88_BETA * (X * X)) / (1.0 + 6.0 * B88_BETA * X * asinh(X)));
+}
+// EX_B88_I, lsda_gga_functionals.cc:207-273
+__device__ __forceinline__ double ex_b88_pt(double ra, double rb, double saa, double sbb) {
+  const double rho = ra + rb;
+  if (!(rho > TOL)) return 0.0;
+  if (ra < TOL) return b88_x_spin(rb, sbb);
+  if (rb < TOL) return b88_x_spin(ra, saa);
+  return b88_x_spin(ra, saa) + b88_x_spin(rb, sbb);
+}
+
+// EC_LYP_I, lsda_gga_functionals.cc:764-829: zero unless both spin densities exceed the threshold
+__device__ __forceinline__ double ec_lyp_pt(double ra, double rb, double saa, double sab, double sbb) {
+  const double rho = ra + rb;
+  if (!(rho > TOL) || ra < TOL || rb < TOL) return 0.0;
+  const double A = 0.04918, B = 0.132, C = 0.2533, Dd = 0.349;
+  const double sigma = saa + sbb + 2.0 * sab;  // from the unclamped values (:787)
+  const double sa = fmax(0.0, saa), sb = fmax(0.0, sbb);
+  const double m13 = rcbrt(rho);               // rho^(-1/3)
+  const double ca = cbrt(ra), cb = cbrt(rb);
+  const double ca2 = ca * ca, cb2 = cb * cb, ca4 = ca2 * ca2, cb4 = cb2 * cb2;
+  const double ra83 = ca4 * ca4, rb83 = cb4 * cb4;
+  const double f = 1.0 / (1.0 + Dd * m13);
+  const double m2 = m13 * m13, m4 = m2 * m2, m8 = m4 * m4;
+  const double omega = exp(-C * m13) * f * (m8 * m2 * m13);  // rho^(-11/3)
+  const double delta = (C + Dd * f) * m13;
+  const double rho2 = rho * rho;
+  return -4.0 * A * ra * rb * f / rho -
+         A * B * omega *
+             (ra * rb *
+                  (36.462398978764777098 * (ra83 + rb83) + (2.6111111111111111111 - 0.38888888888888888889 * delta) * sigma -
+                   (2.5 - 0.055555555555555555556 * delta) * (sa + sb) -
+                   0.11111111111111111111 * (delta - 11.0) * ((ra * sa + rb * sb) / rho)) -
+              0.66666666666666666667 * rho2 * sigma + (0.66666666666666666667 * rho2 - ra * ra) * sb +
+              (0.66666666666666666667 * rho2 - rb * rb) * sa);
+}
+
+// EC_B88_OP, lsda_gga_functionals.cc:478-518.  No density threshold in the reference: 0/0 = NaN
+// where a spin density vanishes, reproduced here.
+__device__ __forceinline__ double b88op_K(double X) {
+  return 1.8610514726982004 + 2.0 * (B88_BETA * (X * X)) / (1.0 + 6.0 * B88_BETA * X * asinh(X));  // 3 (3/4pi)^(1/3) + ...
+}
+__device__ __forceinline__ double ec_b88_op_pt(double ra, double rb, double saa, double sbb) {
+  const double a13 = cbrt(ra), b13 = cbrt(rb);
+  const double Ka = b88op_K(sqrt(saa) / (ra * a13)), Kb = b88op_K(sqrt(sbb) / (rb * b13));
+  const double Bab = 2.3670 * (a13 * b13 * Ka * Kb) / (a13 * Ka + b13 * Kb);
+  const double B2 = Bab * Bab;
+  return -ra * rb * ((1.5214 * Bab + 0.5764) / (B2 * B2 + 1.1284 * (B2 * Bab) + 0.3183 * B2));
 }
 
 // ---------------------------------------------------------------- correlation

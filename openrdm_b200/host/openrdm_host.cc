@@ -209,7 +209,11 @@ double mcpdft_energy(MCPDFT* mc, std::string& functional, const arma::mat&, cons
   if (D2ab.n_rows != n * n) throw std::runtime_error("mcpdft_energy: D2ab must be nbfs^2 x nbfs^2");
   ck(c, ordm_set_rdm2ab_dense(c, (int)n, D2ab.memptr()), "ordm_set_rdm2ab_dense");
   ordm_result r;
-  ck(c, ordm_energy(c, functional == "SVWN" ? ORDM_FUNC_SVWN : ORDM_FUNC_PBE, mc->get_eclass(), &r), "ordm_energy");  // energy.cc:114-120
+  // energy.cc:114-120: "SVWN", else PBE.  Extension: the Psi4 plugin's MCPDFT_FUNCTIONAL names
+  // (mcpdft_solver.cc:742-787) select its functionals instead of silently meaning PBE.
+  const int fid = functional == "SVWN" ? ORDM_FUNC_SVWN : functional == "REVPBE" ? ORDM_FUNC_REVPBE
+                : functional == "BLYP" ? ORDM_FUNC_BLYP : functional == "BOP" ? ORDM_FUNC_BOP : ORDM_FUNC_PBE;
+  ck(c, ordm_energy(c, fid, mc->get_eclass(), &r), "ordm_energy");
   std::printf("\n  Integrated total density = %20.12lf\n  Integrated alpha density = %20.12lf\n  Integrated beta density  = %20.12lf\n", r.n_tot, r.n_a, r.n_b);
   std::printf("\n  Integrated translated total density = %20.12lf\n  Integrated translated alpha density = %20.12lf\n  Integrated translated beta density  = %20.12lf\n\n", r.trn_tot, r.trn_a, r.trn_b);
   std::printf("------------------------------------------\n   Classical energy = %-20.12lf\n   Ex               = %-20.12lf\n   Ec               = %-20.12lf\n------------------------------------------\n\n", r.eclass, r.ex, r.ec);

@@ -315,3 +315,48 @@ def test_ao_to_mo_transform_on_device(engine, port, npts, nao, nmo, gga):
     back = np.zeros((npts, nmo), order="F")
     engine.get_orbitals(back)
     assert np.abs(back - phi).max() <= 1e-13
+
+
+def test_psi4_plugin_functional_terms_on_vectors(engine, port, ordm):
+    """ordm_functional terms 4-7 (EX_PBE_I/revPBE, EX_B88_I, EC_LYP_I, EC_B88_OP of the Psi4 plugin)
+    against the C port, which is pinned to the plugin's compiled code (tests/test_oracle.py)."""
+    rng = np.random.default_rng(23)
+    m = 6000
+    ra = rng.random(m) * 10.0 ** rng.integers(-24, 2, m)
+    rb = rng.random(m) * 10.0 ** rng.integers(-24, 2, m)
+    ra[:50] = 0.0; rb[50:100] = 0.0; ra[100:110] = 0.0; rb[100:110] = 0.0
+    saa, sbb = rng.random(m) * ra ** 2 * 4, rng.random(m) * rb ** 2 * 4
+    sab = np.sqrt(saa * sbb) * rng.uniform(-1, 1, m)
+    w = rng.random(m) / m
+    engine.set_grid(w)
+    for term, name in ((ordm.EX_REVPBE, "EX_REVPBE"), (ordm.EX_B88, "EX_B88"), (ordm.EC_LYP, "EC_LYP")):
+        a, b = engine.functional(term, ra, rb, saa, sab, sbb), port.functional(name, w, ra, rb, saa, sab, sbb)
+        assert np.isfinite(b) and abs(a - b) <= 1e-10, (name, a, b)
+    assert np.isnan(engine.functional(ordm.EC_B88_OP, ra, rb, saa, sab, sbb))  # as the reference: no density threshold
+    pos = (ra > 1e-12) & (rb > 1e-12)
+    engine.set_grid(w[pos])
+    a = engine.functional(ordm.EC_B88_OP, ra[pos], rb[pos], saa[pos], sab[pos], sbb[pos])
+    b = port.functional("EC_B88_OP", w[pos], ra[pos], rb[pos], saa[pos], sab[pos], sbb[pos])
+    assert np.isfinite(b) and abs(a - b) <= 1e-10, (a, b)
+
+
+@pytest.mark.parametrize("fn,ncore", [("REVPBE", 0), ("BLYP", 2), ("BOP", 0), ("BLYP", 0)])
+def test_psi4_plugin_functionals_energy_path(engine, port, ordm, fn, ncore):
+    rng = np.random.default_rng(61 + ncore)
+    nact, npts = 4, 1500
+    phi, grads, w, A1a, A1b, D2 = random_case(rng, nact, npts, "ensemble")
+    if fn == "BOP":  # every point live: B88-OP is NaN on a vanishing spin density
+        phi = np.asfortranarray(np.abs(phi) + 0.05)
+    if ncore:
+        phic = np.asfortranarray(rng.uniform(-0.4, 0.4, (npts, ncore)))
+        gc = [np.asfortranarray(rng.uniform(-0.4, 0.4, (npts, ncore))) for _ in range(3)]
+        phi = np.asfortranarray(np.hstack([phic, phi]))
+        grads = [np.asfortranarray(np.hstack([a, b])) for a, b in zip(gc, grads)]
+    want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, fn, grads, eclass=0.0)
+    if not np.isfinite(want.scalars["ec"]):
+        pytest.skip("reference energy is NaN for this input (B88-OP without density threshold)")
+    engine.set_options(diagnostics=True)
+    engine.set_grid(w); engine.set_orbitals(phi, grads); engine.set_active_space(ncore, A1a, A1b, D2)
+    got = engine.energy(ordm.FUNC_ID[fn], 0.0)
+    check_scalars(got, want.scalars)
+    check_vectors(engine.get_vector, want.vecs, True)
