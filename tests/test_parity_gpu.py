@@ -360,3 +360,40 @@ def test_psi4_plugin_functionals_energy_path(engine, port, ordm, fn, ncore):
     got = engine.energy(ordm.FUNC_ID[fn], 0.0)
     check_scalars(got, want.scalars)
     check_vectors(engine.get_vector, want.vecs, True)
+
+
+@pytest.mark.parametrize("nact,ncore,npts,opts", [
+    (26, 2, 160, {}),                         # config 5's active space: two X buffers just fit (224 KB)
+    (26, 0, 96, {"pi_gradient": True}),       # grad Pi there: single-buffer WS variant (NBUF = 1)
+    (28, 1, 130, {}),                         # beyond the WS kernel: single-buffer k2_ontop<NPG,MT> family
+    (32, 0, 70, {}),                          # largest register-tiled K1 (MAX_ACT) / M = 528
+    (13, 3, 200, {"fully_translated": True}), # odd sizes, ft with core orbitals
+])
+def test_large_active_spaces_vs_oracle(engine, port, ordm, nact, ncore, npts, opts):
+    """Kernel-selection edges (shared-memory limits) against the oracle on small grids: the dense
+    n^4 oracle costs ~0.5-2 ms per point at these sizes."""
+    seed = 500 + nact
+    n = ncore + nact
+    w, phi, grads = ordm.synth_fill_host(seed, npts, 0, npts, n, True)
+    A1a, A1b, D2 = ordm.synth_rdms(seed, nact, nact // 2, nact // 2, 4)
+    ft = bool(opts.get("fully_translated"))
+    port.set_translation(ft)
+    try:
+        want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, "PBE", grads, eclass=0.0,
+                                      with_pi_grad=bool(opts.get("pi_gradient")) or ft)
+    finally:
+        port.set_translation(False)
+    engine.set_options(diagnostics=True, **opts)
+    engine.set_grid(w); engine.set_orbitals(phi, grads); engine.set_active_space(ncore, A1a, A1b, D2)
+    got = engine.energy(FN["PBE"], 0.0)
+    check_scalars(got, want.scalars)
+    if not ft:
+        check_vectors(engine.get_vector, want.vecs, True)
+    else:
+        for k in ("rho", "pi", "pi_x", "pi_y", "pi_z"):
+            a, b = engine.get_vector(k), want.vecs[k]
+            assert (np.abs(a - b) <= 1e-12 * np.maximum(1.0, np.abs(b))).all(), k
+    if opts.get("pi_gradient"):
+        for k in ("pi_x", "pi_y", "pi_z"):
+            a, b = engine.get_vector(k), want.vecs[k]
+            assert (np.abs(a - b) <= 1e-12 * np.maximum(1.0, np.abs(b))).all(), k
