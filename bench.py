@@ -231,6 +231,8 @@ def main():
         dist.broadcast(uid, 0)
         eng.comm_attach(world, rank, bytes(uid.cpu().numpy().tobytes()))
     fid = ordm.FUNC_PBE if gga else ordm.FUNC_SVWN
+    if world > 1:
+        workload["allreduce"] = eng.comm_info()["allreduce"]
 
     def barrier():
         torch.cuda.synchronize()

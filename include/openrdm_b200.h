@@ -220,6 +220,11 @@ int ordm_synth_rdms(uint64_t seed, int nact, int nelec_a, int nelec_b, int ndet,
  * 128 bytes to the other ranks (torch.distributed / MPI / a file), every rank attaches. */
 int ordm_comm_unique_id(char id_out[128]);
 int ordm_comm_attach(ordm_ctx* ctx, int nranks, int rank, const char id[128]);
+/* geometry of the attached communicator; *peer_allreduce = 1 when the eight result scalars are
+ * combined by this library's own NVLink peer-store kernel (exchange buffers of all ranks mapped through
+ * CUDA IPC at attach time, rank-ordered and therefore bitwise identical sums on every rank), 0 when
+ * ncclAllReduce is used (mapping not possible, or ORDM_NO_PEER_ALLREDUCE set).  Pointers may be NULL. */
+int ordm_comm_info(const ordm_ctx* ctx, int* nranks, int* rank, int* peer_allreduce);
 int ordm_comm_detach(ordm_ctx* ctx);
 /* contiguous shard [p0, p0+count) of rank `rank`: balanced in units of 64 points */
 void ordm_shard_range(size_t npts_total, int nranks, int rank, size_t* p0, size_t* count);

@@ -97,6 +97,7 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.ordm_synth_rdms.argtypes = [C.c_uint64, I, I, I, I, D, D, D]
     lib.ordm_comm_unique_id.argtypes = [C.c_char_p]
     lib.ordm_comm_attach.argtypes = [P, I, I, C.c_char_p]
+    lib.ordm_comm_info.argtypes = [P, C.POINTER(I), C.POINTER(I), C.POINTER(I)]
     lib.ordm_shard_range.argtypes = [S, I, I, C.POINTER(S), C.POINTER(S)]
     lib.ordm_shard_range.restype = None
     _lib = lib
@@ -282,6 +283,11 @@ class Engine:
 
     def comm_attach(self, nranks, rank, uid: bytes):
         self._ck(self.lib.ordm_comm_attach(self.ctx, nranks, rank, C.create_string_buffer(uid, 128)))
+
+    def comm_info(self) -> dict:
+        n, r, p = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.ordm_comm_info(self.ctx, C.byref(n), C.byref(r), C.byref(p)))
+        return {"nranks": n.value, "rank": r.value, "allreduce": "nvlink peer stores (own kernel)" if p.value else "ncclAllReduce"}
 
 
 def host_empty(shape, order="F") -> np.ndarray:

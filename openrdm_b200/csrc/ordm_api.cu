@@ -8,6 +8,8 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -50,6 +52,7 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, IdBlob, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -66,6 +69,7 @@ bool load_nccl(std::string& why) {
   g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.handle, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(void**, int, IdBlob, int))dlsym(g_nccl.handle, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.handle, "ncclAllReduce");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.handle, "ncclAllGather");
   g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.handle, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.handle, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
@@ -128,6 +132,7 @@ struct ordm_ctx {
   // RDMs
   int ncore = 0, nact = 0;
   bool have_rdm1 = false, have_rdm2 = false, core_form = false;
+  uint64_t rdm1_version = 0;  // bumped by every install_rdm1 (K1's constant-bank upload is cached on it)
   std::vector<double> h_Dsa, h_Dsb;  // symmetrised, row-major stride k1::MAX_ACT (or nact when generic)
   double *d_Dsa_g = nullptr, *d_Dsb_g = nullptr;
   // K2 operands
@@ -174,6 +179,12 @@ struct ordm_ctx {
   // NCCL
   void* comm = nullptr;
   int nranks = 1, rank = 0;
+  // peer-memory all-reduce of the result scalars (reduce.cuh, k_allreduce_peer); falls back to NCCL
+  bool peer_ok = false;
+  ordm::PeerXchg px{};
+  double* d_xchg = nullptr;
+  int* d_xerr = nullptr;
+  unsigned long long xepoch = 0;
 };
 
 namespace {
@@ -279,8 +290,20 @@ int k3_grid(const ordm_ctx* c, size_t npts) {
 int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaStream_t st = nullptr) {
   if (!st) st = c->stream;
   if (c->nact <= k1::MAX_ACT) {
-    CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsa, c->h_Dsa.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, st));
-    CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsb, c->h_Dsb.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, st));
+    // The __constant__ bank holding Ds is per device and shared by every context of the process
+    // (kernel-parameter space was tried instead: ptxas then LDCs the coefficients into registers,
+    // 254 regs, K1 2.6 -> 3.4 ms).  Upload only when another context, another RDM or another
+    // stream used the bank last; contexts on one device must not run K1 concurrently.
+    static std::mutex mu;
+    static struct { const ordm_ctx* owner; uint64_t version; cudaStream_t stream; } bank[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    auto& b = bank[c->device & 63];
+    if (b.owner != c || b.version != c->rdm1_version || b.stream != st) {
+      if (b.owner && b.stream != st) CU(c, cudaDeviceSynchronize());  // the last user's kernels may still read the bank
+      CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsa, c->h_Dsa.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, st));
+      CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsb, c->h_Dsb.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, st));
+      b.owner = c; b.version = c->rdm1_version; b.stream = st;
+    }
   }
   k1::Params p{};
   p.phi = v.phi; p.phix = v.phix; p.phiy = v.phiy; p.phiz = v.phiz; p.w = v.w;
@@ -534,6 +557,8 @@ int install_rdm1(ordm_ctx* c, int ncore, int nact, const double* A1a, const doub
     CU(c, cudaMemcpy(c->d_Dsb_g, c->h_Dsb.data(), b, cudaMemcpyHostToDevice));
   }
   c->have_rdm1 = true;
+  static std::atomic<uint64_t> next_version{0};
+  c->rdm1_version = ++next_version;
   c->rho_done = c->pi_done = c->xc_done = false;
   return ORDM_OK;
 }
@@ -562,6 +587,89 @@ int fetch_result(ordm_ctx* c, double eclass, ordm_result* out, uint64_t npts, in
   out->npts = npts;
   out->gpu_launches = (uint32_t)launches;
   for (int i = 0; i < 3; ++i) { c->last_n[i] = r[ordm::RES_N + i]; c->last_trn[i] = r[ordm::RES_TRN + i]; }
+  return ORDM_OK;
+}
+
+// all-reduce of d_res over the attached communicator: NVLink peer stores when the exchange buffers
+// could be mapped, NCCL otherwise
+int all_reduce_results(ordm_ctx* c, int* launches) {
+  if (!c->comm) return ORDM_OK;
+  if (c->peer_ok) {
+    ordm::k_allreduce_peer<<<1, 128, 0, c->stream>>>(c->d_res, c->px, ++c->xepoch, c->d_xerr);
+    CU(c, cudaGetLastError());
+  } else {
+    int nr = g_nccl.AllReduce(c->d_res, c->d_res, ordm::RES_COUNT, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream);
+    if (nr != 0) return fail(c, ORDM_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+  }
+  *launches += 1;
+  return ORDM_OK;
+}
+
+void release_peer_xchg(ordm_ctx* c) {
+  if (c->peer_ok)
+    for (int r = 0; r < c->nranks; ++r)
+      if (r != c->rank && c->px.peer[r]) cudaIpcCloseMemHandle(c->px.peer[r]);
+  c->peer_ok = false;
+  c->px = ordm::PeerXchg{};
+  dfree(c->d_xchg);
+  dfree(c->d_xerr);
+}
+
+// exchange CUDA-IPC handles of the per-rank exchange buffers over the fresh NCCL communicator and map
+// every peer's buffer; a failure on any rank just leaves the NCCL path in place on all of them
+int setup_peer_xchg(ordm_ctx* c) {
+  release_peer_xchg(c);
+  if (getenv("ORDM_NO_PEER_ALLREDUCE") || c->nranks < 2 || c->nranks > 16 || !g_nccl.AllGather) return ORDM_OK;
+  const size_t bytes = ordm::peer_xchg_bytes(c->nranks);
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  // the two scratch buffers every rank needs to take part in the collectives below
+  char* d_h = nullptr;
+  int* d_flag = nullptr;
+  CU(c, cudaMalloc(&d_h, sizeof(mine) * (size_t)(c->nranks + 1)));
+  CU(c, cudaMalloc(&d_flag, sizeof(int) * (size_t)(c->nranks + 1)));
+  int ok = cudaMalloc(&c->d_xchg, bytes) == cudaSuccess && cudaMemset(c->d_xchg, 0, bytes) == cudaSuccess &&
+           cudaMalloc(&c->d_xerr, sizeof(int)) == cudaSuccess && cudaMemset(c->d_xerr, 0, sizeof(int)) == cudaSuccess &&
+           cudaIpcGetMemHandle(&mine, c->d_xchg) == cudaSuccess;
+  cudaGetLastError();
+  std::vector<cudaIpcMemHandle_t> all(c->nranks);
+  std::vector<int> flags(c->nranks, 0);
+  auto gather_flag = [&](int v) -> bool {  // all-gather one int per rank into flags[]
+    if (cudaMemcpy(d_flag, &v, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    if (g_nccl.AllGather(d_flag, d_flag + 1, sizeof(int), /*ncclChar*/ 0, c->comm, c->stream) != 0) return false;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
+    return cudaMemcpy(flags.data(), d_flag + 1, sizeof(int) * c->nranks, cudaMemcpyDeviceToHost) == cudaSuccess;
+  };
+  auto all_set = [&]() { for (int r = 0; r < c->nranks; ++r) if (flags[r] != 1) return false; return true; };
+  bool good = gather_flag(ok) && all_set();
+  // handles travel in any case (every rank must issue the same collectives)
+  cudaMemcpy(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+  bool coll = g_nccl.AllGather(d_h, d_h + sizeof(mine), sizeof(mine), 0, c->comm, c->stream) == 0 && cudaStreamSynchronize(c->stream) == cudaSuccess &&
+              cudaMemcpy(all.data(), d_h + sizeof(mine), sizeof(mine) * c->nranks, cudaMemcpyDeviceToHost) == cudaSuccess;
+  int mapped = 0;
+  if (good && coll) {
+    c->px.nranks = c->nranks; c->px.rank = c->rank;
+    c->px.peer[c->rank] = c->d_xchg;
+    mapped = 1;
+    for (int r = 0; r < c->nranks; ++r) {
+      if (r == c->rank) continue;
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mapped = 0; break; }
+      c->px.peer[r] = (double*)p;
+    }
+  }
+  // the fast path is used only if EVERY rank mapped every peer
+  const bool everyone = gather_flag(mapped) && all_set();
+  dfree(d_h);
+  dfree(d_flag);
+  cudaGetLastError();
+  if (everyone) { c->peer_ok = true; c->xepoch = 0; }
+  else {
+    for (int r = 0; r < c->nranks; ++r)
+      if (r != c->rank && c->px.peer[r]) cudaIpcCloseMemHandle(c->px.peer[r]);
+    c->px = ordm::PeerXchg{};
+    release_peer_xchg(c);
+  }
   return ORDM_OK;
 }
 
@@ -668,6 +776,7 @@ void ordm_destroy(ordm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  release_peer_xchg(c);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   if (c->cublas && g_cublas.Destroy) g_cublas.Destroy(c->cublas);
   for (int i = 0; i < ORDM_VEC_COUNT; ++i)
@@ -1062,11 +1171,7 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
     if ((rc = run_k3(c, c->g, functional, ft, 0, &launches))) return rc;
   }
   CU(c, cudaEventRecord(c->ev[3], c->stream));
-  if (c->comm) {
-    int nr = g_nccl.AllReduce(c->d_res, c->d_res, ordm::RES_COUNT, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream);
-    if (nr != 0) return fail(c, ORDM_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
-    launches += 1;
-  }
+  if ((rc = all_reduce_results(c, &launches))) return rc;
   CU(c, cudaEventRecord(c->ev[4], c->stream));
   if ((rc = fetch_result(c, eclass, out, c->g.npts, launches))) return rc;
   float ms;
@@ -1146,13 +1251,10 @@ int ordm_energy_host(ordm_ctx* c, int functional, double eclass, size_t npts, in
     CU(c, cudaEventRecord(s.done, c->stream));
   }
   CU(c, cudaEventRecord(c->ev[3], c->stream));
-  if (c->comm) {
-    int nr = g_nccl.AllReduce(c->d_res, c->d_res, ordm::RES_COUNT, 8, 0, c->comm, c->stream);
-    if (nr != 0) return fail(c, ORDM_ERR_NCCL, "ncclAllReduce failed");
-    launches += 1;
-  }
+  int rc = all_reduce_results(c, &launches);
+  if (rc) return rc;
   CU(c, cudaEventRecord(c->ev[4], c->stream));
-  int rc = fetch_result(c, eclass, out, npts, launches);
+  rc = fetch_result(c, eclass, out, npts, launches);
   if (rc) return rc;
   float ms;
   CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[5])); out->ms_total = ms;
@@ -1264,11 +1366,20 @@ int ordm_comm_attach(ordm_ctx* c, int nranks, int rank, const char id[128]) {
   if (nr != 0) { c->comm = nullptr; return fail(c, ORDM_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?"); }
   c->nranks = nranks;
   c->rank = rank;
+  return setup_peer_xchg(c);  // NVLink peer-store all-reduce when the buffers can be IPC-mapped, else NCCL stays
+}
+
+int ordm_comm_info(const ordm_ctx* c, int* nranks, int* rank, int* peer_allreduce) {
+  if (!c) return fail(nullptr, ORDM_ERR_INVALID, "null context");
+  if (nranks) *nranks = c->nranks;
+  if (rank) *rank = c->rank;
+  if (peer_allreduce) *peer_allreduce = c->peer_ok ? 1 : 0;
   return ORDM_OK;
 }
 
 int ordm_comm_detach(ordm_ctx* c) {
   CHECK_CTX(c);
+  release_peer_xchg(c);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   c->comm = nullptr;
   c->nranks = 1;

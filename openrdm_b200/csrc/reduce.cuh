@@ -60,4 +60,49 @@ __global__ void __launch_bounds__(256) k4_finalize(const double* __restrict__ pa
   }
 }
 
+// ---- C1: all-reduce of the RES_COUNT result scalars across the GPUs of one NVSwitch domain -------
+// An 64-byte payload is pure latency; NCCL needs ~50-65 us for it on 8 ranks.  Here every rank
+// stores its eight doubles straight into each peer's exchange buffer (CUDA-IPC mapped, NVLink
+// stores), releases a per-source flag, waits for the flags of all sources and adds the eight
+// contributions in RANK ORDER -- so the sum is bitwise identical on every rank and independent of
+// arrival order.  One 64-thread block per GPU, one launch.
+//   layout of a rank's exchange buffer:  double vals[2][nranks][RES_COUNT];  uint64 flag[nranks]
+// Double-buffered on the epoch parity: a rank can be at most one all-reduce ahead of the slowest
+// (it needs everybody's flag of epoch e before it can finish e, and starts e+1 only after that).
+struct PeerXchg {
+  double* peer[16];  // exchange buffers of all ranks (own one included), mapped into this process
+  int nranks, rank;
+};
+__host__ __device__ inline size_t peer_xchg_bytes(int nranks) { return sizeof(double) * 2 * nranks * RES_COUNT + sizeof(unsigned long long) * nranks; }
+
+__global__ void __launch_bounds__(128) k_allreduce_peer(double* __restrict__ res, const PeerXchg px, unsigned long long epoch, int* __restrict__ err) {
+  const int t = threadIdx.x, n = px.nranks;
+  const int par = (int)(epoch & 1);
+  if (t < n * RES_COUNT) {  // scatter: my values into slot [par][rank] of every rank's buffer
+    const int r = t / RES_COUNT, k = t % RES_COUNT;
+    px.peer[r][((size_t)par * n + px.rank) * RES_COUNT + k] = res[k];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < n) {
+    unsigned long long* theirs = reinterpret_cast<unsigned long long*>(px.peer[t] + (size_t)2 * n * RES_COUNT) + px.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(px.peer[px.rank] + (size_t)2 * n * RES_COUNT) + t;
+    const long long t0 = clock64();
+    unsigned long long seen = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+      if (seen >= epoch) break;
+    } while (clock64() - t0 < 4000000000ll);  // ~2 s: a rank that never shows up must not hang the GPU
+    if (seen < epoch) *err = 1;
+  }
+  __syncthreads();
+  if (t < RES_COUNT) {
+    const double* v = px.peer[px.rank] + (size_t)par * n * RES_COUNT + t;
+    double s = 0.0;
+    for (int r = 0; r < n; ++r) s += v[(size_t)r * RES_COUNT];
+    res[t] = *err ? (0.0 / 0.0) : s;
+  }
+}
+
 }  // namespace ordm
