@@ -93,3 +93,21 @@ def test_synthetic_rdms_are_n_representable(ordm, nact, ne):
     T = D2.reshape(nact, nact, nact, nact, order="F")  # T[k,i,l,j] = D2[i*n+k, j*n+l]
     assert abs(np.einsum("kiki->", T) - ne * ne) < 1e-10
     assert np.allclose(D2, D2.T, atol=1e-14)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference: OpenRDM's own compiled CPU code on a bounded sample, one JSON line
+    with the contract's keys (no GPU involved)."""
+    import json
+    import sys
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libopenrdm_ref.so")):
+        pytest.skip("oracle/_ref not built")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "3", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample", "512"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "grid points/s" and d["value"] > 0 and d["higher_is_better"] is True
+    for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
