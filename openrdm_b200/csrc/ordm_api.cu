@@ -1146,10 +1146,11 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   // Overlapped mode (default): the tensor-bound K2 is launched first with a trimmed register
   // footprint, and the HBM-bound K1 streams underneath it on a second stream (one K1 CTA stays
   // co-resident per SM); K3 joins both and completes Pi = Pi_act + Pi_core.
-  // (only when a K1 CTA -- 768 B static + the 1 KB per-CTA reserve -- still fits beside K2's shared memory:
-  //  for 26 active orbitals K2 owns the whole SM and K1 would simply queue behind it)
+  // (only when K2 leaves a comfortable part of the SM's shared memory free: with 26 active orbitals K2
+  //  takes 219 KB of the 228 and, although a K1 CTA nominally still fits, it was measured not to
+  //  co-run -- K1 then queues behind the slightly slower lean K2: 93.6 vs 92.7 ms on config 5)
   const bool overlap = !c->serial_stages && !(c->opts & ORDM_OPT_SERIAL_STAGES) && c->k2_ws && !want_pig(c, c->g.gga) &&
-                       c->k2_smem + 8192 <= (size_t)c->max_smem_optin;
+                       c->k2_smem + 32768 <= (size_t)c->max_smem_optin;
   CU(c, cudaEventRecord(c->ev[0], c->stream));
   if (overlap) {
     CU(c, cudaEventRecord(c->ev_fork, c->stream));
