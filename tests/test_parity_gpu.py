@@ -397,3 +397,42 @@ def test_large_active_spaces_vs_oracle(engine, port, ordm, nact, ncore, npts, op
         for k in ("pi_x", "pi_y", "pi_z"):
             a, b = engine.get_vector(k), want.vecs[k]
             assert (np.abs(a - b) <= 1e-12 * np.maximum(1.0, np.abs(b))).all(), k
+
+
+def test_generic_density_path_beyond_32_active_orbitals(engine, port, ordm):
+    """nact > k1::MAX_ACT: k1_density_generic (coefficients from global memory) and the narrow-tile
+    single-buffer K2; M = 595 pairs."""
+    seed, nact, ncore, npts = 91, 34, 1, 48
+    n = ncore + nact
+    w, phi, grads = ordm.synth_fill_host(seed, npts, 0, npts, n, True)
+    A1a, A1b, D2 = ordm.synth_rdms(seed, nact, 17, 16, 3)
+    want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, "PBE", grads, eclass=0.0)
+    engine.set_options(diagnostics=True)
+    engine.set_grid(w); engine.set_orbitals(phi, grads); engine.set_active_space(ncore, A1a, A1b, D2)
+    got = engine.energy(FN["PBE"], 0.0)
+    check_scalars(got, want.scalars)
+    check_vectors(engine.get_vector, want.vecs, True)
+
+
+@pytest.mark.parametrize("opts", [{"pi_gradient": True}, {"fully_translated": True}])
+def test_streamed_host_path_with_grad_pi_and_ft(engine, port, ordm, opts):
+    """ordm_energy_host (point batches streamed from host memory) with grad Pi / the fully-translated
+    scheme: same scalars as the resident path and as the oracle."""
+    seed, npts, ncore, nact = 7, 9000, 2, 5
+    n = ncore + nact
+    w, phi, grads = ordm.synth_fill_host(seed, npts, 0, npts, n, True)
+    A1a, A1b, D2 = ordm.synth_rdms(seed, nact, 3, 2, 4)
+    ft = bool(opts.get("fully_translated"))
+    port.set_translation(ft)
+    try:
+        want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, "PBE", grads, eclass=0.5, with_pi_grad=True, want_vecs=False)
+    finally:
+        port.set_translation(False)
+    engine.set_options(**opts)
+    engine.set_grid(w); engine.set_orbitals(phi, grads); engine.set_active_space(ncore, A1a, A1b, D2)
+    res = engine.energy(FN["PBE"], 0.5)
+    check_scalars(res, want.scalars)
+    for batch in (2048, 0):
+        st = engine.energy_host(FN["PBE"], 0.5, w, phi, grads, batch_points=batch)
+        check_scalars(st, want.scalars)
+        check_scalars(st, res, tol=1e-12)
