@@ -67,11 +67,9 @@ __global__ void __launch_bounds__(THREADS) k3_translate_xc(const Params P) {
     }
     double ex, ec;
     if (FUNC == 1) {
-      ex = xc::ex_pbe_pt(t.ra, t.rb, t.saa, t.sbb);
-      ec = xc::ec_pbe_pt(t.ra, t.rb, t.saa, t.sab, t.sbb);
+      xc::pbe_pair_pt(t.ra, t.rb, t.saa, t.sab, t.sbb, xc::PBE_KAPPA, ex, ec);
     } else if (FUNC == 2) {
-      ex = xc::ex_pbe_pt(t.ra, t.rb, t.saa, t.sbb, xc::REVPBE_KAPPA);
-      ec = xc::ec_pbe_pt(t.ra, t.rb, t.saa, t.sab, t.sbb);
+      xc::pbe_pair_pt(t.ra, t.rb, t.saa, t.sab, t.sbb, xc::REVPBE_KAPPA, ex, ec);
     } else if (FUNC == 3) {
       ex = xc::ex_b88_pt(t.ra, t.rb, t.saa, t.sbb);
       ec = xc::ec_lyp_pt(t.ra, t.rb, t.saa, t.sab, t.sbb);

@@ -269,4 +269,55 @@ __device__ __forceinline__ double ec_pbe_pt(double ra, double rb, double saa, do
   return rho * (H + ec);                                     // functional.cc:301-302
 }
 
+// ---------------------------------------------------------------- fused tPBE / trevPBE point
+// EX_PBE + EC_PBE of one point with the cube roots shared between them (K3's hot case).  With both
+// spin densities above the threshold,  2 rho_a = rho (1 + zeta)  and  2 rho_b = rho (1 - zeta),  so
+//   kF(2 rho_s) = cbrt(3 pi^2 rho) * cbrt(1 +- zeta),    rs = cbrt(9 pi / 4) / cbrt(3 pi^2 rho):
+// three cube roots instead of six and one division fewer; everything else is ex_pbe_pt / ec_pbe_pt
+// term for term.  The single-spin and rho <= tol branches go through those two functions unchanged.
+constexpr double C_RS_KF = 1.9191582926775128;  // cbrt(9 pi / 4) = rs * kF
+
+__device__ __forceinline__ void pbe_pair_pt(double ra, double rb, double saa, double sab, double sbb, double kappa,
+                                            double& ex, double& ec_out) {
+  const double rho = ra + rb;
+  if (!(rho > TOL) || ra < TOL || rb < TOL) {
+    ex = ex_pbe_pt(ra, rb, saa, sbb, kappa);
+    ec_out = ec_pbe_pt(ra, rb, saa, sab, sbb);
+    return;
+  }
+  const double zeta = (ra - rb) / rho;
+  const double k0 = cbrt(THREE_PI2 * rho);
+  const double cu = cbrt(1.0 + zeta), cd = cbrt(1.0 - zeta);
+  // ---- exchange (functional.cc:88-93): rho_s eX(2 rho_s) FX, FX = 1 + k - k^2 d / (k d + mu sigma), d = (kF 2 rho_s)^2
+  {
+    const double ka = k0 * cu, kb = k0 * cd;
+    const double da = (ka * (2.0 * ra)) * (ka * (2.0 * ra)), db = (kb * (2.0 * rb)) * (kb * (2.0 * rb));
+    const double na = kappa * da + PBE_MU * saa, nb = kappa * db + PBE_MU * sbb;
+    const double k2 = kappa * kappa;
+    // both quotients over one division
+    const double inv = 1.0 / (na * nb);
+    const double FXa = 1.0 + kappa - k2 * da * (nb * inv), FXb = 1.0 + kappa - k2 * db * (na * inv);
+    const double c = -3.0 / (4.0 * PI);
+    ex = ra * (c * ka) * FXa + rb * (c * kb) * FXb;
+  }
+  // ---- correlation (functional.cc:296-302; PW92 :243-261, H :210-233,263-271)
+  const double sig = fmax(0.0, saa) + fmax(0.0, sbb) + 2.0 * sab;
+  const double rs = C_RS_KF / k0;
+  const double sr = sqrt(rs);
+  const double mAc = pw92_G(rs, sr, 0.0168869, 0.11125, 10.357, 3.6231, 0.88026, 0.49671);
+  const double eP = pw92_G(rs, sr, 0.0310907, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294);
+  const double eF = pw92_G(rs, sr, 0.01554535, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517);
+  const double fz = spin_f(zeta, cu, cd);
+  const double z2 = zeta * zeta, z4 = z2 * z2;
+  const double ec = eP + ((-mAc) * fz * (1.0 - z4)) / D2FZ + (eF - eP) * fz * z4;
+  const double fi = 0.5 * (cu * cu + cd * cd);
+  const double fi3 = fi * fi * fi;
+  const double ks2 = 4.0 * k0 / PI;
+  const double t2 = sig / (4.0 * ks2 * (fi * fi) * (rho * rho));
+  const double A = (PBE_BETA / PBE_GAMMA) / (exp(-ec / (fi3 * PBE_GAMMA)) - 1.0);
+  const double At2 = A * t2;
+  const double H = fi3 * PBE_GAMMA * log(1.0 + (PBE_BETA / PBE_GAMMA) * t2 * (1.0 + At2) / (1.0 + At2 + At2 * At2));
+  ec_out = rho * (H + ec);
+}
+
 }  // namespace xc
