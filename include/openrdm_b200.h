@@ -43,14 +43,17 @@ enum ordm_status {
 /* energy.cc:114-120 dispatches on the string "SVWN"; every other string means PBE.  REVPBE, BLYP
  * and BOP are the Psi4 plugin's further choices (MCPDFT_FUNCTIONAL, src/libpsi4/mcpdft_solver.cc:742-787):
  * EX_PBE_I(kappa = 1.245) + EC_PBE_I, EX_B88_I + EC_LYP_I, EX_B88_I + EC_B88_OP. */
-enum ordm_functional { ORDM_FUNC_SVWN = 0, ORDM_FUNC_PBE = 1, ORDM_FUNC_REVPBE = 2, ORDM_FUNC_BLYP = 3, ORDM_FUNC_BOP = 4 };
+enum ordm_functional { ORDM_FUNC_SVWN = 0, ORDM_FUNC_PBE = 1, ORDM_FUNC_REVPBE = 2, ORDM_FUNC_BLYP = 3, ORDM_FUNC_BOP = 4,
+                       ORDM_FUNC_WPBE = 5 /* EX_wPBE_I + EC_PBE_I (:747-751), omega from ordm_set_omega */ };
 
 /* 0-3: the four libfunc entry points (functional.h:17-43).  4-7: the plugin's routines
  * (src/libpsi4/lsda_gga_functionals.cc: EX_PBE_I with kappa = 1.245 :317-398, EX_B88_I :207-273,
  * EC_LYP_I :764-829, EC_B88_OP :478-518 -- the last has no density threshold in the reference and is
  * NaN wherever a spin density is zero; so it is here). */
 enum ordm_xc_term { ORDM_EX_LSDA = 0, ORDM_EC_VWN3 = 1, ORDM_EX_PBE = 2, ORDM_EC_PBE = 3,
-                    ORDM_EX_REVPBE = 4, ORDM_EX_B88 = 5, ORDM_EC_LYP = 6, ORDM_EC_B88_OP = 7 };
+                    ORDM_EX_REVPBE = 4, ORDM_EX_B88 = 5, ORDM_EC_LYP = 6, ORDM_EC_B88_OP = 7,
+                    ORDM_EX_WPBE = 8, /* EX_wPBE_I, src/libpsi4/rs_functionals.cc:86-300 (short-range omega-PBE exchange) */
+                    ORDM_EC_PW92 = 9  /* EC_PW92_I, lsda_gga_functionals.cc:997-1093 */ };
 
 /* Per-point vectors held by the engine = the arma::vec members of mcpdft::MCPDFT
  * (mcpdft.h:216-305) that the path reads or writes. */
@@ -106,6 +109,9 @@ const char* ordm_last_error(const ordm_ctx* ctx);
 /* use an existing cudaStream_t (passed as void*) instead of the context's own stream */
 int ordm_set_stream(ordm_ctx* ctx, void* cuda_stream);
 int ordm_set_options(ordm_ctx* ctx, unsigned flags);
+/* MCPDFT_OMEGA of the Psi4 plugin (src/libpsi4/plugin.cc:50, default 0.0): the range-separation parameter
+ * read by EX_wPBE_I (ORDM_FUNC_WPBE, ORDM_EX_WPBE) */
+int ordm_set_omega(ordm_ctx* ctx, double omega);
 int ordm_synchronize(ordm_ctx* ctx);
 
 /* page-locked host memory, so that the H2D copies of set_* / energy_host run at PCIe speed */

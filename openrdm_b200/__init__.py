@@ -18,9 +18,9 @@ from . import build as _build
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libopenrdm_b200.so")
 
-FUNC_SVWN, FUNC_PBE, FUNC_REVPBE, FUNC_BLYP, FUNC_BOP = 0, 1, 2, 3, 4
-FUNC_ID = {"SVWN": 0, "PBE": 1, "REVPBE": 2, "BLYP": 3, "BOP": 4}
-EX_LSDA, EC_VWN3, EX_PBE, EC_PBE, EX_REVPBE, EX_B88, EC_LYP, EC_B88_OP = range(8)
+FUNC_SVWN, FUNC_PBE, FUNC_REVPBE, FUNC_BLYP, FUNC_BOP, FUNC_WPBE = 0, 1, 2, 3, 4, 5
+FUNC_ID = {"SVWN": 0, "PBE": 1, "REVPBE": 2, "BLYP": 3, "BOP": 4, "WPBE": 5}
+EX_LSDA, EC_VWN3, EX_PBE, EC_PBE, EX_REVPBE, EX_B88, EC_LYP, EC_B88_OP, EX_WPBE, EC_PW92 = range(10)
 OPT_DIAGNOSTICS, OPT_PI_GRADIENT, OPT_FULLY_TRANSLATED, OPT_SERIAL_STAGES = 1, 2, 4, 8
 
 VEC_NAMES = [
@@ -73,6 +73,7 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.ordm_set_stream.argtypes = [P, P]
     lib.ordm_set_options.argtypes = [P, C.c_uint]
     lib.ordm_synchronize.argtypes = [P]
+    lib.ordm_set_omega.argtypes = [P, C.c_double]
     lib.ordm_host_alloc.argtypes = [S, C.POINTER(P)]
     lib.ordm_host_free.argtypes = [P]
     lib.ordm_set_grid.argtypes = [P, S, D]
@@ -182,6 +183,9 @@ class Engine:
     def set_options(self, diagnostics=False, pi_gradient=False, fully_translated=False, serial_stages=False):
         self._ck(self.lib.ordm_set_options(self.ctx, (OPT_DIAGNOSTICS if diagnostics else 0) | (OPT_PI_GRADIENT if pi_gradient else 0)
                                            | (OPT_FULLY_TRANSLATED if fully_translated else 0) | (OPT_SERIAL_STAGES if serial_stages else 0)))
+
+    def set_omega(self, omega: float):
+        self._ck(self.lib.ordm_set_omega(self.ctx, float(omega)))
 
     def set_grid(self, w):
         w = _f(w)

@@ -30,6 +30,7 @@ struct Params {
   const double* py;
   const double* pz;
   size_t npts;
+  double omega;      // MCPDFT_OMEGA for FUNC 5 (WPBE)
   // optional diagnostics (null = not written)
   double* R;
   double* tra;
@@ -40,7 +41,7 @@ struct Params {
   double* partial;  // [gridDim.x][5] : trN, trNa, trNb, Ex, Ec
 };
 
-// FUNC: 0 tSVWN, 1 tPBE (the two libfunc choices, energy.cc:114-120), 2 trevPBE, 3 tBLYP, 4 tBOP
+// FUNC: 0 tSVWN, 1 tPBE (the two libfunc choices, energy.cc:114-120), 2 trevPBE, 3 tBLYP, 4 tBOP, 5 twPBE
 //       (the Psi4 plugin's, mcpdft_solver.cc:742-787).  Everything but SVWN consumes sigma.
 // FT:   MCPDFT::fully_translate (mcpdft.cc:418-606) instead of MCPDFT::translate.
 template <int FUNC, bool FT = false>
@@ -76,6 +77,9 @@ __global__ void __launch_bounds__(THREADS) k3_translate_xc(const Params P) {
     } else if (FUNC == 4) {
       ex = xc::ex_b88_pt(t.ra, t.rb, t.saa, t.sbb);
       ec = xc::ec_b88_op_pt(t.ra, t.rb, t.saa, t.sbb);
+    } else if (FUNC == 5) {
+      ex = xc::ex_wpbe_pt(t.ra, t.rb, t.saa, t.sbb, P.omega);
+      ec = xc::ec_pbe_pt(t.ra, t.rb, t.saa, t.sab, t.sbb);
     } else {
       ex = xc::ex_lsda_pt(t.ra, t.rb);
       ec = xc::ec_vwn3_pt(t.ra, t.rb);
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(THREADS) k3_translate_xc(const Params P) {
   ordm::block_sum_store<5>(acc, scratch, P.partial + (size_t)blockIdx.x * 5);
 }
 
-// libfunc's four entry points (functional.h:17-43) and the Psi4 plugin's four (ordm_xc_term 4-7) on caller-provided vectors:
+// libfunc's four entry points (functional.h:17-43) and the Psi4 plugin's four (ordm_xc_term 4-9) on caller-provided vectors:
 // one weighted sum per call, partial[blockIdx.x] = sum over this block's points.
 struct FuncParams {
   const double* ra;
@@ -108,6 +112,7 @@ struct FuncParams {
   const double* w;
   size_t npts;
   double* partial;  // [gridDim.x][1]
+  double omega;     // TERM 8 only
 };
 
 template <int TERM>
@@ -124,7 +129,9 @@ __global__ void __launch_bounds__(THREADS) k3_functional(const FuncParams P) {
     else if (TERM == 4) e = xc::ex_pbe_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sbb + p), xc::REVPBE_KAPPA);
     else if (TERM == 5) e = xc::ex_b88_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sbb + p));
     else if (TERM == 6) e = xc::ec_lyp_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sab + p), __ldg(P.sbb + p));
-    else e = xc::ec_b88_op_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sbb + p));
+    else if (TERM == 7) e = xc::ec_b88_op_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sbb + p));
+    else if (TERM == 8) e = xc::ex_wpbe_pt(ra, rb, __ldg(P.saa + p), __ldg(P.sbb + p), P.omega);
+    else e = xc::ec_pw92_pt(ra, rb);
     acc[0] = fma(e, __ldg(P.w + p), acc[0]);
   }
   ordm::block_sum_store<1>(acc, scratch, P.partial + blockIdx.x);

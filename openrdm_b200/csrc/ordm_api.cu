@@ -118,6 +118,7 @@ struct ordm_ctx {
   bool serial_stages = false;          // ORDM_SERIAL_STAGES=1: K1 -> K2 -> K3 back to back on one stream
   bool own_stream = true;
   unsigned opts = 0;
+  double omega = 0.0;  // MCPDFT_OMEGA
   std::string err;
 
   // resident grid
@@ -442,6 +443,7 @@ int run_k3(ordm_ctx* c, const GridView& v, int functional, bool ft, int accumula
   k3::Params p{};
   p.rho = v.vec[ORDM_VEC_RHO]; p.pi = v.vec[ORDM_VEC_PI]; p.w = v.w;
   if (add_core && c->core_form) { p.pi_core = v.pi_core; p.pi_out = v.vec[ORDM_VEC_PI]; }
+  p.omega = c->omega;
   p.gx = v.gga ? v.gx : nullptr; p.gy = v.gga ? v.gy : nullptr; p.gz = v.gga ? v.gz : nullptr;
   p.npts = v.npts;
   p.R = v.vec[ORDM_VEC_R]; p.tra = v.vec[ORDM_VEC_TR_RHOA]; p.trb = v.vec[ORDM_VEC_TR_RHOB];
@@ -462,7 +464,7 @@ int run_k3(ordm_ctx* c, const GridView& v, int functional, bool ft, int accumula
     else k3::k3_translate_xc<F, false><<<grid, k3::THREADS, 0, c->stream>>>(p);              \
     break;
   switch (functional) {
-    K3CASE(0) K3CASE(1) K3CASE(2) K3CASE(3) K3CASE(4)
+    K3CASE(0) K3CASE(1) K3CASE(2) K3CASE(3) K3CASE(4) K3CASE(5)
     default: return fail(c, ORDM_ERR_INVALID, "unknown functional id %d", functional);
   }
 #undef K3CASE
@@ -826,6 +828,12 @@ int ordm_set_options(ordm_ctx* c, unsigned flags) {
   return ORDM_OK;
 }
 
+int ordm_set_omega(ordm_ctx* c, double omega) {
+  CHECK_CTX(c);
+  c->omega = omega;
+  return ORDM_OK;
+}
+
 int ordm_synchronize(ordm_ctx* c) {
   CHECK_CTX(c);
   CU(c, cudaSetDevice(c->device));
@@ -1087,9 +1095,9 @@ int ordm_integrated_densities(ordm_ctx* c, double n[3], double trn[3]) {
 int ordm_functional(ordm_ctx* c, int term, size_t npts, const double* ra, const double* rb, const double* saa,
                     const double* sab, const double* sbb, double* e_out) {
   CHECK_CTX(c);
-  if (term < 0 || term > 7 || !e_out || (npts && (!ra || !rb))) return fail(c, ORDM_ERR_INVALID, "bad functional call");
+  if (term < 0 || term > 9 || !e_out || (npts && (!ra || !rb))) return fail(c, ORDM_ERR_INVALID, "bad functional call");
   if (!c->g.w || c->g.npts != npts) return fail(c, ORDM_ERR_STATE, "functional: set the %zu-point grid first (ordm_set_grid)", npts);
-  const bool needs_ss = term == ORDM_EX_PBE || term == ORDM_EX_REVPBE || term == ORDM_EX_B88 || term == ORDM_EC_B88_OP;
+  const bool needs_ss = term == ORDM_EX_PBE || term == ORDM_EX_REVPBE || term == ORDM_EX_B88 || term == ORDM_EC_B88_OP || term == ORDM_EX_WPBE;
   const bool needs_all = term == ORDM_EC_PBE || term == ORDM_EC_LYP;
   if ((needs_ss && (!saa || !sbb)) || (needs_all && (!saa || !sab || !sbb)))
     return fail(c, ORDM_ERR_INVALID, "functional: missing sigma vectors");
@@ -1104,7 +1112,7 @@ int ordm_functional(ordm_ctx* c, int term, size_t npts, const double* ra, const 
     if (npts && cudaMemcpyAsync(d[i], h[i], npts * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = fail(c, ORDM_ERR_CUDA, "H2D copy failed");
   }
   if (rc == ORDM_OK) {
-    k3::FuncParams p{d[0], d[1], d[2], d[3], d[4], c->g.w, npts, nullptr};
+    k3::FuncParams p{d[0], d[1], d[2], d[3], d[4], c->g.w, npts, nullptr, c->omega};
     const int grid = k3_grid(c, npts);
     rc = ensure_partials(c, (size_t)c->sm_count * 16 * 8);
     if (rc == ORDM_OK) {
@@ -1117,7 +1125,9 @@ int ordm_functional(ordm_ctx* c, int term, size_t npts, const double* ra, const 
         case 4: k3::k3_functional<4><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
         case 5: k3::k3_functional<5><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
         case 6: k3::k3_functional<6><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
-        default: k3::k3_functional<7><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
+        case 7: k3::k3_functional<7><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
+        case 8: k3::k3_functional<8><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
+        default: k3::k3_functional<9><<<grid, k3::THREADS, 0, c->stream>>>(p); break;
       }
       ordm::k4_finalize<1><<<1, 256, 0, c->stream>>>(c->d_partial, grid, c->d_res, 8, 0);
       cudaError_t e = cudaMemcpyAsync(c->h_res, c->d_res + 8, sizeof(double), cudaMemcpyDeviceToHost, c->stream);

@@ -269,6 +269,61 @@ __device__ __forceinline__ double ec_pbe_pt(double ra, double rb, double saa, do
   return rho * (H + ec);                                     // functional.cc:301-302
 }
 
+// EC_PW92_I, lsda_gga_functionals.cc:997-1093: the LSDA part of ec_pbe_pt (same branches)
+__device__ __forceinline__ double ec_pw92_pt(double ra, double rb) {
+  double rho = ra + rb;
+  if (!(rho > TOL)) return 0.0;
+  double zeta = (ra - rb) / rho;
+  const double rs = cbrt(3.0 / (4.0 * PI * rho));
+  if (ra < TOL) { rho = rb; zeta = 1.0; }
+  else if (rb < TOL) { rho = ra; zeta = 1.0; }
+  const double sr = sqrt(rs);
+  const double mAc = pw92_G(rs, sr, 0.0168869, 0.11125, 10.357, 3.6231, 0.88026, 0.49671);
+  const double eP = pw92_G(rs, sr, 0.0310907, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294);
+  const double eF = pw92_G(rs, sr, 0.01554535, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517);
+  const double fz = spin_f(zeta, cbrt(1.0 + zeta), cbrt(1.0 - zeta));
+  const double z2 = zeta * zeta, z4 = z2 * z2;
+  return rho * (eP + ((-mAc) * fz * (1.0 - z4)) / D2FZ + (eF - eP) * fz * z4);
+}
+
+// EX_wPBE_I, rs_functionals.cc:86-300: short-range omega-PBE exchange (HSE exchange-hole enhancement
+// factor), spin-scaled like EX_PBE_I.  R = 2 rho_s, SG = 4 sigma_ss, omega = MCPDFT_OMEGA.
+__device__ __forceinline__ double wpbe_x_spin(double rs_, double sig, double omega) {
+  const double A_bar = 0.757211, B = -0.106364, C = -0.118649, D = 0.609650, E = -0.0477963;
+  const double R = 2.0 * rs_, SG = 4.0 * sig;
+  const double kF = cbrt(THREE_PI2 * R);
+  const double s1 = sqrt(SG) / (2.0 * kF * R);
+  const double s2 = s1 * s1;
+  // H(s) = (a2 s^2 + ... + a7 s^7) / (1 + b1 s + ... + b9 s^9), rs_functionals.cc:131-149 (Horner)
+  const double Hn = s2 * (0.0159941 + s1 * (0.0852995 + s1 * (-0.160368 + s1 * (0.152645 + s1 * (-0.0971263 + s1 * 0.0422061)))));
+  const double Hd = 1.0 + s1 * (5.33319 + s1 * (-12.4780 + s1 * (11.0988 + s1 * (-5.11013 + s1 * (1.71468 + s1 * (-0.610380 +
+                    s1 * (0.307555 + s1 * (-0.0770547 + s1 * 0.0334840))))))));
+  const double ze = s2 * (Hn / Hd);
+  const double et = A_bar + ze, lam = D + ze;
+  const double nu = omega / kF, nu2 = nu * nu;
+  const double sq_la = sqrt(lam + nu2), sq_ze = sqrt(ze + nu2), sq_et = sqrt(et + nu2);
+  const double chi = nu / sq_la;
+  const double bg = lam / (1.0 - chi);
+  const double Fb = 1.0 - (1.0 / (27.0 * C)) * (s2 / (1.0 + 0.25 * s2)) - (1.0 / (2.0 * C)) * ze;
+  const double lam2 = lam * lam, lam3 = lam2 * lam, lam72 = lam3 * sqrt(lam);
+  const double Gb = (-(2.0 / 5.0) * C * Fb * lam - (4.0 / 15.0) * B * lam2 - (6.0 / 5.0) * A_bar * lam3 -
+                     (4.0 / 5.0) * 1.7724538509055160273 * lam72 - (12.0 / 5.0) * lam72 * (sqrt(ze) - sqrt(et))) * (1.0 / E);
+  const double bg2 = bg * bg, bg3 = bg2 * bg;
+  const double FX = A_bar * (ze / ((sq_ze + sq_et) * (sq_ze + nu)) + et / ((sq_ze + sq_et) * (sq_et + nu))) -
+                    (4.0 / 9.0) * (B / bg) - (4.0 / 9.0) * (C * Fb / bg2) * (1.0 + 0.5 * chi) -
+                    (8.0 / 9.0) * (E * Gb / bg3) * (1.0 + (9.0 / 8.0) * chi + (3.0 / 8.0) * (chi * chi)) +
+                    2.0 * ze * log(1.0 - (lam - ze) / ((nu + sq_la) * (sq_la + sq_ze))) -
+                    2.0 * et * log(1.0 - (lam - et) / ((nu + sq_la) * (sq_la + sq_et)));
+  return rs_ * (-(3.0 * kF) / (4.0 * PI)) * FX;
+}
+__device__ __forceinline__ double ex_wpbe_pt(double ra, double rb, double saa, double sbb, double omega) {
+  const double rho = ra + rb;
+  if (!(rho > TOL)) return 0.0;
+  if (ra < TOL) return wpbe_x_spin(rb, fmax(0.0, sbb), omega);
+  if (rb < TOL) return wpbe_x_spin(ra, fmax(0.0, saa), omega);
+  return wpbe_x_spin(ra, saa, omega) + wpbe_x_spin(rb, sbb, omega);
+}
+
 // ---------------------------------------------------------------- fused tPBE / trevPBE point
 // EX_PBE + EC_PBE of one point with the cube roots shared between them (K3's hot case).  With both
 // spin densities above the threshold,  2 rho_a = rho (1 + zeta)  and  2 rho_b = rho (1 - zeta),  so

@@ -212,7 +212,8 @@ double mcpdft_energy(MCPDFT* mc, std::string& functional, const arma::mat&, cons
   // energy.cc:114-120: "SVWN", else PBE.  Extension: the Psi4 plugin's MCPDFT_FUNCTIONAL names
   // (mcpdft_solver.cc:742-787) select its functionals instead of silently meaning PBE.
   const int fid = functional == "SVWN" ? ORDM_FUNC_SVWN : functional == "REVPBE" ? ORDM_FUNC_REVPBE
-                : functional == "BLYP" ? ORDM_FUNC_BLYP : functional == "BOP" ? ORDM_FUNC_BOP : ORDM_FUNC_PBE;
+                : functional == "BLYP" ? ORDM_FUNC_BLYP : functional == "BOP" ? ORDM_FUNC_BOP
+                : functional == "WPBE" ? ORDM_FUNC_WPBE : ORDM_FUNC_PBE;  // WPBE: omega via ordm_set_omega(mc->context(), w)
   ck(c, ordm_energy(c, fid, mc->get_eclass(), &r), "ordm_energy");
   std::printf("\n  Integrated total density = %20.12lf\n  Integrated alpha density = %20.12lf\n  Integrated beta density  = %20.12lf\n", r.n_tot, r.n_a, r.n_b);
   std::printf("\n  Integrated translated total density = %20.12lf\n  Integrated translated alpha density = %20.12lf\n  Integrated translated beta density  = %20.12lf\n\n", r.trn_tot, r.trn_a, r.trn_b);

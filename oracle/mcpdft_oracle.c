@@ -42,6 +42,9 @@ typedef struct {
 /* 0 = MCPDFT::translate (what mcpdft_energy calls), 1 = MCPDFT::fully_translate */
 static int g_fully_translated = 0;
 void orc_set_translation(int fully) { g_fully_translated = fully; }
+/* MCPDFT_OMEGA of the Psi4 plugin (plugin.cc:50), used by functional id 5 (WPBE) */
+static double g_omega = 0.0;
+void orc_set_omega(double omega) { g_omega = omega; }
 
 /* order of the optional per-point output vectors (orc_energy*'s `vecs` argument) */
 enum {
@@ -550,6 +553,88 @@ double orc_ec_lyp(size_t npts, const double* ra, const double* rb, const double*
   return e;
 }
 
+/* EC_PW92_I, lsda_gga_functionals.cc:997-1093: the LSDA part of EC_PBE (same G, same branches; rs and
+ * zeta from the un-swapped densities, :1065-1066). */
+static double pw92i_G(double r, double T, double a1, double b1, double b2, double b3, double b4, double p) {
+  return -2.0 * T * (1.0 + a1 * r) * log(1.0 + 0.5 * pow(T * (b1 * sqrt(r) + b2 * r + b3 * pow(r, 3.0 / 2.0) + b4 * pow(r, p + 1.0)), -1.0));
+}
+double orc_ec_pw92(size_t npts, const double* ra, const double* rb, const double* w) {
+  const double d2Fz = 1.7099209341613656173;
+  double e = 0.0;
+  for (size_t p = 0; p < npts; ++p) {
+    const double rhoa = ra[p], rhob = rb[p];
+    double rho = rhoa + rhob;
+    double zeta = (rhoa - rhob) / rho;
+    const double rs = pow(3.0 / (4.0 * M_PI * rho), 1.0 / 3.0);
+    if (rho > ORC_TOL) {
+      if (rhoa < ORC_TOL) { rho = rhob; zeta = 1.0; }
+      else if (rhob < ORC_TOL) { rho = rhoa; zeta = 1.0; }
+      const double Fz = (pow(1.0 + zeta, 4.0 / 3.0) + pow(1.0 - zeta, 4.0 / 3.0) - 2.0) / (2.0 * pow(2.0, 1.0 / 3.0) - 2.0);
+      const double Ac = -pw92i_G(rs, 0.0168869, 0.11125, 10.357, 3.6231, 0.88026, 0.49671, 1.0);
+      const double EcP = pw92i_G(rs, 0.0310907, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294, 1.0);
+      const double EcF = pw92i_G(rs, 0.01554535, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517, 1.0);
+      const double zk = EcP + (Ac * Fz * (1.0 - pow(zeta, 4.0))) / d2Fz + (EcF - EcP) * Fz * pow(zeta, 4.0);
+      e += rho * zk * w[p];
+    }
+  }
+  return e;
+}
+
+/* EX_wPBE_I, rs_functionals.cc:86-300: short-range omega-PBE exchange enhancement factor (the HSE
+ * exchange-hole form), spin-scaled like EX_PBE_I.  RHO = 2 rho_s, SIGMA = 4 sigma_ss. */
+static double wpbe_FX(double RHO, double SIGMA, double OMEGA) {
+  const double A_bar = 0.757211, B = -0.106364, C = -0.118649, D = 0.609650, E = -0.0477963;
+  const double a2 = 0.0159941, a3 = 0.0852995, a4 = -0.160368, a5 = 0.152645, a6 = -0.0971263, a7 = 0.0422061;
+  const double b1 = 5.33319, b2 = -12.4780, b3 = 11.0988, b4 = -5.11013, b5 = 1.71468, b6 = -0.610380, b7 = 0.307555,
+               b8 = -0.0770547, b9 = 0.0334840;
+  const double kF = pow(3.0 * M_PI * M_PI * RHO, 1.0 / 3.0);
+  const double s1 = sqrt(SIGMA) / (2.0 * kF * RHO); /* S, :125-129 */
+  const double s2 = s1 * s1, s3 = s2 * s1, s4 = s3 * s1, s5 = s4 * s1, s6 = s5 * s1, s7 = s6 * s1, s8 = s7 * s1, s9 = s8 * s1;
+  const double Hn = a2 * s2 + a3 * s3 + a4 * s4 + a5 * s5 + a6 * s6 + a7 * s7; /* H, :131-149 */
+  const double Hd = 1.0 + b1 * s1 + b2 * s2 + b3 * s3 + b4 * s4 + b5 * s5 + b6 * s6 + b7 * s7 + b8 * s8 + b9 * s9;
+  const double ze_v = pow(s1, 2.0) * (Hn / Hd);          /* ZETA, :157-162 */
+  const double et_v = A_bar + ze_v, lam_v = D + ze_v;    /* ETA, LAMBDA, :164-176 */
+  const double nu_v = OMEGA / kF;                        /* Nu, :151-155 */
+  const double chi_v = nu_v / sqrt(lam_v + pow(nu_v, 2.0)); /* Chi, :178-182 */
+  const double bg = lam_v / (1.0 - chi_v);               /* BG_LAMBDA, :184-189 */
+  const double Fb = 1.0 - (1.0 / (27.0 * C)) * (s2 / (1.0 + (s2 / pow(2.0, 2.0)))) - (1.0 / (2.0 * C)) * ze_v; /* F_bar, :191-202 */
+  const double lam_v2 = lam_v * lam_v, lam_v3 = lam_v2 * lam_v, lam_v72 = pow(lam_v, 7.0 / 2.0);
+  double Gb = -(2.0 / 5.0) * C * Fb * lam_v - (4.0 / 15.0) * B * lam_v2 - (6.0 / 5.0) * A_bar * lam_v3 -
+              (4.0 / 5.0) * sqrt(M_PI) * lam_v72 - (12.0 / 5.0) * lam_v72 * (sqrt(ze_v) - sqrt(et_v)); /* G_bar, :204-223 */
+  Gb *= (1.0 / E);
+  const double chi_v2 = chi_v * chi_v;
+  const double bg2 = bg * bg, bg3 = bg2 * bg;
+  const double sq_ze_nu = sqrt(ze_v + nu_v * nu_v), sq_et_nu = sqrt(et_v + nu_v * nu_v), sq_la_nu = sqrt(lam_v + nu_v * nu_v);
+  return A_bar * (ze_v / ((sq_ze_nu + sq_et_nu) * (sq_ze_nu + nu_v)) + et_v / ((sq_ze_nu + sq_et_nu) * (sq_et_nu + nu_v))) -
+         (4.0 / 9.0) * (B / bg) - (4.0 / 9.0) * (C * Fb / bg2) * (1.0 + (1.0 / 2.0) * chi_v) -
+         (8.0 / 9.0) * (E * Gb / bg3) * (1.0 + (9.0 / 8.0) * chi_v + (3.0 / 8.0) * chi_v2) +
+         2.0 * ze_v * log(1.0 - (lam_v - ze_v) / ((nu_v + sq_la_nu) * (sq_la_nu + sq_ze_nu))) -
+         2.0 * et_v * log(1.0 - (lam_v - et_v) / ((nu_v + sq_la_nu) * (sq_la_nu + sq_et_nu))); /* FX, :231-259 */
+}
+double orc_ex_wpbe(size_t npts, const double* ra, const double* rb, const double* saa, const double* sbb, const double* w, double omega) {
+  double e = 0.0;
+  for (size_t p = 0; p < npts; ++p) {
+    const double a = ra[p], b = rb[p];
+    double rho = a + b;
+    if (rho > ORC_TOL) {
+      if (a < ORC_TOL) {
+        rho = b;
+        const double sg = fmax(0.0, sbb[p]);
+        e += rho * (pbe_eX(2.0 * rho) * wpbe_FX(2.0 * rho, 4.0 * sg, omega)) * w[p];
+      } else if (b < ORC_TOL) {
+        rho = a;
+        const double sg = fmax(0.0, saa[p]);
+        e += rho * (pbe_eX(2.0 * rho) * wpbe_FX(2.0 * rho, 4.0 * sg, omega)) * w[p];
+      } else {
+        const double za = a * pbe_eX(2.0 * a) * wpbe_FX(2.0 * a, 4.0 * saa[p], omega);
+        const double zb = b * pbe_eX(2.0 * b) * wpbe_FX(2.0 * b, 4.0 * sbb[p], omega);
+        e += (za + zb) * w[p];
+      }
+    }
+  }
+  return e;
+}
+
 /* EC_B88_OP, lsda_gga_functionals.cc:478-518: no density threshold at all -- a point with
  * rho_a = 0 or rho_b = 0 gives 0/0 = NaN in the reference, and so it does here. */
 static double b88op_K(double X, double X2) {
@@ -602,7 +687,7 @@ static void orc_finish(size_t npts, int is_gga, int functional_is_svwn, const do
   } /* without gradients tr_sigma stay zero (energy.cc:63-65) */
   double ex, ec;
   /* `functional_is_svwn` doubles as the functional id: 1 SVWN, 0 PBE (energy.cc:114-120), and the
-   * Psi4 plugin's extra choices (mcpdft_solver.cc:742-787): 2 REVPBE, 3 BLYP, 4 BOP */
+   * Psi4 plugin's extra choices (mcpdft_solver.cc:742-787): 2 REVPBE, 3 BLYP, 4 BOP, 5 WPBE */
   double *tra = v[ORC_TR_RHOA], *trb = v[ORC_TR_RHOB], *taa = v[ORC_TR_SIGMA_AA], *tab = v[ORC_TR_SIGMA_AB], *tbb = v[ORC_TR_SIGMA_BB];
   switch (functional_is_svwn) {
     case 1:
@@ -620,6 +705,10 @@ static void orc_finish(size_t npts, int is_gga, int functional_is_svwn, const do
     case 4:
       ex = orc_ex_b88(npts, tra, trb, taa, tbb, w);
       ec = orc_ec_b88_op(npts, tra, trb, taa, tbb, w);
+      break;
+    case 5: /* WPBE: EX_wPBE_I + EC_PBE_I, mcpdft_solver.cc:747-751 */
+      ex = orc_ex_wpbe(npts, tra, trb, taa, tbb, w, g_omega);
+      ec = orc_ec_pbe(npts, tra, trb, taa, tab, tbb, w);
       break;
     default:
       ex = orc_ex_pbe(npts, tra, trb, taa, tbb, w);

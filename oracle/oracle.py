@@ -24,7 +24,7 @@ REF_SO = os.path.join(HERE, "_ref", "libopenrdm_ref.so")
 REF_PSI4_SO = os.path.join(HERE, "_ref", "libopenrdm_ref_psi4.so")
 # functional ids of the C port's drivers: 1 SVWN, 0 PBE (energy.cc:114-120: anything but "SVWN" is PBE),
 # plus the Psi4 plugin's REVPBE / BLYP / BOP (mcpdft_solver.cc:742-787)
-FUNC_ID = {"SVWN": 1, "PBE": 0, "REVPBE": 2, "BLYP": 3, "BOP": 4}
+FUNC_ID = {"SVWN": 1, "PBE": 0, "REVPBE": 2, "BLYP": 3, "BOP": 4, "WPBE": 5}
 
 VEC_NAMES = [
     "rhoa", "rhob", "rho",
@@ -102,7 +102,7 @@ class Port:
         self.lib.orc_ec_vwn3.restype = C.c_double
         self.lib.orc_ex_pbe.restype = C.c_double
         self.lib.orc_ec_pbe.restype = C.c_double
-        for f in ("orc_ex_pbe_kappa", "orc_ex_b88", "orc_ec_lyp", "orc_ec_b88_op"):
+        for f in ("orc_ex_pbe_kappa", "orc_ex_b88", "orc_ec_lyp", "orc_ec_b88_op", "orc_ex_wpbe", "orc_ec_pw92"):
             getattr(self.lib, f).restype = C.c_double
 
     def energy(self, w, phi, D1a, D1b, D2ab, functional="SVWN", grads=None, eclass=0.0,
@@ -159,7 +159,18 @@ class Port:
             return self.lib.orc_ec_lyp(n, _ptr(ra), _ptr(rb), _ptr(saa), _ptr(sab), _ptr(sbb), _ptr(w))
         if which == "EC_B88_OP":
             return self.lib.orc_ec_b88_op(n, _ptr(ra), _ptr(rb), _ptr(saa), _ptr(sbb), _ptr(w))
+        if which == "EC_PW92":
+            return self.lib.orc_ec_pw92(n, _ptr(ra), _ptr(rb), _ptr(w))
+        if which == "EX_WPBE":
+            return self.lib.orc_ex_wpbe(n, _ptr(ra), _ptr(rb), _ptr(saa), _ptr(sbb), _ptr(w), C.c_double(self.omega))
         raise ValueError(which)
+
+    omega = 0.0
+
+    def set_omega(self, omega: float):
+        """MCPDFT_OMEGA (plugin.cc:50): range-separation parameter of EX_wPBE_I / functional "WPBE"."""
+        self.omega = float(omega)
+        self.lib.orc_set_omega(C.c_double(omega))
 
     def kron_tpdm(self, D1a, D1b):
         D1a, D1b = _f64(D1a), _f64(D1b)
@@ -181,7 +192,11 @@ class RefPsi4:
     """The Psi4 plugin's own functional routines (src/libpsi4/lsda_gga_functionals.cc, compiled
     unmodified against stand-in Psi4 headers: oracle/shim_psi4, oracle/ref_psi4_harness.cc)."""
 
-    ID = {"EX_LSDA": 0, "EC_VWN3": 1, "EX_PBE_I": 2, "EC_PBE_I": 3, "EX_REVPBE": 4, "EX_B88": 5, "EC_LYP": 6, "EC_B88_OP": 7}
+    ID = {"EX_LSDA": 0, "EC_VWN3": 1, "EX_PBE_I": 2, "EC_PBE_I": 3, "EX_REVPBE": 4, "EX_B88": 5, "EC_LYP": 6, "EC_B88_OP": 7,
+          "EX_WPBE": 8, "EC_PW92": 9}
+
+    def set_omega(self, omega: float):
+        self.lib.ref_psi4_set_omega(C.c_double(omega))
 
     def __init__(self):
         if not have_ref_psi4():

@@ -188,9 +188,14 @@ def test_psi4_plugin_functionals_port_vs_compiled_reference(port, ref_psi4):
     (src/libpsi4/lsda_gga_functionals.cc, compiled unmodified) against the C restatement, including
     the single-spin and rho <= tol branches; and the plugin's PBE pair against libfunc's."""
     w, ra, rb, saa, sab, sbb = _functional_inputs()
-    for term in ("EX_PBE_I", "EX_REVPBE", "EX_B88", "EC_LYP"):
+    for term in ("EX_PBE_I", "EX_REVPBE", "EX_B88", "EC_LYP", "EC_PW92"):
         a, b = port.functional(term, w, ra, rb, saa, sab, sbb), ref_psi4.functional(term, w, ra, rb, saa, sab, sbb)
         assert np.isfinite(b) and abs(a - b) <= 1e-13 * max(1, abs(b)), (term, a, b)
+    for omega in (0.0, 0.33, 1.1):  # EX_wPBE_I reads MCPDFT_OMEGA (rs_functionals.cc:89)
+        port.set_omega(omega); ref_psi4.set_omega(omega)
+        a, b = port.functional("EX_WPBE", w, ra, rb, saa, sab, sbb), ref_psi4.functional("EX_WPBE", w, ra, rb, saa, sab, sbb)
+        assert np.isfinite(b) and abs(a - b) <= 1e-13 * max(1, abs(b)), (omega, a, b)
+    port.set_omega(0.0); ref_psi4.set_omega(0.0)
     # the plugin's PBE exchange / correlation are the libfunc ones
     assert abs(port.functional("EX_PBE", w, ra, rb, saa, sab, sbb) - ref_psi4.functional("EX_PBE_I", w, ra, rb, saa, sab, sbb)) <= 1e-13
     assert abs(port.functional("EC_PBE", w, ra, rb, saa, sab, sbb) - ref_psi4.functional("EC_PBE_I", w, ra, rb, saa, sab, sbb)) <= 1e-13

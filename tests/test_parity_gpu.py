@@ -329,9 +329,14 @@ def test_psi4_plugin_functional_terms_on_vectors(engine, port, ordm):
     sab = np.sqrt(saa * sbb) * rng.uniform(-1, 1, m)
     w = rng.random(m) / m
     engine.set_grid(w)
-    for term, name in ((ordm.EX_REVPBE, "EX_REVPBE"), (ordm.EX_B88, "EX_B88"), (ordm.EC_LYP, "EC_LYP")):
+    for term, name in ((ordm.EX_REVPBE, "EX_REVPBE"), (ordm.EX_B88, "EX_B88"), (ordm.EC_LYP, "EC_LYP"), (ordm.EC_PW92, "EC_PW92")):
         a, b = engine.functional(term, ra, rb, saa, sab, sbb), port.functional(name, w, ra, rb, saa, sab, sbb)
         assert np.isfinite(b) and abs(a - b) <= 1e-10, (name, a, b)
+    for omega in (0.0, 0.4):
+        engine.set_omega(omega); port.set_omega(omega)
+        a, b = engine.functional(ordm.EX_WPBE, ra, rb, saa, sab, sbb), port.functional("EX_WPBE", w, ra, rb, saa, sab, sbb)
+        assert np.isfinite(b) and abs(a - b) <= 1e-10, (omega, a, b)
+    port.set_omega(0.0)
     assert np.isnan(engine.functional(ordm.EC_B88_OP, ra, rb, saa, sab, sbb))  # as the reference: no density threshold
     pos = (ra > 1e-12) & (rb > 1e-12)
     engine.set_grid(w[pos])
@@ -340,7 +345,7 @@ def test_psi4_plugin_functional_terms_on_vectors(engine, port, ordm):
     assert np.isfinite(b) and abs(a - b) <= 1e-10, (a, b)
 
 
-@pytest.mark.parametrize("fn,ncore", [("REVPBE", 0), ("BLYP", 2), ("BOP", 0), ("BLYP", 0)])
+@pytest.mark.parametrize("fn,ncore", [("REVPBE", 0), ("BLYP", 2), ("BOP", 0), ("BLYP", 0), ("WPBE", 1)])
 def test_psi4_plugin_functionals_energy_path(engine, port, ordm, fn, ncore):
     rng = np.random.default_rng(61 + ncore)
     nact, npts = 4, 1500
@@ -352,10 +357,15 @@ def test_psi4_plugin_functionals_energy_path(engine, port, ordm, fn, ncore):
         gc = [np.asfortranarray(rng.uniform(-0.4, 0.4, (npts, ncore))) for _ in range(3)]
         phi = np.asfortranarray(np.hstack([phic, phi]))
         grads = [np.asfortranarray(np.hstack([a, b])) for a, b in zip(gc, grads)]
-    want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, fn, grads, eclass=0.0)
+    port.set_omega(0.33 if fn == "WPBE" else 0.0)
+    try:
+        want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, fn, grads, eclass=0.0)
+    finally:
+        port.set_omega(0.0)
     if not np.isfinite(want.scalars["ec"]):
         pytest.skip("reference energy is NaN for this input (B88-OP without density threshold)")
     engine.set_options(diagnostics=True)
+    engine.set_omega(0.33 if fn == "WPBE" else 0.0)
     engine.set_grid(w); engine.set_orbitals(phi, grads); engine.set_active_space(ncore, A1a, A1b, D2)
     got = engine.energy(ordm.FUNC_ID[fn], 0.0)
     check_scalars(got, want.scalars)
