@@ -78,6 +78,34 @@ __global__ void __launch_bounds__(128, MINB) core_fma_light(const k1::Params P) 
   }
 }
 
+// core stream with UNR x 4 INDEPENDENT accumulators: every loaded value feeds its own FMA chain, so a
+// warp that wins the FP64 pipe can issue 4*UNR DFMAs back to back before it stalls on a dependency
+template <int UNR, int MINB>
+__global__ void __launch_bounds__(128, MINB) core_fma_ilp(const k1::Params P) {
+  const size_t ld = P.ld;
+  for (size_t p = (size_t)blockIdx.x * 128 + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * 128) {
+    double rc[UNR], cx[UNR], cy[UNR], cz[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) rc[j] = cx[j] = cy[j] = cz[j] = 0.0;
+    const int n = P.ncore + P.nact;
+    int i = 0;
+    for (; i + UNR <= n; i += UNR) {
+      double v[UNR][4];
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+        const size_t o = (size_t)(i + j) * ld + p;
+        v[j][0] = __ldcs(P.phi + o); v[j][1] = __ldcs(P.phix + o); v[j][2] = __ldcs(P.phiy + o); v[j][3] = __ldcs(P.phiz + o);
+      }
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) { rc[j] = fma(v[j][0], v[j][0], rc[j]); cx[j] = fma(v[j][0], v[j][1], cx[j]); cy[j] = fma(v[j][0], v[j][2], cy[j]); cz[j] = fma(v[j][0], v[j][3], cz[j]); }
+    }
+    double a = 0, b = 0, c = 0, d = 0;
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) { a += rc[j]; b += cx[j]; c += cy[j]; d += cz[j]; }
+    P.rho[p] = a; P.gx[p] = b; P.gy[p] = c; P.gz[p] = d;
+  }
+}
+
 int main(int argc, char** argv) {
   const int ncore = 83, nact = 20, n = ncore + nact;
   size_t npts = argc > 1 ? atol(argv[1]) : 5000000;
@@ -129,6 +157,8 @@ int main(int argc, char** argv) {
       case 6: core_fma_light<2, 12><<<g1, 128, 0, s>>>(p1); break;   // <= 40 regs: 3 CTAs next to K2
       case 7: core_fma_light<1, 16><<<g1, 128, 0, s>>>(p1); break;   // <= 32 regs: 4 CTAs next to K2
       case 8: core_fma_light<2, 8><<<g1, 128, 0, s>>>(p1); break;    // <= 64 regs: 2 CTAs next to K2
+      case 9: core_fma_ilp<4, 4><<<g1, 128, 0, s>>>(p1); break;      // 16 independent chains
+      case 10: core_fma_ilp<8, 4><<<g1, 128, 0, s>>>(p1); break;     // 32 independent chains
     }
   };
   // a K1 launched BEFORE K2 must leave the SM's shared-memory carve-out large enough for K2's 147 KB
@@ -138,8 +168,8 @@ int main(int argc, char** argv) {
   CK(cudaFuncSetAttribute(stream_only<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CK(cudaFuncSetAttribute(core_fma<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CK(cudaFuncSetAttribute(core_fma<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  const char* names[] = {"k1_density<20,gga>", "stream_only<4>", "stream_only<8>", "core_fma<4>", "core_fma<8>", "stream_only<16>", "core_fma_light<2,12>", "core_fma_light<1,16>", "core_fma_light<2,8>"};
-  for (int variant = (argc > 4 ? atoi(argv[4]) : 0); variant < 9; ++variant) {
+  const char* names[] = {"k1_density<20,gga>", "stream_only<4>", "stream_only<8>", "core_fma<4>", "core_fma<8>", "stream_only<16>", "core_fma_light<2,12>", "core_fma_light<1,16>", "core_fma_light<2,8>", "core_fma_ilp<4>", "core_fma_ilp<8>"};
+  for (int variant = (argc > 4 ? atoi(argv[4]) : 0); variant < 11; ++variant) {
     float alone = 0, tk2 = 0, tk1 = 0, span = 0;
     for (int r = 0; r < 3; ++r) { cudaEventRecord(b0, sb); launch_k1(variant, sb); cudaEventRecord(b1, sb); CK(cudaEventSynchronize(b1)); cudaEventElapsedTime(&alone, b0, b1); }
     for (int r = 0; r < 3; ++r) {
