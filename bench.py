@@ -184,7 +184,8 @@ def main():
     cores = os.cpu_count() or 1
     workload = {"workload": cfg["name"], "npts": cfg["npts"], "n_occ": n, "ncore": cfg["ncore"], "nact": cfg["nact"], "M_pairs": alg["M"],
                 "functional": "t" + cfg["functional"], "sharding": f"grid points, {world} contiguous shard(s), RDMs replicated",
-                "l2_policy": "inputs larger than L2 (no flush needed)" if cfg["npts"] * n * 8 > 2e8 else "inputs smaller than L2"}
+                "l2_policy": ("inputs larger than L2 (no flush needed)" if cfg["npts"] * n * 8 * (4 if gga else 1) > 1.4e8
+                              else "inputs smaller than the 126 MB L2 (parity-size case, not a bench target)")}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":

@@ -430,7 +430,9 @@ int run_k2(ordm_ctx* c, const GridView& v, int* launches, bool lean = false) {
     k2::k2_ontop_ws<false, 2><<<grid, k2::WS_THREADS, c->k2_smem, c->stream>>>(p);
     CU(c, cudaGetLastError());
     rc = ORDM_OK;
-  } else if (c->k2_npg == 2 && c->k2_mt == 4) rc = launch_k2<2, 4>(c, p);
+  } else if (c->k2_npg == 8 && c->k2_mt == 4) rc = launch_k2<8, 4>(c, p);
+  else if (c->k2_npg == 4 && c->k2_mt == 4) rc = launch_k2<4, 4>(c, p);
+  else if (c->k2_npg == 2 && c->k2_mt == 4) rc = launch_k2<2, 4>(c, p);
   else if (c->k2_npg == 1 && c->k2_mt == 4) rc = launch_k2<1, 4>(c, p);
   else if (c->k2_npg == 1 && c->k2_mt == 2) rc = launch_k2<1, 2>(c, p);
   else rc = launch_k2<1, 1>(c, p);
@@ -487,6 +489,12 @@ int configure_k2(ordm_ctx* c) {
     if (cand[i].bytes <= (size_t)c->max_smem_optin) { pick = i; break; }
   c->k2_ws = !c->k2_force_plain && k2::WsSmem::bytes(Mpad, c->nact) <= (size_t)c->max_smem_optin;
   if (c->k2_ws) { cand[1].bytes = k2::WsSmem::bytes(Mpad, c->nact); pick = 1; }  // 32-point tiles, 8 task lanes
+  // Small active spaces: Dt has too few 32x32 blocks to feed eight task lanes (M = 36 -> 3 blocks), so
+  // the warps split POINTS instead: 8 (or 4) point groups of 32 points per tile, 1 (or 2) task lanes.
+  const int nblocks = nblk * (nblk + 1) / 2;
+  Cand wide8{8, 4, k2::Smem<256>::bytes(Mpad, c->nact)}, wide4{4, 4, k2::Smem<128>::bytes(Mpad, c->nact)};
+  if (!c->k2_force_plain && nblocks <= 3 && wide8.bytes <= (size_t)c->max_smem_optin) { cand[0] = wide8; pick = 0; c->k2_ws = false; }
+  else if (!c->k2_force_plain && nblocks <= 6 && wide4.bytes <= (size_t)c->max_smem_optin) { cand[0] = wide4; pick = 0; c->k2_ws = false; }
   if (pick < 0)
     return fail(c, ORDM_ERR_UNSUPPORTED, "on-top pair density: %d orbitals (M=%d pairs) exceed shared memory; use ordm_set_active_space with a smaller active block", c->nact, M);
   c->k2_npg = cand[pick].npg;
