@@ -166,6 +166,8 @@ def main():
     ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--npts", type=int, default=0, help="override the grid size (debug)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): BASELINE.json's grid sharded over the ranks; weak: that grid PER rank")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0)
@@ -177,6 +179,9 @@ def main():
     cfg = dict(CONFIGS[args.config])
     if args.npts:
         cfg["npts"] = args.npts
+    if args.scaling == "weak":
+        cfg["npts"] *= world
+        cfg["name"] += f" (weak scaling: x{world} points)"
     alg = algorithmic(cfg)
     n = cfg["ncore"] + cfg["nact"]
     gga = cfg["functional"] == "PBE"
@@ -200,7 +205,7 @@ def main():
         v = leg["as_written"]
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 1),
-            "ms_per_step": leg["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": leg["seconds"] * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": leg["sample"],
                              "value_necessary_work_only": leg["necessary"], "value_serial_1_core": leg["serial"]},
@@ -383,7 +388,7 @@ def main():
                    "value_necessary_work_only": leg["necessary"], "value_serial_1_core": leg["serial"]}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
-           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
+           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
            "result": {k: res[k] for k in ("e_tot", "ex", "ec", "n_tot", "trn_tot")}}
     print(json.dumps(out))
