@@ -152,7 +152,13 @@ def cpu_reference_leg(cfg, sample_pts, threads, steps=1, warmup=0):
     ns = max(64, sample_pts // 8)
     gs = [g[:ns] for g in grads] if grads is not None else None
     r1 = ref.energy_threads(1, w[:ns], phi[:ns], cfg["ncore"], A1a, A1b, D2, cfg["functional"], gs, 0.0, with_pi_grad=True)
-    return dict(as_written=sample_pts / t_written, necessary=sample_pts / r2.seconds, serial=ns / r1.seconds, seconds=t_written, e_tot=r.scalars["e_tot"],
+    omp = None
+    try:  # the reference's own OpenMP mode (configure:20), all host cores: slower than its serial build
+        ro = O.Ref(openmp=True).energy_threads(1, w[:ns], phi[:ns], cfg["ncore"], A1a, A1b, D2, cfg["functional"], gs, 0.0, with_pi_grad=True)
+        omp = ns / ro.seconds
+    except Exception:
+        pass
+    return dict(as_written=sample_pts / t_written, necessary=sample_pts / r2.seconds, serial=ns / r1.seconds, omp=omp, seconds=t_written, e_tot=r.scalars["e_tot"],
                 sample=f"first {sample_pts} points of the {cfg['npts']}-point grid, {threads} threads x contiguous slices, "
                        f"reference kernels unmodified (build_rho on all {n} orbitals; build_ontop_pair_density(+_gradients as mcpdft_energy "
                        f"does for GGA) on the {cfg['nact']} active orbitals; closed-form core terms added by the harness)")
@@ -208,7 +214,8 @@ def main():
             "ms_per_step": leg["seconds"] * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": leg["sample"],
-                             "value_necessary_work_only": leg["necessary"], "value_serial_1_core": leg["serial"]},
+                             "value_necessary_work_only": leg["necessary"], "value_serial_1_core": leg["serial"],
+                             "value_reference_openmp_build_all_cores": leg["omp"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }))
@@ -385,7 +392,8 @@ def main():
         leg = cpu_reference_leg(cfg, min(sample, cfg["npts"]), cores)
         if leg:
             cpu = {"value": leg["as_written"], "unit": UNIT, "cores": cores, "kind": "reference", "sample": leg["sample"],
-                   "value_necessary_work_only": leg["necessary"], "value_serial_1_core": leg["serial"]}
+                   "value_necessary_work_only": leg["necessary"], "value_serial_1_core": leg["serial"],
+                   "value_reference_openmp_build_all_cores": leg["omp"]}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,

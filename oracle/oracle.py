@@ -22,6 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "_build", "libmcpdft_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libopenrdm_ref.so")
 REF_PSI4_SO = os.path.join(HERE, "_ref", "libopenrdm_ref_psi4.so")
+REF_OMP_SO = os.path.join(HERE, "_ref", "libopenrdm_ref_omp.so")  # same sources, WITH_OPENMP ON
 # functional ids of the C port's drivers: 1 SVWN, 0 PBE (energy.cc:114-120: anything but "SVWN" is PBE),
 # plus the Psi4 plugin's REVPBE / BLYP / BOP (mcpdft_solver.cc:742-787)
 FUNC_ID = {"SVWN": 1, "PBE": 0, "REVPBE": 2, "BLYP": 3, "BOP": 4, "WPBE": 5}
@@ -219,12 +220,14 @@ class Ref:
 
     FUNC_ID = {"EX_LSDA": 0, "EC_VWN3": 1, "EX_PBE": 2, "EC_PBE": 3}
 
-    def __init__(self):
+    def __init__(self, openmp: bool = False):
+        """openmp=True loads the WITH_OPENMP build of the same sources (timing comparison only)."""
         if not have_ref():
             build(ref=True)
-        if not have_ref():
-            raise FileNotFoundError(REF_SO)
-        self.lib = C.CDLL(REF_SO)
+        so = REF_OMP_SO if openmp else REF_SO
+        if not os.path.exists(so):
+            raise FileNotFoundError(so)
+        self.lib = C.CDLL(so)
         self.lib.ref_functional.restype = C.c_double
         self.lib.ref_energy_threads.restype = C.c_double
 
