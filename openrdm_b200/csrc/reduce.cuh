@@ -78,6 +78,7 @@ __host__ __device__ inline size_t peer_xchg_bytes(int nranks) { return sizeof(do
 __global__ void __launch_bounds__(128) k_allreduce_peer(double* __restrict__ res, const PeerXchg px, unsigned long long epoch, int* __restrict__ err) {
   const int t = threadIdx.x, n = px.nranks;
   const int par = (int)(epoch & 1);
+  if (t == 0) *err = 0;  // a time-out is reported for the call it happened in, not for ever after
   if (t < n * RES_COUNT) {  // scatter: my values into slot [par][rank] of every rank's buffer
     const int r = t / RES_COUNT, k = t % RES_COUNT;
     px.peer[r][((size_t)par * n + px.rank) * RES_COUNT + k] = res[k];
@@ -93,11 +94,11 @@ __global__ void __launch_bounds__(128) k_allreduce_peer(double* __restrict__ res
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
       if (seen >= epoch) break;
-    } while (clock64() - t0 < 4000000000ll);  // ~2 s: a rank that never shows up must not hang the GPU
+    } while (clock64() - t0 < 60000000000ll);  // ~30 s: ranks may enter their first call seconds apart; a rank that never shows up must not hang the GPU for ever
     if (seen < epoch) *err = 1;
   }
   __syncthreads();
-  if (t < RES_COUNT) {
+  if (t < RES_COUNT) {  // (*err was cleared before the first __syncthreads and is only set by the waiters above)
     const double* v = px.peer[px.rank] + (size_t)par * n * RES_COUNT + t;
     double s = 0.0;
     for (int r = 0; r < n; ++r) s += v[(size_t)r * RES_COUNT];
