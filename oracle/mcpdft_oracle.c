@@ -15,7 +15,7 @@
  * PARITY PINNING: the reference's golden values (tests/h2_t*_sto3g/eref.txt) cannot be
  * reproduced in this checkout -- the quadrature weights (grids.txt) and gradients.txt are
  * missing blobs (.MISSING_LARGE_BLOBS:1-3).  This port is therefore pinned against outputs
- * of the reference itself run here (oracle/_ref; tests/test_oracle_vs_ref.py) and against
+ * of the reference itself run here (oracle/_ref; tests/test_oracle.py) and against
  * fixtures generated from it (tests/golden/, made by tests/golden/make_golden.py).
  *
  * Storage convention = the reference's: matrices are column-major, phi(p,mu) at
