@@ -168,37 +168,42 @@ def test_empty_grid(engine):
     assert r["e_tot"] == -1.0 and r["n_tot"] == 0.0
 
 
-@pytest.mark.parametrize("cfg", ["cfg3", "cfg4_slice"])
+@pytest.mark.parametrize("cfg", ["cfg3", "cfg4_slice", "cfg5_slice_pbe", "cfg5_slice_svwn"])
 def test_full_size_properties(engine, port, ordm, cfg):
-    """BASELINE.json configs 3/4 shapes: (i) the oracle on a seeded subsample of the same global
+    """BASELINE.json configs 3/4/5 shapes (config 5 as tPBE and tSVWN): (i) the oracle on a seeded subsample of the same global
     grid agrees point by point; (ii) the energy is additive over grid shards (sum of two halves
     == whole) -- the property the multi-GPU sharding relies on."""
+    fn, gga = "PBE", True
     if cfg == "cfg3":
         seed, npts, ncore, nact, nel = 3, 500_000, 2, 8, 5
-    else:  # config 4's orbital space on a 1/8 shard of its 5M-point grid
+    elif cfg == "cfg4_slice":  # config 4's orbital space on a 1/8 shard of its 5M-point grid
         seed, npts, ncore, nact, nel = 4, 625_000, 83, 20, 10
+    else:  # config 5's orbital space (73 core + 26 active, tSVWN and tPBE) on a 1/64 shard of its 20M-point grid
+        seed, npts, ncore, nact, nel = 5, 312_500, 73, 26, 13
+        if cfg.endswith("svwn"):
+            fn, gga = "SVWN", False
     n = ncore + nact
     A1a, A1b, D2 = ordm.synth_rdms(seed, nact, nel, nel, 8)
     engine.set_options(diagnostics=False)
     engine.set_active_space(ncore, A1a, A1b, D2)
-    engine.synth_fill(seed, npts, 0, npts, n, True)
-    whole = engine.energy(FN["PBE"], 0.0)
+    engine.synth_fill(seed, npts, 0, npts, n, gga)
+    whole = engine.energy(FN[fn], 0.0)
     half = npts // 2 // 64 * 64
-    engine.synth_fill(seed, npts, 0, half, n, True)
-    a = engine.energy(FN["PBE"], 0.0)
-    engine.synth_fill(seed, npts, half, npts - half, n, True)
-    b = engine.energy(FN["PBE"], 0.0)
+    engine.synth_fill(seed, npts, 0, half, n, gga)
+    a = engine.energy(FN[fn], 0.0)
+    engine.synth_fill(seed, npts, half, npts - half, n, gga)
+    b = engine.energy(FN[fn], 0.0)
     for k in ("ex", "ec", "n_tot", "trn_tot"):
         assert abs(a[k] + b[k] - whole[k]) <= 1e-10 * max(1.0, abs(whole[k])), k
     # subsample vs oracle
-    m, p0 = (4096, 123_456 // 64 * 64) if cfg == "cfg3" else (512, 300_032)
-    w, phi, grads = ordm.synth_fill_host(seed, npts, p0, m, n, True)
-    want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, "PBE", grads)
+    m, p0 = (4096, 123_456 // 64 * 64) if cfg == "cfg3" else ((512, 300_032) if cfg == "cfg4_slice" else (256, 200_000 // 64 * 64))
+    w, phi, grads = ordm.synth_fill_host(seed, npts, p0, m, n, gga)
+    want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, fn, grads)
     engine.set_options(diagnostics=True)
-    engine.synth_fill(seed, npts, p0, m, n, True)
-    got = engine.energy(FN["PBE"], 0.0)
+    engine.synth_fill(seed, npts, p0, m, n, gga)
+    got = engine.energy(FN[fn], 0.0)
     check_scalars(got, want.scalars)
-    check_vectors(engine.get_vector, want.vecs, True)
+    check_vectors(engine.get_vector, want.vecs, gga)
 
 
 @pytest.mark.parametrize("ncore,nact,npts,kind", [(0, 3, 500, "ensemble"), (0, 5, 1000, "nonsym"), (2, 4, 333, "ensemble"),
