@@ -374,7 +374,9 @@ def main():
         return {
             "k1_density": {"ms": ms["density"], "bound": "hbm", "achieved": g1, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": g1 / peaks["hbm_gbs"], "bytes_per_point": alg["k1_bytes"]},
             "k2_ontop": {"ms": ms["pi"], "bound": "tensor", "achieved": t2, "peak": dg_sus, "unit": "TFLOP/s", "frac": t2 / dg_sus},
-            "k3_translate_xc": {"ms": ms["xc"], "bound": "hbm (FP64-ALU limited, DESIGN.md)", "achieved": g3, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": g3 / peaks["hbm_gbs"], "bytes_per_point": alg["k3_bytes"]},
+            "k3_translate_xc": {"ms": ms["xc"], "bound": "hbm (FP64-ALU limited, DESIGN.md)", "achieved": g3, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": g3 / peaks["hbm_gbs"], "bytes_per_point": alg["k3_bytes"],
+                                "fp64_alu": {"instr_per_point_estimate": 500 if gga else 330, "achieved_ginstr_s": (500 if gga else 330) * pts_rank / (ms["xc"] * 1e-3) * 1e-9,
+                                             "peak_ginstr_s": 16700.0, "note": "DFMA issue peak 33.4 TFLOP/s / 2 (profiles/r01_fp64_peaks_microbench.log); ncu: FP64 pipe 46-48 % active (profiles/r01c_ncu_full_k1_k2_k3.csv)"}},
             "k4_reduce_allreduce": {"ms": ms["reduce"]},
         }
     kernels = kernel_table(ms_k)
