@@ -16,7 +16,7 @@ import numpy as np
 from . import build as _build
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libopenrdm_b200.so")
+LIB_PATH = os.environ.get("ORDM_LIB") or os.path.join(PKG, "libopenrdm_b200.so")  # ORDM_LIB: A/B builds in the lab
 
 FUNC_SVWN, FUNC_PBE, FUNC_REVPBE, FUNC_BLYP, FUNC_BOP, FUNC_WPBE = 0, 1, 2, 3, 4, 5
 FUNC_ID = {"SVWN": 0, "PBE": 1, "REVPBE": 2, "BLYP": 3, "BOP": 4, "WPBE": 5}

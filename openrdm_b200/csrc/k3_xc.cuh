@@ -16,6 +16,9 @@
 namespace k3 {
 
 constexpr int THREADS = 256;
+#ifndef K3_MINB
+#define K3_MINB 4  // 64 registers, 4 CTAs per SM: 0.294 -> 0.280 ms on config 4 (5 gave it back in spills)
+#endif
 
 struct Params {
   const double* rho;
@@ -45,7 +48,7 @@ struct Params {
 //       (the Psi4 plugin's, mcpdft_solver.cc:742-787).  Everything but SVWN consumes sigma.
 // FT:   MCPDFT::fully_translate (mcpdft.cc:418-606) instead of MCPDFT::translate.
 template <int FUNC, bool FT = false>
-__global__ void __launch_bounds__(THREADS) k3_translate_xc(const Params P) {
+__global__ void __launch_bounds__(THREADS, K3_MINB) k3_translate_xc(const Params P) {
   constexpr bool GGA = FUNC != 0;
   __shared__ double scratch[5 * 32];
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
