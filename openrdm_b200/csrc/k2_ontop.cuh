@@ -423,9 +423,10 @@ __device__ __forceinline__ void ws_cta(const Params& prm) {
   __syncthreads();
   if (BW0 == WARPS ? tid >= WS_THREADS : (wid >= WARPS && wid < BW0)) return;
 
-  // Builders are the HIGHEST warp ids: the SM sub-partition arbiter favours higher warp ids, and
-  // the builders' few FP64 multiplies share the FP64/DMMA pipe with the MMA warps' DMMA stream --
-  // as low-priority warps they were starved (X build 13k clk per tile instead of ~2k).
+  // The builders' few FP64 multiplies share the FP64/DMMA pipe with the MMA warps' DMMA stream and
+  // queue behind it (~260 cycles per DMUL, whichever warp ids the builders get: K2_EXP_TRACE shows
+  // the X build taking ~13 k of the 14.5 k-cycle tile period either way), so X for tile k+1 is
+  // ready just as the lanes finish tile k -- see DESIGN.md section 4 for what was tried against it.
   if (wid >= WARPS) {
     // ================================ builders ================================
     reg_dec<56>();
