@@ -369,9 +369,12 @@ constexpr int WS_BUILDERS = 128;
 
 struct WsSmem {
   static __host__ __device__ size_t x_doubles(int Mpad) { return (size_t)(Mpad + 4) * WS_PS; }
+  // grad: the phi / grad phi tile rows are padded to WS_PS doubles -- the epilogue that forms dX on the
+  // fly reads four different orbital rows per instruction, and with a 32-double stride they all fall
+  // on the same banks (4-way conflicts, 170 M per launch in ncu); stride 36 makes it 2-way, the minimum
   static __host__ __device__ size_t bytes(int Mpad, int nact, bool grad = false, int nbuf = 2) {
-    const size_t nc = grad ? 4 : 1;
-    return sizeof(double) * ((size_t)nbuf * x_doubles(Mpad) + (size_t)nbuf * nc * nact * WS_P + (size_t)nbuf * nc * WARPS * WS_P) + 64 +
+    const size_t nc = grad ? 4 : 1, ph = grad ? WS_PS : WS_P;
+    return sizeof(double) * ((size_t)nbuf * x_doubles(Mpad) + (size_t)nbuf * nc * nact * ph + (size_t)nbuf * nc * WARPS * WS_P) + 64 +
            sizeof(uint32_t) * Mpad;
   }
 };
@@ -396,7 +399,8 @@ __device__ __forceinline__ void ws_cta(const Params& prm) {
   double* Xs0 = reinterpret_cast<double*>(smem_raw);
   const size_t xsz = WsSmem::x_doubles(Mpad);
   double* phis0 = Xs0 + NBUF * xsz;                               // [NBUF][NC][nact][P]
-  double* red0 = phis0 + (size_t)NBUF * NC * nact * P;            // [NBUF][8 lanes][NC][P]
+  constexpr int PH = GRAD ? PS : P;                               // row stride of the phi tiles (see WsSmem::bytes)
+  double* red0 = phis0 + (size_t)NBUF * NC * nact * PH;           // [NBUF][8 lanes][NC][P]
   uint64_t* bars = reinterpret_cast<uint64_t*>(red0 + (size_t)NBUF * NC * WARPS * P);
   uint64_t* full = bars;      // [2] builders -> MMA   (count WS_BUILDERS/32 = 4 warp arrivals)
   uint64_t* done = bars + 2;  // [2] MMA -> builders   (count 8 warp arrivals)
@@ -404,7 +408,7 @@ __device__ __forceinline__ void ws_cta(const Params& prm) {
   uint32_t* pofs = reinterpret_cast<uint32_t*>(bars + 8);  // [Mpad]: (t*P) | (u*P) << 16, 0 beyond M
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int cstride = nact * P;  // component stride inside a phi tile buffer
+  const int cstride = nact * PH;  // component stride inside a phi tile buffer
   const uint32_t tile_bytes = (uint32_t)(NC * nact * P * sizeof(double));
   const int ntiles = prm.ntiles;
   // tiles of this CTA: blockIdx.x + k*gridDim.x, k = 0..nmine-1
@@ -412,7 +416,7 @@ __device__ __forceinline__ void ws_cta(const Params& prm) {
 
   if (tid < WS_THREADS) {
     for (int I = tid; I < Mpad; I += WS_THREADS)
-      pofs[I] = I < prm.M ? ((uint32_t)prm.pairs[2 * I] * P | ((uint32_t)prm.pairs[2 * I + 1] * P) << 16) : 0u;
+      pofs[I] = I < prm.M ? ((uint32_t)prm.pairs[2 * I] * PH | ((uint32_t)prm.pairs[2 * I + 1] * PH) << 16) : 0u;
     for (int b = 0; b < NBUF; ++b)  // rows M..Mpad+3 of the X buffers stay zero for the whole launch
       for (int idx = prm.M * P + tid; idx < (Mpad + 4) * P; idx += WS_THREADS) Xs0[b * xsz + (size_t)(idx / P) * PS + (idx % P)] = 0.0;
   }
@@ -437,11 +441,11 @@ __device__ __forceinline__ void ws_cta(const Params& prm) {
       mbar_expect_tx(&tma[b], tile_bytes);
       double* dst = phis0 + (size_t)b * NC * cstride;
       for (int t = 0; t < nact; ++t) {
-        tma_bulk_g2s(dst + (size_t)t * P, prm.phi_act + (size_t)t * prm.ld + t0, P * sizeof(double), &tma[b]);
+        tma_bulk_g2s(dst + (size_t)t * PH, prm.phi_act + (size_t)t * prm.ld + t0, P * sizeof(double), &tma[b]);
         if (GRAD) {
 #pragma unroll
           for (int d = 0; d < 3; ++d)
-            tma_bulk_g2s(dst + (size_t)(d + 1) * cstride + (size_t)t * P, prm.dphi_act[d] + (size_t)t * prm.ld + t0, P * sizeof(double), &tma[b]);
+            tma_bulk_g2s(dst + (size_t)(d + 1) * cstride + (size_t)t * PH, prm.dphi_act[d] + (size_t)t * prm.ld + t0, P * sizeof(double), &tma[b]);
         }
       }
     };
