@@ -291,7 +291,7 @@ def main():
     value = cfg["npts"] / (ms_step * 1e-3)
     for k in ms_k:
         ms_k[k] = max_over_ranks(ms_k[k] / steps)
-    overlapped = bool(res.get("overlapped", 0))
+    overlapped = int(res.get("overlapped", 0))
 
     # ---- the same step with the stages back to back on one stream: isolated per-kernel durations
     # (in the default mode K1 streams underneath K2, so their event times overlap)
@@ -381,8 +381,10 @@ def main():
         }
     kernels = kernel_table(ms_k)
     kernels["peak_source"] = f"MEASURED_PEAKS.json ({peak_src})"
-    kernels["mode"] = ("overlapped: k1_density streams underneath k2_ontop on a second stream (their ms overlap in time); k3 joins both"
-                       if overlapped else "stages back to back on one stream")
+    kernels["mode"] = {2: "overlapped/split: K1's core-orbital sums (k1_core_light) stream underneath k2_ontop on a second stream, its active-space part "
+                          "follows; k1_density.ms = both parts, overlapping k2_ontop.ms in time",
+                       1: "overlapped: k1_density streams underneath k2_ontop on a second stream (their ms overlap in time); k3 joins both",
+                       0: "stages back to back on one stream"}[overlapped]
     if ms_iso:
         kernels["isolated"] = kernel_table(ms_iso)
         kernels["isolated"]["ms_per_step"] = ms_step_serial

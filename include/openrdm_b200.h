@@ -95,7 +95,8 @@ typedef struct {
   uint64_t npts;          /* points this context (shard) processed */
   uint32_t gpu_launches;  /* kernels launched by that call */
   uint32_t overlapped;    /* 1: the density kernel ran underneath the on-top kernel (ms_density and
-                             ms_pi overlap in time); 0: stages ran back to back */
+                             ms_pi overlap in time); 2: only its core-orbital sums did, the active-space
+                             part followed (ms_density = both parts); 0: stages ran back to back */
 } ordm_result;
 
 /* ---- lifecycle ----------------------------------------------------------------------- */

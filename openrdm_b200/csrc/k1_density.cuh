@@ -104,6 +104,44 @@ __global__ void __launch_bounds__(CORE_THREADS) k1_core(const Params P) {
   }
 }
 
+// The same core sums in a register-light shape (<= 64 registers, 128 threads, 8 loads in flight per
+// thread) for running UNDERNEATH the tensor-bound K2: next to K2's register-trimmed CTA an SM has
+// 16 K registers left, which hold two or three of these CTAs but only one of the 128-register full
+// K1 -- and what limits a co-resident kernel is how often its warps catch a free FP64 slot between
+// K2's DMMAs, so the FMA-light / byte-heavy core part (332 DFMAs for 2 656 bytes per point on config 4)
+// is the part to run there: it finishes about when K2 does (8.6 vs 8.2 ms; the full K1: 10.1 ms).
+constexpr int LIGHT_THREADS = 128;
+template <bool GGA>
+__global__ void __launch_bounds__(LIGHT_THREADS, 8) k1_core_light(const Params P) {
+  const size_t ld = P.ld;
+  for (size_t p = (size_t)blockIdx.x * LIGHT_THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * LIGHT_THREADS) {
+    double rc = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+    int i = 0;
+    for (; i + 2 <= P.ncore; i += 2) {
+      double v[2], vx[2], vy[2], vz[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const size_t o = (size_t)(i + j) * ld + p;
+        v[j] = __ldcs(P.phi + o);
+        if (GGA) { vx[j] = __ldcs(P.phix + o); vy[j] = __ldcs(P.phiy + o); vz[j] = __ldcs(P.phiz + o); }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        rc = fma(v[j], v[j], rc);
+        if (GGA) { cx = fma(v[j], vx[j], cx); cy = fma(v[j], vy[j], cy); cz = fma(v[j], vz[j], cz); }
+      }
+    }
+    for (; i < P.ncore; ++i) {
+      const size_t o = (size_t)i * ld + p;
+      const double v = __ldcs(P.phi + o);
+      rc = fma(v, v, rc);
+      if (GGA) { cx = fma(v, __ldcs(P.phix + o), cx); cy = fma(v, __ldcs(P.phiy + o), cy); cz = fma(v, __ldcs(P.phiz + o), cz); }
+    }
+    P.core_rc[p] = rc;
+    if (GGA) { P.core_cx[p] = cx; P.core_cy[p] = cy; P.core_cz[p] = cz; }
+  }
+}
+
 __device__ __forceinline__ void st(double* p, size_t i, double v) {
   if (p) p[i] = v;
 }

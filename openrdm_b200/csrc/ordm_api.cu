@@ -116,6 +116,7 @@ struct ordm_ctx {
   cudaStream_t side_stream = nullptr;  // K1 runs here underneath K2 (ordm_energy, overlapped mode)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_k1[2] = {nullptr, nullptr};
   bool serial_stages = false;          // ORDM_SERIAL_STAGES=1: K1 -> K2 -> K3 back to back on one stream
+  bool no_split = false;               // ORDM_NO_SPLIT=1: the whole K1 underneath K2 (lab / test hook)
   bool own_stream = true;
   unsigned opts = 0;
   double omega = 0.0;  // MCPDFT_OMEGA
@@ -158,7 +159,7 @@ struct ordm_ctx {
   // reductions
   double *d_partial = nullptr, *d_res = nullptr, *h_res = nullptr;
   size_t partial_cap = 0;
-  cudaEvent_t ev[6] = {};
+  cudaEvent_t ev[8] = {};
 
   // streamed (host-buffer) path
   struct Stage {
@@ -288,7 +289,24 @@ int k3_grid(const ordm_ctx* c, size_t npts) {
   return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 8));
 }
 
-int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaStream_t st = nullptr) {
+// The core sums alone (rc, cx, cy, cz -> v.core[]), in the register-light shape that runs underneath K2.
+int run_k1_core_light(ordm_ctx* c, const GridView& v, int* launches, cudaStream_t st) {
+  k1::Params p{};
+  p.phi = v.phi; p.phix = v.phix; p.phiy = v.phiy; p.phiz = v.phiz;
+  p.ld = v.ld; p.npts = v.npts; p.ncore = c->ncore; p.nact = c->nact;
+  p.core_rc = v.core[0]; p.core_cx = v.core[1]; p.core_cy = v.core[2]; p.core_cz = v.core[3];
+  const size_t want = (v.npts + k1::LIGHT_THREADS - 1) / k1::LIGHT_THREADS;
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 16));
+  if (v.gga) k1::k1_core_light<true><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
+  else k1::k1_core_light<false><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
+  CU(c, cudaGetLastError());
+  *launches += 1;
+  return ORDM_OK;
+}
+
+// core_ready: the core sums are already in v.core[] (run_k1_core_light); only the active-space part and
+// the assembly of rho, grad rho, pi_core are left
+int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaStream_t st = nullptr, bool core_ready = false) {
   if (!st) st = c->stream;
   if (c->nact <= k1::MAX_ACT) {
     // The __constant__ bank holding Ds is per device and shared by every context of the process
@@ -317,7 +335,9 @@ int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaSt
   for (int i = 0; i < 6; ++i) p.grad[i] = v.vec[ORDM_VEC_RHOA_X + i];
   p.saa = v.vec[ORDM_VEC_SIGMA_AA]; p.sab = v.vec[ORDM_VEC_SIGMA_AB]; p.sbb = v.vec[ORDM_VEC_SIGMA_BB];
   p.Dsa_g = c->d_Dsa_g; p.Dsb_g = c->d_Dsb_g;
-  if (c->k1_split && c->ncore >= 8 && v.core[0]) {  // K1a: stream the core columns at full occupancy first
+  if (core_ready) {
+    p.core_rc = v.core[0]; p.core_cx = v.core[1]; p.core_cy = v.core[2]; p.core_cz = v.core[3];
+    } else if (c->k1_split && c->ncore >= 8 && v.core[0]) {  // K1a: stream the core columns at full occupancy first
     p.core_rc = v.core[0]; p.core_cx = v.core[1]; p.core_cy = v.core[2]; p.core_cz = v.core[3];
     const size_t want = (v.npts + k1::CORE_THREADS - 1) / k1::CORE_THREADS;
     const int cgrid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 8));
@@ -774,6 +794,7 @@ int ordm_create(int device, ordm_ctx** out) {
   CU(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (auto& ev : c->ev_k1) CU(c, cudaEventCreate(&ev));
   if (const char* e = getenv("ORDM_SERIAL_STAGES")) c->serial_stages = (e[0] == '1');  // per-kernel timing / test hook
+  if (const char* e = getenv("ORDM_NO_SPLIT")) c->no_split = (e[0] == '1');
   for (auto& ev : c->ev) CU(c, cudaEventCreate(&ev));
   CU(c, cudaMalloc(&c->d_res, 16 * sizeof(double)));
   CU(c, cudaMemset(c->d_res, 0, 16 * sizeof(double)));
@@ -1169,6 +1190,9 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   //  co-run -- K1 then queues behind the slightly slower lean K2: 93.6 vs 92.7 ms on config 5)
   const bool overlap = !c->serial_stages && !(c->opts & ORDM_OPT_SERIAL_STAGES) && c->k2_ws && !want_pig(c, c->g.gga) &&
                        c->k2_smem + 32768 <= (size_t)c->max_smem_optin;
+  // With many core orbitals only their FMA-light, byte-heavy sums run underneath K2 (k1_core_light);
+  // the active-space part of K1 follows on the main stream once both are done.
+  const bool split = overlap && c->core_form && c->ncore >= c->nact && c->g.core[0] && !c->no_split;
   CU(c, cudaEventRecord(c->ev[0], c->stream));
   if (overlap) {
     CU(c, cudaEventRecord(c->ev_fork, c->stream));
@@ -1176,11 +1200,14 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
     if ((rc = run_k2(c, c->g, &launches, /*lean=*/true))) return rc;
     CU(c, cudaEventRecord(c->ev[2], c->stream));
     CU(c, cudaEventRecord(c->ev_k1[0], c->side_stream));
-    if ((rc = run_k1(c, c->g, 0, &launches, c->side_stream))) return rc;
+    if (split) { if ((rc = run_k1_core_light(c, c->g, &launches, c->side_stream))) return rc; }
+    else if ((rc = run_k1(c, c->g, 0, &launches, c->side_stream))) return rc;
     CU(c, cudaEventRecord(c->ev_k1[1], c->side_stream));
     CU(c, cudaEventRecord(c->ev_join, c->side_stream));
     CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-    CU(c, cudaEventRecord(c->ev[1], c->stream));  // = both K1 and K2 done
+    CU(c, cudaEventRecord(c->ev[1], c->stream));  // = K2 and the side-stream part of K1 done
+    if (split && (rc = run_k1(c, c->g, 0, &launches, nullptr, /*core_ready=*/true))) return rc;
+    CU(c, cudaEventRecord(c->ev[6], c->stream));
     if ((rc = run_k3(c, c->g, functional, ft, 0, &launches, /*add_core=*/true))) return rc;
   } else {
     if ((rc = run_k1(c, c->g, 0, &launches))) return rc;
@@ -1194,11 +1221,12 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   CU(c, cudaEventRecord(c->ev[4], c->stream));
   if ((rc = fetch_result(c, eclass, out, c->g.npts, launches))) return rc;
   float ms;
-  if (overlap) {  // K1 and K2 ran concurrently: each is timed on its own stream
+  if (overlap) {  // K1 (or its core part) and K2 ran concurrently: each is timed on its own stream
     CU(c, cudaEventElapsedTime(&ms, c->ev_k1[0], c->ev_k1[1])); out->ms_density = ms;
+    CU(c, cudaEventElapsedTime(&ms, c->ev[1], c->ev[6])); out->ms_density += ms;  // + the active-space part (split mode)
     CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[2])); out->ms_pi = ms;
-    CU(c, cudaEventElapsedTime(&ms, c->ev[1], c->ev[3])); out->ms_xc = ms;
-    out->overlapped = 1;
+    CU(c, cudaEventElapsedTime(&ms, c->ev[6], c->ev[3])); out->ms_xc = ms;
+    out->overlapped = split ? 2 : 1;
   } else {
     CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); out->ms_density = ms;
     CU(c, cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); out->ms_pi = ms;

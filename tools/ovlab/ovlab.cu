@@ -78,6 +78,32 @@ __global__ void __launch_bounds__(128, MINB) core_fma_light(const k1::Params P) 
   }
 }
 
+// the product's split: core orbitals only (what would run underneath K2), UNR orbitals in flight
+template <int UNR, int MINB>
+__global__ void __launch_bounds__(128, MINB) core_only(const k1::Params P) {
+  const size_t ld = P.ld;
+  for (size_t p = (size_t)blockIdx.x * 128 + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * 128) {
+    double rc = 0, cx = 0, cy = 0, cz = 0;
+    int i = 0;
+    for (; i + UNR <= P.ncore; i += UNR) {
+      double v[UNR][4];
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+        const size_t o = (size_t)(i + j) * ld + p;
+        v[j][0] = __ldcs(P.phi + o); v[j][1] = __ldcs(P.phix + o); v[j][2] = __ldcs(P.phiy + o); v[j][3] = __ldcs(P.phiz + o);
+      }
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) { rc = fma(v[j][0], v[j][0], rc); cx = fma(v[j][0], v[j][1], cx); cy = fma(v[j][0], v[j][2], cy); cz = fma(v[j][0], v[j][3], cz); }
+    }
+    for (; i < P.ncore; ++i) {
+      const size_t o = (size_t)i * ld + p;
+      const double v = __ldcs(P.phi + o);
+      rc = fma(v, v, rc); cx = fma(v, __ldcs(P.phix + o), cx); cy = fma(v, __ldcs(P.phiy + o), cy); cz = fma(v, __ldcs(P.phiz + o), cz);
+    }
+    P.core_rc[p] = rc; P.core_cx[p] = cx; P.core_cy[p] = cy; P.core_cz[p] = cz;
+  }
+}
+
 // core stream with UNR x 4 INDEPENDENT accumulators: every loaded value feeds its own FMA chain, so a
 // warp that wins the FP64 pipe can issue 4*UNR DFMAs back to back before it stalls on a dependency
 template <int UNR, int MINB>
@@ -159,6 +185,9 @@ int main(int argc, char** argv) {
       case 8: core_fma_light<2, 8><<<g1, 128, 0, s>>>(p1); break;    // <= 64 regs: 2 CTAs next to K2
       case 9: core_fma_ilp<4, 4><<<g1, 128, 0, s>>>(p1); break;      // 16 independent chains
       case 10: core_fma_ilp<8, 4><<<g1, 128, 0, s>>>(p1); break;     // 32 independent chains
+      case 11: core_only<2, 8><<<g1, 128, 0, s>>>(p1); break;
+      case 12: core_only<4, 8><<<g1, 128, 0, s>>>(p1); break;
+      case 13: k1::k1_core<true><<<g1 / 2, k1::CORE_THREADS, 0, s>>>(p1); break;
     }
   };
   // a K1 launched BEFORE K2 must leave the SM's shared-memory carve-out large enough for K2's 147 KB
@@ -168,8 +197,9 @@ int main(int argc, char** argv) {
   CK(cudaFuncSetAttribute(stream_only<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CK(cudaFuncSetAttribute(core_fma<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CK(cudaFuncSetAttribute(core_fma<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  const char* names[] = {"k1_density<20,gga>", "stream_only<4>", "stream_only<8>", "core_fma<4>", "core_fma<8>", "stream_only<16>", "core_fma_light<2,12>", "core_fma_light<1,16>", "core_fma_light<2,8>", "core_fma_ilp<4>", "core_fma_ilp<8>"};
-  for (int variant = (argc > 4 ? atoi(argv[4]) : 0); variant < 11; ++variant) {
+  p1.core_rc = out[0]; p1.core_cx = out[1]; p1.core_cy = out[2]; p1.core_cz = out[3];
+  const char* names[] = {"k1_density<20,gga>", "stream_only<4>", "stream_only<8>", "core_fma<4>", "core_fma<8>", "stream_only<16>", "core_fma_light<2,12>", "core_fma_light<1,16>", "core_fma_light<2,8>", "core_fma_ilp<4>", "core_fma_ilp<8>", "core_only<2> (83 orb)", "core_only<4> (83 orb)", "k1_core (product, 256 thr)"};
+  for (int variant = (argc > 4 ? atoi(argv[4]) : 0); variant < 14; ++variant) {
     float alone = 0, tk2 = 0, tk1 = 0, span = 0;
     for (int r = 0; r < 3; ++r) { cudaEventRecord(b0, sb); launch_k1(variant, sb); cudaEventRecord(b1, sb); CK(cudaEventSynchronize(b1)); cudaEventElapsedTime(&alone, b0, b1); }
     for (int r = 0; r < 3; ++r) {
@@ -182,6 +212,12 @@ int main(int argc, char** argv) {
       cudaEventElapsedTime(&tk2, a0, a1); cudaEventElapsedTime(&tk1, b0, b1); cudaEventElapsedTime(&span, k1_first ? b0 : a0, k1_first ? a1 : b1);
     }
     printf("%-20s alone %.3f ms (%.0f GB/s) | with K2: K2 %.3f ms, K1 %.3f ms (%.0f GB/s), a0->b1 %.3f ms\n", names[variant], alone, gb / alone * 1e3, tk2, tk1, gb / tk1 * 1e3, span);
+  }
+  {  // the remaining active-space part on the core sums, alone
+    float t = 0;
+    for (int r = 0; r < 4; ++r) { cudaEventRecord(b0, sb); k1::k1_density<20, true><<<g1, 128, 0, sb>>>(p1); cudaEventRecord(b1, sb); CK(cudaEventSynchronize(b1)); cudaEventElapsedTime(&t, b0, b1); }
+    printf("k1_density<20,gga> with core sums given (active part only): %.3f ms\n", t);
+    p1.core_rc = nullptr;
   }
   {  // the fused kernel: density warps inside the K2 CTA
     CK(cudaFuncSetAttribute(k12::k12_fused<20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
