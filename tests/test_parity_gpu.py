@@ -451,3 +451,26 @@ def test_streamed_host_path_with_grad_pi_and_ft(engine, port, ordm, opts):
         st = engine.energy_host(FN["PBE"], 0.5, w, phi, grads, batch_points=batch)
         check_scalars(st, want.scalars)
         check_scalars(st, res, tol=1e-12)
+
+
+@pytest.mark.parametrize("ncore,nact,want_mode", [(9, 6, 2), (2, 8, 1)])
+def test_stage_orchestration_modes_agree(engine, port, ordm, ncore, nact, want_mode):
+    """The three schedules of ordm_energy -- stages back to back (0), the whole density kernel underneath the
+    on-top kernel (1), only its core-orbital sums underneath and the active-space part after (2; chosen when
+    ncore >= nact) -- are picked as documented (ordm_result.overlapped) and give the oracle's numbers."""
+    seed, npts = 77, 3001
+    n = ncore + nact
+    w, phi, grads = ordm.synth_fill_host(seed, npts, 0, npts, n, True)
+    A1a, A1b, D2 = ordm.synth_rdms(seed, nact, nact // 2, nact // 2, 4)
+    want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, "PBE", grads, eclass=0.0)
+    engine.set_grid(w); engine.set_orbitals(phi, grads); engine.set_active_space(ncore, A1a, A1b, D2)
+    seen = {}
+    for serial in (False, True):
+        engine.set_options(diagnostics=True, serial_stages=serial)
+        got = engine.energy(FN["PBE"], 0.0)
+        assert got["overlapped"] == (0 if serial else want_mode), got["overlapped"]
+        check_scalars(got, want.scalars)
+        check_vectors(engine.get_vector, want.vecs, True)
+        seen[serial] = {k: engine.get_vector(k).copy() for k in ("rho", "pi", "rhoa_x")}
+    for k in seen[True]:
+        assert np.abs(seen[True][k] - seen[False][k]).max() <= 1e-13 * max(1.0, np.abs(seen[True][k]).max()), k
