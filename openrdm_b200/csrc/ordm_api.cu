@@ -22,6 +22,7 @@
 #include "../../include/ordm_synth.h"
 #include "k1_density.cuh"
 #include "k2_ontop.cuh"
+#include "k2_int8.cuh"
 #include "k3_xc.cuh"
 #include "rdm_pack.h"
 #include "reduce.cuh"
@@ -143,6 +144,13 @@ struct ordm_ctx {
   double* d_dfrag = nullptr;
   void* d_tasks = nullptr;
   bool k2_ws = false, k2_force_plain = false;
+  // K2 on the int8 tensor cores (k2_int8.cuh): 18..20 active orbitals, Pi only (grad Pi keeps the DMMA kernel)
+  int k2_i8_mode = 1;          // ORDM_K2_INT8: 0 off, 1 on with 26 slice pairs (default), 2 on with 21 slice pairs
+  bool k2_i8 = false;
+  k2i::Params k2ip{};
+  uint8_t* d_timg = nullptr;
+  int* d_i8_fail = nullptr;
+  size_t k2i_smem = 0;
   bool k1_split = false;  // two-kernel K1 (k1_core + active) measured slower than the fused kernel; kept as a test hook
   uint16_t* d_pairs = nullptr;
   // grad-Pi variant of K2: the whole symmetric Dt in fragment order (built on first use)
@@ -415,10 +423,46 @@ int run_k2_grad(ordm_ctx* c, const GridView& v, int* launches) {
   return ORDM_OK;
 }
 
+template <int NA, int GMIN>
+int launch_k2_int8(ordm_ctx* c, const k2i::Params& p, int grid) {
+  static thread_local int dev = -1;
+  static thread_local size_t bytes = 0;
+  if (dev != c->device || bytes < c->k2i_smem) {
+    CU(c, cudaFuncSetAttribute(k2i::k2i_ontop<NA, GMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k2i_smem));
+    dev = c->device; bytes = c->k2i_smem;
+  }
+  k2i::k2i_ontop<NA, GMIN><<<grid, k2i::THREADS, c->k2i_smem, c->stream>>>(p);
+  CU(c, cudaGetLastError());
+  return ORDM_OK;
+}
+
+// Pi of the active space on the int8 tensor cores (18..20 active orbitals); lean as in run_k2: no pi_core add
+int run_k2_int8(ordm_ctx* c, const GridView& v, int* launches, bool lean) {
+  k2i::Params p = c->k2ip;
+  p.phi_act = v.phi + (size_t)c->ncore * v.ld;
+  p.ld = v.ld;
+  p.npts = v.npts;
+  p.pi_core = (c->core_form && !lean) ? v.pi_core : nullptr;
+  p.pi = v.vec[ORDM_VEC_PI];
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((v.npts + k2i::TILE - 1) / k2i::TILE, (size_t)c->sm_count));
+  const bool wide = c->k2_i8_mode == 1;   // 26 slice pairs
+  int rc;
+  switch (c->nact) {
+    case 18: rc = wide ? launch_k2_int8<18, 4>(c, p, grid) : launch_k2_int8<18, 5>(c, p, grid); break;
+    case 19: rc = wide ? launch_k2_int8<19, 4>(c, p, grid) : launch_k2_int8<19, 5>(c, p, grid); break;
+    case 20: rc = wide ? launch_k2_int8<20, 4>(c, p, grid) : launch_k2_int8<20, 5>(c, p, grid); break;
+    default: return fail(c, ORDM_ERR_UNSUPPORTED, "int8 on-top path selected for %d active orbitals", c->nact);
+  }
+  if (rc) return rc;
+  *launches += 1;
+  return ORDM_OK;
+}
+
 // lean = the register-trimmed WS kernel without the pi_core add (K1 is still running underneath;
 // K3 completes Pi)
 int run_k2(ordm_ctx* c, const GridView& v, int* launches, bool lean = false) {
   if (want_pig(c, v.gga)) return run_k2_grad(c, v, launches);
+  if (c->k2_i8) return run_k2_int8(c, v, launches, lean);
   k2::Params p = c->k2p;
   p.phi_act = v.phi + (size_t)c->ncore * v.ld;
   p.ld = v.ld;
@@ -541,6 +585,25 @@ int configure_k2(ordm_ctx* c) {
   for (int i = 0; i <= k2::MAX_LANES; ++i) { c->k2p.seg_ofs[i] = lay.seg_ofs[i]; c->k2p.blk_ofs[i] = lay.blk_ofs[i]; }
   c->k2_dmma_per_mtile = lay.subtiles;
   c->k2g_ready = false;  // the grad-Pi packing follows the same Dt: rebuilt on next use
+  // the int8 tensor-core path for the active-space sizes where K2 dominates the step
+  const int kp = (M + 31) / 32 * 32;
+  c->k2_i8 = c->k2_i8_mode > 0 && c->nact >= k2i::MIN_ACT && c->nact <= k2i::MAX_ACT &&
+             k2i::Smem::bytes(kp, c->nact) <= (size_t)c->max_smem_optin;
+  if (c->k2_i8) {
+    static_assert(k2i::NSLICE == 6 && k2i::FIX_BITS == 46, "ordm::pack_t_int8 is written for six byte slices of a 46-bit image");
+    std::vector<uint8_t> img;
+    int t_exp = 0;
+    ordm::pack_t_int8(M, c->h_Dt, kp, img, t_exp);
+    if (img.size() != k2i::Smem::t_bytes(kp) || ordm::t_int8_slice_bytes(kp) != k2i::Geom::slice_bytes(kp))
+      return fail(c, ORDM_ERR_UNSUPPORTED, "int8 on-top path: host image and kernel geometry disagree");
+    dfree(c->d_timg);
+    CU(c, cudaMalloc(&c->d_timg, img.size()));
+    CU(c, cudaMemcpy(c->d_timg, img.data(), img.size(), cudaMemcpyHostToDevice));
+    if (!c->d_i8_fail) { CU(c, cudaMalloc(&c->d_i8_fail, sizeof(int))); CU(c, cudaMemset(c->d_i8_fail, 0, sizeof(int))); }
+    c->k2ip = k2i::Params{};
+    c->k2ip.timg = c->d_timg; c->k2ip.t_exp = t_exp; c->k2ip.fail = c->d_i8_fail;
+    c->k2i_smem = k2i::Smem::bytes(kp, c->nact);
+  }
   return ORDM_OK;
 }
 
@@ -783,6 +846,7 @@ int ordm_create(int device, ordm_ctx** out) {
     return fail(nullptr, ORDM_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
   ordm_ctx* c = new ordm_ctx();
   c->device = device;
+  if (const char* e = getenv("ORDM_K2_INT8")) c->k2_i8_mode = atoi(e);   // 0: DMMA kernels only; 2: 21 slice pairs
   if (const char* e = getenv("ORDM_K2_PLAIN")) c->k2_force_plain = (e[0] == '1');  // test hook: single-buffer K2
   if (const char* e = getenv("ORDM_K1_SPLIT")) c->k1_split = (e[0] == '1');         // test hook: two-kernel K1
   c->sm_count = prop.multiProcessorCount;
@@ -819,6 +883,7 @@ void ordm_destroy(ordm_ctx* c) {
   dfree(c->d_w);
   for (int k = 0; k < 4; ++k) dfree(c->d_phi[k]);
   dfree(c->d_Dsa_g); dfree(c->d_Dsb_g); dfree(c->d_dfrag); dfree(c->d_tasks); dfree(c->d_pairs);
+  dfree(c->d_timg); dfree(c->d_i8_fail);
   dfree(c->d_partial); dfree(c->d_res);
   if (c->h_res) cudaFreeHost(c->h_res);
   for (auto& s : c->stage) {
@@ -1188,8 +1253,10 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   // (only when K2 leaves a comfortable part of the SM's shared memory free: with 26 active orbitals K2
   //  takes 219 KB of the 228 and, although a K1 CTA nominally still fits, it was measured not to
   //  co-run -- K1 then queues behind the slightly slower lean K2: 93.6 vs 92.7 ms on config 5)
+  // (the int8 K2 owns the SM -- 223 KB of shared memory, all of TMEM -- and is short enough that the density
+  //  kernel does not hide underneath it: 8.47 ms overlapped vs 8.03 ms back to back on config 4)
   const bool overlap = !c->serial_stages && !(c->opts & ORDM_OPT_SERIAL_STAGES) && c->k2_ws && !want_pig(c, c->g.gga) &&
-                       c->k2_smem + 32768 <= (size_t)c->max_smem_optin;
+                       c->k2_smem + 32768 <= (size_t)c->max_smem_optin && !c->k2_i8;
   // With many core orbitals only their FMA-light, byte-heavy sums run underneath K2 (k1_core_light);
   // the active-space part of K1 follows on the main stream once both are done.
   const bool split = overlap && c->core_form && c->ncore >= c->nact && c->g.core[0] && !c->no_split;

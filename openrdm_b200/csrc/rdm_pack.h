@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <cmath>
 #include <vector>
 
 namespace ordm {
@@ -248,6 +249,44 @@ inline void pack_dfrag(int M, const std::vector<double>& Dt, int nlanes, int pre
   }
   for (int l = nlanes; l < 9; ++l) { out.seg_ofs[l] = (uint32_t)out.segs.size(); out.blk_ofs[l] = slot; }
   out.segs.push_back({0, 0, 0, 0, 4});  // sentinel
+}
+
+// ---- K2 on the int8 tensor cores (k2_int8.cuh) ------------------------------------------------
+// T = block upper triangle of Dt (32 x 32 blocks, diagonal blocks halved; Dt = T + T^T), zero-padded to kp pairs,
+// as a 48-bit fixed-point image against max |T| (|image| <= 2^46), cut into six balanced signed bytes
+// (byte l < 5: ((v + 0x8080808080) >> 8l & 255) - 128; byte 5: (v + 0x8080808080) >> 40).
+// Image layout = the kernel's shared memory: slice l, then K chunk kc (pairs I in [32 kc, 32 kc + 32)), each chunk
+// a K-major no-swizzle UMMA operand of kp - 32 kc rows (row n <-> pair J = 32 kc + n) x 32 K bytes:
+// byte (n, k) at ((k >> 4) * rows / 8 + (n >> 3)) * 128 + (n & 7) * 16 + (k & 15).
+inline int t_int8_chunk_off(int kp, int kc) { return 32 * (kc * kp - 16 * kc * (kc - 1)); }
+inline int t_int8_slice_bytes(int kp) { return t_int8_chunk_off(kp, kp / 32); }
+inline void pack_t_int8(int M, const std::vector<double>& Dt, int kp, std::vector<uint8_t>& img, int& t_exp) {
+  const int fix_bits = 46, nslice = 6;
+  double tmax = 0.0;
+  auto T = [&](int I, int J) -> double {
+    if (I >= M || J >= M) return 0.0;
+    const int bi = I / 32, bj = J / 32;
+    return bi < bj ? Dt[(size_t)I * M + J] : (bi == bj ? 0.5 * Dt[(size_t)I * M + J] : 0.0);
+  };
+  for (int I = 0; I < M; ++I)
+    for (int J = 0; J < M; ++J) tmax = std::max(tmax, std::fabs(T(I, J)));
+  t_exp = 0;
+  if (tmax > 0.0) (void)std::frexp(tmax, &t_exp);   // tmax < 2^t_exp
+  const size_t slice = (size_t)t_int8_slice_bytes(kp);
+  img.assign((size_t)nslice * slice, 0);
+  for (int kc = 0; kc < kp / 32; ++kc) {
+    const int rows = kp - 32 * kc;
+    for (int n = 0; n < rows; ++n)
+      for (int k = 0; k < 32; ++k) {
+        const long long v = std::llrint(std::ldexp(T(32 * kc + k, 32 * kc + n), fix_bits - t_exp)) + 0x0000008080808080ll;
+        const size_t at = (size_t)t_int8_chunk_off(kp, kc) + (size_t)((k >> 4) * (rows >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (k & 15);
+        for (int l = 0; l < nslice; ++l) {
+          uint8_t b = (uint8_t)((unsigned long long)v >> (8 * l));
+          if (l < nslice - 1) b ^= 0x80;
+          img[(size_t)l * slice + at] = b;
+        }
+      }
+  }
 }
 
 // Ds = (D + D^T)/2, written row-major with row stride `stride` (zero padded).

@@ -453,12 +453,12 @@ def test_streamed_host_path_with_grad_pi_and_ft(engine, port, ordm, opts):
         check_scalars(st, res, tol=1e-12)
 
 
-@pytest.mark.parametrize("ncore,nact,want_mode", [(9, 6, 2), (2, 8, 1)])
+@pytest.mark.parametrize("ncore,nact,want_mode", [(16, 14, 2), (3, 14, 1), (9, 6, 0)])
 def test_stage_orchestration_modes_agree(engine, port, ordm, ncore, nact, want_mode):
     """The three schedules of ordm_energy -- stages back to back (0), the whole density kernel underneath the
     on-top kernel (1), only its core-orbital sums underneath and the active-space part after (2; chosen when
     ncore >= nact) -- are picked as documented (ordm_result.overlapped) and give the oracle's numbers."""
-    seed, npts = 77, 3001
+    seed, npts = 77, 1501   # 14 active orbitals: enough 32x32 blocks of D~ for the warp-specialised K2 (the one that overlaps)
     n = ncore + nact
     w, phi, grads = ordm.synth_fill_host(seed, npts, 0, npts, n, True)
     A1a, A1b, D2 = ordm.synth_rdms(seed, nact, nact // 2, nact // 2, 4)
@@ -474,3 +474,31 @@ def test_stage_orchestration_modes_agree(engine, port, ordm, ncore, nact, want_m
         seen[serial] = {k: engine.get_vector(k).copy() for k in ("rho", "pi", "rhoa_x")}
     for k in seen[True]:
         assert np.abs(seen[True][k] - seen[False][k]).max() <= 1e-13 * max(1.0, np.abs(seen[True][k]).max()), k
+
+
+@pytest.mark.parametrize("nact,ncore,npts,mode", [(20, 3, 300, "1"), (20, 0, 131, "2"), (19, 2, 257, "1"), (18, 1, 200, "1"), (18, 25, 129, "2")])
+def test_int8_tensor_core_pi_vs_oracle(port, ordm, monkeypatch, nact, ncore, npts, mode):
+    """18..20 active orbitals: Pi comes from the int8 tensor-core kernel (k2_int8.cuh; exact integer slice products
+    of 46-bit fixed-point images, 26 (mode 1, default) or 21 (mode 2) slice pairs).  Same bar as the FP64 kernels:
+    1e-12 per point on Pi, 1e-10 on the energies; and the DMMA kernel (ORDM_K2_INT8=0) must agree with it."""
+    seed = 900 + nact + ncore
+    n = ncore + nact
+    w, phi, grads = ordm.synth_fill_host(seed, npts, 0, npts, n, True)
+    A1a, A1b, D2 = ordm.synth_rdms(seed, nact, nact // 2, nact // 2, 6)
+    want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, "PBE", grads, eclass=0.0)
+    pis = {}
+    for m in (mode, "0"):
+        monkeypatch.setenv("ORDM_K2_INT8", m)
+        eng = ordm.Engine(0)
+        try:
+            eng.set_options(diagnostics=True)
+            eng.set_grid(w); eng.set_orbitals(phi, grads); eng.set_active_space(ncore, A1a, A1b, D2)
+            got = eng.energy(FN["PBE"], 0.0)
+            check_scalars(got, want.scalars)
+            check_vectors(eng.get_vector, want.vecs, True)
+            pis[m] = eng.get_vector("pi").copy()
+        finally:
+            eng.close()
+    d = np.abs(pis[mode] - pis["0"]) / np.maximum(1.0, np.abs(pis["0"]))
+    assert d.max() <= 1e-12, d.max()
+    assert d.max() > 0.0   # the two paths really are different kernels

@@ -1,0 +1,95 @@
+// k2i_lab.cu -- harness for the lab kernel k2i.cuh: random active-space orbitals and a dense symmetric D~,
+// CPU reference in long double on a sample of points, timing with CUDA events.
+// build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o k2i_lab k2i_lab.cu
+// run:   timeout 60 ./k2i_lab [npts=2000000] [ncheck=2048]
+#include "k2i.cuh"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+int main(int argc, char** argv) {
+  const size_t npts = argc > 1 ? (size_t)atoll(argv[1]) : 2000000;
+  const size_t ncheck = std::min(npts, argc > 2 ? (size_t)atoll(argv[2]) : (size_t)2048);
+  constexpr int NA = 20, M = NA * (NA + 1) / 2, KP = 224;
+  std::mt19937_64 rng(42);
+  std::normal_distribution<double> nd(0.0, 1.0);
+  std::uniform_real_distribution<double> ud(-1.0, 1.0);
+  // orbitals: a per-point envelope spanning ~6 decades times per-orbital amplitudes
+  std::vector<double> phi((size_t)NA * npts);
+  for (size_t p = 0; p < npts; ++p) {
+    const double env = std::exp(-14.0 * (double)((p * 2654435761ull) % 1000003ull) / 1000003.0);
+    for (int t = 0; t < NA; ++t) phi[(size_t)t * npts + p] = env * 0.5 * nd(rng) * (1.0 + 0.3 * t);
+  }
+  std::vector<double> D((size_t)M * M);
+  for (int i = 0; i < M; ++i) for (int j = i; j < M; ++j) { const double v = ud(rng) * std::exp(-3.0 * std::fabs(ud(rng))); D[(size_t)i * M + j] = D[(size_t)j * M + i] = v; }
+  std::vector<uint16_t> tu(704, 0);
+  { int I = 0; for (int t = 0; t < NA; ++t) for (int u = t; u < NA; ++u) tu[I++] = (uint16_t)(t | (u << 8)); }
+  // T = block upper triangle of D~ (32 x 32 blocks, diagonal blocks halved), 48-bit fixed point, balanced bytes
+  std::vector<double> T((size_t)KP * KP, 0.0);
+  double tmax = 0.0;
+  for (int i = 0; i < M; ++i) for (int j = 0; j < M; ++j) {
+    const int bi = i / 32, bj = j / 32;
+    const double v = bi < bj ? D[(size_t)i * M + j] : (bi == bj ? 0.5 * D[(size_t)i * M + j] : 0.0);
+    T[(size_t)i * KP + j] = v; tmax = std::max(tmax, std::fabs(v));
+  }
+  int t_exp = 0; (void)std::frexp(tmax, &t_exp);   // tmax < 2^t_exp
+  const size_t slice_bytes = k2i::Geom::slice_bytes(KP);
+  std::vector<uint8_t> timg((size_t)k2i::NSLICE * slice_bytes, 0);
+  for (int kc = 0; kc < KP / 32; ++kc) {
+    const int nrows = k2i::Geom::chunk_rows(KP, kc);
+    for (int n = 0; n < nrows; ++n) for (int k = 0; k < 32; ++k) {
+      const int I = 32 * kc + k, J = 32 * kc + n;
+      const long long v = llrint(std::ldexp(T[(size_t)I * KP + J], k2i::FIX_BITS - t_exp)) + 0x0000008080808080ll;
+      for (int l = 0; l < k2i::NSLICE; ++l) {
+        uint8_t b = (uint8_t)((unsigned long long)v >> (8 * l));
+        if (l < 5) b ^= 0x80;
+        timg[(size_t)l * slice_bytes + k2i::Geom::chunk_off(KP, kc) + ((k >> 4) * (nrows >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (k & 15)] = b;
+      }
+    }
+  }
+  double *dphi, *dpi; uint8_t* dt; int* dfail;
+  CK(cudaMalloc(&dphi, phi.size() * 8)); CK(cudaMalloc(&dpi, npts * 8)); CK(cudaMalloc(&dt, timg.size())); CK(cudaMalloc(&dfail, 4));
+  CK(cudaMemcpy(dphi, phi.data(), phi.size() * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dt, timg.data(), timg.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemset(dfail, 0, 4)); CK(cudaMemset(dpi, 0, npts * 8));
+  CK(cudaMemcpyToSymbol(k2i::c_tu, tu.data(), tu.size() * 2));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  const size_t smem = k2i::Smem::bytes(KP, NA);
+  printf("smem %zu B (opt-in max %zu), T image %zu B, t_exp %d\n", smem, (size_t)prop.sharedMemPerBlockOptin, timg.size(), t_exp);
+  CK(cudaFuncSetAttribute(k2i::k2i_ontop<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long* dprof; CK(cudaMalloc(&dprof, 8 * 8 * 1024)); CK(cudaMemset(dprof, 0, 8 * 8 * 1024));
+  k2i::Params P{dphi, npts, npts, dt, t_exp, dpi, NA, M, KP, dfail, argc > 3 ? atoi(argv[3]) : 0, dprof};
+  const int grid = (int)std::min<size_t>((size_t)prop.multiProcessorCount, (npts + k2i::TILE - 1) / k2i::TILE);
+  k2i::k2i_ontop<NA><<<grid, k2i::THREADS, smem>>>(P);
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaEventRecord(e0)); k2i::k2i_ontop<NA><<<grid, k2i::THREADS, smem>>>(P); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = std::min(best, ms);
+  }
+  std::vector<double> pi(npts); int fail;
+  CK(cudaMemcpy(pi.data(), dpi, npts * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&fail, dfail, 4, cudaMemcpyDeviceToHost));
+  double emax = 0.0, emax_f64 = 0.0, pimax = 0.0; size_t worst = 0;
+  std::vector<long double> x(M);
+  for (size_t c = 0; c < ncheck; ++c) {
+    const size_t p = (c * 7919) % npts;
+    for (int I = 0; I < M; ++I) x[I] = (long double)(phi[(size_t)(tu[I] & 255) * npts + p] * phi[(size_t)(tu[I] >> 8) * npts + p]);
+    long double ref = 0.0L; double f64 = 0.0;
+    for (int I = 0; I < M; ++I) { long double y = 0.0L; double yd = 0.0; for (int J = 0; J < M; ++J) { y += x[J] * (long double)D[(size_t)I * M + J]; yd += (double)x[J] * D[(size_t)I * M + J]; } ref += x[I] * y; f64 += (double)x[I] * yd; }
+    const double sc = std::max(1.0, (double)fabsl(ref));
+    const double e = std::fabs((double)((long double)pi[p] - ref)) / sc;
+    if (e > emax) { emax = e; worst = p; }
+    emax_f64 = std::max(emax_f64, std::fabs((double)((long double)f64 - ref)) / sc); pimax = std::max(pimax, (double)fabsl(ref));
+  }
+  { std::vector<long long> pf(8 * 1024); CK(cudaMemcpy(pf.data(), dprof, pf.size() * 8, cudaMemcpyDeviceToHost));
+    const char* nm[8] = {"phi load", "build", "mma wait", "acc load+sync", "fold", "tail", "issue", "tiles"};
+    for (int w = 0; w < 2; ++w) { printf("CTA 0 %s clk per tile:", w ? "MMA warp" : "warp 0"); for (int i = 0; i < 7; ++i) printf(" %s %.0f;", nm[i], (double)pf[w * 8 + i] / (double)pf[w * 8 + 7]); printf(" (%lld tiles)\n", pf[w * 8 + 7]); } }
+  const double flops = (double)npts * ((double)M * (M + 1) + 2.0 * M);
+  printf("npts %zu: %.3f ms -> %.1f M pts/s (FP64-equivalent %.1f TFLOP/s of the symmetric contraction); barrier timeouts %d\n", npts, best, npts / best / 1e3, flops / best / 1e9, fail);
+  printf("max |dPi| / max(1,|Pi|) over %zu points: int8 path %.3e (worst point %zu: got %.17g), plain FP64 loops %.3e; |Pi|max %.3g\n", ncheck, emax, worst, pi[worst], emax_f64, pimax);
+  return (fail || !(emax < 1e-12)) ? 2 : 0;
+}

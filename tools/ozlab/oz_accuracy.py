@@ -60,4 +60,60 @@ def main():
             err = np.abs((pi - pi_ref).astype(np.float64) / scale).max()
             print(f"S={S} pairs(s+t<={G})={npair:3d}: max |dPi|/max(1,|Pi|) = {err:.3e}")
 
-main()
+if not (len(sys.argv) > 2 and sys.argv[2] == 'bytes'):
+    main()
+
+
+BALANCED = len(sys.argv) > 3 and sys.argv[3] == 'balanced'
+HEAD = 1 if BALANCED else 0   # one bit of headroom so that the carry cannot overflow the top digit
+
+
+def byte_slices(A, axis, S):
+    """Two's-complement byte slicing of a (8 S)-bit fixed-point image: top byte signed, the rest unsigned;
+    pure bit extraction on the device (no per-digit arithmetic)."""
+    amax = np.abs(A).max(axis=axis, keepdims=True)
+    e = np.where(amax > 0, np.floor(np.log2(np.where(amax > 0, amax, 1.0))) + 1, 0.0)
+    V = np.rint(A / np.exp2(e) * np.exp2(8 * S - 1 - HEAD)).astype(np.int64)
+    V = np.clip(V, -(1 << (8 * S - 1)), (1 << (8 * S - 1)) - 1)
+    if BALANCED:   # signed digits in [-128, 127]: add 0x80 to every lower byte (carries ripple up), then re-centre
+        V = V + sum(128 << (8 * k) for k in range(S - 1))
+        out = [(((V >> (8 * k)) & 255) - 128) for k in range(S - 1)] + [V >> (8 * (S - 1))]
+        assert max(int(np.abs(o).max()) for o in out) <= 128 and int(out[-1].max()) <= 127
+    else:
+        out = [((V >> (8 * k)) & 255) for k in range(S - 1)] + [V >> (8 * (S - 1))]
+    return out, e
+
+
+def main_bytes(nact=20, npts=2048, ncore=83):
+    A1a, A1b, D2 = ob.synth_rdms(7, nact, nact // 2, nact // 2)
+    Dt, idx = folded(np.asarray(D2), nact)
+    w, phi, _ = ob.synth_fill_host(11, 5_000_000, 123_456, npts, ncore + nact, False)
+    pa = phi[:, ncore:]
+    X = np.stack([pa[:, t] * pa[:, u] for (t, u) in idx], axis=1)
+    Xl, Dl = X.astype(np.longdouble), Dt.astype(np.longdouble)
+    pi_ref = ((Xl @ Dl) * Xl).sum(axis=1)
+    scale = np.maximum(1.0, np.abs(pi_ref).astype(np.float64))
+    for S in (5, 6, 7):
+        xs, ex = byte_slices(X, 1, S)
+        ds, ed = byte_slices(Dt, 0, S)
+        for drop in (S - 2, S - 1, S):          # keep byte pairs with k + l >= drop
+            acc = np.zeros(X.shape, dtype=object); npair = 0; amax = 0
+            groups = {}
+            for k in range(S):
+                for l in range(S):
+                    if k + l < drop: continue
+                    npair += 1
+                    groups.setdefault(k + l, np.zeros(X.shape, dtype=np.int64))
+                    groups[k + l] += xs[k] @ ds[l]
+            Y = np.zeros(X.shape, dtype=np.longdouble)
+            for gsum, a in groups.items():
+                amax = max(amax, int(np.abs(a).max()))
+                Y += a.astype(np.longdouble) * np.exp2(np.longdouble(8 * gsum - 2 * (8 * S - 1 - HEAD)))
+            Y = Y * np.exp2(ex).astype(np.longdouble) * np.exp2(ed).astype(np.longdouble)
+            pi = (Y.astype(np.float64) * X).sum(axis=1)
+            err = np.abs((pi - pi_ref).astype(np.float64) / scale).max()
+            print(f"bytes S={S} pairs(k+l>={drop})={npair:3d} groups={len(groups)} max|acc|=2^{np.log2(max(amax,1)):.1f}: max |dPi|/max(1,|Pi|) = {err:.3e}")
+
+
+if len(sys.argv) > 2 and sys.argv[2] == "bytes":
+    main_bytes(int(sys.argv[1]))
