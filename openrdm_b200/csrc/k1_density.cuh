@@ -110,23 +110,26 @@ __global__ void __launch_bounds__(CORE_THREADS) k1_core(const Params P) {
 // K1 -- and what limits a co-resident kernel is how often its warps catch a free FP64 slot between
 // K2's DMMAs, so the FMA-light / byte-heavy core part (332 DFMAs for 2 656 bytes per point on config 4)
 // is the part to run there: it finishes about when K2 does (8.6 vs 8.2 ms; the full K1: 10.1 ms).
+// UNR = core orbitals per batch of loads.  UNR = 2: the shape described above (<= 64 registers).  UNR = 8 (<= 128
+// registers, 32 eight-byte loads in flight per thread): for running underneath the int8 K2 (k2_int8.cuh), which
+// leaves 17 K registers and no shared memory -- one such CTA per SM has to keep ~32 KB in flight on its own.
 constexpr int LIGHT_THREADS = 128;
-template <bool GGA>
-__global__ void __launch_bounds__(LIGHT_THREADS, 8) k1_core_light(const Params P) {
+template <bool GGA, int UNR>
+__global__ void __launch_bounds__(LIGHT_THREADS, UNR <= 2 ? 8 : 4) k1_core_light(const Params P) {
   const size_t ld = P.ld;
   for (size_t p = (size_t)blockIdx.x * LIGHT_THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * LIGHT_THREADS) {
     double rc = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
     int i = 0;
-    for (; i + 2 <= P.ncore; i += 2) {
-      double v[2], vx[2], vy[2], vz[2];
+    for (; i + UNR <= P.ncore; i += UNR) {
+      double v[UNR], vx[UNR], vy[UNR], vz[UNR];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < UNR; ++j) {
         const size_t o = (size_t)(i + j) * ld + p;
         v[j] = __ldcs(P.phi + o);
         if (GGA) { vx[j] = __ldcs(P.phix + o); vy[j] = __ldcs(P.phiy + o); vz[j] = __ldcs(P.phiz + o); }
       }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < UNR; ++j) {
         rc = fma(v[j], v[j], rc);
         if (GGA) { cx = fma(v[j], vx[j], cx); cy = fma(v[j], vy[j], cy); cz = fma(v[j], vz[j], cz); }
       }

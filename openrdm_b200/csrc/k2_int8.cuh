@@ -8,7 +8,8 @@
 //     accumulators in TMEM), one accumulator per group G = k + l, highest group first;
 //   * X slices 0..4 live in TMEM (A operand from TMEM, written with tcgen05.st), slice 5 and all of T in shared
 //     memory (K-major, no swizzle: 8 x 16-byte core matrices), the accumulator takes the remaining TMEM columns;
-//   * the epilogue folds two groups in INT32 (Z = 256 acc_G + acc_{G-1}) and dots them with the FP64 X row.
+//   * the accumulator is two independent column halves (own MMA chains and barriers): while the epilogue dots one
+//     half with the FP64 X row, straight from TMEM, the tensor cores fill the other.
 // Error against the FP64 contraction: the dropped pairs (k + l < GMIN) and the 46-bit images, |dPi| ~ 2e-14 (GMIN = 4)
 // or ~1e-13 (GMIN = 5) of max(1, |Pi|) on config-4-like data (tools/ozlab/oz_accuracy.py); the parity bar is 1e-12.
 // One CTA per SM, persistent over 128-point tiles: 8 compute warps (4 TMEM lane quadrants x 2 K halves; a thread
@@ -25,6 +26,9 @@ constexpr int TILE = 128;       // points per tile = MMA M
 constexpr int NSLICE = 6;       // byte slices per operand
 constexpr int CWARPS = 8;       // compute warps (build + epilogue); one more warp issues the MMAs
 constexpr int THREADS = (CWARPS + 1) * 32;
+#ifndef K2I_MAXREG
+#define K2I_MAXREG 128   // 9 warps are allocated as 12: at 128 registers the CTA leaves 16 K registers to a co-resident density CTA
+#endif
 constexpr int FIX_BITS = 46;    // |fixed-point image| <= 2^46 (one bit of headroom for the balancing carry)
 
 struct Geom {                   // everything derived from the padded pair count KP (multiple of 32)
@@ -140,39 +144,117 @@ __device__ __forceinline__ void build_half(const double (&phi)[NA], double scale
   }
 }
 
+// ---- epilogue of one group: sum_J X_J acc_J over this thread's half row, straight from TMEM.
+// Factored as sum_t phi_t (sum_u phi_u acc_tu): one exact int -> double (bit trick + DADD) and one DFMA per pair.
+// The half row is read as four regions of EPT/4 columns, four columns of each per step, so that consecutive DFMAs
+// feed different orbitals' chains (the FP64 pipe needs ~4 independent chains per warp), and the loads of step s + 1
+// are in flight while step s is folded.
+__host__ __device__ constexpr int pair_t_of(int na, int I) { int t = 0; while (I >= na - t) { I -= na - t; ++t; } return t; }
+__host__ __device__ constexpr int pair_u_of(int na, int I) { int t = 0; while (I >= na - t) { I -= na - t; ++t; } return t + I; }
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
+
+template <int NA, int R, int STEP, int J>
+__device__ __forceinline__ void fold_elem(const double (&phi)[NA], double (&s)[NA], const uint32_t (&v)[16]) {
+  constexpr int M = NA * (NA + 1) / 2, KP = (M + 31) / 32 * 32, EPT = KP / 2, Q = EPT / 4;
+  constexpr int I = EPT * R + Q * (J / 4) + 4 * STEP + (J % 4);   // region J / 4, column 4 STEP + J % 4 of it
+  if constexpr (I < M) {
+    constexpr int t = pair_t_of(NA, I), u = pair_u_of(NA, I);
+    const double zd = __hiloint2double(0x43300000, (int)(v[J] ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
+    s[t] = fma(phi[u], zd, s[t]);
+  }
+}
+
+template <int NA, int R, int STEP>
+__device__ __forceinline__ void fold_steps(const double (&phi)[NA], double (&s)[NA], uint32_t tmem_half, uint32_t (&cur)[16], uint32_t (&nxt)[16],
+                                           uint32_t drain_bar) {
+  constexpr int M = NA * (NA + 1) / 2, KP = (M + 31) / 32 * 32, EPT = KP / 2, Q = EPT / 4, NSTEP = Q / 4;
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");   // step STEP is in `cur`
+  if constexpr (STEP + 1 < NSTEP) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tmem_ld4(tmem_half + (uint32_t)(Q * k + 4 * (STEP + 1)), &nxt[4 * k]);
+  } else {   // every column of this half has been read: the next group's MMAs may overwrite it
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(drain_bar) : "memory");
+  }
+  fold_elem<NA, R, STEP, 0>(phi, s, cur); fold_elem<NA, R, STEP, 4>(phi, s, cur); fold_elem<NA, R, STEP, 8>(phi, s, cur); fold_elem<NA, R, STEP, 12>(phi, s, cur);
+  fold_elem<NA, R, STEP, 1>(phi, s, cur); fold_elem<NA, R, STEP, 5>(phi, s, cur); fold_elem<NA, R, STEP, 9>(phi, s, cur); fold_elem<NA, R, STEP, 13>(phi, s, cur);
+  fold_elem<NA, R, STEP, 2>(phi, s, cur); fold_elem<NA, R, STEP, 6>(phi, s, cur); fold_elem<NA, R, STEP, 10>(phi, s, cur); fold_elem<NA, R, STEP, 14>(phi, s, cur);
+  fold_elem<NA, R, STEP, 3>(phi, s, cur); fold_elem<NA, R, STEP, 7>(phi, s, cur); fold_elem<NA, R, STEP, 11>(phi, s, cur); fold_elem<NA, R, STEP, 15>(phi, s, cur);
+  if constexpr (STEP + 1 < NSTEP) fold_steps<NA, R, STEP + 1>(phi, s, tmem_half, nxt, cur, drain_bar);
+}
+
+// tmem_half: this thread's lane, first column of its half of the accumulator
 template <int NA, int R>
-__device__ __forceinline__ double fold_half(const double (&phi)[NA], const int* z) {
+__device__ __forceinline__ double fold_group(const double (&phi)[NA], uint32_t tmem_half, uint32_t drain_bar) {
+  constexpr int M = NA * (NA + 1) / 2, KP = (M + 31) / 32 * 32, EPT = KP / 2, Q = EPT / 4;
+  static_assert(Q % 4 == 0, "four regions of whole 4-column steps");
+  double s[NA];
+#pragma unroll
+  for (int t = 0; t < NA; ++t) s[t] = 0.0;
+  uint32_t va[16], vb[16];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) tmem_ld4(tmem_half + (uint32_t)(Q * k), &va[4 * k]);
+  fold_steps<NA, R, 0>(phi, s, tmem_half, va, vb, drain_bar);
   double part0 = 0.0, part1 = 0.0;
-  for_my_pairs<NA, R>([&](int i, int t, int u) {
-    const double zd = __hiloint2double(0x43300000, (int)((uint32_t)z[i] ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
-    if (i & 1) part1 = fma(phi[t] * phi[u], zd, part1); else part0 = fma(phi[t] * phi[u], zd, part0);
-  });
+#pragma unroll
+  for (int t = 0; t < NA; t += 2) {
+    part0 = fma(phi[t], s[t], part0);
+    if (t + 1 < NA) part1 = fma(phi[t + 1], s[t + 1], part1);
+  }
   return part0 + part1;
 }
 
-// all MMAs of group G = k + l (X slice k, T slice l), every descriptor a compile-time offset from a base:
-// the single issuing lane spends a handful of instructions per MMA
-template <int G, int KP>
-__device__ __forceinline__ void issue_group(uint32_t tmem, uint64_t bdesc0, uint64_t adesc5, uint32_t idesc0) {
-  constexpr int NCH = KP / 32, SL_COLS = KP / 4, A_COL = KP, KMAX = G < NSLICE - 1 ? G : NSLICE - 1, KMIN = G > NSLICE - 1 ? G - (NSLICE - 1) : 0;
+// The MMAs of group G = k + l (X slice k, T slice l) that feed one half of the accumulator columns -- H = 1: columns
+// [KP/2, KP), H = 0: columns [0, KP/2).  The two halves are separate MMA chains with their own completion barriers, so
+// one is drained by the epilogue while the tensor cores run the other.  K chunk kc of T only reaches columns >= 32 kc
+// (block-upper-triangular).  Every descriptor is a compile-time offset from a base: a few instructions per MMA.
+template <int G, int KP, int H>
+__device__ __forceinline__ void issue_half(uint32_t tmem, uint64_t bdesc0, uint64_t adesc5, uint32_t idesc0) {
+  constexpr int NCH = KP / 32, SL_COLS = KP / 4, A_COL = KP, HALF = KP / 2;
+  constexpr int KMAX = G < NSLICE - 1 ? G : NSLICE - 1, KMIN = G > NSLICE - 1 ? G - (NSLICE - 1) : 0;
 #pragma unroll
   for (int k = KMAX; k >= KMIN; --k) {
     const int l = G - k;
 #pragma unroll
     for (int kc = 0; kc < NCH; ++kc) {
-      const int nrows = Geom::chunk_rows(KP, kc);
-      const uint32_t idesc = idesc0 | ((uint32_t)(nrows >> 3) << 17);
-      const uint64_t bd = bdesc0 + (uint64_t)((l * Geom::slice_bytes(KP) + Geom::chunk_off(KP, kc)) >> 4) + ((uint64_t)(nrows * 16 >> 4) << 16);
+      if (H == 0 && 32 * kc >= HALF) continue;
+      const int c0 = H ? (32 * kc > HALF ? 32 * kc : HALF) : 32 * kc;   // first accumulator column written
+      const int n = (H ? KP : HALF) - c0, n0 = c0 - 32 * kc, rows = Geom::chunk_rows(KP, kc);
+      const uint32_t idesc = idesc0 | ((uint32_t)(n >> 3) << 17);
+      const uint64_t bd = bdesc0 + (uint64_t)((l * Geom::slice_bytes(KP) + Geom::chunk_off(KP, kc) + (n0 >> 3) * 128) >> 4) + ((uint64_t)(rows * 16 >> 4) << 16);
       const uint32_t first = (k == KMAX && kc == 0) ? 0u : 1u;
-      if (k < 5) mma_ts(tmem + 32 * kc, tmem + (uint32_t)(A_COL + SL_COLS * k + 8 * kc), bd, idesc, first);
-      else mma_ss(tmem + 32 * kc, adesc5 + (uint64_t)((kc * 2 * (TILE / 8) * 128) >> 4), bd, idesc, first);
+      if (k < 5) mma_ts(tmem + c0, tmem + (uint32_t)(A_COL + SL_COLS * k + 8 * kc), bd, idesc, first);
+      else mma_ss(tmem + c0, adesc5 + (uint64_t)((kc * 2 * (TILE / 8) * 128) >> 4), bd, idesc, first);
     }
   }
 }
 
+template <int KP, int H>
+__device__ __forceinline__ void issue_half_of(int G, uint32_t tmem, uint64_t bdesc0, uint64_t adesc5, uint32_t idesc0) {
+  switch (G) {
+    case 10: issue_half<10, KP, H>(tmem, bdesc0, adesc5, idesc0); break;
+    case 9: issue_half<9, KP, H>(tmem, bdesc0, adesc5, idesc0); break;
+    case 8: issue_half<8, KP, H>(tmem, bdesc0, adesc5, idesc0); break;
+    case 7: issue_half<7, KP, H>(tmem, bdesc0, adesc5, idesc0); break;
+    case 6: issue_half<6, KP, H>(tmem, bdesc0, adesc5, idesc0); break;
+    case 5: issue_half<5, KP, H>(tmem, bdesc0, adesc5, idesc0); break;
+    default: issue_half<4, KP, H>(tmem, bdesc0, adesc5, idesc0); break;
+  }
+}
+
+#ifdef K2I_PROF   // lab only (tools/ozlab): clock64 laps of CTA 0's left-half thread 0, right-half thread 128 and the MMA lane
+__device__ long long k2i_prof[3][8];
+#define K2I_LAP(i) do { if (blockIdx.x == 0 && (tid & 127) == 0) { const long long t_ = clock64(); pf_[i] += t_ - tc_; tc_ = t_; } } while (0)
+#else
+#define K2I_LAP(i) do { } while (0)
+#endif
+
 // GMIN: the slice pairs with k + l >= GMIN are kept (4: 26 pairs in 7 groups; 5: 21 pairs in 6 groups)
 template <int NA, int GMIN>
-__global__ void __launch_bounds__(THREADS, 1) k2i_ontop(Params P) {
+__global__ void __maxnreg__(K2I_MAXREG) k2i_ontop(Params P) {
   constexpr int M = NA * (NA + 1) / 2, KP = (M + 31) / 32 * 32;
   constexpr int EPT = KP / 2;
   static_assert(EPT % 16 == 0, "geometry");
@@ -181,7 +263,7 @@ __global__ void __launch_bounds__(THREADS, 1) k2i_ontop(Params P) {
   static_assert(A_COL + 5 * SL_COLS <= 512, "TMEM columns");
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(8) uint64_t bar_s;
+  __shared__ __align__(8) uint64_t bar_s[4];   // [0..1] accumulator half H complete (tcgen05.commit); [2..3] half H drained by its 128 threads
   uint8_t* s_t = smem;
   uint8_t* s_a5 = smem + Smem::a5_off(KP);
   double* s_part = (double*)(smem + Smem::part_off(KP, 0));
@@ -190,9 +272,12 @@ __global__ void __launch_bounds__(THREADS, 1) k2i_ontop(Params P) {
   const int q = warp & 3, r = (warp >> 2) & 1, p = 32 * q + lane;  // lane quadrant, K half, point within the tile
 
   for (int i = tid; i < (int)(Smem::t_bytes(KP) / 16); i += THREADS) ((int4*)s_t)[i] = ((const int4*)P.timg)[i];
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bar_s);
+  const uint32_t bar_full = (uint32_t)__cvta_generic_to_shared(&bar_s[0]), bar_drain = (uint32_t)__cvta_generic_to_shared(&bar_s[2]);
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    for (int h = 0; h < 2; ++h) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_full + 8 * h));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_drain + 8 * h), "r"(CWARPS * 32 / 2));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -209,9 +294,12 @@ __global__ void __launch_bounds__(THREADS, 1) k2i_ontop(Params P) {
   const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 4) << 24);
   uint8_t* a5_row = s_a5 + (p >> 3) * 128 + (p & 7) * 16;
   const uint64_t bdesc0 = smem_desc(st_addr, 0, 128), adesc5 = smem_desc(a5_addr, (TILE / 8) * 128, 128);
-  static_assert(NSLICE == 6 && (GMIN == 4 || GMIN == 5), "the group dispatch below is written for six slices");
-  uint32_t phase = 0;
-  bool ok = true;
+  static_assert(NSLICE == 6 && GMIN >= 4 && GMIN <= 10, "the group dispatch below is written for six slices, groups 10 .. 4");
+#ifdef K2I_PROF
+  long long pf_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc_ = clock64();
+#endif
+  uint32_t phase = 0;      // parity of the current group's barriers (one completion of each per group)
+  bool first_group = true, ok = true;
 
   const size_t ntiles = (P.npts + TILE - 1) / TILE;
   double* s_nxt = (double*)(smem + Smem::part_off(KP, 0) + 2 * TILE * 8);   // [NA][TILE]: the next tile's orbitals (cp.async)
@@ -232,6 +320,7 @@ __global__ void __launch_bounds__(THREADS, 1) k2i_ontop(Params P) {
     int e_raw = 534;
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();   // S1: this tile's orbitals are in shared memory
+    K2I_LAP(0);
     if (compute) {
       double m = 0.0;
 #pragma unroll
@@ -246,63 +335,42 @@ __global__ void __launch_bounds__(THREADS, 1) k2i_ontop(Params P) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();   // S2: operands ready (and every thread has read its orbitals)
+    K2I_LAP(1);
     if (compute) prefetch(tile + gridDim.x);
     double pi_acc = 0.0;
-    int z[EPT];
-    auto fold = [&](int Gdone) {   // the dot of a finished pair of groups with the FP64 X row
-      const double part = r == 0 ? fold_half<NA, 0>(phi, z) : fold_half<NA, 1>(phi, z);
-      pi_acc = fma(part, __hiloint2double((1023 + 8 * (Gdone - GMIN)) << 20, 0), pi_acc);
-    };
 #pragma unroll 1
     for (int G = 2 * (NSLICE - 1); G >= GMIN; --G) {
-      const bool upper = ((2 * (NSLICE - 1) - G) & 1) == 0;   // G = 10, 8, 6, (4) start a pair of groups; G = 9, 7, 5 finish it
       if (!compute) {
         if (lane == 0) {
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          switch (G) {
-            case 10: issue_group<10, KP>(tmem, bdesc0, adesc5, idesc0); break;
-            case 9: issue_group<9, KP>(tmem, bdesc0, adesc5, idesc0); break;
-            case 8: issue_group<8, KP>(tmem, bdesc0, adesc5, idesc0); break;
-            case 7: issue_group<7, KP>(tmem, bdesc0, adesc5, idesc0); break;
-            case 6: issue_group<6, KP>(tmem, bdesc0, adesc5, idesc0); break;
-            case 5: issue_group<5, KP>(tmem, bdesc0, adesc5, idesc0); break;
-            default: issue_group<4, KP>(tmem, bdesc0, adesc5, idesc0); break;
+#pragma unroll
+          for (int h = 1; h >= 0; --h) {   // right half first: its drain overlaps the left half's MMAs
+            if (!first_group) ok = wait_parity(bar_drain + 8 * h, phase ^ 1) && ok;   // the previous group has left this half
+            K2I_LAP(2);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (h) issue_half_of<KP, 1>(G, tmem, bdesc0, adesc5, idesc0); else issue_half_of<KP, 0>(G, tmem, bdesc0, adesc5, idesc0);
+            commit(bar_full + 8 * h);
+            K2I_LAP(3);
           }
-          commit(bar);
-          ok = wait_parity(bar, phase) && ok;
         }
-        phase ^= 1;
         __syncwarp();
-      } else if (upper && G != 2 * (NSLICE - 1)) {
-        fold(G + 1);   // previous pair of groups, while this group's MMAs run
-      }
-      __syncthreads();   // S3: accumulator complete
-      if (compute) {
+      } else {
+        ok = wait_parity(bar_full + 8 * r, phase) && ok;
+        K2I_LAP(5);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (upper) {
-#pragma unroll
-          for (int j0 = 0; j0 < EPT; j0 += 8) tmem_ld8(tmem + lane_addr + (uint32_t)(EPT * r + j0), (uint32_t*)&z[j0]);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        } else {
-#pragma unroll
-          for (int h = 0; h < EPT; h += 16) {
-            uint32_t v[16];
-            tmem_ld8(tmem + lane_addr + (uint32_t)(EPT * r + h), &v[0]);
-            tmem_ld8(tmem + lane_addr + (uint32_t)(EPT * r + h + 8), &v[8]);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 16; ++j) z[h + j] = z[h + j] * 256 + (int)v[j];
-          }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        const uint32_t tmem_half = tmem + lane_addr + (uint32_t)(EPT * r);
+        const double part = r == 0 ? fold_group<NA, 0>(phi, tmem_half, bar_drain) : fold_group<NA, 1>(phi, tmem_half, bar_drain + 8);
+        pi_acc = fma(part, __hiloint2double((1023 + 8 * (G - GMIN)) << 20, 0), pi_acc);
+        K2I_LAP(6);
+        if (G == GMIN) ok = wait_parity(bar_full + 8 * (r ^ 1), phase) && ok;   // every MMA of the tile is done: the X slices may be rebuilt
+        K2I_LAP(5);
       }
-      __syncthreads();   // S4: the accumulator may be overwritten by the next group
+      phase ^= 1;
+      first_group = false;
     }
-    if (compute) {
-      fold(GMIN);
-      s_part[r * TILE + p] = pi_acc;
-    }
+    if (compute) s_part[r * TILE + p] = pi_acc;
+    K2I_LAP(4);
     __syncthreads();   // S5
+    K2I_LAP(7);
     // ---- Pi = 2 * 2^(2 em - FIX) * 2^(t_exp - FIX) * 2^(8 GMIN) * (sum over the two K halves)
     if (compute && r == 0 && p0 + p < P.npts) {
       const double s = s_part[p] + s_part[TILE + p];
@@ -312,6 +380,9 @@ __global__ void __launch_bounds__(THREADS, 1) k2i_ontop(Params P) {
       P.pi[p0 + p] = P.pi_core ? pi_act + P.pi_core[p0 + p] : pi_act;
     }
   }
+#ifdef K2I_PROF
+  if (blockIdx.x == 0 && (tid & 127) == 0) for (int i = 0; i < 8; ++i) k2i_prof[tid >> 7][i] = pf_[i];
+#endif
   if (!ok && P.fail) atomicAdd(P.fail, 1);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -146,7 +146,7 @@ struct ordm_ctx {
   bool k2_ws = false, k2_force_plain = false;
   // K2 on the int8 tensor cores (k2_int8.cuh): 18..20 active orbitals, Pi only (grad Pi keeps the DMMA kernel)
   int k2_i8_mode = 1;          // ORDM_K2_INT8: 0 off, 1 on with 26 slice pairs (default), 2 on with 21 slice pairs
-  bool k2_i8 = false;
+  bool k2_i8 = false, i8_no_overlap = false;   // ORDM_I8_NO_OVERLAP=1: stages back to back with the int8 K2 (lab / test hook)
   k2i::Params k2ip{};
   uint8_t* d_timg = nullptr;
   int* d_i8_fail = nullptr;
@@ -298,15 +298,26 @@ int k3_grid(const ordm_ctx* c, size_t npts) {
 }
 
 // The core sums alone (rc, cx, cy, cz -> v.core[]), in the register-light shape that runs underneath K2.
-int run_k1_core_light(ordm_ctx* c, const GridView& v, int* launches, cudaStream_t st) {
+int run_k1_core_light(ordm_ctx* c, const GridView& v, int* launches, cudaStream_t st, bool deep = false) {
   k1::Params p{};
   p.phi = v.phi; p.phix = v.phix; p.phiy = v.phiy; p.phiz = v.phiz;
   p.ld = v.ld; p.npts = v.npts; p.ncore = c->ncore; p.nact = c->nact;
   p.core_rc = v.core[0]; p.core_cx = v.core[1]; p.core_cy = v.core[2]; p.core_cz = v.core[3];
   const size_t want = (v.npts + k1::LIGHT_THREADS - 1) / k1::LIGHT_THREADS;
-  const int grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 16));
-  if (v.gga) k1::k1_core_light<true><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
-  else k1::k1_core_light<false><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * (deep ? 1 : 16)));
+  if (deep) {   // next to the int8 K2: one CTA per SM with 32 loads in flight per thread
+    // K2 holds the SM at the maximum shared-memory carve-out, and an SM does not re-partition while a CTA is
+    // resident: ask for the same carve-out or this kernel waits for K2 to leave
+    static thread_local int carve_dev = -1;
+    if (carve_dev != c->device) {
+      CU(c, cudaFuncSetAttribute(k1::k1_core_light<true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CU(c, cudaFuncSetAttribute(k1::k1_core_light<false, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      carve_dev = c->device;
+    }
+    if (v.gga) k1::k1_core_light<true, 8><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
+    else k1::k1_core_light<false, 8><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
+  } else if (v.gga) k1::k1_core_light<true, 2><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
+  else k1::k1_core_light<false, 2><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
   CU(c, cudaGetLastError());
   *launches += 1;
   return ORDM_OK;
@@ -846,6 +857,7 @@ int ordm_create(int device, ordm_ctx** out) {
     return fail(nullptr, ORDM_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
   ordm_ctx* c = new ordm_ctx();
   c->device = device;
+  if (const char* e = getenv("ORDM_I8_NO_OVERLAP")) c->i8_no_overlap = (e[0] == '1');
   if (const char* e = getenv("ORDM_K2_INT8")) c->k2_i8_mode = atoi(e);   // 0: DMMA kernels only; 2: 21 slice pairs
   if (const char* e = getenv("ORDM_K2_PLAIN")) c->k2_force_plain = (e[0] == '1');  // test hook: single-buffer K2
   if (const char* e = getenv("ORDM_K1_SPLIT")) c->k1_split = (e[0] == '1');         // test hook: two-kernel K1
@@ -1253,23 +1265,32 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   // (only when K2 leaves a comfortable part of the SM's shared memory free: with 26 active orbitals K2
   //  takes 219 KB of the 228 and, although a K1 CTA nominally still fits, it was measured not to
   //  co-run -- K1 then queues behind the slightly slower lean K2: 93.6 vs 92.7 ms on config 5)
-  // (the int8 K2 owns the SM -- 223 KB of shared memory, all of TMEM -- and is short enough that the density
-  //  kernel does not hide underneath it: 8.47 ms overlapped vs 8.03 ms back to back on config 4)
-  const bool overlap = !c->serial_stages && !(c->opts & ORDM_OPT_SERIAL_STAGES) && c->k2_ws && !want_pig(c, c->g.gga) &&
-                       c->k2_smem + 32768 <= (size_t)c->max_smem_optin && !c->k2_i8;
   // With many core orbitals only their FMA-light, byte-heavy sums run underneath K2 (k1_core_light);
   // the active-space part of K1 follows on the main stream once both are done.
-  const bool split = overlap && c->core_form && c->ncore >= c->nact && c->g.core[0] && !c->no_split;
+  const bool split_ok = c->core_form && c->ncore >= c->nact && c->g.core[0] && !c->no_split;
+  // The int8 K2 owns the SM's shared memory and TMEM but leaves 17 K registers: only the split form fits beside it
+  // (one deep-unrolled core CTA per SM); without core orbitals to stream the stages run back to back.
+  const bool overlap = !c->serial_stages && !(c->opts & ORDM_OPT_SERIAL_STAGES) && c->k2_ws && !want_pig(c, c->g.gga) &&
+                       c->k2_smem + 32768 <= (size_t)c->max_smem_optin && (!c->k2_i8 || (split_ok && !c->i8_no_overlap));
+  const bool split = overlap && split_ok;
   CU(c, cudaEventRecord(c->ev[0], c->stream));
   if (overlap) {
     CU(c, cudaEventRecord(c->ev_fork, c->stream));
     CU(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
-    if ((rc = run_k2(c, c->g, &launches, /*lean=*/true))) return rc;
-    CU(c, cudaEventRecord(c->ev[2], c->stream));
+    // Launch order: the DMMA K2 goes first and the light core kernel fills the registers it leaves; the int8 K2
+    // takes one CTA slot per SM whatever is there, so the single deep core CTA per SM is placed first.
+    if (!c->k2_i8) {
+      if ((rc = run_k2(c, c->g, &launches, /*lean=*/true))) return rc;
+      CU(c, cudaEventRecord(c->ev[2], c->stream));
+    }
     CU(c, cudaEventRecord(c->ev_k1[0], c->side_stream));
-    if (split) { if ((rc = run_k1_core_light(c, c->g, &launches, c->side_stream))) return rc; }
+    if (split) { if ((rc = run_k1_core_light(c, c->g, &launches, c->side_stream, /*deep=*/c->k2_i8))) return rc; }
     else if ((rc = run_k1(c, c->g, 0, &launches, c->side_stream))) return rc;
     CU(c, cudaEventRecord(c->ev_k1[1], c->side_stream));
+    if (c->k2_i8) {
+      if ((rc = run_k2(c, c->g, &launches, /*lean=*/true))) return rc;
+      CU(c, cudaEventRecord(c->ev[2], c->stream));
+    }
     CU(c, cudaEventRecord(c->ev_join, c->side_stream));
     CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     CU(c, cudaEventRecord(c->ev[1], c->stream));  // = K2 and the side-stream part of K1 done

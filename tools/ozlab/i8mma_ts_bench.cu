@@ -102,6 +102,19 @@ __global__ void __launch_bounds__(128, 1) i8mma_kernel(Args g) {
       // ragged: K-step ks only feeds columns [32 ks, n) (block-upper-triangular B), i.e. rows 32 ks.. of B
       for (int p = 0; p < g.pairs; ++p) {
         const uint32_t a_t = tmem + 256 + 56 * (p % A_SLICES), bbase = sb_addr + (p % B_SLICES) * B_BYTES;
+        if (g.ragged == 2) {   // column halves: right half [112, n) from every K-step, then left half [32 ks, 112) from K-steps 0..3
+          for (int ks = 0; ks < KB / 32; ++ks) {
+            const int c0 = max(112, 32 * ks);
+            const uint32_t id = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((g.n - c0) >> 3) << 17);
+            mma_i8_ts(tmem + c0, a_t + 8 * ks, smem_desc(bbase + ks * 2 * B_LBO + (c0 >> 3) * 128, B_LBO, SBO), id, (it | p | ks) ? 1u : 0u);
+          }
+          for (int ks = 0; ks < 4; ++ks) {
+            const int c0 = 32 * ks;
+            const uint32_t id = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((112 - c0) >> 3) << 17);
+            mma_i8_ts(tmem + c0, a_t + 8 * ks, smem_desc(bbase + ks * 2 * B_LBO + (c0 >> 3) * 128, B_LBO, SBO), id, (it | p | ks) ? 1u : 0u);
+          }
+          continue;
+        }
 #pragma unroll
         for (int ks = 0; ks < KB / 32; ++ks) {
           const int c0 = g.ragged ? 32 * ks : 0;
@@ -182,7 +195,7 @@ int main(int argc, char** argv) {
   }
   double cmean = 0; for (auto c : clk) cmean += (double)c; cmean /= nsm;
   double mma_per_cta = 0, mac = 0;
-  for (int ks = 0; ks < KB / 32; ++ks) { const int c0 = ragged ? 32 * ks : 0; if (c0 < n) { mma_per_cta += (double)iters * pairs; mac += (double)iters * pairs * MROWS * (n - c0) * 32.0; } }
+  for (int ks = 0; ks < KB / 32; ++ks) { const int c0 = ragged ? 32 * ks : 0; if (c0 < n) { mma_per_cta += (double)iters * pairs * (ragged == 2 && ks < 4 ? 2 : 1); mac += (double)iters * pairs * MROWS * (n - c0) * 32.0; } }
   printf("TS%s N=%d pairs=%d iters=%d: %s, barrier timeouts %d; %.1f clk per MMA (ideal %.1f at 8192 MAC/clk/SM); kernel %.3f ms -> %.1f TOP/s int8 on %d SMs\n",
          ragged ? " ragged" : "", n, pairs, iters, bad ? "MISMATCH" : "exact", fail, cmean / mma_per_cta, mac / mma_per_cta / 8192.0, ms, 2.0 * mac * nsm / (ms * 1e-3) / 1e12, nsm);
   return bad || fail ? 2 : 0;

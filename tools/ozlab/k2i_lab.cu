@@ -1,8 +1,10 @@
-// k2i_lab.cu -- harness for the lab kernel k2i.cuh: random active-space orbitals and a dense symmetric D~,
+// k2i_lab.cu -- lab harness for the product kernel openrdm_b200/csrc/k2_int8.cuh: random active-space orbitals and a dense symmetric D~,
 // CPU reference in long double on a sample of points, timing with CUDA events.
 // build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o k2i_lab k2i_lab.cu
 // run:   timeout 60 ./k2i_lab [npts=2000000] [ncheck=2048]
-#include "k2i.cuh"
+#define K2I_PROF 1
+#include "../../openrdm_b200/csrc/k2_int8.cuh"
+#include "../../openrdm_b200/csrc/rdm_pack.h"
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -28,47 +30,27 @@ int main(int argc, char** argv) {
   for (int i = 0; i < M; ++i) for (int j = i; j < M; ++j) { const double v = ud(rng) * std::exp(-3.0 * std::fabs(ud(rng))); D[(size_t)i * M + j] = D[(size_t)j * M + i] = v; }
   std::vector<uint16_t> tu(704, 0);
   { int I = 0; for (int t = 0; t < NA; ++t) for (int u = t; u < NA; ++u) tu[I++] = (uint16_t)(t | (u << 8)); }
-  // T = block upper triangle of D~ (32 x 32 blocks, diagonal blocks halved), 48-bit fixed point, balanced bytes
-  std::vector<double> T((size_t)KP * KP, 0.0);
-  double tmax = 0.0;
-  for (int i = 0; i < M; ++i) for (int j = 0; j < M; ++j) {
-    const int bi = i / 32, bj = j / 32;
-    const double v = bi < bj ? D[(size_t)i * M + j] : (bi == bj ? 0.5 * D[(size_t)i * M + j] : 0.0);
-    T[(size_t)i * KP + j] = v; tmax = std::max(tmax, std::fabs(v));
-  }
-  int t_exp = 0; (void)std::frexp(tmax, &t_exp);   // tmax < 2^t_exp
-  const size_t slice_bytes = k2i::Geom::slice_bytes(KP);
-  std::vector<uint8_t> timg((size_t)k2i::NSLICE * slice_bytes, 0);
-  for (int kc = 0; kc < KP / 32; ++kc) {
-    const int nrows = k2i::Geom::chunk_rows(KP, kc);
-    for (int n = 0; n < nrows; ++n) for (int k = 0; k < 32; ++k) {
-      const int I = 32 * kc + k, J = 32 * kc + n;
-      const long long v = llrint(std::ldexp(T[(size_t)I * KP + J], k2i::FIX_BITS - t_exp)) + 0x0000008080808080ll;
-      for (int l = 0; l < k2i::NSLICE; ++l) {
-        uint8_t b = (uint8_t)((unsigned long long)v >> (8 * l));
-        if (l < 5) b ^= 0x80;
-        timg[(size_t)l * slice_bytes + k2i::Geom::chunk_off(KP, kc) + ((k >> 4) * (nrows >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (k & 15)] = b;
-      }
-    }
-  }
+  std::vector<uint8_t> timg; int t_exp = 0;
+  ordm::pack_t_int8(M, D, KP, timg, t_exp);
   double *dphi, *dpi; uint8_t* dt; int* dfail;
   CK(cudaMalloc(&dphi, phi.size() * 8)); CK(cudaMalloc(&dpi, npts * 8)); CK(cudaMalloc(&dt, timg.size())); CK(cudaMalloc(&dfail, 4));
   CK(cudaMemcpy(dphi, phi.data(), phi.size() * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dt, timg.data(), timg.size(), cudaMemcpyHostToDevice));
   CK(cudaMemset(dfail, 0, 4)); CK(cudaMemset(dpi, 0, npts * 8));
-  CK(cudaMemcpyToSymbol(k2i::c_tu, tu.data(), tu.size() * 2));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   const size_t smem = k2i::Smem::bytes(KP, NA);
   printf("smem %zu B (opt-in max %zu), T image %zu B, t_exp %d\n", smem, (size_t)prop.sharedMemPerBlockOptin, timg.size(), t_exp);
-  CK(cudaFuncSetAttribute(k2i::k2i_ontop<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  long long* dprof; CK(cudaMalloc(&dprof, 8 * 8 * 1024)); CK(cudaMemset(dprof, 0, 8 * 8 * 1024));
-  k2i::Params P{dphi, npts, npts, dt, t_exp, dpi, NA, M, KP, dfail, argc > 3 ? atoi(argv[3]) : 0, dprof};
+  CK(cudaFuncSetAttribute(k2i::k2i_ontop<NA, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k2i::k2i_ontop<NA, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int gmin = argc > 3 ? atoi(argv[3]) : 4;
+  k2i::Params P{dphi, npts, npts, dt, t_exp, nullptr, dpi, dfail};
+  auto launch = [&](int grid, size_t smem) { if (gmin == 4) k2i::k2i_ontop<NA, 4><<<grid, k2i::THREADS, smem>>>(P); else k2i::k2i_ontop<NA, 5><<<grid, k2i::THREADS, smem>>>(P); };
   const int grid = (int)std::min<size_t>((size_t)prop.multiProcessorCount, (npts + k2i::TILE - 1) / k2i::TILE);
-  k2i::k2i_ontop<NA><<<grid, k2i::THREADS, smem>>>(P);
+  launch(grid, smem);
   CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   float best = 1e30f;
   for (int rep = 0; rep < 3; ++rep) {
-    CK(cudaEventRecord(e0)); k2i::k2i_ontop<NA><<<grid, k2i::THREADS, smem>>>(P); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0)); launch(grid, smem); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = std::min(best, ms);
   }
   std::vector<double> pi(npts); int fail;
@@ -85,11 +67,13 @@ int main(int argc, char** argv) {
     if (e > emax) { emax = e; worst = p; }
     emax_f64 = std::max(emax_f64, std::fabs((double)((long double)f64 - ref)) / sc); pimax = std::max(pimax, (double)fabsl(ref));
   }
-  { std::vector<long long> pf(8 * 1024); CK(cudaMemcpy(pf.data(), dprof, pf.size() * 8, cudaMemcpyDeviceToHost));
-    const char* nm[8] = {"phi load", "build", "mma wait", "acc load+sync", "fold", "tail", "issue", "tiles"};
-    for (int w = 0; w < 2; ++w) { printf("CTA 0 %s clk per tile:", w ? "MMA warp" : "warp 0"); for (int i = 0; i < 7; ++i) printf(" %s %.0f;", nm[i], (double)pf[w * 8 + i] / (double)pf[w * 8 + 7]); printf(" (%lld tiles)\n", pf[w * 8 + 7]); } }
+  { long long pf[3][8]; CK(cudaMemcpyFromSymbol(pf, k2i::k2i_prof, sizeof(pf)));
+    const double nt = (double)((npts + 127) / 128 + grid - 1) / grid;
+    const char* who[3] = {"left-half thread", "right-half thread", "MMA lane"};
+    const char* nm[8] = {"S1 phi", "build+S2", "wait drain", "issue", "fold", "wait full", "acc load", "S5"};
+    for (int w = 0; w < 3; ++w) { printf("%s, clk per tile:", who[w]); for (int i = 0; i < 8; ++i) printf(" %s %.0f;", nm[i], (double)pf[w][i] / nt); printf("\n"); } }
   const double flops = (double)npts * ((double)M * (M + 1) + 2.0 * M);
-  printf("npts %zu: %.3f ms -> %.1f M pts/s (FP64-equivalent %.1f TFLOP/s of the symmetric contraction); barrier timeouts %d\n", npts, best, npts / best / 1e3, flops / best / 1e9, fail);
+  printf("GMIN %d: npts %zu: %.3f ms -> %.1f M pts/s (FP64-equivalent %.1f TFLOP/s of the symmetric contraction); barrier timeouts %d\n", gmin, npts, best, npts / best / 1e3, flops / best / 1e9, fail);
   printf("max |dPi| / max(1,|Pi|) over %zu points: int8 path %.3e (worst point %zu: got %.17g), plain FP64 loops %.3e; |Pi|max %.3g\n", ncheck, emax, worst, pi[worst], emax_f64, pimax);
   return (fail || !(emax < 1e-12)) ? 2 : 0;
 }
