@@ -239,6 +239,10 @@ def main():
     A1a, A1b, D2 = ordm.synth_rdms(cfg["seed"], cfg["nact"], cfg["nelec"], cfg["nelec"], 8)
     eng.set_options(diagnostics=False)
     eng.set_active_space(cfg["ncore"], A1a, A1b, D2)
+    pik = eng.pi_kernel_info()   # int8 tensor-core K2 (18..20 active orbitals) or the FP64 DMMA kernels
+    i8_pairs, i8_mma = pik["int8_slice_pairs"], pik["mma_per_tile"]
+    workload["pi_arithmetic"] = (f"exact int8 tensor-core products of {i8_pairs} byte-slice pairs of 46-bit fixed-point images, FP64 epilogue"
+                                 if i8_pairs else "FP64 (DMMA.8x8x4)")
     p0, cnt = ordm.shard_range(cfg["npts"], world, rank)
     eng.synth_fill(cfg["seed"], cfg["npts"], p0, cnt, n, gga)
     if world > 1:
@@ -362,18 +366,46 @@ def main():
             traffic = tr["config4_n1"]["k2_ontop"]
     except Exception:
         pass
-    roofline = {"kernel": "k2_ontop (Pi, DMMA.8x8x4)", "bound": "tensor", "achieved": k2_tf, "peak": dg_sus, "unit": "TFLOP/s", "frac": k2_tf / dg_sus,
-                "traffic": traffic, "peak_source": f"cuBLAS DGEMM 8192^3 measured in this process (sustained {dg_sus:.2f}, burst {dg_burst:.2f} TFLOP/s)",
-                "algorithmic_flops_per_point": alg["k2_flops"], "survey_flops_per_point": alg["k2_flops_survey"],
-                "achieved_survey_count": alg["k2_flops_survey"] * pts_rank / (ms_k["pi"] * 1e-3) * 1e-12,
-                "share_of_step": ms_k["pi"] / ms_step}
+    if i8_pairs:
+        # int8 tensor-core K2 (csrc/k2_int8.cuh): algorithmic work = the exact slice-pair products of the block-upper-
+        # triangular contraction, 2 ops per int8 multiply-add; the FP64 flop count of the same contraction is kept beside it
+        kp = (alg["M"] + 31) // 32 * 32
+        i8_ops = 2 * i8_pairs * 32 * sum(kp - 32 * kc for kc in range(kp // 32))
+        sm_mhz = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        i8_peak = 2 * 8192 * 148 * sm_mhz * 1e6 * 1e-12
+        def i8_top(ms):
+            return i8_ops * pts_rank / (ms * 1e-3) * 1e-12
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01g_traffic.json")) as f:
+                tr = json.load(f)
+            traffic = tr["config4_n1"]["k2_int8"] if args.config == 4 and world == 1 and not args.npts else None
+        except Exception:
+            traffic = None
+        roofline = {"kernel": f"k2i_ontop (Pi, tcgen05.mma kind::i8, {i8_pairs} slice pairs)", "bound": "tensor", "achieved": i8_top(ms_k["pi"]), "peak": i8_peak,
+                    "unit": "TOP/s", "frac": i8_top(ms_k["pi"]) / i8_peak, "traffic": traffic,
+                    "peak_source": f"8192 int8 MAC/clk/SM x 148 SMs x {sm_mhz:.0f} MHz: the issue rate measured by tools/ozlab/i8mma_bench "
+                                   "(112.2 clk per 128x224x32 MMA, profiles/r01f_i8mma_microbench.log); MEASURED_PEAKS.json has no int8 figure "
+                                   f"(2 x its dense bf16 burst = {2 * peaks.get('bf16_tflops', 0):.0f} TOP/s)",
+                    "algorithmic_int8_ops_per_point": i8_ops, "mma_per_128_point_tile": i8_mma,
+                    "fp64_flops_per_point_of_the_same_contraction": alg["k2_flops"], "fp64_equivalent_tflops": k2_tf,
+                    "fp64_equivalent_vs_cublas_dgemm": k2_tf / dg_sus,
+                    "dgemm_peak_source": f"cuBLAS DGEMM 8192^3 measured in this process (sustained {dg_sus:.2f}, burst {dg_burst:.2f} TFLOP/s)",
+                    "share_of_step": ms_k["pi"] / ms_step}
+    else:
+        roofline = {"kernel": "k2_ontop (Pi, DMMA.8x8x4)", "bound": "tensor", "achieved": k2_tf, "peak": dg_sus, "unit": "TFLOP/s", "frac": k2_tf / dg_sus,
+                    "traffic": traffic, "peak_source": f"cuBLAS DGEMM 8192^3 measured in this process (sustained {dg_sus:.2f}, burst {dg_burst:.2f} TFLOP/s)",
+                    "algorithmic_flops_per_point": alg["k2_flops"], "survey_flops_per_point": alg["k2_flops_survey"],
+                    "achieved_survey_count": alg["k2_flops_survey"] * pts_rank / (ms_k["pi"] * 1e-3) * 1e-12,
+                    "share_of_step": ms_k["pi"] / ms_step}
     def kernel_table(ms):
         g1 = alg["k1_bytes"] * pts_rank / (ms["density"] * 1e-3) * 1e-9
         g3 = alg["k3_bytes"] * pts_rank / (ms["xc"] * 1e-3) * 1e-9
         t2 = alg["k2_flops"] * pts_rank / (ms["pi"] * 1e-3) * 1e-12
         return {
             "k1_density": {"ms": ms["density"], "bound": "hbm", "achieved": g1, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": g1 / peaks["hbm_gbs"], "bytes_per_point": alg["k1_bytes"]},
-            "k2_ontop": {"ms": ms["pi"], "bound": "tensor", "achieved": t2, "peak": dg_sus, "unit": "TFLOP/s", "frac": t2 / dg_sus},
+            "k2_ontop": ({"ms": ms["pi"], "bound": "tensor", "achieved": i8_top(ms["pi"]), "peak": i8_peak, "unit": "TOP/s", "frac": i8_top(ms["pi"]) / i8_peak,
+                          "fp64_equivalent_tflops": t2} if i8_pairs else
+                         {"ms": ms["pi"], "bound": "tensor", "achieved": t2, "peak": dg_sus, "unit": "TFLOP/s", "frac": t2 / dg_sus}),
             "k3_translate_xc": {"ms": ms["xc"], "bound": "hbm (FP64-ALU limited, DESIGN.md)", "achieved": g3, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": g3 / peaks["hbm_gbs"], "bytes_per_point": alg["k3_bytes"],
                                 "fp64_alu": {"instr_per_point_estimate": 500 if gga else 330, "achieved_ginstr_s": (500 if gga else 330) * pts_rank / (ms["xc"] * 1e-3) * 1e-9,
                                              "peak_ginstr_s": 16700.0, "note": "DFMA issue peak 33.4 TFLOP/s / 2 (profiles/r01_fp64_peaks_microbench.log); ncu: FP64 pipe 46-48 % active (profiles/r01c_ncu_full_k1_k2_k3.csv)"}},
@@ -385,6 +417,9 @@ def main():
                           "follows; k1_density.ms = both parts, overlapping k2_ontop.ms in time",
                        1: "overlapped: k1_density streams underneath k2_ontop on a second stream (their ms overlap in time); k3 joins both",
                        0: "stages back to back on one stream"}[overlapped]
+    if i8_pairs and overlapped == 2:
+        kernels["mode"] = ("overlapped/split: K1's core-orbital sums (k1_core_light<.,8>, one deep-unrolled CTA per SM) stream beside the int8 k2i_ontop "
+                           "on a second stream, its active-space part follows; k1_density.ms = both parts, overlapping k2_ontop.ms in time")
     if ms_iso:
         kernels["isolated"] = kernel_table(ms_iso)
         kernels["isolated"]["ms_per_step"] = ms_step_serial

@@ -99,6 +99,15 @@ typedef struct {
                              part followed (ms_density = both parts); 0: stages ran back to back */
 } ordm_result;
 
+/* Which kernel computes the active-space on-top pair density for the RDMs currently set (no reference
+ * counterpart; for benchmarks and logs).  *int8_slice_pairs > 0: the int8 tensor-core kernel
+ * (tcgen05.mma.kind::i8 over exact byte slices of 46-bit fixed-point images, csrc/k2_int8.cuh; 18..20 active
+ * orbitals, Pi without grad Pi) with that many slice-pair products; 0: the FP64 tensor-pipe kernels
+ * (DMMA.8x8x4, csrc/k2_ontop.cuh).  Environment ORDM_K2_INT8 = 0 | 1 (26 pairs, default) | 2 (21 pairs) picks
+ * at context creation.  *mma_per_tile = tensor-core instructions per 128-point (int8) / 32-point (FP64) tile.
+ * Pointers may be NULL; ORDM_ERR_STATE before the 2-RDM is set. */
+int ordm_pi_kernel_info(const ordm_ctx* ctx, int* int8_slice_pairs, uint64_t* mma_per_tile);
+
 /* ---- lifecycle ----------------------------------------------------------------------- */
 const char* ordm_version(void);
 int ordm_device_count(void);

@@ -99,6 +99,7 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.ordm_comm_unique_id.argtypes = [C.c_char_p]
     lib.ordm_comm_attach.argtypes = [P, I, I, C.c_char_p]
     lib.ordm_comm_info.argtypes = [P, C.POINTER(I), C.POINTER(I), C.POINTER(I)]
+    lib.ordm_pi_kernel_info.argtypes = [P, C.POINTER(I), C.POINTER(C.c_uint64)]
     lib.ordm_shard_range.argtypes = [S, I, I, C.POINTER(S), C.POINTER(S)]
     lib.ordm_shard_range.restype = None
     _lib = lib
@@ -287,6 +288,12 @@ class Engine:
 
     def comm_attach(self, nranks, rank, uid: bytes):
         self._ck(self.lib.ordm_comm_attach(self.ctx, nranks, rank, C.create_string_buffer(uid, 128)))
+
+    def pi_kernel_info(self) -> dict:
+        """Which kernel builds the active-space on-top pair density (see ordm_pi_kernel_info)."""
+        n, m = C.c_int(), C.c_uint64()
+        self._ck(self.lib.ordm_pi_kernel_info(self.ctx, C.byref(n), C.byref(m)))
+        return {"int8_slice_pairs": n.value, "mma_per_tile": m.value}
 
     def comm_info(self) -> dict:
         n, r, p = C.c_int(), C.c_int(), C.c_int()

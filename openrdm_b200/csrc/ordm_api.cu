@@ -1512,6 +1512,23 @@ int ordm_comm_info(const ordm_ctx* c, int* nranks, int* rank, int* peer_allreduc
   return ORDM_OK;
 }
 
+int ordm_pi_kernel_info(const ordm_ctx* c, int* int8_slice_pairs, uint64_t* mma_per_tile) {
+  if (!c) return fail(nullptr, ORDM_ERR_INVALID, "null context");
+  if (!c->have_rdm2) return fail(const_cast<ordm_ctx*>(c), ORDM_ERR_STATE, "ordm_pi_kernel_info: no 2-RDM set");
+  const bool i8 = c->k2_i8 && !want_pig(c, c->g.gga);
+  const int pairs = c->k2_i8_mode == 1 ? 26 : 21;
+  if (int8_slice_pairs) *int8_slice_pairs = i8 ? pairs : 0;
+  if (mma_per_tile) {
+    if (i8) {   // per slice pair: every 32-pair K chunk feeds the right column half, the chunks below it the left half too
+      const int kp = (ordm::pair_count(c->nact) + 31) / 32 * 32;
+      *mma_per_tile = (uint64_t)pairs * (uint64_t)(kp / 32 + (kp / 2 + 31) / 32);
+    } else {
+      *mma_per_tile = c->k2_dmma_per_mtile;
+    }
+  }
+  return ORDM_OK;
+}
+
 int ordm_comm_detach(ordm_ctx* c) {
   CHECK_CTX(c);
   release_peer_xchg(c);
