@@ -678,8 +678,15 @@ int check_inputs(ordm_ctx* c, bool need_rdm2) {
 
 int fetch_result(ordm_ctx* c, double eclass, ordm_result* out, uint64_t npts, int launches) {
   CU(c, cudaMemcpyAsync(c->h_res, c->d_res, ordm::RES_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  int* h_i8_fail = reinterpret_cast<int*>(c->h_res + 12);   // the pinned block has room beyond the RES_COUNT scalars
+  *h_i8_fail = 0;
+  if (c->k2_i8 && c->d_i8_fail) CU(c, cudaMemcpyAsync(h_i8_fail, c->d_i8_fail, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaEventRecord(c->ev[5], c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  if (*h_i8_fail) {   // a tcgen05 completion barrier never flipped (bounded spin in k2_int8.cuh): the Pi of this call is not valid
+    cudaMemsetAsync(c->d_i8_fail, 0, sizeof(int), c->stream);
+    return fail(c, ORDM_ERR_CUDA, "int8 on-top kernel: %d CTA(s) timed out waiting for a tensor-core completion barrier", *h_i8_fail);
+  }
   const double* r = c->h_res;
   std::memset(out, 0, sizeof(*out));
   out->eclass = eclass;
