@@ -34,6 +34,18 @@ def test_library_carries_sm100a_tensor_and_tma_code():
     assert "DMMA.8x8x4" in sass      # FP64 tensor pipe (K2)
     assert "UBLKCP" in sass          # TMA bulk copy (K2 tile loads)
     assert "SYNCS" in sass           # mbarrier
+    assert "UTCIMMA" in sass         # tcgen05.mma kind::i8 (K2 for 18..20 active orbitals, csrc/k2_int8.cuh)
+    assert "LDTM" in sass and "STTM" in sass   # tcgen05.ld / tcgen05.st: TMEM accumulators and A operand
+
+
+@pytest.mark.parametrize("nact", [18, 19, 20])
+def test_int8_operand_image_decodes_to_the_folded_rdm(tmp_path, nact):
+    """ordm::pack_t_int8 (host side of the int8 tensor-core K2): the six balanced byte slices in shared-memory order
+    decode to the block-upper-triangular T with T + T^T = D~ to within one unit of the 46-bit image."""
+    exe = str(tmp_path / "pack_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "pack_t_int8_check.cc")], check=True)
+    r = subprocess.run([exe, str(nact)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
 
 
 def test_create_fails_loudly_without_gpu(ordm):
