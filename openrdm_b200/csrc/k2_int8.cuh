@@ -3,7 +3,7 @@
 // i.e. MCPDFT::build_ontop_pair_density (/root/reference/src/libmcpdft/mcpdft.cc:185-212) restricted to the active
 // orbitals, contracted by tcgen05.mma.kind::i8 through an Ozaki-style exact integer split:
 //   * D~ = T + T^T with T block-upper-triangular (32 x 32 blocks, diagonal blocks halved), so Pi = 2 sum_J X_J (X T)_J;
-//   * every X row (against (max_t |phi_t|)^2) and T (against max |T|) becomes a 48-bit fixed-point image cut into
+//   * every X row (against (max_t |phi_t|)^2) and T (against max |T|) becomes a 46-bit fixed-point image cut into
 //     six balanced signed bytes; the slice pairs (k, l) with k + l >= GMIN are multiplied exactly (INT32
 //     accumulators in TMEM), one accumulator per group G = k + l, highest group first;
 //   * X slices 0..4 live in TMEM (A operand from TMEM, written with tcgen05.st), slice 5 and all of T in shared
@@ -32,14 +32,10 @@ constexpr int THREADS = (CWARPS + 1) * 32;
 constexpr int FIX_BITS = 46;    // |fixed-point image| <= 2^46 (one bit of headroom for the balancing carry)
 
 struct Geom {                   // everything derived from the padded pair count KP (multiple of 32)
-  int kp, nchunk;
   __host__ __device__ static constexpr int chunk_rows(int kp, int kc) { return kp - 32 * kc; }                 // N of K-chunk kc
   __host__ __device__ static constexpr int chunk_off(int kp, int kc) { return 32 * (kc * kp - 16 * kc * (kc - 1)); }  // bytes before chunk kc
   __host__ __device__ static constexpr int slice_bytes(int kp) { return chunk_off(kp, kp / 32); }
 };
-
-// byte offset of element (row r, K-byte k) in a K-major no-swizzle canonical operand with R rows
-__host__ __device__ inline int canon(int r, int k, int R) { return ((k >> 4) * (R >> 3) + (r >> 3)) * 128 + (r & 7) * 16 + (k & 15); }
 
 struct Params {
   const double* phi_act;   // [nact][ld]: orbital t of point p at phi_act[t * ld + p]
@@ -71,22 +67,14 @@ __device__ __forceinline__ bool wait_parity(uint32_t bar, uint32_t parity) {
   }
   return false;
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
-               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
-}
-
-// shared-memory plan (dynamic): T image | X slice 5 (canonical 128 x KP) | partial sums [2][128]  (pass nact = 0)
+// shared-memory plan (dynamic): T image | X slice 5 (K-major no-swizzle operand, 128 rows x KP bytes) |
+// partial sums [2][128] doubles | the next tile's orbitals [nact][128] doubles (cp.async)
 struct Smem {
   __host__ __device__ static size_t t_bytes(int kp) { return (size_t)NSLICE * Geom::slice_bytes(kp); }
   __host__ __device__ static size_t a5_off(int kp) { return t_bytes(kp); }
-  __host__ __device__ static size_t phi_off(int kp) { return a5_off(kp) + (size_t)TILE * kp; }
-  __host__ __device__ static size_t part_off(int kp, int nact) { return phi_off(kp) + (size_t)nact * TILE * 8; }
-  __host__ __device__ static size_t bytes(int kp, int nact_next) { return part_off(kp, 0) + 2 * TILE * 8 + (size_t)nact_next * TILE * 8; }
+  __host__ __device__ static size_t part_off(int kp) { return a5_off(kp) + (size_t)TILE * kp; }
+  __host__ __device__ static size_t next_off(int kp) { return part_off(kp) + 2 * TILE * 8; }
+  __host__ __device__ static size_t bytes(int kp, int nact) { return next_off(kp) + (size_t)nact * TILE * 8; }
 };
 
 // Thread layout: 8 compute warps = 4 lane quadrants x 2 K halves: a thread owns one point of the tile and EPT = KP/2
@@ -266,7 +254,7 @@ __global__ void __maxnreg__(K2I_MAXREG) k2i_ontop(Params P) {
   __shared__ __align__(8) uint64_t bar_s[4];   // [0..1] accumulator half H complete (tcgen05.commit); [2..3] half H drained by its 128 threads
   uint8_t* s_t = smem;
   uint8_t* s_a5 = smem + Smem::a5_off(KP);
-  double* s_part = (double*)(smem + Smem::part_off(KP, 0));
+  double* s_part = (double*)(smem + Smem::part_off(KP));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool compute = warp < CWARPS;
   const int q = warp & 3, r = (warp >> 2) & 1, p = 32 * q + lane;  // lane quadrant, K half, point within the tile
@@ -302,7 +290,7 @@ __global__ void __maxnreg__(K2I_MAXREG) k2i_ontop(Params P) {
   bool first_group = true, ok = true;
 
   const size_t ntiles = (P.npts + TILE - 1) / TILE;
-  double* s_nxt = (double*)(smem + Smem::part_off(KP, 0) + 2 * TILE * 8);   // [NA][TILE]: the next tile's orbitals (cp.async)
+  double* s_nxt = (double*)(smem + Smem::next_off(KP));   // [NA][TILE]: the next tile's orbitals (cp.async)
   auto prefetch = [&](size_t tile) {   // K half r fetches the orbitals t = r, r + 2, ... of point p
     const size_t pp = tile * TILE + p;
 #pragma unroll
@@ -322,11 +310,11 @@ __global__ void __maxnreg__(K2I_MAXREG) k2i_ontop(Params P) {
     __syncthreads();   // S1: this tile's orbitals are in shared memory
     K2I_LAP(0);
     if (compute) {
-      double m = 0.0;
+      uint32_t mh = 0;   // max over t of the high word of |phi_t|: its exponent field is that of max |phi_t| (integer max: no FP64 chain)
 #pragma unroll
-      for (int t = 0; t < NA; ++t) { phi[t] = s_nxt[t * TILE + p]; m = fmax(m, fabs(phi[t])); }
-      // row scale: max |X| = (max_t |phi_t|)^2 < 2^(2 em)
-      e_raw = max((__double2hiint(m) >> 20) & 0x7FF, 534);
+      for (int t = 0; t < NA; ++t) { phi[t] = s_nxt[t * TILE + p]; mh = max(mh, (uint32_t)__double2hiint(phi[t]) & 0x7FFFFFFFu); }
+      // row scale: max |X| = (max_t |phi_t|)^2 < 2^(2 em); the clamps keep the two scale factors finite normal numbers
+      e_raw = min(max((int)(mh >> 20), 534), 1500);
       const double scale = __hiloint2double((3113 - 2 * e_raw + (FIX_BITS - 46)) << 20, 0);  // 2^(FIX_BITS - 2 em)
       const uint32_t tmem_row = tmem + lane_addr + (uint32_t)A_COL;
       if (r == 0) build_half<NA, 0>(phi, scale, tmem_row, a5_row); else build_half<NA, 1>(phi, scale, tmem_row, a5_row);
