@@ -502,3 +502,36 @@ def test_int8_tensor_core_pi_vs_oracle(port, ordm, monkeypatch, nact, ncore, npt
     d = np.abs(pis[mode] - pis["0"]) / np.maximum(1.0, np.abs(pis["0"]))
     assert d.max() <= 1e-12, d.max()
     assert d.max() > 0.0   # the two paths really are different kernels
+
+
+@pytest.mark.parametrize("nact,ncore,npts,kind,mode", [(18, 0, 257, "ensemble", "1"), (20, 0, 200, "nonsym", "1"), (20, 2, 129, "ensemble", "2"),
+                                                       (19, 0, 130, "nonsym", "2")])
+def test_int8_tensor_core_pi_dense_rotated_rdms(port, ordm, monkeypatch, nact, ncore, npts, kind, mode):
+    """The int8 on-top kernel on the golden-vector construction (tests/golden/make_golden.py::random_case): dense 2-RDMs of
+    rotated determinants, optionally with sign-indefinite noise ("nonsym"), orbital rows whose magnitudes span 2^-47 .. 1
+    (the per-row power-of-two scaling of the fixed-point images), with and without core orbitals."""
+    rng = np.random.default_rng(4000 + 10 * nact + ncore)
+    phi, grads, w, A1a, A1b, D2 = random_case(rng, nact, npts, kind, ndet=4)
+    if ncore:
+        phic = np.asfortranarray(rng.uniform(-0.4, 0.4, (npts, ncore)))
+        gc = [np.asfortranarray(rng.uniform(-0.4, 0.4, (npts, ncore))) for _ in range(3)]
+        phi = np.asfortranarray(np.hstack([phic, phi]))
+        grads = [np.asfortranarray(np.hstack([a, b])) for a, b in zip(gc, grads)]
+    want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, "PBE", grads, eclass=0.0)
+    monkeypatch.setenv("ORDM_K2_INT8", mode)
+    eng = ordm.Engine(0)
+    try:
+        eng.set_options(diagnostics=True)
+        eng.set_grid(w); eng.set_orbitals(phi, grads); eng.set_active_space(ncore, A1a, A1b, D2)
+        assert eng.pi_kernel_info()["int8_slice_pairs"] == (26 if mode == "1" else 21)
+        got = eng.energy(FN["PBE"], 0.0)
+        check_scalars(got, want.scalars)
+        check_vectors(eng.get_vector, want.vecs, True)
+        a, b = eng.get_vector("pi"), want.vecs["pi"]
+        # rows far below 1 must be resolved relative to themselves, not to the largest row of the grid
+        small = np.abs(b) < 1e-6
+        if small.any() and (np.abs(b[small]) > 1e-300).any():
+            rel = np.abs(a[small] - b[small]) / np.maximum(np.abs(b[small]), 1e-300)
+            assert np.median(rel) < 1e-9, np.median(rel)
+    finally:
+        eng.close()
