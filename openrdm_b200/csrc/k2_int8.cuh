@@ -235,9 +235,12 @@ __device__ __forceinline__ void issue_half_of(int G, uint32_t tmem, uint64_t bde
 
 #ifdef K2I_PROF   // lab only (tools/ozlab): clock64 laps of CTA 0's left-half thread 0, right-half thread 128 and the MMA lane
 __device__ long long k2i_prof[3][8];
+__device__ long long k2i_trace[3][40];   // clock64 stamps of CTA 0's 40th tile: [0] left-half thread, [1] right-half thread, [2] MMA lane
+#define K2I_STAMP(i) do { if (blockIdx.x == 0 && (tid & 127) == 0 && ntile_ == 40) k2i_trace[tid >> 7][i] = clock64(); } while (0)
 #define K2I_LAP(i) do { if (blockIdx.x == 0 && (tid & 127) == 0) { const long long t_ = clock64(); pf_[i] += t_ - tc_; tc_ = t_; } } while (0)
 #else
 #define K2I_LAP(i) do { } while (0)
+#define K2I_STAMP(i) do { } while (0)
 #endif
 
 // GMIN: the slice pairs with k + l >= GMIN are kept (4: 26 pairs in 7 groups; 5: 21 pairs in 6 groups)
@@ -285,6 +288,7 @@ __global__ void __maxnreg__(K2I_MAXREG) k2i_ontop(Params P) {
   static_assert(NSLICE == 6 && GMIN >= 4 && GMIN <= 10, "the group dispatch below is written for six slices, groups 10 .. 4");
 #ifdef K2I_PROF
   long long pf_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc_ = clock64();
+  int ntile_ = -1;
 #endif
   uint32_t phase = 0;      // parity of the current group's barriers (one completion of each per group)
   bool first_group = true, ok = true;
@@ -306,6 +310,11 @@ __global__ void __maxnreg__(K2I_MAXREG) k2i_ontop(Params P) {
     const size_t p0 = tile * TILE;
     double phi[NA];
     int e_raw = 534;
+#ifdef K2I_PROF
+    ++ntile_;
+    int gi_ = 0;
+#endif
+    K2I_STAMP(0);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();   // S1: this tile's orbitals are in shared memory
     K2I_LAP(0);
@@ -324,6 +333,7 @@ __global__ void __maxnreg__(K2I_MAXREG) k2i_ontop(Params P) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();   // S2: operands ready (and every thread has read its orbitals)
     K2I_LAP(1);
+    K2I_STAMP(1);
     if (compute) prefetch(tile + gridDim.x);
     double pi_acc = 0.0;
 #pragma unroll 1
@@ -334,31 +344,39 @@ __global__ void __maxnreg__(K2I_MAXREG) k2i_ontop(Params P) {
           for (int h = 1; h >= 0; --h) {   // right half first: its drain overlaps the left half's MMAs
             if (!first_group) ok = wait_parity(bar_drain + 8 * h, phase ^ 1) && ok;   // the previous group has left this half
             K2I_LAP(2);
+            K2I_STAMP(2 + 4 * gi_ + 2 * (1 - h));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (h) issue_half_of<KP, 1>(G, tmem, bdesc0, adesc5, idesc0); else issue_half_of<KP, 0>(G, tmem, bdesc0, adesc5, idesc0);
             commit(bar_full + 8 * h);
             K2I_LAP(3);
+            K2I_STAMP(3 + 4 * gi_ + 2 * (1 - h));
           }
         }
         __syncwarp();
       } else {
         ok = wait_parity(bar_full + 8 * r, phase) && ok;
         K2I_LAP(5);
+        K2I_STAMP(2 + 2 * gi_);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_half = tmem + lane_addr + (uint32_t)(EPT * r);
         const double part = r == 0 ? fold_group<NA, 0>(phi, tmem_half, bar_drain) : fold_group<NA, 1>(phi, tmem_half, bar_drain + 8);
         pi_acc = fma(part, __hiloint2double((1023 + 8 * (G - GMIN)) << 20, 0), pi_acc);
         K2I_LAP(6);
+        K2I_STAMP(3 + 2 * gi_);
         if (G == GMIN) ok = wait_parity(bar_full + 8 * (r ^ 1), phase) && ok;   // every MMA of the tile is done: the X slices may be rebuilt
         K2I_LAP(5);
       }
       phase ^= 1;
       first_group = false;
+#ifdef K2I_PROF
+      ++gi_;
+#endif
     }
     if (compute) s_part[r * TILE + p] = pi_acc;
     K2I_LAP(4);
     __syncthreads();   // S5
     K2I_LAP(7);
+    K2I_STAMP(38);
     // ---- Pi = 2 * 2^(2 em - FIX) * 2^(t_exp - FIX) * 2^(8 GMIN) * (sum over the two K halves)
     if (compute && r == 0 && p0 + p < P.npts) {
       const double s = s_part[p] + s_part[TILE + p];

@@ -74,6 +74,12 @@ int main(int argc, char** argv) {
     const char* who[3] = {"left-half thread", "right-half thread", "MMA lane"};
     const char* nm[8] = {"S1 phi", "build+S2", "wait drain", "issue", "fold", "wait full", "acc load", "S5"};
     for (int w = 0; w < 3; ++w) { printf("%s, clk per tile:", who[w]); for (int i = 0; i < 8; ++i) printf(" %s %.0f;", nm[i], (double)pf[w][i] / nt); printf("\n"); } }
+  if (!pair) { long long tr[3][40]; CK(cudaMemcpyFromSymbol(tr, k2i::k2i_trace, sizeof(tr)));
+    const long long t0 = tr[2][0];
+    printf("timeline of CTA 0's tile 40 (clk after the tile start; groups in issue order)\n  MMA lane: build done %lld;", tr[2][1] - t0);
+    for (int g = 0; g < (gmin == 4 ? 7 : 6); ++g) printf(" g%d R[wait %lld issued %lld] L[wait %lld issued %lld];", g, tr[2][2 + 4 * g] - t0, tr[2][3 + 4 * g] - t0, tr[2][4 + 4 * g] - t0, tr[2][5 + 4 * g] - t0);
+    printf(" end %lld\n", tr[2][38] - t0);
+    for (int w = 0; w < 2; ++w) { printf("  %s thread: build done %lld;", w ? "right" : "left", tr[w][1] - t0); for (int g = 0; g < (gmin == 4 ? 7 : 6); ++g) printf(" g%d [full %lld folded %lld];", g, tr[w][2 + 2 * g] - t0, tr[w][3 + 2 * g] - t0); printf(" end %lld\n", tr[w][38] - t0); } }
   const double flops = (double)npts * ((double)M * (M + 1) + 2.0 * M);
   printf("GMIN %d: npts %zu: %.3f ms -> %.1f M pts/s (FP64-equivalent %.1f TFLOP/s of the symmetric contraction); barrier timeouts %d\n", gmin, npts, best, npts / best / 1e3, flops / best / 1e9, fail);
   printf("max |dPi| / max(1,|Pi|) over %zu points: int8 path %.3e (worst point %zu: got %.17g), plain FP64 loops %.3e; |Pi|max %.3g\n", ncheck, emax, worst, pi[worst], emax_f64, pimax);
