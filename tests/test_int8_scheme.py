@@ -1,0 +1,78 @@
+"""CPU restatement (numpy, exact integers) of the arithmetic of the int8 tensor-core on-top kernel
+(openrdm_b200/csrc/k2_int8.cuh): 46-bit fixed-point images against power-of-two row / matrix maxima, six balanced
+signed bytes, block-upper-triangular T with D~ = T + T^T, slice pairs k + l >= GMIN, FP64 dot with the unquantised X.
+Pins (a) the digit identity the kernel relies on and (b) the error model quoted in DESIGN.md section 4 ("K2i")."""
+import numpy as np
+import pytest
+
+FIX = 46
+C_BAL = sum(0x80 << (8 * k) for k in range(5))
+
+
+def digits(V):
+    """six balanced signed bytes of an int64 image: bytes 0..4 of V + 0x8080808080 minus 128, byte 5 signed."""
+    W = V + C_BAL
+    d = [((W >> (8 * k)) & 255) - 128 for k in range(5)] + [W >> 40]
+    assert all(int(np.abs(x).max()) <= 128 for x in d)
+    return d
+
+
+def folded(D2, n):
+    idx = [(t, u) for t in range(n) for u in range(t, n)]
+    D4 = D2.reshape(n, n, n, n)
+    M = len(idx)
+    F = np.zeros((M, M))
+    for I, (t, u) in enumerate(idx):
+        for J, (v, w) in enumerate(idx):
+            F[I, J] = sum(D4[a, b, c, d] for (a, b) in {(t, u), (u, t)} for (c, d) in {(v, w), (w, v)})
+    return 0.5 * (F + F.T), idx
+
+
+def int8_pi(phi_act, Dt, idx, gmin):
+    M = len(idx)
+    X = np.stack([phi_act[:, t] * phi_act[:, u] for (t, u) in idx], axis=1)
+    blk = np.arange(M) // 32
+    T = np.where(blk[:, None] < blk[None, :], Dt, np.where(blk[:, None] == blk[None, :], 0.5 * Dt, 0.0))
+    te = int(np.frexp(np.abs(T).max())[1])                        # max |T| < 2^te
+    m = np.abs(phi_act).max(axis=1)
+    em = np.where(m > 0, np.frexp(np.where(m > 0, m, 1.0))[1], 0)  # max_t |phi_t| < 2^em  ->  max |X| < 2^(2 em)
+    VX = np.rint(np.ldexp(X, (FIX - 2 * em)[:, None])).astype(np.int64)
+    VT = np.rint(np.ldexp(T, FIX - te)).astype(np.int64)
+    assert np.abs(VX).max() <= 1 << FIX and np.abs(VT).max() <= 1 << FIX
+    xb, tb = digits(VX), digits(VT)
+    for V, d in ((VX, xb), (VT, tb)):                              # the digit identity
+        assert (sum(d[k].astype(object) * (1 << (8 * k)) for k in range(6)) == V.astype(object)).all()
+    Z = np.zeros(X.shape, dtype=np.longdouble)
+    npairs = 0
+    for k in range(6):
+        for l in range(6):
+            if k + l < gmin:
+                continue
+            npairs += 1
+            acc = xb[k] @ tb[l]                                    # exact: |acc| <= 224 * 128^2 per pair, INT32 on the tensor core
+            assert np.abs(acc).max() < 1 << 31
+            Z += acc.astype(np.longdouble) * np.exp2(np.longdouble(8 * (k + l)))
+    Y = Z * np.exp2((2 * em - FIX).astype(np.longdouble))[:, None] * np.exp2(np.longdouble(te - FIX))
+    return 2.0 * (X * Y.astype(np.float64)).sum(axis=1), X, npairs
+
+
+@pytest.mark.parametrize("nact", [18, 20])
+def test_slice_scheme_error_model(ordm, nact):
+    npts, ncore = 192, 5
+    A1a, A1b, D2 = ordm.synth_rdms(7, nact, nact // 2, nact // 2, 6)
+    Dt, idx = folded(np.asarray(D2), nact)
+    w, phi, _ = ordm.synth_fill_host(11, 5_000_000, 123_456, npts, ncore + nact, False)
+    pa = phi[:, ncore:]
+    Xl = np.stack([pa[:, t] * pa[:, u] for (t, u) in idx], axis=1).astype(np.longdouble)
+    ref = ((Xl @ Dt.astype(np.longdouble)) * Xl).sum(axis=1)
+    scale = np.maximum(1.0, np.abs(ref).astype(np.float64))
+    err = {}
+    for gmin, want_pairs in ((0, 36), (4, 26), (5, 21)):
+        pi, X, npairs = int8_pi(pa, Dt, idx, gmin)
+        assert npairs == want_pairs
+        err[gmin] = float(np.abs((pi - ref).astype(np.float64) / scale).max())
+    print(nact, err)
+    assert err[0] < 5e-14      # all 36 pairs: only the 46-bit images are left (~2e-14)
+    assert err[4] < 1e-13      # shipped default (26 pairs); DESIGN.md quotes 2.5e-14 on 2048 points
+    assert err[5] < 1e-12      # ORDM_K2_INT8=2 (21 pairs); DESIGN.md quotes 1.4e-13
+    assert err[5] > err[4] and err[4] < 3 * err[0] + 1e-14   # 26 pairs: the dropped products are below the image error
