@@ -49,6 +49,7 @@ __device__ __forceinline__ bool wait_parity(uint32_t bar, uint32_t parity) {
 
 struct Args {
   const int8_t* a; const int8_t* b; int32_t* out; long long* clocks; int* fail;
+  long long* ldlat;   // ldlat[2]: tcgen05.ld round trip (clk) of warp 1 while the MMAs run / when the tensor pipe is idle
   int n, pairs, iters, ragged;
 };
 
@@ -95,6 +96,21 @@ __global__ void __launch_bounds__(128, 1) i8mma_kernel(Args g) {
   constexpr uint32_t A_LBO = (MROWS / 8) * 128, B_LBO = (NMAX / 8) * 128, SBO = 128;
   bool ok = true;
   long long t0 = 0, t1 = 0;
+  if (warp == 1 && g.ldlat) {   // TMEM round trips from another lane quadrant, unused columns, while warp 0's lane issues the MMAs
+    long long acc = 0; const int nld = g.iters * g.pairs * 2;
+    for (int i = 0; i < nld; ++i) {
+      uint32_t v[16];
+      const long long c0 = clock64();
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                     "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                   : "r"(tmem + ((uint32_t)32 << 16) + 400u));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      acc += clock64() - c0;
+      if (v[0] == 0x7fffffffu) acc += 1;
+    }
+    if (tid == 32 && blockIdx.x == 0) g.ldlat[0] = acc / nld;
+  }
   if (tid == 0) {
     t0 = clock64();
     for (int it = 0; it < g.iters; ++it) {
@@ -132,6 +148,22 @@ __global__ void __launch_bounds__(128, 1) i8mma_kernel(Args g) {
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 1 && g.ldlat) {   // the same with the tensor pipe idle
+    long long acc = 0;
+    for (int i = 0; i < 1000; ++i) {
+      uint32_t v[16];
+      const long long c0 = clock64();
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                     "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                   : "r"(tmem + ((uint32_t)32 << 16) + 400u));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      acc += clock64() - c0;
+      if (v[0] == 0x7fffffffu) acc += 1;
+    }
+    if (tid == 32 && blockIdx.x == 0) g.ldlat[1] = acc / 1000;
+  }
+  __syncthreads();
   // epilogue: the last two chains' accumulators -> global (block 0 only), lanes 32*warp.. of each
   if (blockIdx.x == 0) {
     for (int acc = 0; acc < 1; ++acc) {
@@ -172,7 +204,8 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(da, A.data(), A.size(), cudaMemcpyHostToDevice)); CK(cudaMemcpy(db, cb.data(), cb.size(), cudaMemcpyHostToDevice));
   CK(cudaMemset(dout, 0, sizeof(int32_t) * 2 * MROWS * NMAX)); CK(cudaMemset(dfail, 0, sizeof(int)));
   CK(cudaFuncSetAttribute(i8mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  Args g{da, db, dout, dclk, dfail, n, pairs, 1, ragged};
+  long long* dlat; CK(cudaMalloc(&dlat, 16)); CK(cudaMemset(dlat, 0, 16));
+  Args g{da, db, dout, dclk, dfail, dlat, n, pairs, 1, ragged};
   Args gt = g; gt.iters = iters;
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   i8mma_kernel<<<nsm, 128, SMEM_BYTES>>>(g); CK(cudaDeviceSynchronize());
@@ -198,5 +231,7 @@ int main(int argc, char** argv) {
   for (int ks = 0; ks < KB / 32; ++ks) { const int c0 = ragged ? 32 * ks : 0; if (c0 < n) { mma_per_cta += (double)iters * pairs * (ragged == 2 && ks < 4 ? 2 : 1); mac += (double)iters * pairs * MROWS * (n - c0) * 32.0; } }
   printf("TS%s N=%d pairs=%d iters=%d: %s, barrier timeouts %d; %.1f clk per MMA (ideal %.1f at 8192 MAC/clk/SM); kernel %.3f ms -> %.1f TOP/s int8 on %d SMs\n",
          ragged ? " ragged" : "", n, pairs, iters, bad ? "MISMATCH" : "exact", fail, cmean / mma_per_cta, mac / mma_per_cta / 8192.0, ms, 2.0 * mac * nsm / (ms * 1e-3) / 1e12, nsm);
+  { long long lat[2]; CK(cudaMemcpy(lat, dlat, 16, cudaMemcpyDeviceToHost));
+    printf("tcgen05.ld.32x32b.x16 + wait::ld round trip from another warp: %lld clk while the MMAs run, %lld clk with the tensor pipe idle\n", lat[0], lat[1]); }
   return bad || fail ? 2 : 0;
 }
