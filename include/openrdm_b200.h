@@ -97,6 +97,11 @@ typedef struct {
   uint32_t overlapped;    /* 1: the density kernel ran underneath the on-top kernel (ms_density and
                              ms_pi overlap in time); 2: only its core-orbital sums did, the active-space
                              part followed (ms_density = both parts); 0: stages ran back to back */
+  uint32_t pi_guard_points; /* > 0: the int8 tensor-core on-top kernel's error guard flagged that many points
+                             (its a-posteriori estimate exceeded 1e-12 max(1, |Pi|)), and the whole call was
+                             repeated with the FP64 tensor-pipe kernels -- which then stay selected until the
+                             RDMs or the orbitals change; this result is the FP64 one */
+  uint32_t reserved_;
 } ordm_result;
 
 /* Which kernel computes the active-space on-top pair density for the RDMs currently set (no reference
@@ -104,7 +109,13 @@ typedef struct {
  * (tcgen05.mma.kind::i8 over exact byte slices of 46-bit fixed-point images, csrc/k2_int8.cuh; 18..20 active
  * orbitals, Pi without grad Pi) with that many slice-pair products; 0: the FP64 tensor-pipe kernels
  * (DMMA.8x8x4, csrc/k2_ontop.cuh).  Environment ORDM_K2_INT8 = 0 | 1 (26 pairs, default) | 2 (21 pairs) picks
- * at context creation.  *mma_per_tile = tensor-core instructions per 128-point (int8) / 32-point (FP64) tile.
+ * at context creation.  Error model of the int8 path (k2_int8.cuh, guard_flag): the 46-bit images and the dropped
+ * low-order slice pairs leave, per point, an error of standard deviation
+ *     sqrt( 2^(4 em) g1 S2^2 + g2 S2^4 ) / 4,   S2 = sum_t phi_t^2,  2^em > max_t |phi_t|,
+ * g1, g2 from the 2-RDM (ordm::int8_guard_constants); the kernel evaluates 4 standard deviations for every point
+ * against the parity bar 1e-12 max(1, |Pi|).  If any point exceeds it the call is repeated with the FP64 kernels
+ * (ordm_result.pi_guard_points), so the int8 path never returns a Pi it cannot vouch for; with 21 pairs (mode 2, opt-in)
+ * the dropped-pair term is ~300x larger and the guard trips correspondingly earlier.  *mma_per_tile = tensor-core instructions per 128-point (int8) / 32-point (FP64) tile.
  * Pointers may be NULL; ORDM_ERR_STATE before the 2-RDM is set. */
 int ordm_pi_kernel_info(const ordm_ctx* ctx, int* int8_slice_pairs, uint64_t* mma_per_tile);
 
@@ -176,6 +187,16 @@ int ordm_set_active_space_sparse(ordm_ctx* ctx, int ncore, int nact,
  * (mcpdft.cc:204) that ordm_set_rdm2ab_dense / mcpdft_energy take.  D2ab_out is overwritten. */
 int ordm_rdm2ab_sparse_to_dense(int n, size_t nnz, const int* i2, const int* j2, const int* k2, const int* l2,
                                 const double* v2, int upper_packed, double* D2ab_out);
+
+/* MCPDFT::set_rhoa ... set_tr_sigma_bb, set_pi, set_pi_x/_y/_z, set_R (mcpdft.h:125-153): install a caller-provided
+ * per-point vector (npts host doubles, copied).  What the reference's later stages read from its members is read
+ * from the installed vector here too: rho and Pi by build_R / translate (mcpdft.cc:276-283,297-330), R by translate
+ * and fully_translate (:321, :460) until the next ordm_build_R recomputes it, the spin-density gradient components
+ * by translate_density_gradients (:383-398; needs ORDM_OPT_DIAGNOSTICS so that both spins of a direction exist),
+ * grad Pi by fully_translate (:541-590).  The remaining vectors (rho_a, rho_b, sigma, translated quantities) only
+ * feed the getters, as in the reference.  ordm_energy / ordm_energy_host rebuild every vector from the inputs, as
+ * mcpdft_energy does.  Call ordm_set_options before installing vectors (changing the options re-allocates them). */
+int ordm_set_vector(ordm_ctx* ctx, int which, const double* host_in, size_t npts);
 
 /* ---- stages = the public methods of mcpdft::MCPDFT ------------------------------------ */
 int ordm_build_rho(ordm_ctx* ctx);   /* MCPDFT::build_rho,  mcpdft.cc:35-40  */

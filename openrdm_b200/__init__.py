@@ -44,7 +44,8 @@ class Result(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         "e_tot", "ex", "ec", "eclass", "n_tot", "n_a", "n_b", "trn_tot", "trn_a", "trn_b",
         "ms_density", "ms_pi", "ms_xc", "ms_reduce", "ms_total")] + [
-        ("npts", C.c_uint64), ("gpu_launches", C.c_uint32), ("overlapped", C.c_uint32)]
+        ("npts", C.c_uint64), ("gpu_launches", C.c_uint32), ("overlapped", C.c_uint32),
+        ("pi_guard_points", C.c_uint32), ("reserved_", C.c_uint32)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ }
@@ -58,7 +59,7 @@ def load(rebuild: bool = False) -> C.CDLL:
     global _lib
     if _lib is not None and not rebuild:
         return _lib
-    if rebuild or not os.path.exists(LIB_PATH):
+    if not os.environ.get("ORDM_LIB") and (rebuild or _build.stale()):   # missing, or older than any source under csrc/ / include/
         _build.build(force=rebuild)
     lib = C.CDLL(LIB_PATH)
     P, D, S, I = C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.c_int
@@ -92,6 +93,7 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.ordm_energy.argtypes = [P, I, C.c_double, C.POINTER(Result)]
     lib.ordm_energy_host.argtypes = [P, I, C.c_double, S, I, S, D, D, D, D, D, S, C.POINTER(Result)]
     lib.ordm_get_vector.argtypes = [P, I, D, S]
+    lib.ordm_set_vector.argtypes = [P, I, D, S]
     lib.ordm_get_orbitals.argtypes = [P, I, D, S]
     lib.ordm_synth_fill_device.argtypes = [P, C.c_uint64, S, S, S, I, I]
     lib.ordm_synth_fill_host.argtypes = [C.c_uint64, S, S, S, I, D, D, D, D, D]
@@ -269,6 +271,11 @@ class Engine:
         out = np.zeros(self.npts)
         self._ck(self.lib.ordm_get_vector(self.ctx, VEC_ID[name], _d(out), self.npts))
         return out
+
+    def set_vector(self, name, values):
+        """MCPDFT::set_<name> (mcpdft.h:125-153): install a caller-provided per-point vector."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        self._ck(self.lib.ordm_set_vector(self.ctx, VEC_ID[name], _d(v), v.shape[0]))
 
     def get_orbitals(self, phi_out, grads_out=None):
         """Copy the resident phi (and grad phi) into caller-provided F-ordered (npts, n) arrays."""

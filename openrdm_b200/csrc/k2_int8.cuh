@@ -44,7 +44,8 @@ struct Params {
   int t_exp;               // max |T| < 2^t_exp
   const double* pi_core;   // optional: closed-form core part, added here (nullptr: K3 adds it)
   double* pi;              // [npts] out
-  int* fail;               // bumped if an MMA-completion barrier ever times out
+  int* fail;               // fail[0]: bumped if an MMA-completion barrier ever times out; fail[1]: points flagged by the error guard
+  double guard_g1, guard_g2;   // constants of the a-posteriori error estimate (k2_int8_pair.cuh: guard_flag; ordm::int8_guard_constants)
 };
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -67,6 +68,26 @@ __device__ __forceinline__ bool wait_parity(uint32_t bar, uint32_t parity) {
   }
   return false;
 }
+// ---- a-posteriori error estimate of the fixed-point scheme for one point ("guard") -------------
+// With q_x = 2^(2 em - 46) the unit of the point's X image, q_t = 2^(t_exp - 46) that of T, independent uniform rounding
+// errors and the final dot taken with the unquantised X:
+//   var(dPi) <= q_x^2/3 |T|_F^2 |X|^2  +  q_t^2/3 |X|^4  +  4 d^2 2^(4 em) M |X|^2,     |X|^2 <= (sum_t phi_t^2)^2,
+// the last term being the dropped slice pairs (d = their r.m.s. per element of X T: 2^-54.6 (GMIN 4), 2^-46.4 (GMIN 5)
+// of 2^(2 em + t_exp)).  The host folds the three constants and z^2 (z = 4 standard deviations) into g1, g2
+// (ordm::int8_guard_constants):   z^2 var = 2^(4 em) g1 S2^2 + g2 S2^4,  S2 = sum_t phi_t^2.
+// The point is flagged when that exceeds (1e-12 max(1, |Pi|))^2.  tests/test_int8_scheme.py pins the model against the
+// exact-integer restatement of the arithmetic (measured |dPi| <= 2.5 standard deviations on every case tried).
+template <int NA>
+__device__ __forceinline__ bool guard_flag(const double (&phi)[NA], int e_raw, double pi_abs, double g1, double g2) {
+  double s2 = 0.0;
+#pragma unroll
+  for (int t = 0; t < NA; ++t) s2 = fma(phi[t], phi[t], s2);
+  const double xs2 = __hiloint2double((4 * e_raw - 3065) << 20, 0);   // 2^(4 em), em = e_raw - 1022
+  const double x2 = s2 * s2;
+  const double bar = 1e-12 * fmax(1.0, pi_abs);
+  return fma(xs2 * g1, x2, g2 * x2 * x2) > bar * bar;
+}
+
 // shared-memory plan (dynamic): T image | X slice 5 (K-major no-swizzle operand, 128 rows x KP bytes) |
 // partial sums [2][128] doubles | the next tile's orbitals [nact][128] doubles (cp.async)
 struct Smem {
@@ -292,6 +313,7 @@ __global__ void __maxnreg__(K2I_MAXREG) k2i_ontop(Params P) {
 #endif
   uint32_t phase = 0;      // parity of the current group's barriers (one completion of each per group)
   bool first_group = true, ok = true;
+  int nflag = 0;   // points of this thread whose error estimate exceeds the parity bar (guard_flag)
 
   const size_t ntiles = (P.npts + TILE - 1) / TILE;
   double* s_nxt = (double*)(smem + Smem::next_off(KP));   // [NA][TILE]: the next tile's orbitals (cp.async)
@@ -383,13 +405,16 @@ __global__ void __maxnreg__(K2I_MAXREG) k2i_ontop(Params P) {
       const double f1 = __hiloint2double((2 * e_raw - 1067 - (FIX_BITS - 46)) << 20, 0);        // 2^(2 em - FIX_BITS)
       const double f2 = __hiloint2double((1023 + P.t_exp - FIX_BITS + 8 * GMIN + 1) << 20, 0);  // 2 * 2^(t_exp - FIX_BITS + 8 GMIN)
       const double pi_act = s * f1 * f2;
-      P.pi[p0 + p] = P.pi_core ? pi_act + P.pi_core[p0 + p] : pi_act;
+      const double pi_tot = P.pi_core ? pi_act + P.pi_core[p0 + p] : pi_act;
+      P.pi[p0 + p] = pi_tot;
+      if (guard_flag<NA>(phi, e_raw, fabs(pi_tot), P.guard_g1, P.guard_g2)) ++nflag;
     }
   }
 #ifdef K2I_PROF
   if (blockIdx.x == 0 && (tid & 127) == 0) for (int i = 0; i < 8; ++i) k2i_prof[tid >> 7][i] = pf_[i];
 #endif
   if (!ok && P.fail) atomicAdd(P.fail, 1);
+  if (nflag && P.fail) atomicAdd(P.fail + 1, nflag);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");

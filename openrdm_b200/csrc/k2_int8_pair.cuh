@@ -1,0 +1,385 @@
+// k2_int8_pair.cuh -- K2 on the 5th-generation tensor cores, CTA-pair form: the active-space on-top pair density
+//     Pi_act(p) = sum_{I,J} X_pI D~_IJ X_pJ,   X_pI = phi_t(p) phi_u(p)   (I = packed pair t <= u),
+// i.e. MCPDFT::build_ontop_pair_density (/root/reference/src/libmcpdft/mcpdft.cc:185-212) restricted to the active
+// orbitals.  Same arithmetic as k2_int8.cuh (exact int8 products of the byte slices of 46-bit fixed-point images,
+// D~ = T + T^T with T block-upper-triangular, slice pairs k + l >= GMIN, FP64 dot with the unquantised X; DESIGN.md
+// section 4 "K2i"); what changes is where things live and who does what:
+//   * two SMs of a cluster run tcgen05.mma.cta_group::2 (M = 256: 128 points per CTA); each CTA keeps only HALF of the
+//     rows of every T chunk in shared memory (84 KB), which makes room for X slices 0..4 there (140 KB);
+//   * TMEM then holds TWO full-width accumulators (2 x KP columns) + X slice 5: consecutive slice-pair groups alternate
+//     between them, so the epilogue of one group runs under the MMAs of the next;
+//   * the epilogue is spread over EW warps per TMEM lane quadrant (= per SM sub-partition): each thread owns one point
+//     and a contiguous range of 16-pair units of its accumulator row, read with tcgen05.ld.x16 one unit ahead, converted
+//     exactly (2^52 bit trick) and folded as sum_t phi_t (sum_u phi_u acc_tu) with the pair -> (t, u) map resolved at
+//     compile time; more warps per sub-partition is what hides the TMEM round trip and the FP64 dependent-issue
+//     latency that bound the 2-warp epilogue of k2_int8.cuh (profiles/r01h_k2i_timeline.log);
+//   * the same threads build the X slices of their pair range: one DFMA per pair leaves the balanced image in the
+//     mantissa (the re-centring constant rides in the FMA addend), byte transposes cut it into slices;
+//   * every point carries an a-posteriori error estimate of the 46-bit scheme (guard_flag below): points whose estimate
+//     exceeds the parity bar 1e-12 max(1, |Pi|) are counted, and the host repeats the stage with the FP64 kernels.
+// Only the leader CTA's MMA lane issues; tcgen05.commit multicasts "accumulator full" to both CTAs, both CTAs' epilogue
+// threads arrive on the leader's "drained" barrier, and one cluster barrier per tile says "both CTAs' operands are built".
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <utility>
+#include "k2_int8.cuh"
+
+namespace k2i {
+
+// shared-memory plan (dynamic) of one CTA of the pair: T half image | X slices 0..4 (the partial sums [EW][128] of the
+// tile's end alias the first KB of the X slices, which are dead by then)
+struct PairSmem {
+  __host__ __device__ static size_t t_bytes(int kp) { return (size_t)NSLICE * Geom::slice_bytes(kp) / 2; }
+  __host__ __device__ static size_t x_off(int kp) { return t_bytes(kp); }
+  __host__ __device__ static size_t bytes(int kp) { return x_off(kp) + (size_t)5 * TILE * kp; }
+};
+
+__device__ __forceinline__ void mma2_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma2_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void commit2(uint32_t bar) {   // arrives on the barrier at this offset in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---- build: the X slices of pairs [16 U0, 16 U1) of this thread's point --------------------------------------------
+// slices 0..4 -> shared memory (K-major no-swizzle operand of 128 rows: 16 K bytes of a row are contiguous, so the
+// four slice words of 16 pairs go out as one 16-byte store, conflict-free across the lanes of a warp), slice 5 -> TMEM
+struct BuildRegs { uint32_t lo[4], hi[4], w[6][4]; };
+
+template <int NA, int I>
+__device__ __forceinline__ void build_elem(const double (&phi)[NA], const double (&ps)[NA], BuildRegs& r, uint8_t* x_row, uint32_t tmem_x5_row) {
+  constexpr int M = NA * (NA + 1) / 2, KP = (M + 31) / 32 * 32;
+  if constexpr (I < M) {
+    constexpr int t = pair_t_of(NA, I), u = pair_u_of(NA, I);
+    // bits(x + 1.5 2^52 + C) hold the integer round(x) + C in the low 48 bits: C = 0x8080808080 re-centres bytes 0..4
+    const unsigned long long v = (unsigned long long)__double_as_longlong(fma(ps[t], phi[u], 6755399441055744.0 + 551911719040.0));
+    r.lo[I & 3] = (uint32_t)v; r.hi[I & 3] = (uint32_t)(v >> 32);
+  } else {   // padding pairs: zero digits (the image of 0 is 0x..80 80 80 80 80 before re-centring)
+    r.lo[I & 3] = 0x80808080u; r.hi[I & 3] = 0x00000080u;
+  }
+  if constexpr ((I & 3) == 3) {
+    constexpr int j = (I >> 2) & 3;
+    const uint32_t t0 = __byte_perm(r.lo[0], r.lo[1], 0x5140), t1 = __byte_perm(r.lo[2], r.lo[3], 0x5140);
+    const uint32_t t2 = __byte_perm(r.lo[0], r.lo[1], 0x7362), t3 = __byte_perm(r.lo[2], r.lo[3], 0x7362);
+    const uint32_t h0 = __byte_perm(r.hi[0], r.hi[1], 0x5140), h1 = __byte_perm(r.hi[2], r.hi[3], 0x5140);
+    r.w[0][j] = __byte_perm(t0, t1, 0x5410) ^ 0x80808080u;
+    r.w[1][j] = __byte_perm(t0, t1, 0x7632) ^ 0x80808080u;
+    r.w[2][j] = __byte_perm(t2, t3, 0x5410) ^ 0x80808080u;
+    r.w[3][j] = __byte_perm(t2, t3, 0x7632) ^ 0x80808080u;
+    r.w[4][j] = __byte_perm(h0, h1, 0x5410) ^ 0x80808080u;
+    r.w[5][j] = __byte_perm(h0, h1, 0x7632);
+    if constexpr (j == 3) {
+      constexpr int k = I - 15;   // first K byte of the four words: a multiple of 16
+#pragma unroll
+      for (int s = 0; s < 5; ++s)
+        *(uint4*)(x_row + (size_t)s * TILE * KP + (k >> 4) * (TILE / 8) * 128) = make_uint4(r.w[s][0], r.w[s][1], r.w[s][2], r.w[s][3]);
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tmem_x5_row + (uint32_t)(k >> 2)),
+                   "r"(r.w[5][0]), "r"(r.w[5][1]), "r"(r.w[5][2]), "r"(r.w[5][3]) : "memory");
+    }
+  }
+}
+
+template <int NA, int I0, int... Is>
+__device__ __forceinline__ void build_seq(const double (&phi)[NA], const double (&ps)[NA], BuildRegs& r, uint8_t* x_row, uint32_t tmem_x5_row,
+                                          std::integer_sequence<int, Is...>) {
+  (build_elem<NA, I0 + Is>(phi, ps, r, x_row, tmem_x5_row), ...);
+}
+
+template <int NA, int U0, int U1>
+__device__ __forceinline__ void build_units(const double (&phi)[NA], double scale, uint8_t* x_row, uint32_t tmem_x5_row) {
+  BuildRegs r;
+  double ps[NA];
+#pragma unroll
+  for (int t = 0; t < NA; ++t) ps[t] = phi[t] * scale;
+  build_seq<NA, 16 * U0>(phi, ps, r, x_row, tmem_x5_row, std::make_integer_sequence<int, 16 * (U1 - U0)>{});
+}
+
+// ---- epilogue of one group over the 16-pair units [U0, U1) of this thread's accumulator row ---------------------------
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr));
+}
+
+// last pair of orbital row t inside [lo, hi) (the row's running sum is folded into the total right after it)
+__host__ __device__ constexpr bool row_ends_at(int na, int I, int hi, int m) {
+  return I + 1 >= hi || I + 1 >= m || pair_t_of(na, I + 1) != pair_t_of(na, I);
+}
+
+// two DFMA chains per orbital row (even / odd pair index): with EW warps per sub-partition that is 2 EW independent
+// chains in flight; a row's partial sums die as soon as the row ends, so few are live at any time
+template <int NA, int I, int IEND>
+__device__ __forceinline__ void fold_elem(const double (&phi)[NA], double (&s0)[NA], double (&s1)[NA], double& tot, uint32_t v) {
+  constexpr int M = NA * (NA + 1) / 2;
+  if constexpr (I < M) {
+    constexpr int t = pair_t_of(NA, I), u = pair_u_of(NA, I);
+    const double zd = __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;  // exact int32 -> double (2^52 + 2^31)
+    if constexpr (I & 1) s1[t] = fma(phi[u], zd, s1[t]); else s0[t] = fma(phi[u], zd, s0[t]);
+    if constexpr (row_ends_at(NA, I, IEND, M)) tot = fma(phi[t], s0[t] + s1[t], tot);
+  }
+}
+
+template <int NA, int U, int UEND, int... Js>
+__device__ __forceinline__ void fold_unit(const double (&phi)[NA], double (&s0)[NA], double (&s1)[NA], double& tot, const uint32_t (&v)[16],
+                                          std::integer_sequence<int, Js...>) {
+  (fold_elem<NA, 16 * U + Js, 16 * UEND>(phi, s0, s1, tot, v[Js]), ...);
+}
+
+// tcgen05.wait::ld with the loaded registers as in/out operands: nothing that reads them can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :: "memory");
+}
+
+template <int NA, int U, int U1>
+__device__ __forceinline__ void fold_units(const double (&phi)[NA], double (&s0)[NA], double (&s1)[NA], double& tot, uint32_t tmem_row,
+                                           uint32_t (&cur)[16], uint32_t (&nxt)[16], uint32_t drain_bar) {
+  tmem_wait_ld16(cur);   // unit U is in `cur`
+  if constexpr (U + 1 < U1) {
+    tmem_ld16(tmem_row + (uint32_t)(16 * (U + 1)), nxt);
+  } else {   // every column of this thread's range has been read: the group after next may overwrite this accumulator
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(drain_bar) : "memory");
+  }
+  fold_unit<NA, U, U1>(phi, s0, s1, tot, cur, std::make_integer_sequence<int, 16>{});
+  if constexpr (U + 1 < U1) fold_units<NA, U + 1, U1>(phi, s0, s1, tot, tmem_row, nxt, cur, drain_bar);
+}
+
+template <int NA, int U0, int U1>
+__device__ __forceinline__ double fold_group_units(const double (&phi)[NA], uint32_t tmem_row, uint32_t drain_bar) {
+  double s0[NA], s1[NA], tot = 0.0;
+#pragma unroll
+  for (int t = 0; t < NA; ++t) s0[t] = s1[t] = 0.0;
+  uint32_t va[16], vb[16];
+  tmem_ld16(tmem_row + (uint32_t)(16 * U0), va);
+  fold_units<NA, U0, U1>(phi, s0, s1, tot, tmem_row, va, vb, drain_bar);
+  return tot;
+}
+
+// every MMA of group G into the accumulator at tmem_acc: one per (slice pair, K chunk), N = the chunk's column range
+template <int G, int KP>
+__device__ __forceinline__ void issue_group_pair(uint32_t tmem_acc, uint32_t tmem_x5, uint64_t tdesc0, uint64_t xdesc0, uint32_t idesc0) {
+  constexpr int NCH = KP / 32, KMAX = G < NSLICE - 1 ? G : NSLICE - 1, KMIN = G > NSLICE - 1 ? G - (NSLICE - 1) : 0;
+#pragma unroll
+  for (int k = KMAX; k >= KMIN; --k) {
+    const int l = G - k;
+#pragma unroll
+    for (int kc = 0; kc < NCH; ++kc) {
+      const int n = Geom::chunk_rows(KP, kc);   // columns [32 kc, KP); each CTA holds n / 2 rows of the chunk
+      const uint32_t idesc = idesc0 | ((uint32_t)(n >> 3) << 17);
+      const uint64_t bd = tdesc0 + (uint64_t)((l * (Geom::slice_bytes(KP) / 2) + Geom::chunk_off(KP, kc) / 2) >> 4) + ((uint64_t)((n / 2) * 16 >> 4) << 16);
+      const uint32_t first = (k == KMAX && kc == 0) ? 0u : 1u;
+      if (k == 5) mma2_ts(tmem_acc + 32 * kc, tmem_x5 + 8 * kc, bd, idesc, first);
+      else mma2_ss(tmem_acc + 32 * kc, xdesc0 + (uint64_t)((k * TILE * KP + kc * 2 * (TILE / 8) * 128) >> 4), bd, idesc, first);
+    }
+  }
+}
+
+template <int KP>
+__device__ __forceinline__ void issue_group_pair_of(int G, uint32_t tmem_acc, uint32_t tmem_x5, uint64_t tdesc0, uint64_t xdesc0, uint32_t idesc0) {
+  switch (G) {
+    case 10: issue_group_pair<10, KP>(tmem_acc, tmem_x5, tdesc0, xdesc0, idesc0); break;
+    case 9: issue_group_pair<9, KP>(tmem_acc, tmem_x5, tdesc0, xdesc0, idesc0); break;
+    case 8: issue_group_pair<8, KP>(tmem_acc, tmem_x5, tdesc0, xdesc0, idesc0); break;
+    case 7: issue_group_pair<7, KP>(tmem_acc, tmem_x5, tdesc0, xdesc0, idesc0); break;
+    case 6: issue_group_pair<6, KP>(tmem_acc, tmem_x5, tdesc0, xdesc0, idesc0); break;
+    case 5: issue_group_pair<5, KP>(tmem_acc, tmem_x5, tdesc0, xdesc0, idesc0); break;
+    default: issue_group_pair<4, KP>(tmem_acc, tmem_x5, tdesc0, xdesc0, idesc0); break;
+  }
+}
+
+// unit range of epilogue part `part` of EW: the KP / 16 units split as evenly as whole units allow, larger parts first
+__host__ __device__ constexpr int part_u0(int nunits, int ew, int part) { return part * (nunits / ew) + (part < nunits % ew ? part : nunits % ew); }
+
+// group order within a tile: light groups first (the epilogue starts early), the heaviest last (its MMAs cover the
+// epilogues before it and only one epilogue is left uncovered at the tile's end)
+__device__ __forceinline__ int group_at(int i, int gmin) {
+  // GMIN 4: 10 9 8 7 4 6 5 (1 2 3 4 5 5 6 slice pairs);  GMIN 5: 10 9 8 7 6 5
+  if (gmin == 4) return i < 4 ? 10 - i : (i == 4 ? 4 : (i == 5 ? 6 : 5));
+  return 10 - i;
+}
+
+// register cap: 13 warps (EW = 3) are allocated as 16; at 96 registers the CTA leaves 16 K registers to a co-resident
+// density CTA (k1_core_light), at 128 it owns the register file
+#ifndef K2P_MAXREG
+#define K2P_MAXREG 128
+#endif
+
+#ifdef K2I_PROF
+__device__ long long k2p_prof[3][8];
+#define K2P_LAP(i) do { if (blockIdx.x == 0 && (tid == 0 || tid == 32 * 4 * EW)) { const long long t_ = clock64(); pf_[i] += t_ - tc_; tc_ = t_; } } while (0)
+#else
+#define K2P_LAP(i) do { } while (0)
+#endif
+
+// P.timg here is the PAIR image (ordm::pack_t_int8_pair): CTA rank c of the cluster reads block c.
+// P.guard_g1/g2: constants of guard_flag; P.fail[0] counts barrier time-outs, P.fail[1] flagged points.
+template <int NA, int GMIN, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(K2P_MAXREG) k2i_ontop_pair(Params P) {
+  constexpr int M = NA * (NA + 1) / 2, KP = (M + 31) / 32 * 32, NUNITS = KP / 16;
+  constexpr int ACC_COLS = KP, X5_COL = 2 * KP;   // TMEM: accumulator b at [b KP, (b + 1) KP), X slice 5 at [2 KP, 2 KP + KP / 4)
+  constexpr int NGROUPS = 2 * (NSLICE - 1) - GMIN + 1;
+  constexpr int ETHREADS = 4 * EW * 32;
+  static_assert(2 * KP + KP / 4 <= 512, "TMEM columns");
+  static_assert(NSLICE == 6 && (GMIN == 4 || GMIN == 5), "six slices, groups 10 .. GMIN");
+  static_assert(EW >= 2 && EW <= 4 && NUNITS >= EW, "epilogue warps per lane quadrant");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bar_s[4];   // [0..1] accumulator b complete (multicast commit); [2..3] (leader's copy) accumulator b drained by both CTAs
+  uint8_t* s_t = smem;
+  uint8_t* s_x = smem + PairSmem::x_off(KP);
+  double* s_part = (double*)s_x;   // [EW][TILE]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool compute = warp < 4 * EW;
+  const int q = warp & 3, part = warp >> 2, p = 32 * q + lane;  // lane quadrant, unit range, point within the CTA's tile
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+
+  {
+    const int4* src = (const int4*)(P.timg + (size_t)crank * PairSmem::t_bytes(KP));
+    for (int i = tid; i < (int)(PairSmem::t_bytes(KP) / 16); i += blockDim.x) ((int4*)s_t)[i] = src[i];
+  }
+  const uint32_t bar_full = (uint32_t)__cvta_generic_to_shared(&bar_s[0]), bar_drain = (uint32_t)__cvta_generic_to_shared(&bar_s[2]);
+  if (tid == 0) {
+    for (int h = 0; h < 2; ++h) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_full + 8 * h));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_drain + 8 * h), "r"(2 * ETHREADS));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+  const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * TILE) >> 4) << 24);   // M = 256 over the pair
+  uint8_t* x_row = s_x + (p >> 3) * 128 + (p & 7) * 16;
+  const uint64_t tdesc0 = smem_desc((uint32_t)__cvta_generic_to_shared(s_t), 0, 128);
+  const uint64_t xdesc0 = smem_desc((uint32_t)__cvta_generic_to_shared(s_x), (TILE / 8) * 128, 128);
+  uint32_t drain_remote;   // the leader's "drained" barriers, as seen from this CTA
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(drain_remote) : "r"(bar_drain), "r"(0));
+#ifdef K2I_PROF
+  long long pf_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc_ = clock64();
+#endif
+  uint32_t n = 0;   // groups issued / consumed so far (each accumulator sees every other one)
+  bool ok = true;
+  int nflag = 0;
+
+  const size_t ntiles = (P.npts + 2 * TILE - 1) / (2 * TILE);   // pair tiles of 256 points
+  for (size_t tile = blockIdx.x / 2; tile < ntiles; tile += gridDim.x / 2) {
+    const size_t p0 = tile * 2 * TILE + (size_t)crank * TILE;
+    double phi[NA];
+    int e_raw = 534;
+    K2P_LAP(7);
+    if (compute) {
+      uint32_t mh = 0;   // max over t of the high word of |phi_t|: its exponent field is that of max |phi_t|
+#pragma unroll
+      for (int t = 0; t < NA; ++t) {
+        phi[t] = (p0 + p < P.npts) ? __ldg(P.phi_act + (size_t)t * P.ld + p0 + p) : 0.0;
+        mh = max(mh, (uint32_t)__double2hiint(phi[t]) & 0x7FFFFFFFu);
+      }
+      // row scale: max |X| = (max_t |phi_t|)^2 < 2^(2 em); the clamps keep the two scale factors finite normal numbers
+      e_raw = min(max((int)(mh >> 20), 534), 1500);
+      const double scale = __hiloint2double((3113 - 2 * e_raw + (FIX_BITS - 46)) << 20, 0);  // 2^(FIX_BITS - 2 em)
+      const uint32_t tmem_x5_row = tmem + lane_addr + (uint32_t)X5_COL;
+      K2P_LAP(0);
+      if (part == 0) build_units<NA, part_u0(NUNITS, EW, 0), part_u0(NUNITS, EW, 1)>(phi, scale, x_row, tmem_x5_row);
+      else if (part == 1) build_units<NA, part_u0(NUNITS, EW, 1), part_u0(NUNITS, EW, 2)>(phi, scale, x_row, tmem_x5_row);
+      else if (EW > 2 && part == 2) build_units<NA, part_u0(NUNITS, EW, 2 < EW ? 2 : 0), part_u0(NUNITS, EW, 2 < EW ? 3 : 1)>(phi, scale, x_row, tmem_x5_row);
+      else if (EW > 3 && part == 3) build_units<NA, part_u0(NUNITS, EW, 3 < EW ? 3 : 0), part_u0(NUNITS, EW, 3 < EW ? 4 : 1)>(phi, scale, x_row, tmem_x5_row);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      // next pair tile's orbitals towards L2 while this one is contracted
+      const size_t pn = p0 + (size_t)(gridDim.x / 2) * 2 * TILE + p;
+      if (pn < P.npts) {
+#pragma unroll
+        for (int t = part; t < NA; t += EW) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.phi_act + (size_t)t * P.ld + pn));
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    cluster_sync_all();   // both CTAs' operands are built
+    K2P_LAP(1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    double pi_acc = 0.0;
+#pragma unroll 1
+    for (int gi = 0; gi < NGROUPS; ++gi, ++n) {
+      const int G = group_at(gi, GMIN);
+      const uint32_t b = n & 1, use = n >> 1;   // accumulator, and how often it has been used before
+      if (!compute) {
+        if (lane == 0 && crank == 0) {
+          if (use > 0) ok = wait_parity(bar_drain + 8 * b, (use - 1) & 1) && ok;   // both CTAs have read this accumulator's previous group
+          K2P_LAP(2);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          issue_group_pair_of<KP>(G, tmem + b * ACC_COLS, tmem + X5_COL, tdesc0, xdesc0, idesc0);
+          commit2(bar_full + 8 * b);
+          K2P_LAP(3);
+        }
+        __syncwarp();
+      } else {
+        ok = wait_parity(bar_full + 8 * b, use & 1) && ok;
+        K2P_LAP(5);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_row = tmem + lane_addr + (uint32_t)(b * ACC_COLS);
+        const uint32_t db = drain_remote + 8 * b;
+        double g;
+        if (part == 0) g = fold_group_units<NA, part_u0(NUNITS, EW, 0), part_u0(NUNITS, EW, 1)>(phi, tmem_row, db);
+        else if (part == 1) g = fold_group_units<NA, part_u0(NUNITS, EW, 1), part_u0(NUNITS, EW, 2)>(phi, tmem_row, db);
+        else if (EW > 2 && part == 2) g = fold_group_units<NA, part_u0(NUNITS, EW, 2 < EW ? 2 : 0), part_u0(NUNITS, EW, 2 < EW ? 3 : 1)>(phi, tmem_row, db);
+        else g = fold_group_units<NA, part_u0(NUNITS, EW, 3 < EW ? 3 : 0), part_u0(NUNITS, EW, 3 < EW ? 4 : 1)>(phi, tmem_row, db);
+        pi_acc = fma(g, __hiloint2double((1023 + 8 * (G - GMIN)) << 20, 0), pi_acc);
+        K2P_LAP(6);
+      }
+    }
+    // every epilogue thread has seen the last group's "full": all MMAs of the tile are done, the X slices are dead
+    if (compute) {
+      if (part > 0) s_part[part * TILE + p] = pi_acc;
+      asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
+      if (part == 0) {
+        double s = pi_acc;
+#pragma unroll
+        for (int k = 1; k < EW; ++k) s += s_part[k * TILE + p];
+        // Pi = 2 * 2^(2 em - FIX) * 2^(t_exp - FIX) * 2^(8 GMIN) * (sum over the parts)
+        const double f1 = __hiloint2double((2 * e_raw - 1067 - (FIX_BITS - 46)) << 20, 0);        // 2^(2 em - FIX_BITS)
+        const double f2 = __hiloint2double((1023 + P.t_exp - FIX_BITS + 8 * GMIN + 1) << 20, 0);  // 2 * 2^(t_exp - FIX_BITS + 8 GMIN)
+        const double pi_act = s * f1 * f2;
+        if (p0 + p < P.npts) {
+          const double pi_tot = P.pi_core ? pi_act + P.pi_core[p0 + p] : pi_act;
+          P.pi[p0 + p] = pi_tot;
+          if (guard_flag<NA>(phi, e_raw, fabs(pi_tot), P.guard_g1, P.guard_g2)) ++nflag;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");   // the partial sums alias the X slices: read before the next tile's build writes them
+    }
+    K2P_LAP(4);
+  }
+#ifdef K2I_PROF
+  if (blockIdx.x == 0 && (tid == 0 || tid == ETHREADS)) for (int i = 0; i < 8; ++i) k2p_prof[tid ? 2 : 0][i] = pf_[i];
+#endif
+  if (P.fail) {
+    if (!ok) atomicAdd(P.fail, 1);
+    if (nflag) atomicAdd(P.fail + 1, nflag);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+}  // namespace k2i

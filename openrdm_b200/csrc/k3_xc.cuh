@@ -32,6 +32,7 @@ struct Params {
   const double* px;  // grad Pi (fully-translated GGA only)
   const double* py;
   const double* pz;
+  const double* R_in;  // nullable: R installed by the caller (MCPDFT::set_R) instead of build_R's 4 Pi / rho^2; may alias R
   size_t npts;
   double omega;      // MCPDFT_OMEGA for FUNC 5 (WPBE)
   // optional diagnostics (null = not written)
@@ -61,13 +62,14 @@ __global__ void __launch_bounds__(THREADS, K3_MINB) k3_translate_xc(const Params
     }
     double gx = 0.0, gy = 0.0, gz = 0.0;
     if (GGA && P.gx) { gx = __ldg(P.gx + p); gy = __ldg(P.gy + p); gz = __ldg(P.gz + p); }
+    const double R = P.R_in ? P.R_in[p] : xc::r_factor(rho, pi);   // build_R, or the caller's set_R
     xc::Translated t;
     if (FT) {
       double px = 0.0, py = 0.0, pz = 0.0;
       if (GGA && P.px) { px = __ldg(P.px + p); py = __ldg(P.py + p); pz = __ldg(P.pz + p); }
-      t = xc::fully_translate_pt<GGA>(rho, pi, gx, gy, gz, px, py, pz);
+      t = xc::fully_translate_pt<GGA>(rho, pi, gx, gy, gz, px, py, pz, R);
     } else {
-      t = xc::translate_pt<GGA>(rho, pi, gx, gy, gz);
+      t = xc::translate_pt<GGA>(rho, pi, gx, gy, gz, R);
     }
     double ex, ec;
     if (FUNC == 1) {

@@ -32,7 +32,13 @@ namespace {
 
 thread_local std::string g_last_error;
 
-constexpr size_t PT_ALIGN = 64;  // device leading dimensions are multiples of 64 points
+constexpr int RETRY_FP64 = -1000;   // internal: the int8 on-top kernel's error guard tripped, repeat the call with the FP64 kernels
+
+constexpr size_t PT_ALIGN = 64;   // shard boundaries (ordm_shard_range) are multiples of 64 points
+// Device leading dimensions, the weight / per-point vectors and the staging batches are multiples of the widest
+// point tile any kernel moves with one bulk copy (k2_ontop<8,4>: 8 * 4 * 8 = 256 points; the CTA-pair int8 kernel:
+// 2 * 128), so that the last tile of every column stays inside the allocation (padding is zero-filled).
+constexpr size_t LD_ALIGN = 256;
 inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct GridView {  // one resident grid or one streamed batch
@@ -110,6 +116,7 @@ bool load_cublas(std::string& why) {
 }  // namespace
 
 struct ordm_ctx {
+  uint64_t ctx_id = 0;   // unique per process (never reused, unlike the address)
   int device = 0;
   int sm_count = 148;
   int max_smem_optin = 0;
@@ -147,6 +154,10 @@ struct ordm_ctx {
   // K2 on the int8 tensor cores (k2_int8.cuh): 18..20 active orbitals, Pi only (grad Pi keeps the DMMA kernel)
   int k2_i8_mode = 1;          // ORDM_K2_INT8: 0 off, 1 on with 26 slice pairs (default), 2 on with 21 slice pairs
   bool k2_i8 = false, i8_no_overlap = false;   // ORDM_I8_NO_OVERLAP=1: stages back to back with the int8 K2 (lab / test hook)
+  // k2_i8 = k2_i8_cfg (the RDMs' size and the build allow the int8 kernel) && !i8_blocked (its error guard flagged
+  // points of the current inputs: the FP64 kernels take over until the RDMs or the orbitals change)
+  bool k2_i8_cfg = false, i8_blocked = false;
+  uint32_t guard_points = 0;   // points the guard flagged in the call that switched to the FP64 kernels
   k2i::Params k2ip{};
   uint8_t* d_timg = nullptr;
   int* d_i8_fail = nullptr;
@@ -181,6 +192,9 @@ struct ordm_ctx {
 
   // stage bookkeeping
   bool rho_done = false, pi_done = false, xc_done = false, xc_ft = false, pig_done = false;
+  // vectors installed by the caller through ordm_set_vector (MCPDFT::set_R, set_rhoa_x, ...: mcpdft.h:125-153)
+  bool inj_R = false;      // translate / fully_translate read the caller's R instead of build_R's
+  bool inj_grad = false;   // a spin-density gradient component changed: total gradient re-summed before the next translate
   double last_n[3] = {0, 0, 0}, last_trn[3] = {0, 0, 0};
 
   // cuBLAS handle (AO -> MO transform), created on first use
@@ -327,20 +341,25 @@ int run_k1_core_light(ordm_ctx* c, const GridView& v, int* launches, cudaStream_
 // the assembly of rho, grad rho, pi_core are left
 int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaStream_t st = nullptr, bool core_ready = false) {
   if (!st) st = c->stream;
-  if (c->nact <= k1::MAX_ACT) {
-    // The __constant__ bank holding Ds is per device and shared by every context of the process
-    // (kernel-parameter space was tried instead: ptxas then LDCs the coefficients into registers,
-    // 254 regs, K1 2.6 -> 3.4 ms).  Upload only when another context, another RDM or another
-    // stream used the bank last; contexts on one device must not run K1 concurrently.
-    static std::mutex mu;
-    static struct { const ordm_ctx* owner; uint64_t version; cudaStream_t stream; } bank[64] = {};
-    std::lock_guard<std::mutex> lock(mu);
+  // The __constant__ bank holding Ds is per device and shared by every context of the process
+  // (kernel-parameter space was tried instead: ptxas then LDCs the coefficients into registers,
+  // 254 regs, K1 2.6 -> 3.4 ms).  The bank is uploaded only when another context, another RDM or
+  // another stream used it last.  The lock is held from the ownership check to the K1 launch, and
+  // the last user's K1 is followed by an event that the next uploader's stream waits for: two
+  // contexts on one device (two host threads) serialise their K1s on the GPU instead of racing.
+  static std::mutex bank_mu;
+  static struct { uint64_t owner_id; uint64_t version; cudaStream_t stream; cudaEvent_t last_k1; } bank[64] = {};
+  std::unique_lock<std::mutex> bank_lock(bank_mu, std::defer_lock);
+  const bool use_bank = c->nact <= k1::MAX_ACT;
+  if (use_bank) {
+    bank_lock.lock();
     auto& b = bank[c->device & 63];
-    if (b.owner != c || b.version != c->rdm1_version || b.stream != st) {
-      if (b.owner && b.stream != st) CU(c, cudaDeviceSynchronize());  // the last user's kernels may still read the bank
+    if (!b.last_k1) CU(c, cudaEventCreateWithFlags(&b.last_k1, cudaEventDisableTiming));
+    if (b.owner_id != c->ctx_id || b.version != c->rdm1_version || b.stream != st) {
+      if (b.owner_id && b.stream != st) CU(c, cudaStreamWaitEvent(st, b.last_k1, 0));  // the last user's K1 may still read the bank
       CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsa, c->h_Dsa.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, st));
       CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsb, c->h_Dsb.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, st));
-      b.owner = c; b.version = c->rdm1_version; b.stream = st;
+      b.owner_id = c->ctx_id; b.version = c->rdm1_version; b.stream = st;
     }
   }
   k1::Params p{};
@@ -371,6 +390,10 @@ int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaSt
   p.partial = c->d_partial;
   rc = v.gga ? launch_k1_np<true>(c, p, grid, st) : launch_k1_np<false>(c, p, grid, st);
   if (rc) return rc;
+  if (use_bank) {
+    CU(c, cudaEventRecord(bank[c->device & 63].last_k1, st));
+    bank_lock.unlock();
+  }
   ordm::k4_finalize<3><<<1, 256, 0, st>>>(c->d_partial, grid, c->d_res, ordm::RES_N, accumulate);
   CU(c, cudaGetLastError());
   *launches += 2;
@@ -516,9 +539,11 @@ int run_k2(ordm_ctx* c, const GridView& v, int* launches, bool lean = false) {
   return ORDM_OK;
 }
 
-int run_k3(ordm_ctx* c, const GridView& v, int functional, bool ft, int accumulate, int* launches, bool add_core = false) {
+int run_k3(ordm_ctx* c, const GridView& v, int functional, bool ft, int accumulate, int* launches, bool add_core = false,
+           const double* R_in = nullptr) {
   k3::Params p{};
   p.rho = v.vec[ORDM_VEC_RHO]; p.pi = v.vec[ORDM_VEC_PI]; p.w = v.w;
+  p.R_in = R_in;
   if (add_core && c->core_form) { p.pi_core = v.pi_core; p.pi_out = v.vec[ORDM_VEC_PI]; }
   p.omega = c->omega;
   p.gx = v.gga ? v.gx : nullptr; p.gy = v.gga ? v.gy : nullptr; p.gz = v.gga ? v.gz : nullptr;
@@ -598,8 +623,10 @@ int configure_k2(ordm_ctx* c) {
   c->k2g_ready = false;  // the grad-Pi packing follows the same Dt: rebuilt on next use
   // the int8 tensor-core path for the active-space sizes where K2 dominates the step
   const int kp = (M + 31) / 32 * 32;
-  c->k2_i8 = c->k2_i8_mode > 0 && c->nact >= k2i::MIN_ACT && c->nact <= k2i::MAX_ACT &&
-             k2i::Smem::bytes(kp, c->nact) <= (size_t)c->max_smem_optin;
+  c->k2_i8_cfg = c->k2_i8_mode > 0 && c->nact >= k2i::MIN_ACT && c->nact <= k2i::MAX_ACT &&
+                 k2i::Smem::bytes(kp, c->nact) <= (size_t)c->max_smem_optin;
+  c->i8_blocked = false;
+  c->k2_i8 = c->k2_i8_cfg;
   if (c->k2_i8) {
     static_assert(k2i::NSLICE == 6 && k2i::FIX_BITS == 46, "ordm::pack_t_int8 is written for six byte slices of a 46-bit image");
     std::vector<uint8_t> img;
@@ -610,9 +637,10 @@ int configure_k2(ordm_ctx* c) {
     dfree(c->d_timg);
     CU(c, cudaMalloc(&c->d_timg, img.size()));
     CU(c, cudaMemcpy(c->d_timg, img.data(), img.size(), cudaMemcpyHostToDevice));
-    if (!c->d_i8_fail) { CU(c, cudaMalloc(&c->d_i8_fail, sizeof(int))); CU(c, cudaMemset(c->d_i8_fail, 0, sizeof(int))); }
+    if (!c->d_i8_fail) { CU(c, cudaMalloc(&c->d_i8_fail, 2 * sizeof(int))); CU(c, cudaMemset(c->d_i8_fail, 0, 2 * sizeof(int))); }
     c->k2ip = k2i::Params{};
     c->k2ip.timg = c->d_timg; c->k2ip.t_exp = t_exp; c->k2ip.fail = c->d_i8_fail;
+    ordm::int8_guard_constants(M, c->h_Dt, t_exp, c->k2_i8_mode == 1 ? 4 : 5, c->k2ip.guard_g1, c->k2ip.guard_g2);
     c->k2i_smem = k2i::Smem::bytes(kp, c->nact);
   }
   return ORDM_OK;
@@ -663,7 +691,7 @@ int install_rdm1(ordm_ctx* c, int ncore, int nact, const double* A1a, const doub
   c->have_rdm1 = true;
   static std::atomic<uint64_t> next_version{0};
   c->rdm1_version = ++next_version;
-  c->rho_done = c->pi_done = c->xc_done = false;
+  c->rho_done = c->pi_done = c->xc_done = c->pig_done = false;
   return ORDM_OK;
 }
 
@@ -680,12 +708,25 @@ int fetch_result(ordm_ctx* c, double eclass, ordm_result* out, uint64_t npts, in
   CU(c, cudaMemcpyAsync(c->h_res, c->d_res, ordm::RES_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   int* h_i8_fail = reinterpret_cast<int*>(c->h_res + 12);   // the pinned block has room beyond the RES_COUNT scalars
   *h_i8_fail = 0;
-  if (c->k2_i8 && c->d_i8_fail) CU(c, cudaMemcpyAsync(h_i8_fail, c->d_i8_fail, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  h_i8_fail[1] = 0;
+  if (c->k2_i8 && c->d_i8_fail) CU(c, cudaMemcpyAsync(h_i8_fail, c->d_i8_fail, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  int* h_xerr = h_i8_fail + 2;
+  *h_xerr = 0;
+  if (c->comm && c->peer_ok && c->d_xerr) CU(c, cudaMemcpyAsync(h_xerr, c->d_xerr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaEventRecord(c->ev[5], c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  if (*h_xerr)   // k_allreduce_peer (reduce.cuh): a peer's flag never arrived; the result scalars were set to NaN
+    return fail(c, ORDM_ERR_NCCL, "peer all-reduce timed out waiting for another rank (rank %d of %d)", c->rank, c->nranks);
   if (*h_i8_fail) {   // a tcgen05 completion barrier never flipped (bounded spin in k2_int8.cuh): the Pi of this call is not valid
-    cudaMemsetAsync(c->d_i8_fail, 0, sizeof(int), c->stream);
+    cudaMemsetAsync(c->d_i8_fail, 0, 2 * sizeof(int), c->stream);
     return fail(c, ORDM_ERR_CUDA, "int8 on-top kernel: %d CTA(s) timed out waiting for a tensor-core completion barrier", *h_i8_fail);
+  }
+  if (h_i8_fail[1]) {   // the error guard flagged points: this call's Pi is not trusted; the caller repeats it with the FP64 kernels
+    cudaMemsetAsync(c->d_i8_fail, 0, 2 * sizeof(int), c->stream);
+    c->guard_points = (uint32_t)h_i8_fail[1];
+    c->i8_blocked = true;
+    c->k2_i8 = false;
+    return RETRY_FP64;
   }
   const double* r = c->h_res;
   std::memset(out, 0, sizeof(*out));
@@ -737,26 +778,34 @@ int setup_peer_xchg(ordm_ctx* c) {
   // the two scratch buffers every rank needs to take part in the collectives below
   char* d_h = nullptr;
   int* d_flag = nullptr;
-  CU(c, cudaMalloc(&d_h, sizeof(mine) * (size_t)(c->nranks + 1)));
-  CU(c, cudaMalloc(&d_flag, sizeof(int) * (size_t)(c->nranks + 1)));
-  int ok = cudaMalloc(&c->d_xchg, bytes) == cudaSuccess && cudaMemset(c->d_xchg, 0, bytes) == cudaSuccess &&
+  // d_flag is the one buffer the gathers below cannot do without: if even that fails, this rank still has to issue
+  // the same collectives as its peers (they would hang in ncclAllGather otherwise), so fall back to the result
+  // vector as scratch -- 16 doubles hold nranks + 1 <= 17 ints -- and report "not ok"
+  const bool scratch_ok = cudaMalloc(&d_h, sizeof(mine) * (size_t)(c->nranks + 1)) == cudaSuccess &&
+                          cudaMalloc(&d_flag, sizeof(int) * (size_t)(c->nranks + 1)) == cudaSuccess;
+  cudaGetLastError();
+  int* flag_buf = d_flag ? d_flag : reinterpret_cast<int*>(c->d_res);
+  int ok = scratch_ok && cudaMalloc(&c->d_xchg, bytes) == cudaSuccess && cudaMemset(c->d_xchg, 0, bytes) == cudaSuccess &&
            cudaMalloc(&c->d_xerr, sizeof(int)) == cudaSuccess && cudaMemset(c->d_xerr, 0, sizeof(int)) == cudaSuccess &&
            cudaIpcGetMemHandle(&mine, c->d_xchg) == cudaSuccess;
   cudaGetLastError();
   std::vector<cudaIpcMemHandle_t> all(c->nranks);
   std::vector<int> flags(c->nranks, 0);
   auto gather_flag = [&](int v) -> bool {  // all-gather one int per rank into flags[]
-    if (cudaMemcpy(d_flag, &v, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return false;
-    if (g_nccl.AllGather(d_flag, d_flag + 1, sizeof(int), /*ncclChar*/ 0, c->comm, c->stream) != 0) return false;
+    if (cudaMemcpy(flag_buf, &v, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    if (g_nccl.AllGather(flag_buf, flag_buf + 1, sizeof(int), /*ncclChar*/ 0, c->comm, c->stream) != 0) return false;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
-    return cudaMemcpy(flags.data(), d_flag + 1, sizeof(int) * c->nranks, cudaMemcpyDeviceToHost) == cudaSuccess;
+    return cudaMemcpy(flags.data(), flag_buf + 1, sizeof(int) * c->nranks, cudaMemcpyDeviceToHost) == cudaSuccess;
   };
   auto all_set = [&]() { for (int r = 0; r < c->nranks; ++r) if (flags[r] != 1) return false; return true; };
   bool good = gather_flag(ok) && all_set();
-  // handles travel in any case (every rank must issue the same collectives)
-  cudaMemcpy(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice);
-  bool coll = g_nccl.AllGather(d_h, d_h + sizeof(mine), sizeof(mine), 0, c->comm, c->stream) == 0 && cudaStreamSynchronize(c->stream) == cudaSuccess &&
-              cudaMemcpy(all.data(), d_h + sizeof(mine), sizeof(mine) * c->nranks, cudaMemcpyDeviceToHost) == cudaSuccess;
+  // the handles travel only if EVERY rank got its buffers (all ranks see the same flags, so all take the same branch)
+  bool coll = false;
+  if (good) {
+    cudaMemcpy(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+    coll = g_nccl.AllGather(d_h, d_h + sizeof(mine), sizeof(mine), 0, c->comm, c->stream) == 0 && cudaStreamSynchronize(c->stream) == cudaSuccess &&
+           cudaMemcpy(all.data(), d_h + sizeof(mine), sizeof(mine) * c->nranks, cudaMemcpyDeviceToHost) == cudaSuccess;
+  }
   int mapped = 0;
   if (good && coll) {
     c->px.nranks = c->nranks; c->px.rank = c->rank;
@@ -771,9 +820,11 @@ int setup_peer_xchg(ordm_ctx* c) {
   }
   // the fast path is used only if EVERY rank mapped every peer
   const bool everyone = gather_flag(mapped) && all_set();
+  const bool used_res_as_scratch = (d_flag == nullptr);
   dfree(d_h);
   dfree(d_flag);
   cudaGetLastError();
+  if (used_res_as_scratch) cudaMemset(c->d_res, 0, 16 * sizeof(double));   // the result vector served as scratch
   if (everyone) { c->peer_ok = true; c->xepoch = 0; }
   else {
     for (int r = 0; r < c->nranks; ++r)
@@ -782,6 +833,13 @@ int setup_peer_xchg(ordm_ctx* c) {
     release_peer_xchg(c);
   }
   return ORDM_OK;
+}
+
+// total density gradient from the spin components (MCPDFT::translate_density_gradients adds them per point,
+// mcpdft.cc:383-388); only needed after the caller installed components through ordm_set_vector
+__global__ void k_sum2(double* __restrict__ dst, const double* __restrict__ a, const double* __restrict__ b, size_t n) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) dst[p] = a[p] + b[p];
 }
 
 // synthetic fill kernels ----------------------------------------------------------------
@@ -798,7 +856,7 @@ __global__ void k_synth_w(double* __restrict__ dst, size_t npts_local, size_t p0
 }
 
 int alloc_grid(ordm_ctx* c, size_t npts, int n, bool gga) {
-  const size_t ld = round_up(std::max<size_t>(npts, 1), PT_ALIGN);
+  const size_t ld = round_up(std::max<size_t>(npts, 1), LD_ALIGN);
   if (ld > c->cap_pts || n > c->cap_n || (gga && !c->cap_gga) || !c->d_phi[0]) {
     for (int k = 0; k < 4; ++k) dfree(c->d_phi[k]);
     const size_t bytes = ld * (size_t)n * sizeof(double);
@@ -816,18 +874,19 @@ int alloc_grid(ordm_ctx* c, size_t npts, int n, bool gga) {
   c->g.phix = gga ? c->d_phi[1] : nullptr;
   c->g.phiy = gga ? c->d_phi[2] : nullptr;
   c->g.phiz = gga ? c->d_phi[3] : nullptr;
-  c->rho_done = c->pi_done = c->xc_done = false;
+  c->rho_done = c->pi_done = c->xc_done = c->pig_done = false;
+  c->i8_blocked = false; c->k2_i8 = c->k2_i8_cfg;   // the int8 guard is re-evaluated on the new orbitals
   return ORDM_OK;
 }
 
 int alloc_w(ordm_ctx* c, size_t npts) {
-  const size_t ld = round_up(std::max<size_t>(npts, 1), PT_ALIGN);
+  const size_t ld = round_up(std::max<size_t>(npts, 1), LD_ALIGN);
   dfree(c->d_w);
   CU(c, cudaMalloc(&c->d_w, ld * sizeof(double)));
   CU(c, cudaMemsetAsync(c->d_w, 0, ld * sizeof(double), c->stream));
   c->g.w = c->d_w;
   c->g.vec[ORDM_VEC_W] = c->d_w;
-  c->rho_done = c->pi_done = c->xc_done = false;
+  c->rho_done = c->pi_done = c->xc_done = c->pig_done = false;
   return ORDM_OK;
 }
 
@@ -863,6 +922,8 @@ int ordm_create(int device, ordm_ctx** out) {
   if (prop.major != 10)
     return fail(nullptr, ORDM_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
   ordm_ctx* c = new ordm_ctx();
+  static std::atomic<uint64_t> next_ctx_id{0};
+  c->ctx_id = ++next_ctx_id;
   c->device = device;
   if (const char* e = getenv("ORDM_I8_NO_OVERLAP")) c->i8_no_overlap = (e[0] == '1');
   if (const char* e = getenv("ORDM_K2_INT8")) c->k2_i8_mode = atoi(e);   // 0: DMMA kernels only; 2: 21 slice pairs
@@ -1011,8 +1072,8 @@ int ordm_set_orbitals_ao(ordm_ctx* c, size_t npts, int nao, size_t ld, const dou
   if (rc) return rc;
   if (!npts) return ORDM_OK;
   // point batches: two staging buffers of [nao][batch] doubles (<= 256 MB each)
-  size_t batch = std::max<size_t>(PT_ALIGN, ((size_t)1 << 25) / (size_t)nao / PT_ALIGN * PT_ALIGN);
-  batch = std::min(batch, round_up(npts, PT_ALIGN));
+  size_t batch = std::max<size_t>(LD_ALIGN, ((size_t)1 << 25) / (size_t)nao / LD_ALIGN * LD_ALIGN);
+  batch = std::min(batch, round_up(npts, LD_ALIGN));
   double *d_C = nullptr, *d_stage[2] = {nullptr, nullptr};
   cudaEvent_t copied[2] = {nullptr, nullptr}, used[2] = {nullptr, nullptr};
   auto cleanup = [&]() {
@@ -1074,7 +1135,7 @@ int ordm_set_rdm2ab_dense(ordm_ctx* c, int n, const double* D2ab) {
   int rc = configure_k2(c);
   if (rc) return rc;
   c->have_rdm2 = true;
-  c->pi_done = c->xc_done = false;
+  c->pi_done = c->xc_done = c->pig_done = false;
   return ORDM_OK;
 }
 
@@ -1156,6 +1217,17 @@ int ordm_build_pi(ordm_ctx* c) {
   if ((rc = ensure_vectors(c))) return rc;
   int launches = 0;
   if ((rc = run_k2(c, c->g, &launches))) return rc;
+  if (c->k2_i8 && !want_pig(c, c->g.gga)) {   // the int8 kernel ran: consult its time-out flag and its error guard
+    int* h = reinterpret_cast<int*>(c->h_res + 12);
+    CU(c, cudaMemcpyAsync(h, c->d_i8_fail, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (h[0] || h[1]) CU(c, cudaMemsetAsync(c->d_i8_fail, 0, 2 * sizeof(int), c->stream));
+    if (h[0]) return fail(c, ORDM_ERR_CUDA, "int8 on-top kernel: %d CTA(s) timed out waiting for a tensor-core completion barrier", h[0]);
+    if (h[1]) {   // flagged points: Pi again from the FP64 tensor-pipe kernels
+      c->guard_points = (uint32_t)h[1]; c->i8_blocked = true; c->k2_i8 = false;
+      if ((rc = run_k2(c, c->g, &launches))) return rc;
+    }
+  }
   CU(c, cudaStreamSynchronize(c->stream));
   c->pi_done = true;
   c->pig_done = want_pig(c, c->g.gga);
@@ -1169,7 +1241,17 @@ static int staged_xc(ordm_ctx* c, bool ft) {
     return fail(c, ORDM_ERR_STATE, "fully_translate with orbital gradients needs grad Pi: set ORDM_OPT_PI_GRADIENT (or ORDM_OPT_FULLY_TRANSLATED) before build_pi");
   if (c->xc_done && c->xc_ft == ft) return ORDM_OK;
   int launches = 0;
-  int rc = run_k3(c, c->g, c->g.gga ? ORDM_FUNC_PBE : ORDM_FUNC_SVWN, ft, 0, &launches);
+  if (c->inj_grad && c->g.gga) {   // the caller replaced spin-gradient components: rebuild the total gradient K3 reads
+    double* tot[3] = {c->g.gx, c->g.gy, c->g.gz};
+    for (int k = 0; k < 3; ++k) {
+      const double *a = c->g.vec[ORDM_VEC_RHOA_X + k], *b = c->g.vec[ORDM_VEC_RHOB_X + k];
+      if (!a || !b) return fail(c, ORDM_ERR_STATE, "translate after set_rhoa_x/...: both spin components of every gradient direction must exist (ORDM_OPT_DIAGNOSTICS)");
+      if (c->g.npts) k_sum2<<<(unsigned)((c->g.npts + 255) / 256), 256, 0, c->stream>>>(tot[k], a, b, c->g.npts);
+    }
+    CU(c, cudaGetLastError());
+    c->inj_grad = false;
+  }
+  int rc = run_k3(c, c->g, c->g.gga ? ORDM_FUNC_PBE : ORDM_FUNC_SVWN, ft, 0, &launches, false, c->inj_R ? c->g.vec[ORDM_VEC_R] : nullptr);
   if (rc) return rc;
   CU(c, cudaMemcpyAsync(c->h_res, c->d_res, ordm::RES_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
@@ -1182,6 +1264,7 @@ static int staged_xc(ordm_ctx* c, bool ft) {
 int ordm_build_R(ordm_ctx* c) {  // R is the same vector under both translations
   CHECK_CTX(c);
   CU(c, cudaSetDevice(c->device));
+  if (c->inj_R) { c->inj_R = false; c->xc_done = false; }   // MCPDFT::build_R overwrites whatever set_R installed
   if (c->xc_done) return ORDM_OK;
   return staged_xc(c, (c->opts & ORDM_OPT_FULLY_TRANSLATED) != 0 && (!c->g.gga || c->pig_done));
 }
@@ -1255,9 +1338,18 @@ int ordm_functional(ordm_ctx* c, int term, size_t npts, const double* ra, const 
 }
 
 // ---- the path in one call -----------------------------------------------------------------
+static int energy_resident(ordm_ctx* c, int functional, double eclass, ordm_result* out);
 int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   CHECK_CTX(c);
   if (!out) return fail(c, ORDM_ERR_INVALID, "null result");
+  int rc = energy_resident(c, functional, eclass, out);
+  if (rc == RETRY_FP64) {   // the int8 kernel's guard flagged points: same call again, Pi from the FP64 tensor-pipe kernels
+    rc = energy_resident(c, functional, eclass, out);
+    if (rc == ORDM_OK) out->pi_guard_points = c->guard_points;
+  }
+  return rc;
+}
+static int energy_resident(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   CU(c, cudaSetDevice(c->device));
   int rc = check_inputs(c, true);
   if (rc) return rc;
@@ -1265,6 +1357,7 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
     return fail(c, ORDM_ERR_STATE, "ORDM_OPT_PI_GRADIENT needs the orbital gradients (phi_x, phi_y, phi_z)");
   if ((rc = ensure_vectors(c))) return rc;
   const bool ft = (c->opts & ORDM_OPT_FULLY_TRANSLATED) != 0;
+  c->inj_R = c->inj_grad = false;   // mcpdft_energy rebuilds every vector from the inputs (energy.cc:49-58)
   int launches = 0;
   // Overlapped mode (default): the tensor-bound K2 is launched first with a trimmed register
   // footprint, and the HBM-bound K1 streams underneath it on a second stream (one K1 CTA stays
@@ -1336,18 +1429,31 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   return ORDM_OK;
 }
 
+static int energy_streamed(ordm_ctx* c, int functional, double eclass, size_t npts, int n, size_t ld, const double* w,
+                           const double* phi, const double* px, const double* py, const double* pz, size_t batch, ordm_result* out);
 int ordm_energy_host(ordm_ctx* c, int functional, double eclass, size_t npts, int n, size_t ld, const double* w,
                      const double* phi, const double* px, const double* py, const double* pz, size_t batch,
                      ordm_result* out) {
   CHECK_CTX(c);
   if (!out || !w || !phi || n <= 0 || ld < npts) return fail(c, ORDM_ERR_INVALID, "bad host buffers");
+  // the host buffers are new inputs as far as the int8 guard is concerned
+  c->i8_blocked = false; c->k2_i8 = c->k2_i8_cfg;
+  int rc = energy_streamed(c, functional, eclass, npts, n, ld, w, phi, px, py, pz, batch, out);
+  if (rc == RETRY_FP64) {
+    rc = energy_streamed(c, functional, eclass, npts, n, ld, w, phi, px, py, pz, batch, out);
+    if (rc == ORDM_OK) out->pi_guard_points = c->guard_points;
+  }
+  return rc;
+}
+static int energy_streamed(ordm_ctx* c, int functional, double eclass, size_t npts, int n, size_t ld, const double* w,
+                           const double* phi, const double* px, const double* py, const double* pz, size_t batch, ordm_result* out) {
   const bool gga = px || py || pz;
   if (gga && !(px && py && pz)) return fail(c, ORDM_ERR_INVALID, "give all of phi_x, phi_y, phi_z or none");
   if (!c->have_rdm1 || !c->have_rdm2) return fail(c, ORDM_ERR_STATE, "RDMs not set");
   if (c->ncore + c->nact != n) return fail(c, ORDM_ERR_STATE, "RDM dimension %d+%d does not match n=%d", c->ncore, c->nact, n);
   CU(c, cudaSetDevice(c->device));
   if (batch == 0) batch = 1u << 18;
-  batch = round_up(std::min(batch, std::max<size_t>(npts, 1)), PT_ALIGN);
+  batch = round_up(std::min(batch, std::max<size_t>(npts, 1)), LD_ALIGN);
   // (re)allocate the two staging sets
   if (batch > c->stage_pts || n > c->stage_n || (gga && !c->stage_gga)) {
     for (auto& s : c->stage) {
@@ -1404,6 +1510,33 @@ int ordm_energy_host(ordm_ctx* c, int functional, double eclass, size_t npts, in
   return ORDM_OK;
 }
 
+// MCPDFT::set_rhoa ... set_tr_sigma_bb, set_pi, set_pi_x/y/z, set_R (mcpdft.h:125-153): the caller's vector replaces
+// the engine's and is what the following stages and getters see.
+int ordm_set_vector(ordm_ctx* c, int which, const double* host_in, size_t npts) {
+  CHECK_CTX(c);
+  if (which < 0 || which >= ORDM_VEC_COUNT || (npts && !host_in)) return fail(c, ORDM_ERR_INVALID, "bad vector");
+  if (which == ORDM_VEC_W) return ordm_set_grid(c, npts, host_in);
+  if (!c->g.w || npts != c->g.npts) return fail(c, ORDM_ERR_INVALID, "vector length %zu != grid size %zu (ordm_set_grid first)", npts, c->g.npts);
+  CU(c, cudaSetDevice(c->device));
+  if (c->g.ld < round_up(std::max<size_t>(npts, 1), LD_ALIGN)) c->g.ld = round_up(std::max<size_t>(npts, 1), LD_ALIGN);  // no orbitals yet
+  int rc = ensure_vectors(c);
+  if (rc) return rc;
+  double*& dst = c->g.vec[which];
+  if (!dst) {   // energy-only mode keeps few vectors: an installed one is materialised on its own
+    CU(c, cudaMalloc(&dst, c->g.ld * sizeof(double)));
+    CU(c, cudaMemsetAsync(dst, 0, c->g.ld * sizeof(double), c->stream));
+  }
+  if (npts) CU(c, cudaMemcpyAsync(dst, host_in, npts * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->xc_done = false;
+  if (which == ORDM_VEC_RHO) c->rho_done = true;         // what build_R / translate read (mcpdft.cc:276,297)
+  else if (which == ORDM_VEC_PI) c->pi_done = true;      // the complete Pi (core part included)
+  else if (which == ORDM_VEC_R) c->inj_R = true;
+  else if (which >= ORDM_VEC_RHOA_X && which <= ORDM_VEC_RHOB_Z) c->inj_grad = true;
+  else if (which >= ORDM_VEC_PI_X && which <= ORDM_VEC_PI_Z) c->pig_done = true;
+  return ORDM_OK;
+}
+
 // ---- outputs --------------------------------------------------------------------------------
 int ordm_get_vector(ordm_ctx* c, int which, double* host_out, size_t npts) {
   CHECK_CTX(c);
@@ -1416,7 +1549,12 @@ int ordm_get_vector(ordm_ctx* c, int which, double* host_out, size_t npts) {
     if (rc) return rc;
   }
   const double* src = c->g.vec[which];
-  if (which >= ORDM_VEC_PI_X && which <= ORDM_VEC_PI_Z && !c->pig_done) src = nullptr;  // stale or never built
+  // a vector whose producing stage is not current (inputs changed since, or never run) is an error, not old data
+  const bool from_rho = which <= ORDM_VEC_SIGMA_BB;
+  const bool is_pig = which >= ORDM_VEC_PI_X && which <= ORDM_VEC_PI_Z;
+  if (src && ((from_rho && !c->rho_done) || (which == ORDM_VEC_PI && !c->pi_done) || (is_pig && !c->pig_done)))
+    return fail(c, ORDM_ERR_STATE, "vector %d is stale: run %s after changing the inputs", which, from_rho ? "build_rho" : "build_pi");
+  if (is_pig && !c->pig_done) src = nullptr;  // never built
   if (!src) return fail(c, ORDM_ERR_STATE, "vector %d is not materialised (enable ORDM_OPT_DIAGNOSTICS%s before the build_* calls)", which,
                         which >= ORDM_VEC_PI_X && which <= ORDM_VEC_PI_Z ? " and ORDM_OPT_PI_GRADIENT" : (which >= ORDM_VEC_RHOA_X && which <= ORDM_VEC_SIGMA_BB) || which >= ORDM_VEC_TR_SIGMA_AA ? "; gradients need phi_x/y/z" : "");
   if (npts) CU(c, cudaMemcpyAsync(host_out, src, npts * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1502,6 +1640,7 @@ int ordm_comm_attach(ordm_ctx* c, int nranks, int rank, const char id[128]) {
   std::string why;
   if (!load_nccl(why)) return fail(c, ORDM_ERR_NCCL, "%s", why.c_str());
   CU(c, cudaSetDevice(c->device));
+  if (c->comm) ordm_comm_detach(c);   // re-attach: release the previous communicator and its peer mappings first
   IdBlob blob;
   std::memcpy(blob.b, id, 128);
   int nr = g_nccl.CommInitRank(&c->comm, nranks, blob, rank);

@@ -289,6 +289,47 @@ inline void pack_t_int8(int M, const std::vector<double>& Dt, int kp, std::vecto
   }
 }
 
+// The same image for the CTA-pair kernel (k2_int8_pair.cuh): block c (c = 0, 1) is what CTA rank c of a cluster keeps
+// in shared memory -- of every K chunk only rows [c rows/2, (c+1) rows/2) (tcgen05.mma.cta_group::2 takes half of B's
+// N from each CTA), each half chunk a K-major no-swizzle operand of rows/2 rows.  Slice stride and chunk offsets
+// are half of pack_t_int8's.
+inline void pack_t_int8_pair(int M, const std::vector<double>& Dt, int kp, std::vector<uint8_t>& img, int& t_exp) {
+  std::vector<uint8_t> whole;
+  pack_t_int8(M, Dt, kp, whole, t_exp);
+  const int nslice = 6;
+  const size_t slice = (size_t)t_int8_slice_bytes(kp), half = slice / 2;
+  img.assign((size_t)2 * nslice * half, 0);
+  for (int l = 0; l < nslice; ++l)
+    for (int kc = 0; kc < kp / 32; ++kc) {
+      const int rows = kp - 32 * kc, hr = rows / 2;
+      for (int n = 0; n < rows; ++n)
+        for (int k = 0; k < 32; ++k) {
+          const size_t from = (size_t)l * slice + (size_t)t_int8_chunk_off(kp, kc) + (size_t)((k >> 4) * (rows >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (k & 15);
+          const int c = n / hr, nl = n % hr;
+          const size_t to = ((size_t)c * nslice + l) * half + (size_t)t_int8_chunk_off(kp, kc) / 2 + (size_t)((k >> 4) * (hr >> 3) + (nl >> 3)) * 128 + (nl & 7) * 16 + (k & 15);
+          img[to] = whole[from];
+        }
+    }
+}
+
+// Constants of the int8 path's a-posteriori error estimate (k2_int8_pair.cuh: guard_flag):
+//   z^2 var(dPi) = 2^(4 em) g1 S2^2 + g2 S2^4,   z = 4,   S2 = sum_t phi_t^2,   2^em > max_t |phi_t|
+// g1 = z^2 (2^-92 |T|_F^2 / 3 + 4 d^2 4^t_exp M)   (X image rounding; slice pairs dropped below GMIN, d = 2^-54.6 | 2^-46.4)
+// g2 = z^2 4^t_exp 2^-92 / 3                        (T image rounding)
+inline void int8_guard_constants(int M, const std::vector<double>& Dt, int t_exp, int gmin, double& g1, double& g2) {
+  double tf2 = 0.0;
+  for (int I = 0; I < M; ++I)
+    for (int J = 0; J < M; ++J) {
+      const int bi = I / 32, bj = J / 32;
+      const double t = bi < bj ? Dt[(size_t)I * M + J] : (bi == bj ? 0.5 * Dt[(size_t)I * M + J] : 0.0);
+      tf2 += t * t;
+    }
+  const double z2 = 16.0, q2 = std::ldexp(1.0, -92) / 3.0, ts2 = std::ldexp(1.0, 2 * t_exp);
+  const double d = std::exp2(gmin <= 4 ? -54.6 : -46.4);
+  g1 = z2 * (q2 * tf2 + 4.0 * d * d * ts2 * (double)M);
+  g2 = z2 * ts2 * q2;
+}
+
 // Ds = (D + D^T)/2, written row-major with row stride `stride` (zero padded).
 inline void symmetrise_opdm(int n, const double* D, int stride, std::vector<double>& Ds) {
   Ds.assign((size_t)stride * stride, 0.0);

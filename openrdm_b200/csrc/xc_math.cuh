@@ -36,10 +36,15 @@ struct Translated {
   double saa, sab, sbb;    // translated sigma, mcpdft.cc:407-409 (zero when !GGA, energy.cc:63-65)
 };
 
+// build_R's formula, mcpdft.cc:282 (unguarded; inf/NaN are masked by the rho / Pi tests of the translation)
+__device__ __forceinline__ double r_factor(double rho, double pi) { return 4.0 * pi / (rho * rho); }
+
+// R is an argument because MCPDFT::translate reads the member R_ -- normally what build_R left there, but a caller
+// may have installed its own through set_R (mcpdft.h:149)
 template <bool GGA>
-__device__ __forceinline__ Translated translate_pt(double rho, double pi, double gx, double gy, double gz) {
+__device__ __forceinline__ Translated translate_pt(double rho, double pi, double gx, double gy, double gz, double R_in) {
   Translated t;
-  t.R = 4.0 * pi / (rho * rho);  // mcpdft.cc:282 (unguarded; inf/NaN masked by the test below)
+  t.R = R_in;
   const bool live = !(rho < TOL) && !(pi < 0.0);  // mcpdft.cc:319
   double z = 0.0;
   if (live && (1.0 - t.R) > TOL) z = sqrt(1.0 - t.R);  // mcpdft.cc:321-325
@@ -68,9 +73,9 @@ constexpr double FT_A = -475.60656009, FT_B = -379.47331922, FT_C = -85.38149682
 
 template <bool GGA>
 __device__ __forceinline__ Translated fully_translate_pt(double rho, double pi, double gx, double gy, double gz,
-                                                         double px, double py, double pz) {
+                                                         double px, double py, double pz, double R_in) {
   Translated t;
-  t.R = 4.0 * pi / (rho * rho);
+  t.R = R_in;
   const bool live = !(rho < TOL) && !(pi < 0.0);  // mcpdft.cc:458
   const double R = t.R, dR = R - FT_R1;
   const double d2 = dR * dR, d3 = d2 * dR, d4 = d2 * d2, d5 = d4 * dR;

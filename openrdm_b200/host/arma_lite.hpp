@@ -6,8 +6,12 @@
 #if defined(ORDM_USE_ARMADILLO)
 #include <armadillo>
 #else
+#include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <string>
 #include <vector>
 namespace arma {
 namespace fill { struct zeros_t {}; static const zeros_t zeros{}; }
@@ -18,6 +22,7 @@ class mat {
   mat() = default;
   mat(std::size_t r, std::size_t c) : n_rows(r), n_cols(c), n_elem(r * c), v_(r * c, 0.0) {}
   mat(std::size_t r, std::size_t c, fill::zeros_t) : mat(r, c) {}
+  inline mat(const vec& v);   // column vector -> n x 1 matrix, as Armadillo converts (utility.cc:31 relies on it)
   double& operator()(std::size_t i, std::size_t j) { return v_[i + j * n_rows]; }
   double operator()(std::size_t i, std::size_t j) const { return v_[i + j * n_rows]; }
   double* memptr() { return v_.data(); }
@@ -39,9 +44,19 @@ class vec {
   double operator()(std::size_t i) const { return v_[i]; }
   double* memptr() { return v_.data(); }
   const double* memptr() const { return v_.data(); }
+  void print(const char* tag = "") const {
+    std::printf("%s\n", tag);
+    for (std::size_t i = 0; i < n_elem; ++i) std::printf(" %14.8f\n", v_[i]);
+  }
  private:
   std::vector<double> v_;
 };
+inline mat::mat(const vec& v) : n_rows(v.n_elem), n_cols(1), n_elem(v.n_elem), v_(v.memptr(), v.memptr() + v.n_elem) {}
+inline vec operator+(const vec& a, const vec& b) {
+  vec r(a.n_elem);
+  for (std::size_t i = 0; i < a.n_elem; ++i) r(i) = a(i) + b(i);
+  return r;
+}
 inline mat kron(const mat& A, const mat& B) {
   mat K(A.n_rows * B.n_rows, A.n_cols * B.n_cols);
   for (std::size_t j = 0; j < A.n_cols; ++j) for (std::size_t i = 0; i < A.n_rows; ++i)

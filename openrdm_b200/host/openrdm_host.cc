@@ -186,7 +186,17 @@ arma::vec MCPDFT::fetch(int which) const {
   ck(ctx_, ordm_get_vector(ctx_, which, v.memptr(), npts_), "ordm_get_vector");
   return v;
 }
-#define ORDM_HOST_GET(name, id) arma::vec MCPDFT::get_##name() const { return fetch(id); }
+void MCPDFT::install(int which, const arma::vec& v) {
+  // the device copy of the grid must exist before a per-point vector can be placed on it; a setter called right
+  // after the constructor (as oracle-style harnesses do: set_npts, set_w, then vectors) uploads the weights first
+  ensure_ctx();
+  if (v.n_elem != npts_) throw std::runtime_error("MCPDFT: vector length differs from npts");
+  if (dirty_inputs_ && phi_.n_rows == npts_ && phi_.n_cols == nbfs_ && nbfs_ && D1a_.n_rows == nbfs_) sync_inputs();
+  else if (dirty_inputs_ && w_.n_elem == npts_) ck(ctx_, ordm_set_grid(ctx_, npts_, w_.memptr()), "ordm_set_grid");
+  ck(ctx_, ordm_set_vector(ctx_, which, v.memptr(), npts_), "ordm_set_vector");
+}
+#define ORDM_HOST_GET(name, id) arma::vec MCPDFT::get_##name() const { return fetch(id); } \
+  void MCPDFT::set_##name(const arma::vec& v) { install(id, v); }
 ORDM_HOST_GET(rhoa, ORDM_VEC_RHOA) ORDM_HOST_GET(rhoa_x, ORDM_VEC_RHOA_X) ORDM_HOST_GET(rhoa_y, ORDM_VEC_RHOA_Y) ORDM_HOST_GET(rhoa_z, ORDM_VEC_RHOA_Z)
 ORDM_HOST_GET(rhob, ORDM_VEC_RHOB) ORDM_HOST_GET(rhob_x, ORDM_VEC_RHOB_X) ORDM_HOST_GET(rhob_y, ORDM_VEC_RHOB_Y) ORDM_HOST_GET(rhob_z, ORDM_VEC_RHOB_Z)
 ORDM_HOST_GET(rho, ORDM_VEC_RHO) ORDM_HOST_GET(tr_rhoa, ORDM_VEC_TR_RHOA) ORDM_HOST_GET(tr_rhob, ORDM_VEC_TR_RHOB) ORDM_HOST_GET(pi, ORDM_VEC_PI)
@@ -230,6 +240,8 @@ double run_term(const MCPDFT* mc, int term, const arma::vec& a, const arma::vec&
   return e;
 }
 }  // namespace
+Functional::Functional() {}
+Functional::~Functional() {}
 double Functional::EX_LSDA(const MCPDFT* mc, const arma::vec& a, const arma::vec& b) { return run_term(mc, ORDM_EX_LSDA, a, b, nullptr, nullptr, nullptr); }
 double Functional::EC_VWN3(const MCPDFT* mc, const arma::vec& a, const arma::vec& b) { return run_term(mc, ORDM_EC_VWN3, a, b, nullptr, nullptr, nullptr); }
 double Functional::EX_PBE(const MCPDFT* mc, const arma::vec& a, const arma::vec& b, const arma::vec& saa, const arma::vec& sbb) { return run_term(mc, ORDM_EX_PBE, a, b, &saa, nullptr, &sbb); }

@@ -59,8 +59,11 @@ class MCPDFT {
   ORDM_HOST_INPUT(arma::mat, phi_z, phi_z_) ORDM_HOST_INPUT(arma::mat, cmat, cmat_) ORDM_HOST_INPUT(arma::mat, D1a, D1a_)
   ORDM_HOST_INPUT(arma::mat, D1b, D1b_) ORDM_HOST_INPUT(arma::mat, D2ab, D2ab_)
 #undef ORDM_HOST_INPUT
-  // per-point results live on the device; each getter copies npts doubles back (mcpdft.cc:672-690)
-#define ORDM_HOST_OUTPUT(name) arma::vec get_##name() const;
+  // per-point results live on the device; each getter copies npts doubles back (mcpdft.cc:672-690), each setter
+  // (mcpdft.cc:708-736) installs the caller's vector on the device (ordm_set_vector), where the following stages
+  // read it exactly where the reference reads its members: rho, Pi and R by build_R / translate, the spin-density
+  // gradients by translate_density_gradients, grad Pi by fully_translate
+#define ORDM_HOST_OUTPUT(name) arma::vec get_##name() const; void set_##name(const arma::vec& v);
   ORDM_HOST_OUTPUT(rhoa) ORDM_HOST_OUTPUT(rhoa_x) ORDM_HOST_OUTPUT(rhoa_y) ORDM_HOST_OUTPUT(rhoa_z)
   ORDM_HOST_OUTPUT(rhob) ORDM_HOST_OUTPUT(rhob_x) ORDM_HOST_OUTPUT(rhob_y) ORDM_HOST_OUTPUT(rhob_z)
   ORDM_HOST_OUTPUT(rho) ORDM_HOST_OUTPUT(tr_rhoa) ORDM_HOST_OUTPUT(tr_rhob) ORDM_HOST_OUTPUT(pi) ORDM_HOST_OUTPUT(R)
@@ -70,6 +73,14 @@ class MCPDFT {
   // (mcpdft.cc:268); here all three components are retrievable
   ORDM_HOST_OUTPUT(pi_x) ORDM_HOST_OUTPUT(pi_y) ORDM_HOST_OUTPUT(pi_z)
 #undef ORDM_HOST_OUTPUT
+  // translated total density and translated spin-density gradients: the reference keeps members with setters
+  // (mcpdft.cc:718-725) that none of its stages reads or writes (translate_density_gradients works on locals,
+  // mcpdft.cc:350-372); get_tr_rho returns what set_tr_rho stored (mcpdft.cc:682), the gradient getters are
+  // declared but never defined there (mcpdft.h:92-98) and are defined here
+#define ORDM_HOST_PLAIN(name) arma::vec get_##name() const { return name##_; } void set_##name(const arma::vec& v) { name##_ = v; }
+  ORDM_HOST_PLAIN(tr_rho) ORDM_HOST_PLAIN(tr_rhoa_x) ORDM_HOST_PLAIN(tr_rhoa_y) ORDM_HOST_PLAIN(tr_rhoa_z)
+  ORDM_HOST_PLAIN(tr_rhob_x) ORDM_HOST_PLAIN(tr_rhob_y) ORDM_HOST_PLAIN(tr_rhob_z)
+#undef ORDM_HOST_PLAIN
   void print_banner() const;
 
   // ---- extensions (no reference counterpart) ----
@@ -95,7 +106,9 @@ class MCPDFT {
 
  private:
   arma::vec fetch(int which) const;
+  void install(int which, const arma::vec& v);
   void ensure_ctx() const;
+  arma::vec tr_rho_, tr_rhoa_x_, tr_rhoa_y_, tr_rhoa_z_, tr_rhob_x_, tr_rhob_y_, tr_rhob_z_;
   bool is_gga_ = false;
   std::size_t npts_ = 0, nbfs_ = 0;
   double eref_ = 0.0, eclass_ = 0.0;
@@ -114,6 +127,8 @@ double mcpdft_energy(MCPDFT* mc, std::string& functional, const arma::mat& D1a, 
 
 class Functional {  // functional.h:9-44: vectors in, quadrature-summed energy out (weights from mc)
  public:
+  Functional();    // functional.cc:9
+  ~Functional();   // functional.cc:10
   double EX_LSDA(const MCPDFT* mc, const arma::vec& rho_a, const arma::vec& rho_b);
   double EX_PBE(const MCPDFT* mc, const arma::vec& rho_a, const arma::vec& rho_b, const arma::vec& sigma_aa,
                 const arma::vec& sigma_bb);

@@ -535,3 +535,111 @@ def test_int8_tensor_core_pi_dense_rotated_rdms(port, ordm, monkeypatch, nact, n
             assert np.median(rel) < 1e-9, np.median(rel)
     finally:
         eng.close()
+
+
+# ---- the int8 path's error guard (k2_int8.cuh: guard_flag; ORDM retries with the FP64 kernels) -----------------------
+@pytest.mark.parametrize("case,mode", [("benchmark", "1"), ("phi3", "1"), ("dominant", "1"), ("indefinite", "1"), ("dominant", "2"), ("indefinite", "2")])
+def test_int8_guard_and_fp64_fallback(port, ordm, monkeypatch, case, mode):
+    """The inputs of the round-1 review, 20 active orbitals: |phi| up to 3, a dominant-orbital row, a sign-indefinite
+    pair matrix.  Whatever the guard decides, the Pi that comes back meets 1e-12 max(1, |Pi|) against the oracle; the
+    benchmark-like case stays on the int8 kernel, the sign-indefinite one is sent to the FP64 kernels."""
+    monkeypatch.setenv("ORDM_K2_INT8", mode)
+    rng = np.random.default_rng(77)
+    nact, npts = 20, 400
+    if case == "indefinite":
+        M2 = nact * nact
+        S = rng.uniform(-1, 1, (M2, M2)) * np.exp(-3 * np.abs(rng.uniform(-1, 1, (M2, M2))))
+        D2 = np.asfortranarray(0.5 * (S + S.T))
+        A1a = A1b = np.asfortranarray(np.eye(nact) * 0.5)
+    else:
+        A1a, A1b, D2 = ordm.synth_rdms(7, nact, 10, 10, 6)
+    if case == "benchmark":
+        phi = rng.uniform(-0.5, 0.5, (npts, nact))
+    elif case == "dominant":
+        phi = rng.uniform(-1e-3, 1e-3, (npts, nact)); phi[:, 3] = rng.uniform(-3, 3, npts)
+    else:
+        phi = rng.uniform(-3, 3, (npts, nact))
+    phi = np.asfortranarray(phi)
+    w = rng.random(npts) / npts
+    want = port.energy(w, phi, A1a, A1b, D2, "SVWN", None, want_vecs=True)
+    eng = ordm.Engine(0)
+    try:
+        eng.set_options(diagnostics=True)
+        eng.set_grid(w); eng.set_orbitals(phi, None); eng.set_rdm1(A1a, A1b); eng.set_rdm2ab_dense(D2, nact)
+        assert eng.pi_kernel_info()["int8_slice_pairs"] == (26 if mode == "1" else 21)
+        r = eng.energy(FN["SVWN"], 0.0)
+        a, b = eng.get_vector("pi"), want.vecs["pi"]
+        err = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+        assert err.max() <= 1e-12, (case, mode, float(err.max()), r["pi_guard_points"])
+        if case == "benchmark" and mode == "1":
+            assert r["pi_guard_points"] == 0 and eng.pi_kernel_info()["int8_slice_pairs"] == 26
+        if case == "indefinite":
+            assert r["pi_guard_points"] > 0 and eng.pi_kernel_info()["int8_slice_pairs"] == 0   # FP64 kernels stay selected
+            r2 = eng.energy(FN["SVWN"], 0.0)
+            assert r2["pi_guard_points"] == 0 and abs(r2["e_tot"] - r["e_tot"]) <= 1e-12 * max(1.0, abs(r["e_tot"]))
+        # staged API: build_pi consults the guard too
+        eng.set_orbitals(phi, None)   # new orbitals re-arm the int8 path
+        eng.build_rho(); eng.build_pi()
+        a = eng.get_vector("pi")
+        assert (np.abs(a - b) / np.maximum(1.0, np.abs(b))).max() <= 1e-12
+    finally:
+        eng.close()
+
+
+# ---- MCPDFT's output setters (mcpdft.h:125-153) through ordm_set_vector ------------------------------------------------
+def test_installed_vectors_feed_the_following_stages(engine, port):
+    """set_rho / set_pi / set_R / set_rhoa_x... : what the reference's build_R, translate and
+    translate_density_gradients read from its members (mcpdft.cc:276-283, 297-330, 383-398) is read from the
+    caller's vectors here too.  Oracle: the same stages on inputs that PRODUCE those vectors."""
+    rng = np.random.default_rng(21)
+    n, npts = 4, 700
+    phi, grads, w, D1a, D1b, D2 = random_case(rng, n, npts, "ensemble")
+    phi2, grads2, _, E1a, E1b, E2 = random_case(rng, n, npts, "ensemble")      # a second, unrelated case
+    want2 = port.energy(w, phi2, E1a, E1b, E2, "PBE", grads2)
+    engine.set_options(diagnostics=True)
+    engine.set_grid(w); engine.set_orbitals(phi, grads); engine.set_rdm1(D1a, D1b); engine.set_rdm2ab_dense(D2, n)
+    engine.build_rho(); engine.build_pi()
+    # install case 2's rho, Pi and spin gradients over case 1's: R / translate must follow case 2
+    v = want2.vecs
+    for k in ("rho", "pi", "rhoa_x", "rhoa_y", "rhoa_z", "rhob_x", "rhob_y", "rhob_z"):
+        engine.set_vector(k, v[k])
+    engine.build_R(); engine.translate()
+    live = v["rho"] > 1e-8
+    assert np.allclose(engine.get_vector("R")[live], v["R"][live], rtol=1e-10, atol=0)
+    assert (np.abs(engine.get_vector("tr_rhoa") - v["tr_rhoa"]) <= 1e-7 * np.abs(v["rho"]) + 1e-300).all()
+    g2 = v["sigma_aa"] + v["sigma_bb"] + 2 * v["sigma_ab"]
+    for k in ("tr_sigma_aa", "tr_sigma_ab", "tr_sigma_bb"):
+        assert (np.abs(engine.get_vector(k) - v[k]) <= 1e-7 * np.abs(g2) + 1e-300).all(), k
+    _, trn = engine.integrated_densities()
+    assert abs(trn[0] - want2.scalars["trn_tot"]) <= 1e-10
+    # an installed R is what translate reads (closed-shell R = 1 -> zeta = 0 -> equal spin densities) ...
+    engine.set_vector("R", np.ones(npts))
+    engine.translate()
+    ta, tb = engine.get_vector("tr_rhoa"), engine.get_vector("tr_rhob")
+    keep = (v["rho"] >= 1e-20) & (v["pi"] >= 0)
+    assert np.array_equal(ta[keep], tb[keep]) and np.allclose(ta[keep], 0.5 * v["rho"][keep], rtol=1e-15)
+    # ... until build_R recomputes it (MCPDFT::build_R overwrites R_)
+    engine.build_R()
+    assert np.allclose(engine.get_vector("R")[live], v["R"][live], rtol=1e-10, atol=0)
+    # plain stores: what the getters return is what was installed
+    for k in ("rhoa", "sigma_ab", "tr_rhob", "tr_sigma_bb"):
+        x = rng.random(npts)
+        engine.set_vector(k, x)
+        assert np.array_equal(engine.get_vector(k), x)
+
+
+def test_stale_vectors_are_errors_not_old_data(engine, ordm):
+    rng = np.random.default_rng(3)
+    phi, grads, w, D1a, D1b, D2 = random_case(rng, 3, 200, "ensemble")
+    engine.set_options(diagnostics=True, pi_gradient=True)
+    engine.set_grid(w); engine.set_orbitals(phi, grads); engine.set_rdm1(D1a, D1b); engine.set_rdm2ab_dense(D2, 3)
+    engine.build_rho(); engine.build_pi()
+    engine.get_vector("rho"); engine.get_vector("pi_y")
+    engine.set_orbitals(phi * 0.5, grads)            # new inputs: every per-point vector is stale
+    for k in ("rho", "rhoa_x", "pi", "pi_y"):
+        with pytest.raises(ordm.OrdmError):
+            engine.get_vector(k)
+    engine.build_rho()
+    engine.get_vector("rho")
+    with pytest.raises(ordm.OrdmError):
+        engine.get_vector("pi")

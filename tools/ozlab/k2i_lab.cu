@@ -3,7 +3,8 @@
 // build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o k2i_lab k2i_lab.cu
 // run:   timeout 60 ./k2i_lab [npts=2000000] [ncheck=2048]
 #define K2I_PROF 1
-#include "k2_int8_pair.cuh"
+#include "../../openrdm_b200/csrc/k2_int8.cuh"
+#include "../../openrdm_b200/csrc/rdm_pack.h"
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -30,22 +31,20 @@ int main(int argc, char** argv) {
   std::vector<uint16_t> tu(704, 0);
   { int I = 0; for (int t = 0; t < NA; ++t) for (int u = t; u < NA; ++u) tu[I++] = (uint16_t)(t | (u << 8)); }
   std::vector<uint8_t> timg; int t_exp = 0;
-  const bool pair = argc > 4 && atoi(argv[4]) == 1;   // CTA-pair kernel
-  if (pair) ordm::pack_t_int8_pair(M, D, KP, timg, t_exp); else ordm::pack_t_int8(M, D, KP, timg, t_exp);
+  const bool pair = false;   // the CTA-pair kernel has its own harness: k2p_lab.cu
+  ordm::pack_t_int8(M, D, KP, timg, t_exp);
   double *dphi, *dpi; uint8_t* dt; int* dfail;
-  CK(cudaMalloc(&dphi, phi.size() * 8)); CK(cudaMalloc(&dpi, npts * 8)); CK(cudaMalloc(&dt, timg.size())); CK(cudaMalloc(&dfail, 4));
+  CK(cudaMalloc(&dphi, phi.size() * 8)); CK(cudaMalloc(&dpi, npts * 8)); CK(cudaMalloc(&dt, timg.size())); CK(cudaMalloc(&dfail, 8));
   CK(cudaMemcpy(dphi, phi.data(), phi.size() * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dt, timg.data(), timg.size(), cudaMemcpyHostToDevice));
-  CK(cudaMemset(dfail, 0, 4)); CK(cudaMemset(dpi, 0, npts * 8));
+  CK(cudaMemset(dfail, 0, 8)); CK(cudaMemset(dpi, 0, npts * 8));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
-  const size_t smem = pair ? k2i::PairSmem::bytes(KP) : k2i::Smem::bytes(KP, NA);
+  const size_t smem = k2i::Smem::bytes(KP, NA);
   printf("smem %zu B (opt-in max %zu), T image %zu B, t_exp %d\n", smem, (size_t)prop.sharedMemPerBlockOptin, timg.size(), t_exp);
   CK(cudaFuncSetAttribute(k2i::k2i_ontop<NA, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2i::Smem::bytes(KP, NA)));
   CK(cudaFuncSetAttribute(k2i::k2i_ontop<NA, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2i::Smem::bytes(KP, NA)));
-  CK(cudaFuncSetAttribute(k2i::k2i_ontop_pair<NA, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2i::PairSmem::bytes(KP)));
-  CK(cudaFuncSetAttribute(k2i::k2i_ontop_pair<NA, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2i::PairSmem::bytes(KP)));
     const int gmin = argc > 3 ? atoi(argv[3]) : 4;
-  k2i::Params P{dphi, npts, npts, dt, t_exp, nullptr, dpi, dfail};
-  auto launch = [&](int grid, size_t smem) { if (pair) { if (gmin == 4) k2i::k2i_ontop_pair<NA, 4><<<grid / 2 * 2, k2i::THREADS, smem>>>(P); else k2i::k2i_ontop_pair<NA, 5><<<grid / 2 * 2, k2i::THREADS, smem>>>(P); } else if (gmin == 4) k2i::k2i_ontop<NA, 4><<<grid, k2i::THREADS, smem>>>(P); else k2i::k2i_ontop<NA, 5><<<grid, k2i::THREADS, smem>>>(P); };
+  k2i::Params P{dphi, npts, npts, dt, t_exp, nullptr, dpi, dfail, 0.0, 0.0};
+  auto launch = [&](int grid, size_t smem) { if (gmin == 4) k2i::k2i_ontop<NA, 4><<<grid, k2i::THREADS, smem>>>(P); else k2i::k2i_ontop<NA, 5><<<grid, k2i::THREADS, smem>>>(P); };
   const int grid = (int)std::min<size_t>((size_t)prop.multiProcessorCount, (npts + k2i::TILE - 1) / k2i::TILE);
   launch(grid, smem);
   CK(cudaDeviceSynchronize());
