@@ -78,10 +78,13 @@ __device__ __forceinline__ bool wait_parity(uint32_t bar, uint32_t parity) {
 // The point is flagged when that exceeds (1e-12 max(1, |Pi|))^2.  tests/test_int8_scheme.py pins the model against the
 // exact-integer restatement of the arithmetic (measured |dPi| <= 2.5 standard deviations on every case tried).
 template <int NA>
-__device__ __forceinline__ bool guard_flag(const double (&phi)[NA], int e_raw, double pi_abs, double g1, double g2) {
+__device__ __forceinline__ double sum_squares(const double (&phi)[NA]) {
   double s2 = 0.0;
 #pragma unroll
   for (int t = 0; t < NA; ++t) s2 = fma(phi[t], phi[t], s2);
+  return s2;
+}
+__device__ __forceinline__ bool guard_flag(double s2, int e_raw, double pi_abs, double g1, double g2) {
   const double xs2 = __hiloint2double((4 * e_raw - 3065) << 20, 0);   // 2^(4 em), em = e_raw - 1022
   const double x2 = s2 * s2;
   const double bar = 1e-12 * fmax(1.0, pi_abs);
@@ -407,7 +410,7 @@ __global__ void __maxnreg__(K2I_MAXREG) k2i_ontop(Params P) {
       const double pi_act = s * f1 * f2;
       const double pi_tot = P.pi_core ? pi_act + P.pi_core[p0 + p] : pi_act;
       P.pi[p0 + p] = pi_tot;
-      if (guard_flag<NA>(phi, e_raw, fabs(pi_tot), P.guard_g1, P.guard_g2)) ++nflag;
+      if (guard_flag(sum_squares<NA>(phi), e_raw, fabs(pi_tot), P.guard_g1, P.guard_g2)) ++nflag;
     }
   }
 #ifdef K2I_PROF

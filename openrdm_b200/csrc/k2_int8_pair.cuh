@@ -9,10 +9,9 @@
 //   * TMEM then holds TWO full-width accumulators (2 x KP columns) + X slice 5: consecutive slice-pair groups alternate
 //     between them, so the epilogue of one group runs under the MMAs of the next;
 //   * the epilogue is spread over EW warps per TMEM lane quadrant (= per SM sub-partition): each thread owns one point
-//     and a contiguous range of 16-pair units of its accumulator row, read with tcgen05.ld.x16 one unit ahead, converted
-//     exactly (2^52 bit trick) and folded as sum_t phi_t (sum_u phi_u acc_tu) with the pair -> (t, u) map resolved at
-//     compile time; more warps per sub-partition is what hides the TMEM round trip and the FP64 dependent-issue
-//     latency that bound the 2-warp epilogue of k2_int8.cuh (profiles/r01h_k2i_timeline.log);
+//     and a contiguous range of 16-pair units of its accumulator row, read with tcgen05.ld.x16 one unit ahead and folded
+//     as sum_t phi_t (sum_u phi_u acc_tu) with the pair -> (t, u) map resolved at compile time; the three low-order
+//     groups, which weigh <= 2^-32 of the top one, are folded in FP32 (2 instructions per element instead of 4);
 //   * the same threads build the X slices of their pair range: one DFMA per pair leaves the balanced image in the
 //     mantissa (the re-centring constant rides in the FMA addend), byte transposes cut it into slices;
 //   * every point carries an a-posteriori error estimate of the 46-bit scheme (guard_flag below): points whose estimate
@@ -114,23 +113,48 @@ __host__ __device__ constexpr bool row_ends_at(int na, int I, int hi, int m) {
   return I + 1 >= hi || I + 1 >= m || pair_t_of(na, I + 1) != pair_t_of(na, I);
 }
 
-// two DFMA chains per orbital row (even / odd pair index): with EW warps per sub-partition that is 2 EW independent
-// chains in flight; a row's partial sums die as soon as the row ends, so few are live at any time
-template <int NA, int I, int IEND>
-__device__ __forceinline__ void fold_elem(const double (&phi)[NA], double (&s0)[NA], double (&s1)[NA], double& tot, uint32_t v) {
+// Arithmetic of the fold, per accumulator element v (an exact int32) of pair (t, u):
+//   groups G >  K2P_F32_MAX:  FP64.  v -> double exactly (2^52 bit trick: xor, hi word, DADD; every K2P_I2F_EVERY-th
+//       element through I2F.F64.S32 instead, which runs on the otherwise idle conversion pipe), then one DFMA into the
+//       row's running sum  sum_u phi_u v.
+//   groups G <= K2P_F32_MAX:  FP32.  v -> float (I2FP, rounding 2^-24), one FFMA with phi_u 2^-em as a float.  These
+//       groups weigh <= 2^-32 of the top group, so 2^-22-grade row sums change Pi by < 1e-15 of its scale
+//       (tests/test_int8_scheme.py restates both paths; K2P_F32_MAX = 7 would cost 1e-13).
+// Beside the running MMAs the SM issues roughly one instruction per 3 clk per sub-partition whatever the pipe
+// (profiles/r02*_k2p_*.log: tensor and CUDA-core work add up instead of overlapping), so the instruction count is what
+// is minimised here.  Two chains per row (even / odd pair); a row's sums are folded into the FP64 outer sum
+// sum_t phi_t row_t as soon as the row ends, so few are live at any time.
+#ifndef K2P_F32_MAX
+#define K2P_F32_MAX 6
+#endif
+#ifndef K2P_I2F_EVERY
+#define K2P_I2F_EVERY 3
+#endif
+struct RowAcc { double d0, d1; float f0, f1; };
+
+template <int NA, int I, int IEND, bool F32>
+__device__ __forceinline__ void fold_elem(const double (&phi)[NA], const float (&phif)[NA], RowAcc& r, double& tot, uint32_t v) {
   constexpr int M = NA * (NA + 1) / 2;
   if constexpr (I < M) {
     constexpr int t = pair_t_of(NA, I), u = pair_u_of(NA, I);
-    const double zd = __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;  // exact int32 -> double (2^52 + 2^31)
-    if constexpr (I & 1) s1[t] = fma(phi[u], zd, s1[t]); else s0[t] = fma(phi[u], zd, s0[t]);
-    if constexpr (row_ends_at(NA, I, IEND, M)) tot = fma(phi[t], s0[t] + s1[t], tot);
+    if constexpr (F32) {
+      const float vf = __int2float_rn((int)v);
+      if constexpr (I & 1) r.f1 = fmaf(phif[u], vf, r.f1); else r.f0 = fmaf(phif[u], vf, r.f0);
+      if constexpr (row_ends_at(NA, I, IEND, M)) { tot = fma(phi[t], (double)(r.f0 + r.f1), tot); r.f0 = r.f1 = 0.f; }
+    } else {
+      double zd;
+      if constexpr (K2P_I2F_EVERY > 0 && (I % (K2P_I2F_EVERY > 0 ? K2P_I2F_EVERY : 1)) == 0) zd = __int2double_rn((int)v);
+      else zd = __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;  // exact int32 -> double (2^52 + 2^31)
+      if constexpr (I & 1) r.d1 = fma(phi[u], zd, r.d1); else r.d0 = fma(phi[u], zd, r.d0);
+      if constexpr (row_ends_at(NA, I, IEND, M)) { tot = fma(phi[t], r.d0 + r.d1, tot); r.d0 = r.d1 = 0.0; }
+    }
   }
 }
 
-template <int NA, int U, int UEND, int... Js>
-__device__ __forceinline__ void fold_unit(const double (&phi)[NA], double (&s0)[NA], double (&s1)[NA], double& tot, const uint32_t (&v)[16],
+template <int NA, int U, int UEND, bool F32, int... Js>
+__device__ __forceinline__ void fold_unit(const double (&phi)[NA], const float (&phif)[NA], RowAcc& r, double& tot, const uint32_t (&v)[16],
                                           std::integer_sequence<int, Js...>) {
-  (fold_elem<NA, 16 * U + Js, 16 * UEND>(phi, s0, s1, tot, v[Js]), ...);
+  (fold_elem<NA, 16 * U + Js, 16 * UEND, F32>(phi, phif, r, tot, v[Js]), ...);
 }
 
 // tcgen05.wait::ld with the loaded registers as in/out operands: nothing that reads them can be scheduled above it
@@ -141,28 +165,40 @@ __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
                :: "memory");
 }
 
-template <int NA, int U, int U1>
-__device__ __forceinline__ void fold_units(const double (&phi)[NA], double (&s0)[NA], double (&s1)[NA], double& tot, uint32_t tmem_row,
+template <int NA, int U, int U1, bool F32>
+__device__ __forceinline__ void fold_units(const double (&phi)[NA], const float (&phif)[NA], RowAcc& r, double& tot, uint32_t tmem_row,
                                            uint32_t (&cur)[16], uint32_t (&nxt)[16], uint32_t drain_bar) {
+#ifndef K2P_LAB_NOLOAD   // lab switch (tools/ozlab): no TMEM loads, arithmetic on whatever the registers hold
   tmem_wait_ld16(cur);   // unit U is in `cur`
+#endif
   if constexpr (U + 1 < U1) {
+#ifndef K2P_LAB_NOLOAD
     tmem_ld16(tmem_row + (uint32_t)(16 * (U + 1)), nxt);
+#endif
   } else {   // every column of this thread's range has been read: the group after next may overwrite this accumulator
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(drain_bar) : "memory");
   }
-  fold_unit<NA, U, U1>(phi, s0, s1, tot, cur, std::make_integer_sequence<int, 16>{});
-  if constexpr (U + 1 < U1) fold_units<NA, U + 1, U1>(phi, s0, s1, tot, tmem_row, nxt, cur, drain_bar);
+#ifndef K2P_LAB_NOMATH   // lab switch: loads and barriers only
+  fold_unit<NA, U, U1, F32>(phi, phif, r, tot, cur, std::make_integer_sequence<int, 16>{});
+#else
+  if (cur[0] == 0x12345678u && cur[15] == 0x9abcdefu) tot += 1.0;
+#endif
+  if constexpr (U + 1 < U1) fold_units<NA, U + 1, U1, F32>(phi, phif, r, tot, tmem_row, nxt, cur, drain_bar);
 }
 
-template <int NA, int U0, int U1>
-__device__ __forceinline__ double fold_group_units(const double (&phi)[NA], uint32_t tmem_row, uint32_t drain_bar) {
-  double s0[NA], s1[NA], tot = 0.0;
-#pragma unroll
-  for (int t = 0; t < NA; ++t) s0[t] = s1[t] = 0.0;
+template <int NA, int U0, int U1, bool F32>
+__device__ __forceinline__ double fold_group_units(const double (&phi)[NA], const float (&phif)[NA], uint32_t tmem_row, uint32_t drain_bar) {
+  RowAcc r{0.0, 0.0, 0.f, 0.f};
+  double tot = 0.0;
   uint32_t va[16], vb[16];
+#ifndef K2P_LAB_NOLOAD
   tmem_ld16(tmem_row + (uint32_t)(16 * U0), va);
-  fold_units<NA, U0, U1>(phi, s0, s1, tot, tmem_row, va, vb, drain_bar);
+#else
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { va[j] = tmem_row * (j + 1); vb[j] = tmem_row * (j + 17); }
+#endif
+  fold_units<NA, U0, U1, F32>(phi, phif, r, tot, tmem_row, va, vb, drain_bar);
   return tot;
 }
 
@@ -217,18 +253,166 @@ __device__ __forceinline__ int group_at(int i, int gmin) {
 
 #ifdef K2I_PROF
 __device__ long long k2p_prof[3][8];
-#define K2P_LAP(i) do { if (blockIdx.x == 0 && (tid == 0 || tid == 32 * 4 * EW)) { const long long t_ = clock64(); pf_[i] += t_ - tc_; tc_ = t_; } } while (0)
+#define K2P_LAP(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && prof_slot >= 0) { const long long t_ = clock64(); pf_[i] += t_ - tc_; tc_ = t_; } } while (0)
 #else
 #define K2P_LAP(i) do { } while (0)
 #endif
+
+// what every thread of the CTA knows after the prologue
+struct PairCtx {
+  uint32_t tmem, lane_addr, crank;
+  uint32_t bar_full, bar_drain, drain_remote;   // shared-memory addresses; drain_remote = the leader's copy as seen from this CTA
+  uint8_t* x_row;        // this thread's row of the X operand (slice 0) in shared memory
+  double* s_part;        // [EW][TILE] partial sums (alias the X slices, dead at the tile's end)
+  uint64_t tdesc0, xdesc0;
+  uint32_t idesc0;
+  int p;                 // point within the CTA's 128-point tile
+};
+
+// ---- the epilogue / build role: one instantiation per unit range, so that a thread keeps in registers only the
+// orbital values its own rows and columns need
+template <int NA, int GMIN, int EW, int PART>
+__device__ __forceinline__ void pair_compute_role(const Params& P, const PairCtx& c, bool& ok, int& nflag) {
+  constexpr int M = NA * (NA + 1) / 2, KP = (M + 31) / 32 * 32, NUNITS = KP / 16;
+  constexpr int U0 = part_u0(NUNITS, EW, PART), U1 = part_u0(NUNITS, EW, PART + 1);
+  constexpr int ACC_COLS = KP, X5_COL = 2 * KP;
+  constexpr int NGROUPS = 2 * (NSLICE - 1) - GMIN + 1;
+  constexpr int ETHREADS = 4 * EW * 32;
+  const int p = c.p;
+#ifdef K2I_PROF
+  long long pf_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc_ = clock64();
+  const int prof_slot = (threadIdx.x == 0) ? 0 : (threadIdx.x == 32 ? 1 : -1);   // warp 0 shares its sub-partition with the MMA warp, warp 1 does not
+#endif
+  uint32_t n = 0;   // groups consumed so far (each accumulator sees every other one)
+  const size_t ntiles = (P.npts + 2 * TILE - 1) / (2 * TILE);   // pair tiles of 256 points
+  for (size_t tile = blockIdx.x / 2; tile < ntiles; tile += gridDim.x / 2) {
+    const size_t p0 = tile * 2 * TILE + (size_t)c.crank * TILE;
+    double phi[NA];
+    double s2 = 0.0;   // sum_t phi_t^2 for the error guard
+    K2P_LAP(7);
+    uint32_t mh = 0;   // max over t of the high word of |phi_t|: its exponent field is that of max |phi_t|
+#pragma unroll
+    for (int t = 0; t < NA; ++t) {
+      phi[t] = (p0 + p < P.npts) ? __ldg(P.phi_act + (size_t)t * P.ld + p0 + p) : 0.0;
+      mh = max(mh, (uint32_t)__double2hiint(phi[t]) & 0x7FFFFFFFu);
+    }
+    // row scale: max |X| = (max_t |phi_t|)^2 < 2^(2 em); the clamps keep the scale factors finite normal numbers
+    const int e_raw = min(max((int)(mh >> 20), 534), 1500);
+    const double scale = __hiloint2double((3113 - 2 * e_raw + (FIX_BITS - 46)) << 20, 0);  // 2^(FIX_BITS - 2 em)
+    K2P_LAP(0);
+    build_units<NA, U0, U1>(phi, scale, c.x_row, c.tmem + c.lane_addr + (uint32_t)X5_COL);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if constexpr (PART == 0) s2 = sum_squares<NA>(phi);
+    float phif[NA];   // phi_u 2^-em as floats for the FP32 groups of the epilogue (|.| < 1: no range trouble whatever em)
+    {
+      const double sc0 = __hiloint2double((2045 - e_raw) << 20, 0);   // 2^-em, em = e_raw - 1022
+#pragma unroll
+      for (int t = 0; t < NA; ++t) phif[t] = (float)(phi[t] * sc0);
+    }
+    {   // next pair tile's orbitals towards L2 while this one is contracted
+      const size_t pn = p0 + (size_t)(gridDim.x / 2) * 2 * TILE + p;
+      if (pn < P.npts) {
+#pragma unroll
+#ifdef K2P_PF_L1
+        for (int t = PART; t < NA; t += EW) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.phi_act + (size_t)t * P.ld + pn));
+#else
+        for (int t = PART; t < NA; t += EW) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.phi_act + (size_t)t * P.ld + pn));
+#endif
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    cluster_sync_all();   // both CTAs' operands are built
+    K2P_LAP(1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    double pi_acc = 0.0, pi_acc32 = 0.0;   // FP64 groups; FP32 groups (in units of 2^em)
+#pragma unroll 1
+    for (int gi = 0; gi < NGROUPS; ++gi, ++n) {
+      const int G = group_at(gi, GMIN);
+      const uint32_t b = n & 1, use = n >> 1;   // accumulator, and how often it has been used before
+      ok = wait_parity(c.bar_full + 8 * b, use & 1) && ok;
+      K2P_LAP(5);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_row = c.tmem + c.lane_addr + (uint32_t)(b * ACC_COLS), db = c.drain_remote + 8 * b;
+      const double wG = __hiloint2double((1023 + 8 * (G - GMIN)) << 20, 0);
+      if (G > K2P_F32_MAX) pi_acc = fma(fold_group_units<NA, U0, U1, false>(phi, phif, tmem_row, db), wG, pi_acc);
+      else pi_acc32 = fma(fold_group_units<NA, U0, U1, true>(phi, phif, tmem_row, db), wG, pi_acc32);
+      K2P_LAP(6);
+    }
+    // every epilogue thread has seen the last group's "full": all MMAs of the tile are done, the X slices are dead
+    pi_acc = fma(pi_acc32, __hiloint2double((e_raw + 1) << 20, 0), pi_acc);   // 2^em
+    if constexpr (PART > 0) c.s_part[PART * TILE + p] = pi_acc;
+    asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
+    if constexpr (PART == 0) {
+      double s = pi_acc;
+#pragma unroll
+      for (int k = 1; k < EW; ++k) s += c.s_part[k * TILE + p];
+      // Pi = 2 * 2^(2 em - FIX) * 2^(t_exp - FIX) * 2^(8 GMIN) * (sum over the parts)
+      const double f1 = __hiloint2double((2 * e_raw - 1067 - (FIX_BITS - 46)) << 20, 0);        // 2^(2 em - FIX_BITS)
+      const double f2 = __hiloint2double((1023 + P.t_exp - FIX_BITS + 8 * GMIN + 1) << 20, 0);  // 2 * 2^(t_exp - FIX_BITS + 8 GMIN)
+      const double pi_act = s * f1 * f2;
+      if (p0 + p < P.npts) {
+        const double pi_tot = P.pi_core ? pi_act + P.pi_core[p0 + p] : pi_act;
+        P.pi[p0 + p] = pi_tot;
+        if (guard_flag(s2, e_raw, fabs(pi_tot), P.guard_g1, P.guard_g2)) ++nflag;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");   // the partial sums alias the X slices: read before the next tile's build writes them
+    K2P_LAP(4);
+  }
+#ifdef K2I_PROF
+  if (blockIdx.x == 0 && prof_slot >= 0) for (int i = 0; i < 8; ++i) k2p_prof[prof_slot][i] = pf_[i];
+#endif
+}
+
+// ---- the MMA role: one warp; lane 0 of the leader CTA issues, the other CTA's warp only keeps the cluster barriers company
+template <int NA, int GMIN>
+__device__ __forceinline__ void pair_mma_role(const Params& P, const PairCtx& c, bool& ok) {
+  constexpr int M = NA * (NA + 1) / 2, KP = (M + 31) / 32 * 32;
+  constexpr int ACC_COLS = KP, X5_COL = 2 * KP;
+  constexpr int NGROUPS = 2 * (NSLICE - 1) - GMIN + 1;
+  const int lane = threadIdx.x & 31;
+#ifdef K2I_PROF
+  long long pf_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc_ = clock64();
+  const int prof_slot = (lane == 0) ? 2 : -1;
+#endif
+  uint32_t n = 0;
+  const size_t ntiles = (P.npts + 2 * TILE - 1) / (2 * TILE);
+  for (size_t tile = blockIdx.x / 2; tile < ntiles; tile += gridDim.x / 2) {
+    K2P_LAP(7);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    cluster_sync_all();   // both CTAs' operands are built
+    K2P_LAP(1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int gi = 0; gi < NGROUPS; ++gi, ++n) {
+      const int G = group_at(gi, GMIN);
+      const uint32_t b = n & 1, use = n >> 1;
+      if (lane == 0 && c.crank == 0) {
+        if (use > 0) ok = wait_parity(c.bar_drain + 8 * b, (use - 1) & 1) && ok;   // both CTAs have read this accumulator's previous group
+        K2P_LAP(2);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifndef K2P_LAB_NOMMA   // lab switch: the epilogue without tensor-core traffic beside it
+        issue_group_pair_of<KP>(G, c.tmem + b * ACC_COLS, c.tmem + X5_COL, c.tdesc0, c.xdesc0, c.idesc0);
+#endif
+        commit2(c.bar_full + 8 * b);
+        K2P_LAP(3);
+      }
+      __syncwarp();
+    }
+  }
+#ifdef K2I_PROF
+  if (blockIdx.x == 0 && prof_slot >= 0) for (int i = 0; i < 8; ++i) k2p_prof[prof_slot][i] = pf_[i];
+#endif
+}
 
 // P.timg here is the PAIR image (ordm::pack_t_int8_pair): CTA rank c of the cluster reads block c.
 // P.guard_g1/g2: constants of guard_flag; P.fail[0] counts barrier time-outs, P.fail[1] flagged points.
 template <int NA, int GMIN, int EW>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(K2P_MAXREG) k2i_ontop_pair(Params P) {
   constexpr int M = NA * (NA + 1) / 2, KP = (M + 31) / 32 * 32, NUNITS = KP / 16;
-  constexpr int ACC_COLS = KP, X5_COL = 2 * KP;   // TMEM: accumulator b at [b KP, (b + 1) KP), X slice 5 at [2 KP, 2 KP + KP / 4)
-  constexpr int NGROUPS = 2 * (NSLICE - 1) - GMIN + 1;
   constexpr int ETHREADS = 4 * EW * 32;
   static_assert(2 * KP + KP / 4 <= 512, "TMEM columns");
   static_assert(NSLICE == 6 && (GMIN == 4 || GMIN == 5), "six slices, groups 10 .. GMIN");
@@ -238,22 +422,20 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(K2P_MAXREG) k2i_ontop_pair
   __shared__ __align__(8) uint64_t bar_s[4];   // [0..1] accumulator b complete (multicast commit); [2..3] (leader's copy) accumulator b drained by both CTAs
   uint8_t* s_t = smem;
   uint8_t* s_x = smem + PairSmem::x_off(KP);
-  double* s_part = (double*)s_x;   // [EW][TILE]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool compute = warp < 4 * EW;
-  const int q = warp & 3, part = warp >> 2, p = 32 * q + lane;  // lane quadrant, unit range, point within the CTA's tile
-  uint32_t crank;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-
+  const int q = warp & 3, part = warp >> 2;   // lane quadrant, unit range (part == EW: the MMA warp)
+  PairCtx c;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(c.crank));
   {
-    const int4* src = (const int4*)(P.timg + (size_t)crank * PairSmem::t_bytes(KP));
+    const int4* src = (const int4*)(P.timg + (size_t)c.crank * PairSmem::t_bytes(KP));
     for (int i = tid; i < (int)(PairSmem::t_bytes(KP) / 16); i += blockDim.x) ((int4*)s_t)[i] = src[i];
   }
-  const uint32_t bar_full = (uint32_t)__cvta_generic_to_shared(&bar_s[0]), bar_drain = (uint32_t)__cvta_generic_to_shared(&bar_s[2]);
+  c.bar_full = (uint32_t)__cvta_generic_to_shared(&bar_s[0]);
+  c.bar_drain = (uint32_t)__cvta_generic_to_shared(&bar_s[2]);
   if (tid == 0) {
     for (int h = 0; h < 2; ++h) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_full + 8 * h));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_drain + 8 * h), "r"(2 * ETHREADS));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(c.bar_full + 8 * h));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(c.bar_drain + 8 * h), "r"(2 * ETHREADS));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -266,112 +448,22 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(K2P_MAXREG) k2i_ontop_pair
   __syncthreads();
   cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-  const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * TILE) >> 4) << 24);   // M = 256 over the pair
-  uint8_t* x_row = s_x + (p >> 3) * 128 + (p & 7) * 16;
-  const uint64_t tdesc0 = smem_desc((uint32_t)__cvta_generic_to_shared(s_t), 0, 128);
-  const uint64_t xdesc0 = smem_desc((uint32_t)__cvta_generic_to_shared(s_x), (TILE / 8) * 128, 128);
-  uint32_t drain_remote;   // the leader's "drained" barriers, as seen from this CTA
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(drain_remote) : "r"(bar_drain), "r"(0));
-#ifdef K2I_PROF
-  long long pf_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc_ = clock64();
-#endif
-  uint32_t n = 0;   // groups issued / consumed so far (each accumulator sees every other one)
+  c.tmem = tmem_base_s;
+  c.lane_addr = (uint32_t)(q * 32) << 16;
+  c.idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * TILE) >> 4) << 24);   // M = 256 over the pair
+  c.p = 32 * q + lane;
+  c.x_row = s_x + (c.p >> 3) * 128 + (c.p & 7) * 16;
+  c.s_part = (double*)s_x;
+  c.tdesc0 = smem_desc((uint32_t)__cvta_generic_to_shared(s_t), 0, 128);
+  c.xdesc0 = smem_desc((uint32_t)__cvta_generic_to_shared(s_x), (TILE / 8) * 128, 128);
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(c.drain_remote) : "r"(c.bar_drain), "r"(0));
   bool ok = true;
-  int nflag = 0;
-
-  const size_t ntiles = (P.npts + 2 * TILE - 1) / (2 * TILE);   // pair tiles of 256 points
-  for (size_t tile = blockIdx.x / 2; tile < ntiles; tile += gridDim.x / 2) {
-    const size_t p0 = tile * 2 * TILE + (size_t)crank * TILE;
-    double phi[NA];
-    int e_raw = 534;
-    K2P_LAP(7);
-    if (compute) {
-      uint32_t mh = 0;   // max over t of the high word of |phi_t|: its exponent field is that of max |phi_t|
-#pragma unroll
-      for (int t = 0; t < NA; ++t) {
-        phi[t] = (p0 + p < P.npts) ? __ldg(P.phi_act + (size_t)t * P.ld + p0 + p) : 0.0;
-        mh = max(mh, (uint32_t)__double2hiint(phi[t]) & 0x7FFFFFFFu);
-      }
-      // row scale: max |X| = (max_t |phi_t|)^2 < 2^(2 em); the clamps keep the two scale factors finite normal numbers
-      e_raw = min(max((int)(mh >> 20), 534), 1500);
-      const double scale = __hiloint2double((3113 - 2 * e_raw + (FIX_BITS - 46)) << 20, 0);  // 2^(FIX_BITS - 2 em)
-      const uint32_t tmem_x5_row = tmem + lane_addr + (uint32_t)X5_COL;
-      K2P_LAP(0);
-      if (part == 0) build_units<NA, part_u0(NUNITS, EW, 0), part_u0(NUNITS, EW, 1)>(phi, scale, x_row, tmem_x5_row);
-      else if (part == 1) build_units<NA, part_u0(NUNITS, EW, 1), part_u0(NUNITS, EW, 2)>(phi, scale, x_row, tmem_x5_row);
-      else if (EW > 2 && part == 2) build_units<NA, part_u0(NUNITS, EW, 2 < EW ? 2 : 0), part_u0(NUNITS, EW, 2 < EW ? 3 : 1)>(phi, scale, x_row, tmem_x5_row);
-      else if (EW > 3 && part == 3) build_units<NA, part_u0(NUNITS, EW, 3 < EW ? 3 : 0), part_u0(NUNITS, EW, 3 < EW ? 4 : 1)>(phi, scale, x_row, tmem_x5_row);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      // next pair tile's orbitals towards L2 while this one is contracted
-      const size_t pn = p0 + (size_t)(gridDim.x / 2) * 2 * TILE + p;
-      if (pn < P.npts) {
-#pragma unroll
-        for (int t = part; t < NA; t += EW) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.phi_act + (size_t)t * P.ld + pn));
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncwarp();
-    cluster_sync_all();   // both CTAs' operands are built
-    K2P_LAP(1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    double pi_acc = 0.0;
-#pragma unroll 1
-    for (int gi = 0; gi < NGROUPS; ++gi, ++n) {
-      const int G = group_at(gi, GMIN);
-      const uint32_t b = n & 1, use = n >> 1;   // accumulator, and how often it has been used before
-      if (!compute) {
-        if (lane == 0 && crank == 0) {
-          if (use > 0) ok = wait_parity(bar_drain + 8 * b, (use - 1) & 1) && ok;   // both CTAs have read this accumulator's previous group
-          K2P_LAP(2);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          issue_group_pair_of<KP>(G, tmem + b * ACC_COLS, tmem + X5_COL, tdesc0, xdesc0, idesc0);
-          commit2(bar_full + 8 * b);
-          K2P_LAP(3);
-        }
-        __syncwarp();
-      } else {
-        ok = wait_parity(bar_full + 8 * b, use & 1) && ok;
-        K2P_LAP(5);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_row = tmem + lane_addr + (uint32_t)(b * ACC_COLS);
-        const uint32_t db = drain_remote + 8 * b;
-        double g;
-        if (part == 0) g = fold_group_units<NA, part_u0(NUNITS, EW, 0), part_u0(NUNITS, EW, 1)>(phi, tmem_row, db);
-        else if (part == 1) g = fold_group_units<NA, part_u0(NUNITS, EW, 1), part_u0(NUNITS, EW, 2)>(phi, tmem_row, db);
-        else if (EW > 2 && part == 2) g = fold_group_units<NA, part_u0(NUNITS, EW, 2 < EW ? 2 : 0), part_u0(NUNITS, EW, 2 < EW ? 3 : 1)>(phi, tmem_row, db);
-        else g = fold_group_units<NA, part_u0(NUNITS, EW, 3 < EW ? 3 : 0), part_u0(NUNITS, EW, 3 < EW ? 4 : 1)>(phi, tmem_row, db);
-        pi_acc = fma(g, __hiloint2double((1023 + 8 * (G - GMIN)) << 20, 0), pi_acc);
-        K2P_LAP(6);
-      }
-    }
-    // every epilogue thread has seen the last group's "full": all MMAs of the tile are done, the X slices are dead
-    if (compute) {
-      if (part > 0) s_part[part * TILE + p] = pi_acc;
-      asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
-      if (part == 0) {
-        double s = pi_acc;
-#pragma unroll
-        for (int k = 1; k < EW; ++k) s += s_part[k * TILE + p];
-        // Pi = 2 * 2^(2 em - FIX) * 2^(t_exp - FIX) * 2^(8 GMIN) * (sum over the parts)
-        const double f1 = __hiloint2double((2 * e_raw - 1067 - (FIX_BITS - 46)) << 20, 0);        // 2^(2 em - FIX_BITS)
-        const double f2 = __hiloint2double((1023 + P.t_exp - FIX_BITS + 8 * GMIN + 1) << 20, 0);  // 2 * 2^(t_exp - FIX_BITS + 8 GMIN)
-        const double pi_act = s * f1 * f2;
-        if (p0 + p < P.npts) {
-          const double pi_tot = P.pi_core ? pi_act + P.pi_core[p0 + p] : pi_act;
-          P.pi[p0 + p] = pi_tot;
-          if (guard_flag<NA>(phi, e_raw, fabs(pi_tot), P.guard_g1, P.guard_g2)) ++nflag;
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");   // the partial sums alias the X slices: read before the next tile's build writes them
-    }
-    K2P_LAP(4);
-  }
-#ifdef K2I_PROF
-  if (blockIdx.x == 0 && (tid == 0 || tid == ETHREADS)) for (int i = 0; i < 8; ++i) k2p_prof[tid ? 2 : 0][i] = pf_[i];
-#endif
+  int nflag = 0;   // points of this thread whose error estimate exceeds the parity bar (guard_flag)
+  if (part == 0) pair_compute_role<NA, GMIN, EW, 0>(P, c, ok, nflag);
+  else if (part == 1) pair_compute_role<NA, GMIN, EW, 1>(P, c, ok, nflag);
+  else if (EW > 2 && part == 2) pair_compute_role<NA, GMIN, EW, (EW > 2 ? 2 : 0)>(P, c, ok, nflag);
+  else if (EW > 3 && part == 3) pair_compute_role<NA, GMIN, EW, (EW > 3 ? 3 : 0)>(P, c, ok, nflag);
+  else pair_mma_role<NA, GMIN>(P, c, ok);
   if (P.fail) {
     if (!ok) atomicAdd(P.fail, 1);
     if (nflag) atomicAdd(P.fail + 1, nflag);
@@ -379,7 +471,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(K2P_MAXREG) k2i_ontop_pair
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   cluster_sync_all();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(c.tmem) : "memory");
 }
 
 }  // namespace k2i

@@ -23,6 +23,7 @@
 #include "k1_density.cuh"
 #include "k2_ontop.cuh"
 #include "k2_int8.cuh"
+#include "k2_int8_pair.cuh"
 #include "k3_xc.cuh"
 #include "rdm_pack.h"
 #include "reduce.cuh"
@@ -160,6 +161,11 @@ struct ordm_ctx {
   uint32_t guard_points = 0;   // points the guard flagged in the call that switched to the FP64 kernels
   k2i::Params k2ip{};
   uint8_t* d_timg = nullptr;
+  // CTA-pair form of the int8 kernel (k2_int8_pair.cuh; ORDM_K2_PAIR=0 keeps the single-CTA kernel)
+  bool k2_pair = true;
+  k2i::Params k2pp{};
+  uint8_t* d_timg_pair = nullptr;
+  size_t k2p_smem = 0;
   int* d_i8_fail = nullptr;
   size_t k2i_smem = 0;
   bool k1_split = false;  // two-kernel K1 (k1_core + active) measured slower than the fused kernel; kept as a test hook
@@ -470,8 +476,46 @@ int launch_k2_int8(ordm_ctx* c, const k2i::Params& p, int grid) {
   return ORDM_OK;
 }
 
+constexpr int K2P_EW = 2;   // epilogue warps per TMEM lane quadrant of the CTA-pair kernel (9 warps, allocated as 12, x 128 registers
+                            // leave 16 K registers to the co-resident k1_core_light CTA)
+template <int NA, int GMIN>
+int launch_k2_pair(ordm_ctx* c, const k2i::Params& p, int grid) {
+  static thread_local int dev = -1;
+  static thread_local size_t bytes = 0;
+  if (dev != c->device || bytes < c->k2p_smem) {
+    CU(c, cudaFuncSetAttribute(k2i::k2i_ontop_pair<NA, GMIN, K2P_EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k2p_smem));
+    dev = c->device; bytes = c->k2p_smem;
+  }
+  k2i::k2i_ontop_pair<NA, GMIN, K2P_EW><<<grid, (4 * K2P_EW + 1) * 32, c->k2p_smem, c->stream>>>(p);   // clusters of 2 (__cluster_dims__)
+  CU(c, cudaGetLastError());
+  return ORDM_OK;
+}
+
+int run_k2_int8_pair(ordm_ctx* c, const GridView& v, int* launches, bool lean) {
+  k2i::Params p = c->k2pp;
+  p.phi_act = v.phi + (size_t)c->ncore * v.ld;
+  p.ld = v.ld;
+  p.npts = v.npts;
+  p.pi_core = (c->core_form && !lean) ? v.pi_core : nullptr;
+  p.pi = v.vec[ORDM_VEC_PI];
+  const size_t pair_tiles = (v.npts + 2 * k2i::TILE - 1) / (2 * k2i::TILE);
+  const int grid = 2 * (int)std::max<size_t>(1, std::min<size_t>(pair_tiles, (size_t)c->sm_count / 2));
+  const bool wide = c->k2_i8_mode == 1;   // 26 slice pairs
+  int rc;
+  switch (c->nact) {
+    case 18: rc = wide ? launch_k2_pair<18, 4>(c, p, grid) : launch_k2_pair<18, 5>(c, p, grid); break;
+    case 19: rc = wide ? launch_k2_pair<19, 4>(c, p, grid) : launch_k2_pair<19, 5>(c, p, grid); break;
+    case 20: rc = wide ? launch_k2_pair<20, 4>(c, p, grid) : launch_k2_pair<20, 5>(c, p, grid); break;
+    default: return fail(c, ORDM_ERR_UNSUPPORTED, "int8 on-top path selected for %d active orbitals", c->nact);
+  }
+  if (rc) return rc;
+  *launches += 1;
+  return ORDM_OK;
+}
+
 // Pi of the active space on the int8 tensor cores (18..20 active orbitals); lean as in run_k2: no pi_core add
 int run_k2_int8(ordm_ctx* c, const GridView& v, int* launches, bool lean) {
+  if (c->k2_pair) return run_k2_int8_pair(c, v, launches, lean);
   k2i::Params p = c->k2ip;
   p.phi_act = v.phi + (size_t)c->ncore * v.ld;
   p.ld = v.ld;
@@ -641,6 +685,20 @@ int configure_k2(ordm_ctx* c) {
     c->k2ip = k2i::Params{};
     c->k2ip.timg = c->d_timg; c->k2ip.t_exp = t_exp; c->k2ip.fail = c->d_i8_fail;
     ordm::int8_guard_constants(M, c->h_Dt, t_exp, c->k2_i8_mode == 1 ? 4 : 5, c->k2ip.guard_g1, c->k2ip.guard_g2);
+    c->k2_pair = c->k2_pair && k2i::PairSmem::bytes(kp) + 1024 <= (size_t)c->max_smem_optin;
+    if (c->k2_pair) {   // the same image cut in two: each CTA of a pair keeps half of the rows of every chunk
+      std::vector<uint8_t> pimg;
+      int te2 = 0;
+      ordm::pack_t_int8_pair(M, c->h_Dt, kp, pimg, te2);
+      if (pimg.size() != 2 * k2i::PairSmem::t_bytes(kp) || te2 != t_exp)
+        return fail(c, ORDM_ERR_UNSUPPORTED, "int8 on-top path: pair image and kernel geometry disagree");
+      dfree(c->d_timg_pair);
+      CU(c, cudaMalloc(&c->d_timg_pair, pimg.size()));
+      CU(c, cudaMemcpy(c->d_timg_pair, pimg.data(), pimg.size(), cudaMemcpyHostToDevice));
+      c->k2pp = c->k2ip;
+      c->k2pp.timg = c->d_timg_pair;
+      c->k2p_smem = k2i::PairSmem::bytes(kp);
+    }
     c->k2i_smem = k2i::Smem::bytes(kp, c->nact);
   }
   return ORDM_OK;
@@ -927,6 +985,7 @@ int ordm_create(int device, ordm_ctx** out) {
   c->device = device;
   if (const char* e = getenv("ORDM_I8_NO_OVERLAP")) c->i8_no_overlap = (e[0] == '1');
   if (const char* e = getenv("ORDM_K2_INT8")) c->k2_i8_mode = atoi(e);   // 0: DMMA kernels only; 2: 21 slice pairs
+  if (const char* e = getenv("ORDM_K2_PAIR")) c->k2_pair = (e[0] != '0');   // 0: single-CTA int8 kernel (k2_int8.cuh)
   if (const char* e = getenv("ORDM_K2_PLAIN")) c->k2_force_plain = (e[0] == '1');  // test hook: single-buffer K2
   if (const char* e = getenv("ORDM_K1_SPLIT")) c->k1_split = (e[0] == '1');         // test hook: two-kernel K1
   c->sm_count = prop.multiProcessorCount;
@@ -963,7 +1022,7 @@ void ordm_destroy(ordm_ctx* c) {
   dfree(c->d_w);
   for (int k = 0; k < 4; ++k) dfree(c->d_phi[k]);
   dfree(c->d_Dsa_g); dfree(c->d_Dsb_g); dfree(c->d_dfrag); dfree(c->d_tasks); dfree(c->d_pairs);
-  dfree(c->d_timg); dfree(c->d_i8_fail);
+  dfree(c->d_timg); dfree(c->d_timg_pair); dfree(c->d_i8_fail);
   dfree(c->d_partial); dfree(c->d_res);
   if (c->h_res) cudaFreeHost(c->h_res);
   for (auto& s : c->stage) {
@@ -1528,7 +1587,9 @@ int ordm_set_vector(ordm_ctx* c, int which, const double* host_in, size_t npts) 
   }
   if (npts) CU(c, cudaMemcpyAsync(dst, host_in, npts * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
-  c->xc_done = false;
+  // the translated vectors are outputs of translate(): installing one makes the set caller-managed (the getters hand
+  // back what is stored, as the reference's do) until the next translate; anything upstream invalidates them
+  c->xc_done = which >= ORDM_VEC_TR_RHOA && which <= ORDM_VEC_TR_SIGMA_BB;
   if (which == ORDM_VEC_RHO) c->rho_done = true;         // what build_R / translate read (mcpdft.cc:276,297)
   else if (which == ORDM_VEC_PI) c->pi_done = true;      // the complete Pi (core part included)
   else if (which == ORDM_VEC_R) c->inj_R = true;
@@ -1665,9 +1726,10 @@ int ordm_pi_kernel_info(const ordm_ctx* c, int* int8_slice_pairs, uint64_t* mma_
   const int pairs = c->k2_i8_mode == 1 ? 26 : 21;
   if (int8_slice_pairs) *int8_slice_pairs = i8 ? pairs : 0;
   if (mma_per_tile) {
-    if (i8) {   // per slice pair: every 32-pair K chunk feeds the right column half, the chunks below it the left half too
+    if (i8) {   // per slice pair: every 32-pair K chunk feeds the right column half, the chunks below it the left half too;
+                // the CTA-pair kernel issues one full-width MMA per slice pair and chunk (for a 2 x 128-point tile)
       const int kp = (ordm::pair_count(c->nact) + 31) / 32 * 32;
-      *mma_per_tile = (uint64_t)pairs * (uint64_t)(kp / 32 + (kp / 2 + 31) / 32);
+      *mma_per_tile = c->k2_pair ? (uint64_t)pairs * (uint64_t)(kp / 32) : (uint64_t)pairs * (uint64_t)(kp / 32 + (kp / 2 + 31) / 32);
     } else {
       *mma_per_tile = c->k2_dmma_per_mtile;
     }

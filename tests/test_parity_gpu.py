@@ -476,8 +476,15 @@ def test_stage_orchestration_modes_agree(engine, port, ordm, ncore, nact, want_m
         assert np.abs(seen[True][k] - seen[False][k]).max() <= 1e-13 * max(1.0, np.abs(seen[True][k]).max()), k
 
 
-@pytest.mark.parametrize("nact,ncore,npts,mode", [(20, 3, 300, "1"), (20, 0, 131, "2"), (19, 2, 257, "1"), (18, 1, 200, "1"), (18, 25, 129, "2")])
-def test_int8_tensor_core_pi_vs_oracle(port, ordm, monkeypatch, nact, ncore, npts, mode):
+@pytest.fixture(params=["1", "0"], ids=["cta-pair", "single-cta"])
+def int8_kernel(request, monkeypatch):
+    """Both int8 on-top kernels: the CTA-pair form (k2_int8_pair.cuh, default) and the single-CTA one (k2_int8.cuh)."""
+    monkeypatch.setenv("ORDM_K2_PAIR", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("nact,ncore,npts,mode", [(20, 3, 300, "1"), (20, 0, 131, "2"), (19, 2, 257, "1"), (18, 1, 200, "1"), (18, 25, 129, "2"), (20, 5, 1301, "1")])
+def test_int8_tensor_core_pi_vs_oracle(port, ordm, monkeypatch, int8_kernel, nact, ncore, npts, mode):
     """18..20 active orbitals: Pi comes from the int8 tensor-core kernel (k2_int8.cuh; exact integer slice products
     of 46-bit fixed-point images, 26 (mode 1, default) or 21 (mode 2) slice pairs).  Same bar as the FP64 kernels:
     1e-12 per point on Pi, 1e-10 on the energies; and the DMMA kernel (ORDM_K2_INT8=0) must agree with it."""
@@ -506,7 +513,7 @@ def test_int8_tensor_core_pi_vs_oracle(port, ordm, monkeypatch, nact, ncore, npt
 
 @pytest.mark.parametrize("nact,ncore,npts,kind,mode", [(18, 0, 257, "ensemble", "1"), (20, 0, 200, "nonsym", "1"), (20, 2, 129, "ensemble", "2"),
                                                        (19, 0, 130, "nonsym", "2")])
-def test_int8_tensor_core_pi_dense_rotated_rdms(port, ordm, monkeypatch, nact, ncore, npts, kind, mode):
+def test_int8_tensor_core_pi_dense_rotated_rdms(port, ordm, monkeypatch, int8_kernel, nact, ncore, npts, kind, mode):
     """The int8 on-top kernel on the golden-vector construction (tests/golden/make_golden.py::random_case): dense 2-RDMs of
     rotated determinants, optionally with sign-indefinite noise ("nonsym"), orbital rows whose magnitudes span 2^-47 .. 1
     (the per-row power-of-two scaling of the fixed-point images), with and without core orbitals."""
@@ -539,7 +546,7 @@ def test_int8_tensor_core_pi_dense_rotated_rdms(port, ordm, monkeypatch, nact, n
 
 # ---- the int8 path's error guard (k2_int8.cuh: guard_flag; ORDM retries with the FP64 kernels) -----------------------
 @pytest.mark.parametrize("case,mode", [("benchmark", "1"), ("phi3", "1"), ("dominant", "1"), ("indefinite", "1"), ("dominant", "2"), ("indefinite", "2")])
-def test_int8_guard_and_fp64_fallback(port, ordm, monkeypatch, case, mode):
+def test_int8_guard_and_fp64_fallback(port, ordm, monkeypatch, int8_kernel, case, mode):
     """The inputs of the round-1 review, 20 active orbitals: |phi| up to 3, a dominant-orbital row, a sign-indefinite
     pair matrix.  Whatever the guard decides, the Pi that comes back meets 1e-12 max(1, |Pi|) against the oracle; the
     benchmark-like case stays on the int8 kernel, the sign-indefinite one is sent to the FP64 kernels."""

@@ -45,7 +45,8 @@ int main(int argc, char** argv) {
   CK(cudaFuncSetAttribute(k2i::k2i_ontop_pair<NA, 5, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k2i::Params P{dphi, npts, npts, dt, t_exp, nullptr, dpi, dfail, g1, g2};
   const int threads = (4 * EW + 1) * 32;
-  const int grid = std::max(2, (int)std::min<size_t>((size_t)prop.multiProcessorCount, 2 * ((npts + 255) / 256)) / 2 * 2);
+  int grid = std::max(2, (int)std::min<size_t>((size_t)prop.multiProcessorCount, 2 * ((npts + 255) / 256)) / 2 * 2);
+  if (argc > 4) grid = std::max(2, atoi(argv[4]) / 2 * 2);   // fewer CTA pairs: per-tile clocks with most of the chip idle
   auto launch = [&]() { if (gmin == 4) k2i::k2i_ontop_pair<NA, 4, EW><<<grid, threads, smem>>>(P); else k2i::k2i_ontop_pair<NA, 5, EW><<<grid, threads, smem>>>(P); };
   launch();
   CK(cudaGetLastError());
@@ -74,9 +75,9 @@ int main(int argc, char** argv) {
   }
   { long long pf[3][8]; CK(cudaMemcpyFromSymbol(pf, k2i::k2p_prof, sizeof(pf)));
     const double nt = (double)((npts + 255) / 256 + grid / 2 - 1) / (grid / 2);
-    const char* who[3] = {"epilogue thread 0", "-", "MMA lane"};
+    const char* who[3] = {"epilogue warp 0 (sub-partition of the MMA warp)", "epilogue warp 1 (another sub-partition)", "MMA lane"};
     const char* nm[8] = {"phi load", "build+cluster sync", "wait drain", "issue", "partials+store", "wait full", "fold", "tile head"};
-    for (int w = 0; w < 3; w += 2) { printf("%s, clk per tile:", who[w]); double tot = 0; for (int i = 0; i < 8; ++i) { printf(" %s %.0f;", nm[i], (double)pf[w][i] / nt); tot += (double)pf[w][i] / nt; } printf(" total %.0f\n", tot); } }
+    for (int w = 0; w < 3; ++w) { printf("%s, clk per tile:", who[w]); double tot = 0; for (int i = 0; i < 8; ++i) { printf(" %s %.0f;", nm[i], (double)pf[w][i] / nt); tot += (double)pf[w][i] / nt; } printf(" total %.0f\n", tot); } }
   const double flops = (double)npts * ((double)M * (M + 1) + 2.0 * M);
   printf("EW %d GMIN %d: npts %zu: %.3f ms -> %.1f M pts/s (FP64-equivalent %.1f TFLOP/s of the symmetric contraction); barrier timeouts %d, guard-flagged points %d\n", EW, gmin, npts, best, npts / best / 1e3, flops / best / 1e9, fail[0], fail[1]);
   printf("max |dPi| / max(1,|Pi|) over %zu points: int8 path %.3e (worst point %zu: got %.17g; %zu above 1e-12), plain FP64 loops %.3e; |Pi|max %.3g\n", ncheck, emax, worst, pi[worst], nbad, emax_f64, pimax);
