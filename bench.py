@@ -16,7 +16,13 @@ one NCCL all-reduce combines the eight scalars.  Prints ONE JSON line on rank 0.
               DGEMM rate measured in this process; K1/K3 against MEASURED_PEAKS.json's HBM GB/s
     cpu_baseline   OpenRDM's own compiled code (oracle/_ref) on a bounded sample, all host cores
 
---impl reference times only the reference CPU arm (rank 0), same metric/config.
+--impl reference times only the reference CPU arm (rank 0), same metric/config (its inputs come from the host-only
+generator openrdm_b200/host/libordm_synth.so: the GPU library is not mapped in that arm).
+
+Also in the line: `parity` (config 4: E_xc of the timed run against the full-grid golden of OpenRDM's own code,
+tests/golden/fullgrid.json, asserted to 1e-10 Eh at every N), `value_fp64_dmma` (the same step with Pi from the FP64 DMMA
+kernels, ORDM_K2_INT8=0), `e2e.grid_resident` (grid resident, RDMs re-uploaded and result read back every step: the
+SCF-loop use) and `config5` (BASELINE.json's largest config, 20 M points / 26 active orbitals, tSVWN and tPBE, same N).
 """
 from __future__ import annotations
 
@@ -33,6 +39,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "MCPDFT grid points/sec (rho+Pi+tXC+quadrature)"
 UNIT = "grid points/s"
+# the arithmetic type of the path (not a precision claim): FP64 throughout; for 18..20 active orbitals the products of the
+# on-top contraction are formed exactly on the int8 tensor cores (roofline.pi_arithmetic says which kernel ran)
+DTYPE = "f64"
 
 # BASELINE.json configs 3-5 ("Config sizes")
 CONFIGS = {
@@ -133,7 +142,7 @@ def cpu_reference_leg(cfg, sample_pts, threads, steps=1, warmup=0):
     """OpenRDM's own compiled code (oracle/_ref) on a bounded sample of the same synthetic grid.
     Returns (points/s as written, points/s necessary-work-only, description)."""
     from oracle import oracle as O
-    import openrdm_b200 as ordm
+    from openrdm_b200 import synth as ordm   # host-only generator (libordm_synth.so): no CUDA library in this arm
     if not O.have_ref():
         return None
     ref = O.Ref()
@@ -176,6 +185,7 @@ def main():
                     help="strong (default): BASELINE.json's grid sharded over the ranks; weak: that grid PER rank")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the config-5 sub-record (20 M points; needs ~64 GB per rank at N=1)")
     ap.add_argument("--cpu-sample", type=int, default=0)
     args = ap.parse_args()
 
@@ -204,14 +214,14 @@ def main():
             return 0
         sample = args.cpu_sample or (16384 if cfg["nact"] >= 20 else 131072)
         sample = min(sample, cfg["npts"])
-        leg = cpu_reference_leg(cfg, sample, cores, steps=steps, warmup=min(warmup, 1))
+        leg = cpu_reference_leg(cfg, sample, cores, steps=steps, warmup=warmup)
         if leg is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
             return 0
         v = leg["as_written"]
         print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 1),
-            "ms_per_step": leg["seconds"] * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": leg["seconds"] * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": DTYPE,
             "data": "synthetic", "config": workload,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": leg["sample"],
                              "value_necessary_work_only": leg["necessary"], "value_serial_1_core": leg["serial"],
@@ -241,8 +251,9 @@ def main():
     eng.set_active_space(cfg["ncore"], A1a, A1b, D2)
     pik = eng.pi_kernel_info()   # int8 tensor-core K2 (18..20 active orbitals) or the FP64 DMMA kernels
     i8_pairs, i8_mma = pik["int8_slice_pairs"], pik["mma_per_tile"]
-    workload["pi_arithmetic"] = (f"exact int8 tensor-core products of {i8_pairs} byte-slice pairs of 46-bit fixed-point images, FP64 epilogue"
-                                 if i8_pairs else "FP64 (DMMA.8x8x4)")
+    pi_arithmetic = (f"exact int8 tensor-core products (tcgen05.mma kind::i8, CTA pairs) of {i8_pairs} byte-slice pairs of 46-bit fixed-point images; "
+                     "epilogue FP64 for the four high-order groups, FP32 for the three that weigh <= 2^-32; guarded by an a-posteriori error estimate "
+                     "with FP64 (DMMA) retry" if i8_pairs else "FP64 (DMMA.8x8x4)")
     p0, cnt = ordm.shard_range(cfg["npts"], world, rank)
     eng.synth_fill(cfg["seed"], cfg["npts"], p0, cnt, n, gga)
     if world > 1:
@@ -252,8 +263,7 @@ def main():
         dist.broadcast(uid, 0)
         eng.comm_attach(world, rank, bytes(uid.cpu().numpy().tobytes()))
     fid = ordm.FUNC_PBE if gga else ordm.FUNC_SVWN
-    if world > 1:
-        workload["allreduce"] = eng.comm_info()["allreduce"]
+    allreduce = eng.comm_info()["allreduce"] if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -344,7 +354,95 @@ def main():
         ms_e2e = max(ms_e2e, wall_e2e)  # host-side call time (the copies are issued from the host) bounds it from below
         h2d = 8 * cfg["npts"] * (n * (4 if gga else 1) + 1)
         e2e = {"value": cfg["npts"] / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * 8 * world,
-               "ms_per_step": ms_e2e, "steps": e2e_steps, "e_tot_matches_resident": abs(r2["e_tot"] - res["e_tot"]) <= 1e-10 * max(1.0, abs(res["e_tot"]))}
+               "ms_per_step": ms_e2e, "steps": e2e_steps, "e_tot_matches_resident": abs(r2["e_tot"] - res["e_tot"]) <= 1e-10 * max(1.0, abs(res["e_tot"])),
+               "what": "ordm_energy_host: grid, orbitals and weights in pinned host memory, streamed H2D inside the timed region every step"}
+        del w_h, phi_h, g_h
+        # the SCF-loop use of the same API: the grid stays resident, every step uploads new RDMs (host folding / packing of the
+        # 2-RDM included), runs the path and reads the result scalars back
+        scf_steps = max(3, min(steps, 10))
+        eng.set_active_space(cfg["ncore"], A1a, A1b, D2); eng.energy(fid, 0.0)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(scf_steps):
+            eng.set_active_space(cfg["ncore"], A1a, A1b, D2)
+            r3 = eng.energy(fid, 0.0)
+        barrier()
+        ms_scf = max_over_ranks((time.perf_counter() - t0) * 1e3) / scf_steps
+        e2e["grid_resident"] = {"value": cfg["npts"] / (ms_scf * 1e-3), "unit": UNIT, "ms_per_step": ms_scf, "steps": scf_steps,
+                                "h2d_bytes_per_step": 8 * (2 * cfg["nact"] ** 2 + cfg["nact"] ** 4) * world, "d2h_bytes_per_step": 8 * 8 * world,
+                                "timed_with": "host wall clock around ordm_set_active_space + ordm_energy (both synchronous), max over ranks",
+                                "e_tot_matches_resident": abs(r3["e_tot"] - res["e_tot"]) <= 1e-12 * max(1.0, abs(res["e_tot"]))}
+
+    # ---- parity of the timed run: config 4's E_xc against OpenRDM's own code over the same 5 M points
+    parity = None
+    if args.config == 4 and not args.npts and args.scaling == "strong":
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "fullgrid.json")) as f:
+                gold = json.load(f)["config4_tPBE_full"]["totals"]
+            parity = {"e_xc": res["e_tot"], "reference_e_xc": gold["e_xc"], "abs_diff": abs(res["e_tot"] - gold["e_xc"]),
+                      "n_tot_abs_diff": abs(res["n_tot"] - gold["n_tot"]), "tolerance": 1e-10,
+                      "reference": "oracle/_ref (OpenRDM's unmodified sources) over the whole grid, tests/golden/fullgrid.json"}
+            assert parity["abs_diff"] <= 1e-10 and parity["n_tot_abs_diff"] <= 1e-10, parity
+        except FileNotFoundError:
+            pass
+    eng.close()
+    del eng
+
+    def quick_rate(config_id, functional, k2_int8, nsteps):
+        """resident rate of another configuration / kernel choice at the same N: (points/s, ms per step, e_tot)"""
+        c5 = dict(CONFIGS[config_id]); c5["functional"] = functional
+        g5 = functional == "PBE"
+        n5 = c5["ncore"] + c5["nact"]
+        old_env = os.environ.get("ORDM_K2_INT8")
+        if k2_int8 is not None:
+            os.environ["ORDM_K2_INT8"] = k2_int8
+        e5 = ordm.Engine(local_rank)
+        if old_env is None:
+            os.environ.pop("ORDM_K2_INT8", None)
+        else:
+            os.environ["ORDM_K2_INT8"] = old_env
+        try:
+            e5.set_stream(stream.cuda_stream)
+            a, b, d2 = ordm.synth_rdms(c5["seed"], c5["nact"], c5["nelec"], c5["nelec"], 8)
+            e5.set_options(diagnostics=False)
+            e5.set_active_space(c5["ncore"], a, b, d2)
+            q0, qn = ordm.shard_range(c5["npts"], world, rank)
+            e5.synth_fill(c5["seed"], c5["npts"], q0, qn, n5, g5)
+            if world > 1:
+                uid5 = torch.zeros(128, dtype=torch.uint8, device="cuda")
+                if rank == 0:
+                    uid5 = torch.frombuffer(bytearray(ordm.Engine.comm_unique_id()), dtype=torch.uint8).cuda()
+                dist.broadcast(uid5, 0)
+                e5.comm_attach(world, rank, bytes(uid5.cpu().numpy().tobytes()))
+            f5 = ordm.FUNC_PBE if g5 else ordm.FUNC_SVWN
+            for _ in range(3):
+                r5 = e5.energy(f5, 0.0)
+            barrier()
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                for _ in range(nsteps):
+                    r5 = e5.energy(f5, 0.0)
+                e1.record(stream)
+            barrier()
+            ms5 = max_over_ranks(e0.elapsed_time(e1)) / nsteps
+            return c5["npts"] / (ms5 * 1e-3), ms5, r5["e_tot"], e5.pi_kernel_info()["int8_slice_pairs"]
+        finally:
+            e5.close()
+
+    # ---- the same step with Pi from the FP64 tensor-pipe kernels (no int8 path): the FP64-pure rate
+    fp64_pure = None
+    if i8_pairs:
+        v64, ms64, e64, _ = quick_rate(args.config, cfg["functional"], "0", max(3, min(steps, 10)))
+        fp64_pure = {"value": v64, "ms_per_step": ms64, "pi_arithmetic": "FP64 (DMMA.8x8x4), ORDM_K2_INT8=0",
+                     "abs_diff_e_tot_vs_int8_path": abs(e64 - res["e_tot"])}
+    # ---- BASELINE.json's largest config at this N (20 M points, 73 core + 26 active orbitals), tSVWN and tPBE
+    config5 = None
+    if args.config == 4 and not args.npts and not args.no_config5:
+        config5 = {"workload": CONFIGS[5]["name"].replace(", tPBE", ""), "npts": CONFIGS[5]["npts"], "n_gpus": world, "scaling": "strong"}
+        for fn5 in ("SVWN", "PBE"):
+            v5, ms5, e5tot, p5 = quick_rate(5, fn5, None, 5)
+            config5["t" + fn5] = {"value": v5, "unit": UNIT, "ms_per_step": ms5, "steps": 5, "warmup": 3, "e_tot": e5tot,
+                                  "pi_arithmetic": "int8 tensor cores" if p5 else "FP64 (DMMA.8x8x4)"}
 
     if rank != 0:
         if world > 1:
@@ -375,25 +473,27 @@ def main():
         i8_peak = 2 * 8192 * 148 * sm_mhz * 1e6 * 1e-12
         def i8_top(ms):
             return i8_ops * pts_rank / (ms * 1e-3) * 1e-12
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01g_traffic.json")) as f:
+        traffic, traffic_source = None, None
+        try:   # dram__bytes of one launch from the committed ncu --set full capture of this kernel on this config (not re-measured here)
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
                 tr = json.load(f)
-            traffic = tr["config4_n1"]["k2_int8"] if args.config == 4 and world == 1 and not args.npts else None
+            if args.config == 4 and world == 1 and not args.npts:
+                traffic, traffic_source = tr["config4_n1"]["k2i_ontop_pair"], "profiles/r02_traffic.json (ncu --set full, same command; not measured in this run)"
         except Exception:
-            traffic = None
-        roofline = {"kernel": f"k2i_ontop (Pi, tcgen05.mma kind::i8, {i8_pairs} slice pairs)", "bound": "tensor", "achieved": i8_top(ms_k["pi"]), "peak": i8_peak,
-                    "unit": "TOP/s", "frac": i8_top(ms_k["pi"]) / i8_peak, "traffic": traffic,
+            pass
+        roofline = {"kernel": f"k2i_ontop_pair (Pi, tcgen05.mma cta_group::2 kind::i8, {i8_pairs} slice pairs)", "bound": "tensor", "achieved": i8_top(ms_k["pi"]), "peak": i8_peak,
+                    "unit": "TOP/s", "frac": i8_top(ms_k["pi"]) / i8_peak, "traffic": traffic, "traffic_source": traffic_source, "pi_arithmetic": pi_arithmetic,
                     "peak_source": f"8192 int8 MAC/clk/SM x 148 SMs x {sm_mhz:.0f} MHz: the issue rate measured by tools/ozlab/i8mma_bench "
                                    "(112.2 clk per 128x224x32 MMA, profiles/r01f_i8mma_microbench.log); MEASURED_PEAKS.json has no int8 figure "
                                    f"(2 x its dense bf16 burst = {2 * peaks.get('bf16_tflops', 0):.0f} TOP/s)",
-                    "algorithmic_int8_ops_per_point": i8_ops, "mma_per_128_point_tile": i8_mma,
+                    "algorithmic_int8_ops_per_point": i8_ops, "mma_per_256_point_pair_tile": i8_mma,
                     "fp64_flops_per_point_of_the_same_contraction": alg["k2_flops"], "fp64_equivalent_tflops": k2_tf,
                     "fp64_equivalent_vs_cublas_dgemm": k2_tf / dg_sus,
                     "dgemm_peak_source": f"cuBLAS DGEMM 8192^3 measured in this process (sustained {dg_sus:.2f}, burst {dg_burst:.2f} TFLOP/s)",
                     "share_of_step": ms_k["pi"] / ms_step}
     else:
         roofline = {"kernel": "k2_ontop (Pi, DMMA.8x8x4)", "bound": "tensor", "achieved": k2_tf, "peak": dg_sus, "unit": "TFLOP/s", "frac": k2_tf / dg_sus,
-                    "traffic": traffic, "peak_source": f"cuBLAS DGEMM 8192^3 measured in this process (sustained {dg_sus:.2f}, burst {dg_burst:.2f} TFLOP/s)",
+                    "traffic": traffic, "traffic_source": "profiles/r01c_traffic.json (ncu --set full; not measured in this run)" if traffic else None, "pi_arithmetic": pi_arithmetic, "peak_source": f"cuBLAS DGEMM 8192^3 measured in this process (sustained {dg_sus:.2f}, burst {dg_burst:.2f} TFLOP/s)",
                     "algorithmic_flops_per_point": alg["k2_flops"], "survey_flops_per_point": alg["k2_flops_survey"],
                     "achieved_survey_count": alg["k2_flops_survey"] * pts_rank / (ms_k["pi"] * 1e-3) * 1e-12,
                     "share_of_step": ms_k["pi"] / ms_step}
@@ -435,9 +535,10 @@ def main():
                    "value_reference_openmp_build_all_cores": leg["omp"]}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
-           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
+           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": workload,
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
-           "result": {k: res[k] for k in ("e_tot", "ex", "ec", "n_tot", "trn_tot")}}
+           "result": {k: res[k] for k in ("e_tot", "ex", "ec", "n_tot", "trn_tot")}, "parity": parity,
+           "value_fp64_dmma": fp64_pure, "config5": config5, "allreduce": allreduce}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -150,9 +150,9 @@ int ordm_set_orbitals(ordm_ctx* ctx, size_t npts, int n, size_t ld, const double
  * F_DGEMMs per irrep) / mo_values = np.matmul(ao_values, C_mo) (src/libpyscf/libpyscf.py:608).
  * ao, ao_x, ao_y, ao_z: npts x nao column-major host arrays (leading dimension ld; gradients NULL =
  * LDA); C: nao x nmo column-major MO coefficients.  The AO values are streamed through the device in
- * point batches (H2D overlapped with the FP64 GEMM, cuBLAS DGEMM = DMMA on sm_100a) and
- * phi = ao . C (and its gradients) become the context's resident orbitals, exactly as if
- * ordm_set_orbitals had been called with the transformed matrices. */
+ * point batches (H2D overlapped with the FP64 GEMM of the previous batch: this library's own DMMA kernel,
+ * csrc/k0_ao2mo.cuh -- no cuBLAS) and phi = ao . C (and its gradients) become the context's resident orbitals,
+ * exactly as if ordm_set_orbitals had been called with the transformed matrices. */
 int ordm_set_orbitals_ao(ordm_ctx* ctx, size_t npts, int nao, size_t ld, const double* ao, const double* ao_x,
                          const double* ao_y, const double* ao_z, int nmo, const double* C);
 /* MCPDFT::set_D1a + set_D1b (mcpdft.h:125-126).  n x n, not assumed symmetric (mcpdft.cc:148). */
@@ -215,6 +215,63 @@ int ordm_integrated_densities(ordm_ctx* ctx, double out_n[3], double out_trn[3])
 int ordm_functional(ordm_ctx* ctx, int term, size_t npts, const double* rho_a, const double* rho_b,
                     const double* sigma_aa, const double* sigma_ab, const double* sigma_bb,
                     double* energy_out);
+
+/* ---- input files (north_star "Data loading (libio)") -------------------------------
+ * The grid + orbitals + RDM container of the reference's ecosystem is the PySCF exporter's data.h5
+ * (src/libpyscf/libpyscf.py:613-690: groups /N, /C, /E, /D/D1, /D/D2, /GRIDS/{W,X,Y,Z}, /PHI/PHI_{AO,MO}{,_X,_Y,_Z},
+ * /SP_SYMM_D1, /SP_SYMM_D2 with the upper-packed COO RDMs :246-463); libio's own opdm.h5 / tpdm.h5 (src/libio/HDF5_Read_Compact.cc:8-12)
+ * are a round trip whose result mcpdft_energy discards (energy.cc:132-140).  ordm_file_open reads that schema from
+ * HDF5 itself when this library was built with <hdf5.h> available, and from the raw little-endian container with the
+ * same dataset names (format: csrc/rawio.h; writer: openrdm_b200/rawio.py) otherwise.  Arrays are row-major (numpy). */
+typedef struct ordm_file ordm_file;
+enum { ORDM_DT_F64 = 0, ORDM_DT_I64 = 1, ORDM_DT_I32 = 2 };
+int ordm_file_open(const char* path, ordm_file** out);
+void ordm_file_close(ordm_file* f);
+/* dataset by its data.h5 path, e.g. "/GRIDS/W": element type, rank, dims (padded with 1), pointer valid until close */
+int ordm_file_dataset(ordm_file* f, const char* name, int* dtype, int* ndim, uint64_t dims[4], const void** data);
+/* Everything the path needs from one file into the context: weights /GRIDS/W; orbitals on the grid from /PHI/PHI_MO
+ * (first N_COR + N_CAS_ORB columns; transposed to the engine's column-major layout on the device) or, with
+ * ORDM_LOAD_PREFER_AO or when PHI_MO is absent, from /PHI/PHI_AO and /C through the device AO -> MO transform;
+ * gradients when all of _X, _Y, _Z are there; the active-space RDMs from the upper-packed COO groups
+ * /SP_SYMM_D1/ACT_D1{a,b}_MO, /SP_SYMM_D2/ACT_D2ab_MO (or, with ORDM_LOAD_DENSE_RDM / when those are absent, from
+ * /D/D1/ACT_D1{A,B}_MO and /D/D2/ACT_D2AB_MO); N_COR doubly occupied orbitals precede the N_CAS_ORB active ones.
+ * Afterwards ordm_energy etc. run exactly as after the ordm_set_* calls.  info (nullable) reports what was found;
+ * e_core + e_hartree (+ V_nn, which the exporter only prints) is the classical energy `eclass` of mcpdft_energy. */
+enum { ORDM_LOAD_PREFER_AO = 1, ORDM_LOAD_DENSE_RDM = 2, ORDM_LOAD_NO_GRADIENTS = 4 };
+typedef struct {
+  uint64_t npts;
+  int nao, nmo, ncore, nact;
+  int gga, used_ao, used_sparse_rdm;
+  double e_core, e_hartree;     /* /E/E_CORE, /E/E_HARTREE (libpyscf.py:629-630) */
+} ordm_data_info;
+int ordm_load_data(ordm_ctx* ctx, const char* path, unsigned flags, ordm_data_info* info);
+
+/* ---- the Psi4 plugin's extras around the path -------------------------- */
+/* MCPDFTSolver::polyradical_analysis (src/libpsi4/mcpdft_solver.cc:3001-3240): densities of effectively unpaired
+ * electrons  U(r), D(r), N(r) = sum_ij phi_i phi_j {U, D, N}_ij  with, element by element on n = D1a + D1b,
+ * U = 1 - |1 - n|, D = n (2 - n), N = n^2 (2 - n)^2 (:3104-3108), on the resident grid, orbitals and 1-RDMs
+ * (doubly occupied core orbitals contribute nothing).  traces = sum_p w_p {U, D, N}(r_p) (:3185-3187); U_r, D_r, N_r:
+ * optional npts-long host arrays (what the plugin writes to mygrids.txt, :3213-3227).  At most 32 active orbitals. */
+int ordm_polyradical(ordm_ctx* ctx, double traces[3], double* U_r, double* D_r, double* N_r, size_t npts);
+
+/* Energy assembly of MCPDFTSolver::compute_energy (mcpdft_solver.cc:849-925): the scalars the plugin takes from Psi4
+ * (reference energy, V_nn, kinetic and nuclear-attraction energies of the 1-RDMs, classical Coulomb energy, and for
+ * the double hybrids the HF-exchange and MP2-correlation energies) together with Ex, Ec of ordm_energy:
+ *   two_electron = e_reference - V_nn - (T + V_ne);   wf = (T + V_ne) + lambda two_electron;
+ *   dft = (1 - lambda)(J + Ex) + (1 - lambda^2) Ec;   E = wf + dft + V_nn  (+ lambda E_x^HF + lambda^2 E_c^MP2 for 1DH_MCPDFT).
+ * lambda = MCPDFT_LAMBDA (plugin.cc:51); it is ignored (0) for method MCPDFT, as in the plugin (:717-737).  The
+ * range-separated methods use the same assembly with the functional evaluated at MCPDFT_OMEGA (ordm_set_omega +
+ * ORDM_FUNC_WPBE).  Host arithmetic only; no context needed. */
+enum ordm_method { ORDM_METHOD_MCPDFT = 0, ORDM_METHOD_1H_MCPDFT, ORDM_METHOD_1DH_MCPDFT, ORDM_METHOD_RS_MCPDFT,
+                   ORDM_METHOD_RS1H_MCPDFT, ORDM_METHOD_RS1DH_MCPDFT };   /* MCPDFT_METHOD, plugin.cc:47 */
+typedef struct {
+  double e_reference;            /* reference (CASSCF / v2RDM) total energy */
+  double e_nuclear_repulsion, e_kinetic, e_nuclear_attraction;
+  double e_coulomb;              /* classical Coulomb energy J */
+  double e_hf_exchange, e_mp2_correlation;   /* 1DH_MCPDFT only */
+} ordm_hybrid_inputs;
+typedef struct { double e_total, wf_contribution, dft_contribution, one_electron, two_electron, lambda; } ordm_hybrid_result;
+int ordm_hybrid_energy(int method, double lambda, const ordm_hybrid_inputs* in, double ex, double ec, ordm_hybrid_result* out);
 
 /* ---- the path in one call -------------------------------------------------------------- */
 /* mcpdft::mcpdft_energy (energy.cc:27-188) on the device-resident inputs: density -> Pi ->

@@ -51,6 +51,73 @@ class Result(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ }
 
 
+LOAD_PREFER_AO, LOAD_DENSE_RDM, LOAD_NO_GRADIENTS = 1, 2, 4
+
+
+class DataInfo(C.Structure):
+    _fields_ = [("npts", C.c_uint64), ("nao", C.c_int), ("nmo", C.c_int), ("ncore", C.c_int), ("nact", C.c_int),
+                ("gga", C.c_int), ("used_ao", C.c_int), ("used_sparse_rdm", C.c_int), ("e_core", C.c_double), ("e_hartree", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class InputFile:
+    """ordm_file_*: the data.h5 schema from the raw container (or HDF5 when the library was built with it)."""
+    _NP = {0: np.float64, 1: np.int64, 2: np.int32}
+
+    def __init__(self, path: str):
+        self.lib = load()
+        self.h = C.c_void_p()
+        rc = self.lib.ordm_file_open(path.encode(), C.byref(self.h))
+        if rc:
+            raise OrdmError(rc, self.lib.ordm_last_error(None).decode())
+
+    def dataset(self, name: str) -> np.ndarray:
+        dt, nd, dims, ptr = C.c_int(), C.c_int(), (C.c_uint64 * 4)(), C.c_void_p()
+        rc = self.lib.ordm_file_dataset(self.h, name.encode(), C.byref(dt), C.byref(nd), dims, C.byref(ptr))
+        if rc:
+            raise KeyError(self.lib.ordm_last_error(None).decode())
+        shape = tuple(int(dims[i]) for i in range(nd.value))
+        n = int(np.prod(shape)) if shape else 1
+        item = np.dtype(self._NP[dt.value]).itemsize
+        buf = (C.c_char * (n * item)).from_address(ptr.value) if n else b""
+        return np.frombuffer(buf, dtype=self._NP[dt.value], count=n).reshape(shape).copy()
+
+    def close(self):
+        if self.h:
+            self.lib.ordm_file_close(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HybridInputs(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("e_reference", "e_nuclear_repulsion", "e_kinetic", "e_nuclear_attraction", "e_coulomb",
+                                          "e_hf_exchange", "e_mp2_correlation")]
+
+
+class HybridResult(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("e_total", "wf_contribution", "dft_contribution", "one_electron", "two_electron", "lambda_")]
+
+
+METHODS = {"MCPDFT": 0, "1H_MCPDFT": 1, "1DH_MCPDFT": 2, "RS_MCPDFT": 3, "RS1H_MCPDFT": 4, "RS1DH_MCPDFT": 5}
+
+
+def hybrid_energy(method: str, lam: float, ex: float, ec: float, **scalars) -> dict:
+    """MCPDFTSolver::compute_energy's assembly (mcpdft_solver.cc:849-925); scalars = the fields of ordm_hybrid_inputs."""
+    inp = HybridInputs(**{k: float(v) for k, v in scalars.items()})
+    out = HybridResult()
+    rc = load().ordm_hybrid_energy(METHODS[method], float(lam), C.byref(inp), float(ex), float(ec), C.byref(out))
+    if rc:
+        raise OrdmError(rc, load().ordm_last_error(None).decode())
+    return {k: getattr(out, k) for k, _ in out._fields_}
+
+
 _lib = None
 
 
@@ -92,6 +159,13 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.ordm_functional.argtypes = [P, I, S, D, D, D, D, D, D]
     lib.ordm_energy.argtypes = [P, I, C.c_double, C.POINTER(Result)]
     lib.ordm_energy_host.argtypes = [P, I, C.c_double, S, I, S, D, D, D, D, D, S, C.POINTER(Result)]
+    lib.ordm_file_open.argtypes = [C.c_char_p, C.POINTER(P)]
+    lib.ordm_file_close.argtypes = [P]
+    lib.ordm_file_close.restype = None
+    lib.ordm_file_dataset.argtypes = [P, C.c_char_p, C.POINTER(I), C.POINTER(I), C.POINTER(C.c_uint64), C.POINTER(P)]
+    lib.ordm_load_data.argtypes = [P, C.c_char_p, C.c_uint, C.POINTER(DataInfo)]
+    lib.ordm_polyradical.argtypes = [P, D, D, D, D, S]
+    lib.ordm_hybrid_energy.argtypes = [I, C.c_double, C.POINTER(HybridInputs), C.c_double, C.c_double, C.POINTER(HybridResult)]
     lib.ordm_get_vector.argtypes = [P, I, D, S]
     lib.ordm_set_vector.argtypes = [P, I, D, S]
     lib.ordm_get_orbitals.argtypes = [P, I, D, S]
@@ -266,6 +340,20 @@ class Engine:
         self._ck(self.lib.ordm_energy_host(self.ctx, functional, eclass, npts, n, ld or max(npts, 1), _d(w), _d(phi),
                                            _d(g[0]), _d(g[1]), _d(g[2]), batch_points, C.byref(r)))
         return r.asdict()
+
+    def load_data(self, path: str, flags: int = 0) -> dict:
+        """ordm_load_data: grid, orbitals and active-space RDMs from a data.h5-schema file into this context."""
+        info = DataInfo()
+        self._ck(self.lib.ordm_load_data(self.ctx, path.encode(), flags, C.byref(info)))
+        self.npts = int(info.npts)
+        return info.asdict()
+
+    def polyradical(self, want_vectors=True):
+        """MCPDFTSolver::polyradical_analysis: ([Tr U, Tr D, Tr N], U(r), D(r), N(r))."""
+        tr = (C.c_double * 3)()
+        v = [np.zeros(self.npts) for _ in range(3)] if want_vectors else [None] * 3
+        self._ck(self.lib.ordm_polyradical(self.ctx, tr, _d(v[0]), _d(v[1]), _d(v[2]), self.npts))
+        return list(tr), v[0], v[1], v[2]
 
     def get_vector(self, name) -> np.ndarray:
         out = np.zeros(self.npts)

@@ -250,6 +250,56 @@ __global__ void __launch_bounds__(THREADS) k1_density(const Params P) {
   ordm::block_sum_store<3>(acc, scratch, P.partial + (size_t)blockIdx.x * 3);
 }
 
+// Polyradical analysis, MCPDFTSolver::polyradical_analysis (src/libpsi4/mcpdft_solver.cc:3001-3240): the "effectively
+// unpaired electron" densities  U(r), D(r), N(r) = sum_ij phi_i(r) phi_j(r) {U, D, N}_ij  with
+//   U_ij = 1 - |1 - n_ij|,  D_ij = n_ij (2 - n_ij),  N_ij = n_ij^2 (2 - n_ij)^2,  n = D1a + D1b   (:3104-3108)
+// and their quadrature traces (:3185-3187).  Doubly occupied core orbitals (n = 2) contribute nothing, so only the
+// active block is contracted: the same shape as the active part of K1, three matrices instead of two.  The matrices
+// (host-built, row-major [3][nact][nact]) are read through the read-only path: every lane of a warp reads the same
+// element.  Not on the energy path: a diagnostic the plugin prints and writes to mygrids.txt.
+struct PolyParams {
+  const double* phi_act;   // [nact][ld]
+  const double* w;
+  const double* udn;       // [3][nact][nact]
+  size_t ld, npts;
+  int nact;
+  double *U, *D, *N;       // per-point outputs (nullable)
+  double* partial;         // [gridDim.x][3]: sum w U, sum w D, sum w N
+};
+
+template <int NP>
+__global__ void __launch_bounds__(THREADS) k1_polyradical(const PolyParams P) {
+  __shared__ double scratch[3 * 32];
+  double acc[3] = {0.0, 0.0, 0.0};
+  const int na = P.nact;
+  const double *Um = P.udn, *Dm = P.udn + (size_t)na * na, *Nm = P.udn + (size_t)2 * na * na;
+  for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS) {
+    double f[NP];
+#pragma unroll
+    for (int t = 0; t < NP; ++t) f[t] = (t < na) ? __ldcs(P.phi_act + (size_t)t * P.ld + p) : 0.0;
+    double du = 0.0, dd = 0.0, dn = 0.0;
+#pragma unroll
+    for (int t = 0; t < NP; ++t) {
+      if (t < na) {
+        double ru = 0.0, rd = 0.0, rn = 0.0;   // row t of the three matrices against phi
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+          if (u < na) {
+            ru = fma(__ldg(Um + t * na + u), f[u], ru);
+            rd = fma(__ldg(Dm + t * na + u), f[u], rd);
+            rn = fma(__ldg(Nm + t * na + u), f[u], rn);
+          }
+        }
+        du = fma(ru, f[t], du); dd = fma(rd, f[t], dd); dn = fma(rn, f[t], dn);
+      }
+    }
+    st(P.U, p, du); st(P.D, p, dd); st(P.N, p, dn);
+    const double wp = __ldg(P.w + p);
+    acc[0] = fma(du, wp, acc[0]); acc[1] = fma(dd, wp, acc[1]); acc[2] = fma(dn, wp, acc[2]);
+  }
+  ordm::block_sum_store<3>(acc, scratch, P.partial + (size_t)blockIdx.x * 3);
+}
+
 // Generic path for nact > MAX_ACT: same math, coefficients from global memory (L1/L2
 // resident), active orbital values re-read through L1.  Correct for any size; not tuned.
 template <bool GGA>

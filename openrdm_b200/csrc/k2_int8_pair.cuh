@@ -314,11 +314,7 @@ __device__ __forceinline__ void pair_compute_role(const Params& P, const PairCtx
       const size_t pn = p0 + (size_t)(gridDim.x / 2) * 2 * TILE + p;
       if (pn < P.npts) {
 #pragma unroll
-#ifdef K2P_PF_L1
-        for (int t = PART; t < NA; t += EW) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.phi_act + (size_t)t * P.ld + pn));
-#else
         for (int t = PART; t < NA; t += EW) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.phi_act + (size_t)t * P.ld + pn));
-#endif
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

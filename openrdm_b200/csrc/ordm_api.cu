@@ -20,11 +20,13 @@
 
 #include "../../include/openrdm_b200.h"
 #include "../../include/ordm_synth.h"
+#include "k0_ao2mo.cuh"
 #include "k1_density.cuh"
 #include "k2_ontop.cuh"
 #include "k2_int8.cuh"
 #include "k2_int8_pair.cuh"
 #include "k3_xc.cuh"
+#include "rawio.h"
 #include "rdm_pack.h"
 #include "reduce.cuh"
 #include "synth_rdm.h"
@@ -87,33 +89,6 @@ bool load_nccl(std::string& why) {
   return true;
 }
 
-// ---- cuBLAS through dlopen (plain library DGEMM for the AO -> MO transform only) ----
-struct CublasApi {
-  void* handle = nullptr;
-  int (*Create)(void**) = nullptr;
-  int (*Destroy)(void*) = nullptr;
-  int (*SetStream)(void*, cudaStream_t) = nullptr;
-  int (*Dgemm)(void*, int, int, int, int, int, const double*, const double*, int, const double*, int, const double*, double*, int) = nullptr;
-};
-CublasApi g_cublas;
-
-bool load_cublas(std::string& why) {
-  if (g_cublas.handle) return true;
-  const char* names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so"};
-  for (const char* nm : names) {
-    g_cublas.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-    if (g_cublas.handle) break;
-  }
-  if (!g_cublas.handle) { why = std::string("dlopen libcublas.so.12 failed: ") + dlerror(); return false; }
-  g_cublas.Create = (int (*)(void**))dlsym(g_cublas.handle, "cublasCreate_v2");
-  g_cublas.Destroy = (int (*)(void*))dlsym(g_cublas.handle, "cublasDestroy_v2");
-  g_cublas.SetStream = (int (*)(void*, cudaStream_t))dlsym(g_cublas.handle, "cublasSetStream_v2");
-  g_cublas.Dgemm = (int (*)(void*, int, int, int, int, int, const double*, const double*, int, const double*, int, const double*, double*, int))
-      dlsym(g_cublas.handle, "cublasDgemm_v2");
-  if (!g_cublas.Create || !g_cublas.Destroy || !g_cublas.SetStream || !g_cublas.Dgemm) { why = "libcublas is missing a required symbol"; return false; }
-  return true;
-}
-
 }  // namespace
 
 struct ordm_ctx {
@@ -145,6 +120,7 @@ struct ordm_ctx {
   bool have_rdm1 = false, have_rdm2 = false, core_form = false;
   uint64_t rdm1_version = 0;  // bumped by every install_rdm1 (K1's constant-bank upload is cached on it)
   std::vector<double> h_Dsa, h_Dsb;  // symmetrised, row-major stride k1::MAX_ACT (or nact when generic)
+  std::vector<double> h_A1a, h_A1b;  // the active 1-RDM blocks as given (nact x nact column-major): polyradical analysis
   double *d_Dsa_g = nullptr, *d_Dsb_g = nullptr;
   // K2 operands
   int k2_npg = 0, k2_mt = 0;
@@ -202,9 +178,6 @@ struct ordm_ctx {
   bool inj_R = false;      // translate / fully_translate read the caller's R instead of build_R's
   bool inj_grad = false;   // a spin-density gradient component changed: total gradient re-summed before the next translate
   double last_n[3] = {0, 0, 0}, last_trn[3] = {0, 0, 0};
-
-  // cuBLAS handle (AO -> MO transform), created on first use
-  void* cublas = nullptr;
 
   // NCCL
   void* comm = nullptr;
@@ -737,6 +710,8 @@ int install_rdm1(ordm_ctx* c, int ncore, int nact, const double* A1a, const doub
   const int stride = (nact <= k1::MAX_ACT) ? k1::MAX_ACT : nact;
   ordm::symmetrise_opdm(nact, A1a, stride, c->h_Dsa);
   ordm::symmetrise_opdm(nact, A1b, stride, c->h_Dsb);
+  c->h_A1a.assign(A1a, A1a + (size_t)nact * nact);
+  c->h_A1b.assign(A1b, A1b + (size_t)nact * nact);
   dfree(c->d_Dsa_g);
   dfree(c->d_Dsb_g);
   if (nact > k1::MAX_ACT) {
@@ -900,6 +875,25 @@ __global__ void k_sum2(double* __restrict__ dst, const double* __restrict__ a, c
   if (p < n) dst[p] = a[p] + b[p];
 }
 
+// row-major [m][ncols_src] (numpy / data.h5 layout of /PHI/PHI_MO) -> the first ncols columns, column-major with
+// leading dimension ld: a 32 x 32 shared-memory transpose, coalesced on both sides
+__global__ void k_rows_to_columns(double* __restrict__ dst, size_t ld, const double* __restrict__ src, size_t m, int ncols_src, int ncols) {
+  __shared__ double tile[32][33];
+  const size_t r0 = (size_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {   // read: consecutive threads along a source row
+    const size_t r = r0 + i;
+    const int cc = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < m && cc < ncols) ? src[r * (size_t)ncols_src + cc] : 0.0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {   // write: consecutive threads along a destination column
+    const int cc = c0 + i;
+    const size_t r = r0 + threadIdx.x;
+    if (r < m && cc < ncols) dst[(size_t)cc * ld + r] = tile[threadIdx.x][i];
+  }
+}
+
 // synthetic fill kernels ----------------------------------------------------------------
 __global__ void k_synth_phi(double* __restrict__ dst, size_t ld, size_t npts_local, size_t p0, size_t npts_total,
                             int n, uint64_t comp_key, uint64_t env_key) {
@@ -945,6 +939,79 @@ int alloc_w(ordm_ctx* c, size_t npts) {
   c->g.w = c->d_w;
   c->g.vec[ORDM_VEC_W] = c->d_w;
   c->rho_done = c->pi_done = c->xc_done = c->pig_done = false;
+  return ORDM_OK;
+}
+
+// K0 launcher: C[m x N] = A[m x K] B[K x N] on the context's stream (k0_ao2mo.cuh)
+template <int NT>
+int launch_k0(ordm_ctx* c, const k0::Params& p) {
+  static thread_local int dev = -1;
+  if (dev != c->device) {
+    CU(c, cudaFuncSetAttribute(k0::k0_ao2mo<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k0::Smem<NT>::bytes));
+    dev = c->device;
+  }
+  dim3 grid((unsigned)((p.m + k0::BM - 1) / k0::BM), (unsigned)((p.N + 8 * NT - 1) / (8 * NT)));
+  k0::k0_ao2mo<NT><<<grid, k0::THREADS, k0::Smem<NT>::bytes, c->stream>>>(p);
+  CU(c, cudaGetLastError());
+  return ORDM_OK;
+}
+int run_k0(ordm_ctx* c, const k0::Params& p) {
+  if (p.m == 0) return ORDM_OK;
+  if (p.N <= 32) return launch_k0<4>(c, p);
+  if (p.N <= 64) return launch_k0<8>(c, p);
+  return launch_k0<13>(c, p);   // 104 columns per CTA: config 4's 103 occupied MOs in one pass over A
+}
+
+// The AO values are streamed through the device in point batches (H2D on the copy stream overlapped with the GEMM of
+// the previous batch).  row_major = 0: ao(p, mu) at ao[p + mu * ld] (the C ABI's convention); 1: at ao[p * ld + mu]
+// (numpy / data.h5: /PHI/PHI_AO is [npts][nao]); C is nao x nmo column-major in both cases.
+int ao_to_mo(ordm_ctx* c, size_t npts, int nao, size_t ld, const double* const src[4], bool gga, int nmo, const double* C, bool row_major) {
+  int rc = alloc_grid(c, npts, nmo, gga);
+  if (rc) return rc;
+  if (!npts) return ORDM_OK;
+  // point batches: two staging buffers of batch x nao doubles (<= 256 MB each)
+  size_t batch = std::max<size_t>(LD_ALIGN, ((size_t)1 << 25) / (size_t)nao / LD_ALIGN * LD_ALIGN);
+  batch = std::min(batch, round_up(npts, LD_ALIGN));
+  double *d_C = nullptr, *d_stage[2] = {nullptr, nullptr};
+  cudaEvent_t copied[2] = {nullptr, nullptr}, used[2] = {nullptr, nullptr};
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamSynchronize(c->stream);
+    dfree(d_C);
+    for (int b = 0; b < 2; ++b) { dfree(d_stage[b]); if (copied[b]) cudaEventDestroy(copied[b]); if (used[b]) cudaEventDestroy(used[b]); }
+  };
+#define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(c, ORDM_ERR_CUDA, "CUDA error '%s' in %s", cudaGetErrorString(e_), #call); } } while (0)
+  CUX(cudaMalloc(&d_C, (size_t)nao * nmo * sizeof(double)));
+  CUX(cudaMemcpyAsync(d_C, C, (size_t)nao * nmo * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  for (int b = 0; b < 2; ++b) {
+    CUX(cudaMalloc(&d_stage[b], batch * (size_t)nao * sizeof(double)));
+    CUX(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    CUX(cudaEventCreateWithFlags(&used[b], cudaEventDisableTiming));
+  }
+  size_t it = 0;
+  for (int k = 0; k < (gga ? 4 : 1); ++k)
+    for (size_t p0 = 0; p0 < npts; p0 += batch, ++it) {
+      const int b = (int)(it & 1);
+      const size_t m = std::min(batch, npts - p0);
+      if (it >= 2) CUX(cudaStreamWaitEvent(c->copy_stream, used[b], 0));
+      if (row_major)   // m rows of nao values (row stride ld) -> packed [m][nao]
+        CUX(cudaMemcpy2DAsync(d_stage[b], (size_t)nao * sizeof(double), src[k] + p0 * ld, ld * sizeof(double), (size_t)nao * sizeof(double), m,
+                              cudaMemcpyHostToDevice, c->copy_stream));
+      else
+        CUX(cudaMemcpy2DAsync(d_stage[b], batch * sizeof(double), src[k] + p0, ld * sizeof(double), m * sizeof(double), (size_t)nao,
+                              cudaMemcpyHostToDevice, c->copy_stream));
+      CUX(cudaEventRecord(copied[b], c->copy_stream));
+      CUX(cudaStreamWaitEvent(c->stream, copied[b], 0));
+      // phi[p0:p0+m, 0:nmo] = stage[0:m, 0:nao] . C
+      k0::Params gp{};
+      gp.A = d_stage[b]; gp.lda = row_major ? (size_t)nao : batch; gp.a_row_major = row_major ? 1 : 0;
+      gp.B = d_C; gp.C = c->d_phi[k] + p0; gp.ldc = c->g.ld; gp.m = m; gp.K = nao; gp.N = nmo;
+      if ((rc = run_k0(c, gp))) { cleanup(); return rc; }
+      CUX(cudaEventRecord(used[b], c->stream));
+    }
+  CUX(cudaStreamSynchronize(c->stream));
+#undef CUX
+  cleanup();
   return ORDM_OK;
 }
 
@@ -1012,7 +1079,6 @@ void ordm_destroy(ordm_ctx* c) {
   cudaDeviceSynchronize();
   release_peer_xchg(c);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  if (c->cublas && g_cublas.Destroy) g_cublas.Destroy(c->cublas);
   for (int i = 0; i < ORDM_VEC_COUNT; ++i)
     if (i != ORDM_VEC_W) dfree(c->g.vec[i]);
   dfree(c->g.gx); dfree(c->g.gy); dfree(c->g.gz); dfree(c->g.pi_core);
@@ -1123,55 +1189,8 @@ int ordm_set_orbitals_ao(ordm_ctx* c, size_t npts, int nao, size_t ld, const dou
   if (gga && !(ax && ay && az)) return fail(c, ORDM_ERR_INVALID, "give all of ao_x, ao_y, ao_z or none");
   if (c->g.w && c->g.npts != npts) return fail(c, ORDM_ERR_INVALID, "orbitals have %zu points but the grid has %zu", npts, c->g.npts);
   CU(c, cudaSetDevice(c->device));
-  std::string why;
-  if (!load_cublas(why)) return fail(c, ORDM_ERR_CUDA, "%s", why.c_str());
-  if (!c->cublas && g_cublas.Create(&c->cublas) != 0) { c->cublas = nullptr; return fail(c, ORDM_ERR_CUDA, "cublasCreate failed"); }
-  if (g_cublas.SetStream(c->cublas, c->stream) != 0) return fail(c, ORDM_ERR_CUDA, "cublasSetStream failed");
-  int rc = alloc_grid(c, npts, nmo, gga);
-  if (rc) return rc;
-  if (!npts) return ORDM_OK;
-  // point batches: two staging buffers of [nao][batch] doubles (<= 256 MB each)
-  size_t batch = std::max<size_t>(LD_ALIGN, ((size_t)1 << 25) / (size_t)nao / LD_ALIGN * LD_ALIGN);
-  batch = std::min(batch, round_up(npts, LD_ALIGN));
-  double *d_C = nullptr, *d_stage[2] = {nullptr, nullptr};
-  cudaEvent_t copied[2] = {nullptr, nullptr}, used[2] = {nullptr, nullptr};
-  auto cleanup = [&]() {
-    cudaStreamSynchronize(c->copy_stream);
-    cudaStreamSynchronize(c->stream);
-    dfree(d_C);
-    for (int b = 0; b < 2; ++b) { dfree(d_stage[b]); if (copied[b]) cudaEventDestroy(copied[b]); if (used[b]) cudaEventDestroy(used[b]); }
-  };
-#define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(c, ORDM_ERR_CUDA, "CUDA error '%s' in %s", cudaGetErrorString(e_), #call); } } while (0)
-  CUX(cudaMalloc(&d_C, (size_t)nao * nmo * sizeof(double)));
-  CUX(cudaMemcpyAsync(d_C, C, (size_t)nao * nmo * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  for (int b = 0; b < 2; ++b) {
-    CUX(cudaMalloc(&d_stage[b], batch * (size_t)nao * sizeof(double)));
-    CUX(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
-    CUX(cudaEventCreateWithFlags(&used[b], cudaEventDisableTiming));
-  }
-  const double one = 1.0, zero = 0.0;
   const double* src[4] = {ao, ax, ay, az};
-  size_t it = 0;
-  for (int k = 0; k < (gga ? 4 : 1); ++k)
-    for (size_t p0 = 0; p0 < npts; p0 += batch, ++it) {
-      const int b = (int)(it & 1);
-      const size_t m = std::min(batch, npts - p0);
-      if (it >= 2) CUX(cudaStreamWaitEvent(c->copy_stream, used[b], 0));
-      CUX(cudaMemcpy2DAsync(d_stage[b], batch * sizeof(double), src[k] + p0, ld * sizeof(double), m * sizeof(double), (size_t)nao,
-                            cudaMemcpyHostToDevice, c->copy_stream));
-      CUX(cudaEventRecord(copied[b], c->copy_stream));
-      CUX(cudaStreamWaitEvent(c->stream, copied[b], 0));
-      // phi[p0:p0+m, 0:nmo] = stage[0:m, 0:nao] . C   (all column-major)
-      if (g_cublas.Dgemm(c->cublas, 0, 0, (int)m, nmo, nao, &one, d_stage[b], (int)batch, d_C, nao, &zero, c->d_phi[k] + p0, (int)c->g.ld) != 0) {
-        cleanup();
-        return fail(c, ORDM_ERR_CUDA, "cublasDgemm failed in the AO -> MO transform");
-      }
-      CUX(cudaEventRecord(used[b], c->stream));
-    }
-  CUX(cudaStreamSynchronize(c->stream));
-#undef CUX
-  cleanup();
-  return ORDM_OK;
+  return ao_to_mo(c, npts, nao, ld, src, gga, nmo, C, /*row_major=*/false);
 }
 
 int ordm_set_rdm1(ordm_ctx* c, int n, const double* D1a, const double* D1b) {
@@ -1396,6 +1415,72 @@ int ordm_functional(ordm_ctx* c, int term, size_t npts, const double* ra, const 
   return rc;
 }
 
+// MCPDFTSolver::polyradical_analysis (src/libpsi4/mcpdft_solver.cc:3001-3240) on the resident grid and 1-RDMs
+int ordm_polyradical(ordm_ctx* c, double traces[3], double* U_r, double* D_r, double* N_r, size_t npts) {
+  CHECK_CTX(c);
+  if (!traces) return fail(c, ORDM_ERR_INVALID, "null traces");
+  CU(c, cudaSetDevice(c->device));
+  int rc = check_inputs(c, false);
+  if (rc) return rc;
+  if ((U_r || D_r || N_r) && npts != c->g.npts) return fail(c, ORDM_ERR_INVALID, "vector length %zu != grid size %zu", npts, c->g.npts);
+  if (c->nact > k1::MAX_ACT) return fail(c, ORDM_ERR_UNSUPPORTED, "polyradical analysis: %d active orbitals (limit %d)", c->nact, k1::MAX_ACT);
+  const int na = c->nact;
+  std::vector<double> udn((size_t)3 * na * na);
+  for (int t = 0; t < na; ++t)
+    for (int u = 0; u < na; ++u) {   // element (t, u) of the column-major inputs, row-major here
+      const double pop = c->h_A1a[t + (size_t)u * na] + c->h_A1b[t + (size_t)u * na];   // mcpdft_solver.cc:3082-3084, 3102
+      udn[(size_t)t * na + u] = 1.0 - std::fabs(1.0 - pop);                              // :3104
+      udn[(size_t)na * na + (size_t)t * na + u] = pop * (2.0 - pop);                     // :3105
+      udn[(size_t)2 * na * na + (size_t)t * na + u] = pop * pop * (2.0 - pop) * (2.0 - pop);   // :3106
+    }
+  double* d_udn = nullptr;
+  double* d_out[3] = {nullptr, nullptr, nullptr};
+  double* h_out[3] = {U_r, D_r, N_r};
+  auto cleanup = [&]() { cudaStreamSynchronize(c->stream); dfree(d_udn); for (auto& q : d_out) dfree(q); };
+#define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(c, ORDM_ERR_CUDA, "CUDA error '%s' in %s", cudaGetErrorString(e_), #call); } } while (0)
+  CUP(cudaMalloc(&d_udn, udn.size() * sizeof(double)));
+  CUP(cudaMemcpyAsync(d_udn, udn.data(), udn.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  for (int k = 0; k < 3; ++k)
+    if (h_out[k]) CUP(cudaMalloc(&d_out[k], std::max<size_t>(c->g.ld, 1) * sizeof(double)));
+  k1::PolyParams p{};
+  p.phi_act = c->g.phi + (size_t)c->ncore * c->g.ld; p.w = c->g.w; p.udn = d_udn;
+  p.ld = c->g.ld; p.npts = c->g.npts; p.nact = na;
+  p.U = d_out[0]; p.D = d_out[1]; p.N = d_out[2];
+  const int grid = k1_grid(c, c->g.npts);
+  if ((rc = ensure_partials(c, (size_t)c->sm_count * 16 * 8))) { cleanup(); return rc; }
+  p.partial = c->d_partial;
+  switch ((int)round_up((size_t)std::max(na, 1), 4)) {
+#define PCASE(N) case N: k1::k1_polyradical<N><<<grid, k1::THREADS, 0, c->stream>>>(p); break;
+    PCASE(4) PCASE(8) PCASE(12) PCASE(16) PCASE(20) PCASE(24) PCASE(28) default: k1::k1_polyradical<32><<<grid, k1::THREADS, 0, c->stream>>>(p); break;
+#undef PCASE
+  }
+  CUP(cudaGetLastError());
+  ordm::k4_finalize<3><<<1, 256, 0, c->stream>>>(c->d_partial, grid, c->d_res, 8, 0);
+  CUP(cudaGetLastError());
+  CUP(cudaMemcpyAsync(c->h_res, c->d_res + 8, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  for (int k = 0; k < 3; ++k)
+    if (h_out[k] && npts) CUP(cudaMemcpyAsync(h_out[k], d_out[k], npts * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUP(cudaStreamSynchronize(c->stream));
+#undef CUP
+  for (int k = 0; k < 3; ++k) traces[k] = c->h_res[k];
+  cleanup();
+  return ORDM_OK;
+}
+
+// Energy assembly of MCPDFTSolver::compute_energy (src/libpsi4/mcpdft_solver.cc:849-925); host arithmetic only
+int ordm_hybrid_energy(int method, double lambda, const ordm_hybrid_inputs* in, double ex, double ec, ordm_hybrid_result* out) {
+  if (!in || !out || method < ORDM_METHOD_MCPDFT || method > ORDM_METHOD_RS1DH_MCPDFT) return fail(nullptr, ORDM_ERR_INVALID, "bad hybrid-energy request");
+  const double lmbd = method == ORDM_METHOD_MCPDFT ? 0.0 : lambda;                     // :717-737: lambda is read for every method but MCPDFT
+  out->lambda = lmbd;
+  out->one_electron = in->e_nuclear_attraction + in->e_kinetic;                      // :830
+  out->two_electron = in->e_reference - in->e_nuclear_repulsion - out->one_electron; // :852
+  out->wf_contribution = out->one_electron + lmbd * out->two_electron;               // :918
+  out->dft_contribution = (1.0 - lmbd) * (in->e_coulomb + ex) + (1.0 - lmbd * lmbd) * ec;   // :919
+  out->e_total = out->wf_contribution + out->dft_contribution + in->e_nuclear_repulsion;    // :920
+  if (method == ORDM_METHOD_1DH_MCPDFT) out->e_total += (lmbd * in->e_hf_exchange) + (lmbd * lmbd * in->e_mp2_correlation);   // :921-922
+  return ORDM_OK;
+}
+
 // ---- the path in one call -----------------------------------------------------------------
 static int energy_resident(ordm_ctx* c, int functional, double eclass, ordm_result* out);
 int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
@@ -1595,6 +1680,134 @@ int ordm_set_vector(ordm_ctx* c, int which, const double* host_in, size_t npts) 
   else if (which == ORDM_VEC_R) c->inj_R = true;
   else if (which >= ORDM_VEC_RHOA_X && which <= ORDM_VEC_RHOB_Z) c->inj_grad = true;
   else if (which >= ORDM_VEC_PI_X && which <= ORDM_VEC_PI_Z) c->pig_done = true;
+  return ORDM_OK;
+}
+
+// ---- input files: the PySCF exporter's data.h5 schema (raw container, or HDF5 when built with it; rawio.h) ----------
+struct ordm_file { ordm::RawFile f; };
+
+int ordm_file_open(const char* path, ordm_file** out) {
+  if (!path || !out) return fail(nullptr, ORDM_ERR_INVALID, "null path / output");
+  *out = nullptr;
+  ordm_file* h = new ordm_file();
+  if (!h->f.open(path)) { const int rc = fail(nullptr, ORDM_ERR_INVALID, "%s", h->f.error.c_str()); delete h; return rc; }
+  *out = h;
+  return ORDM_OK;
+}
+void ordm_file_close(ordm_file* f) { delete f; }
+int ordm_file_dataset(ordm_file* f, const char* name, int* dtype, int* ndim, uint64_t dims[4], const void** data) {
+  if (!f || !name) return fail(nullptr, ORDM_ERR_INVALID, "null file / name");
+  const ordm::RawDataset* d = f->f.find(name);
+  if (!d) return fail(nullptr, ORDM_ERR_INVALID, "dataset %s not in the file", name);
+  if (dtype) *dtype = d->dtype;
+  if (ndim) *ndim = d->ndim;
+  if (dims) for (int i = 0; i < 4; ++i) dims[i] = i < d->ndim ? d->dims[i] : 1;
+  if (data) *data = d->data;
+  return ORDM_OK;
+}
+
+int ordm_load_data(ordm_ctx* c, const char* path, unsigned flags, ordm_data_info* info) {
+  CHECK_CTX(c);
+  if (!path) return fail(c, ORDM_ERR_INVALID, "null path");
+  CU(c, cudaSetDevice(c->device));
+  ordm::RawFile f;
+  if (!f.open(path)) return fail(c, ORDM_ERR_INVALID, "%s", f.error.c_str());
+  ordm_data_info di;
+  std::memset(&di, 0, sizeof(di));
+  double v = 0.0;
+  if (!f.scalar("/N/N_COR", v)) return fail(c, ORDM_ERR_INVALID, "%s: /N/N_COR missing", path);
+  di.ncore = (int)v;
+  if (!f.scalar("/N/N_CAS_ORB", v)) return fail(c, ORDM_ERR_INVALID, "%s: /N/N_CAS_ORB missing", path);
+  di.nact = (int)v;
+  if (f.scalar("/N/N_AO", v)) di.nao = (int)v;
+  if (f.scalar("/N/N_MO", v)) di.nmo = (int)v;
+  if (f.scalar("/E/E_CORE", v)) di.e_core = v;
+  if (f.scalar("/E/E_HARTREE", v)) di.e_hartree = v;
+  const int nocc = di.ncore + di.nact;
+  if (di.ncore < 0 || di.nact <= 0) return fail(c, ORDM_ERR_INVALID, "%s: bad orbital space (%d core, %d active)", path, di.ncore, di.nact);
+  // ---- grid: /GRIDS/W (libpyscf.py:654)
+  const ordm::RawDataset* w = f.find("/GRIDS/W");
+  if (!w || w->dtype != ordm::RAW_F64 || w->ndim != 1) return fail(c, ORDM_ERR_INVALID, "%s: /GRIDS/W missing or not a float64 vector", path);
+  const size_t npts = (size_t)w->dims[0];
+  di.npts = npts;
+  int rc = ordm_set_grid(c, npts, (const double*)w->data);
+  if (rc) return rc;
+  // ---- orbitals: /PHI/PHI_MO[npts][nmo] (+ _X, _Y, _Z), or /PHI/PHI_AO[npts][nao] with /C[nao][nmo] (libpyscf.py:608,659-667)
+  const char* suffix[4] = {"", "_X", "_Y", "_Z"};
+  const ordm::RawDataset* mo[4]; const ordm::RawDataset* ao[4];
+  for (int k = 0; k < 4; ++k) { mo[k] = f.find(std::string("/PHI/PHI_MO") + suffix[k]); ao[k] = f.find(std::string("/PHI/PHI_AO") + suffix[k]); }
+  const ordm::RawDataset* Cm = f.find("/C");
+  auto shaped = [&](const ordm::RawDataset* d) { return d && d->dtype == ordm::RAW_F64 && d->ndim == 2 && d->dims[0] == npts; };
+  const bool have_mo = shaped(mo[0]) && (int)mo[0]->dims[1] >= nocc;
+  const bool have_ao = shaped(ao[0]) && Cm && Cm->dtype == ordm::RAW_F64 && Cm->ndim == 2 && Cm->dims[0] == ao[0]->dims[1] && (int)Cm->dims[1] >= nocc;
+  const bool use_ao = have_ao && ((flags & ORDM_LOAD_PREFER_AO) || !have_mo);
+  if (!use_ao && !have_mo) return fail(c, ORDM_ERR_INVALID, "%s: neither /PHI/PHI_MO nor /PHI/PHI_AO + /C with %zu points and >= %d orbitals", path, npts, nocc);
+  const ordm::RawDataset* const* phi = use_ao ? ao : mo;
+  const bool gga = !(flags & ORDM_LOAD_NO_GRADIENTS) && shaped(phi[1]) && shaped(phi[2]) && shaped(phi[3]) &&
+                   phi[1]->dims[1] == phi[0]->dims[1] && phi[2]->dims[1] == phi[0]->dims[1] && phi[3]->dims[1] == phi[0]->dims[1];
+  di.gga = gga; di.used_ao = use_ao;
+  if (use_ao) {
+    const int nao = (int)ao[0]->dims[1], nmo_all = (int)Cm->dims[1];
+    di.nao = nao; di.nmo = nmo_all;
+    std::vector<double> Ccm((size_t)nao * nocc);   // /C is row-major [nao][nmo]: the occupied columns, column-major
+    for (int i = 0; i < nocc; ++i)
+      for (int mu = 0; mu < nao; ++mu) Ccm[(size_t)i * nao + mu] = ((const double*)Cm->data)[(size_t)mu * nmo_all + i];
+    const double* src[4] = {(const double*)ao[0]->data, gga ? (const double*)ao[1]->data : nullptr, gga ? (const double*)ao[2]->data : nullptr,
+                            gga ? (const double*)ao[3]->data : nullptr};
+    if ((rc = ao_to_mo(c, npts, nao, (size_t)nao, src, gga, nocc, Ccm.data(), /*row_major=*/true))) return rc;
+  } else {
+    const int nmo_all = (int)mo[0]->dims[1];
+    di.nmo = nmo_all;
+    if ((rc = alloc_grid(c, npts, nocc, gga))) return rc;
+    const size_t batch = std::max<size_t>(1024, ((size_t)1 << 24) / (size_t)nmo_all);   // rows per staging buffer (<= 128 MB)
+    double* d_stage = nullptr;
+    CU(c, cudaMalloc(&d_stage, batch * (size_t)nmo_all * sizeof(double)));
+    for (int k = 0; k < (gga ? 4 : 1); ++k)
+      for (size_t p0 = 0; p0 < npts; p0 += batch) {
+        const size_t m = std::min(batch, npts - p0);
+        cudaError_t e = cudaMemcpyAsync(d_stage, (const double*)mo[k]->data + p0 * nmo_all, m * (size_t)nmo_all * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) {
+          dim3 grid((unsigned)((m + 31) / 32), (unsigned)((nocc + 31) / 32)), block(32, 8);
+          k_rows_to_columns<<<grid, block, 0, c->stream>>>(c->d_phi[k] + p0, c->g.ld, d_stage, m, nmo_all, nocc);
+          e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // the staging buffer is reused (and the source may be pageable)
+        if (e != cudaSuccess) { dfree(d_stage); return fail(c, ORDM_ERR_CUDA, "loading /PHI/PHI_MO%s: %s", suffix[k], cudaGetErrorString(e)); }
+      }
+    dfree(d_stage);
+  }
+  // ---- RDMs of the active space: the upper-packed COO groups (libpyscf.py:246-463) or the dense blocks (:636-648)
+  std::vector<int> i1a, j1a, i1b, j1b, q1, q2, q3, q4;
+  const ordm::RawDataset *v1a = f.find("/SP_SYMM_D1/ACT_D1a_MO/VAL"), *v1b = f.find("/SP_SYMM_D1/ACT_D1b_MO/VAL"), *v2 = f.find("/SP_SYMM_D2/ACT_D2ab_MO/VAL");
+  const bool sparse_ok = !(flags & ORDM_LOAD_DENSE_RDM) && v1a && v1b && v2 && v1a->dtype == ordm::RAW_F64 && v1b->dtype == ordm::RAW_F64 && v2->dtype == ordm::RAW_F64 &&
+                         f.ints("/SP_SYMM_D1/ACT_D1a_MO/ROW_IDX", i1a) && f.ints("/SP_SYMM_D1/ACT_D1a_MO/COL_IDX", j1a) &&
+                         f.ints("/SP_SYMM_D1/ACT_D1b_MO/ROW_IDX", i1b) && f.ints("/SP_SYMM_D1/ACT_D1b_MO/COL_IDX", j1b) &&
+                         f.ints("/SP_SYMM_D2/ACT_D2ab_MO/DIM1_IDX", q1) && f.ints("/SP_SYMM_D2/ACT_D2ab_MO/DIM2_IDX", q2) &&
+                         f.ints("/SP_SYMM_D2/ACT_D2ab_MO/DIM3_IDX", q3) && f.ints("/SP_SYMM_D2/ACT_D2ab_MO/DIM4_IDX", q4) &&
+                         i1a.size() == v1a->count() && j1a.size() == i1a.size() && i1b.size() == v1b->count() && j1b.size() == i1b.size() &&
+                         q1.size() == v2->count() && q2.size() == q1.size() && q3.size() == q1.size() && q4.size() == q1.size();
+  di.used_sparse_rdm = sparse_ok;
+  if (sparse_ok) {
+    rc = ordm_set_active_space_sparse(c, di.ncore, di.nact, i1a.size(), i1a.data(), j1a.data(), (const double*)v1a->data,
+                                      i1b.size(), i1b.data(), j1b.data(), (const double*)v1b->data,
+                                      q1.size(), q1.data(), q2.data(), q3.data(), q4.data(), (const double*)v2->data, /*upper_packed=*/1);
+  } else {
+    const ordm::RawDataset *d1a = f.find("/D/D1/ACT_D1A_MO"), *d1b = f.find("/D/D1/ACT_D1B_MO"), *d2 = f.find("/D/D2/ACT_D2AB_MO");
+    const size_t na = (size_t)di.nact;
+    if (!d1a || !d1b || !d2 || d1a->count() != na * na || d1b->count() != na * na || d2->count() != na * na * na * na ||
+        d1a->dtype != ordm::RAW_F64 || d1b->dtype != ordm::RAW_F64 || d2->dtype != ordm::RAW_F64)
+      return fail(c, ORDM_ERR_INVALID, "%s: no usable active-space RDMs (/SP_SYMM_D1,2/ACT_* or /D/D1/ACT_D1A_MO, ACT_D1B_MO, /D/D2/ACT_D2AB_MO)", path);
+    // dm2ab[i][j][k][l] multiplies phi_i phi_j (alpha) phi_k phi_l (beta): every element once, as a Psi4-style list
+    std::vector<int> ii(d2->count()), jj(d2->count()), kk(d2->count()), ll(d2->count());
+    size_t e = 0;
+    for (int i = 0; i < di.nact; ++i) for (int j = 0; j < di.nact; ++j) for (int k = 0; k < di.nact; ++k) for (int l = 0; l < di.nact; ++l, ++e) { ii[e] = i; jj[e] = j; kk[e] = k; ll[e] = l; }
+    std::vector<int> ri(na * na), ci(na * na);
+    for (size_t i = 0, q = 0; i < na; ++i) for (size_t j = 0; j < na; ++j, ++q) { ri[q] = (int)i; ci[q] = (int)j; }
+    rc = ordm_set_active_space_sparse(c, di.ncore, di.nact, na * na, ri.data(), ci.data(), (const double*)d1a->data, na * na, ri.data(), ci.data(),
+                                      (const double*)d1b->data, d2->count(), ii.data(), jj.data(), kk.data(), ll.data(), (const double*)d2->data, /*upper_packed=*/0);
+  }
+  if (rc) return rc;
+  if (info) *info = di;
   return ORDM_OK;
 }
 

@@ -846,3 +846,68 @@ void orc_kron_tpdm(int n, const double* D1a, const double* D1b, double* D2ab) {
         for (int k = 0; k < n; ++k)
           D2ab[((size_t)i * n + k) + ((size_t)j * n + l) * n2] = D1a[i + j * n] * D1b[k + l * n];
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Rank-4 rows of SURVEY.md section 8f (the Psi4 plugin, src/libpsi4/mcpdft_solver.cc).  The plugin
+ * cannot be compiled here (Psi4 is not installed), so these two are restatements only: PARITY
+ * UNPINNED for them (no golden vector, no compiled reference); the tests compare the GPU path
+ * with this restatement and with closed-form properties.
+ * ------------------------------------------------------------------------------------------ */
+
+/* MCPDFTSolver::polyradical_analysis, mcpdft_solver.cc:3001-3240: with n_ij = (D1a + D1b)_ij
+ * (:3082-3084), U_ij = 1 - |1 - n_ij|, D_ij = n_ij (2 - n_ij), N_ij = n_ij^2 (2 - n_ij)^2
+ * element by element (:3104-3108); U(r) = sum_ij phi_i phi_j U_ij etc. (:3146-3157) and the
+ * traces sum_p w_p U(r_p) ... (:3185-3187).  The plugin walks the list of stored 1-RDM elements;
+ * an absent (zero) element gives U = D = N = 0, so the dense double loop here is the same sum.
+ * phi: npts x n column-major, D1a/D1b n x n column-major.  Ur/Dr/Nr may be NULL.
+ * traces[0..2] = Tr U, Tr D, Tr N. */
+void orc_polyradical(size_t npts, int n, const double* w, const double* phi, const double* D1a, const double* D1b,
+                     double* Ur, double* Dr, double* Nr, double traces[3]) {
+  double* Um = (double*)malloc(sizeof(double) * 3 * (size_t)n * n);
+  double *Dm = Um + (size_t)n * n, *Nm = Dm + (size_t)n * n;
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) {
+      const double pop = D1a[i + (size_t)j * n] + D1b[i + (size_t)j * n];
+      Um[i + (size_t)j * n] = 1.0 - fabs(1.0 - pop);
+      Dm[i + (size_t)j * n] = pop * (2.0 - pop);
+      Nm[i + (size_t)j * n] = pop * pop * (2.0 - pop) * (2.0 - pop);
+    }
+  double tu = 0.0, td = 0.0, tn = 0.0;
+  for (size_t p = 0; p < npts; ++p) {
+    double du = 0.0, dd = 0.0, dn = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        const double pp = phi[p + (size_t)i * npts] * phi[p + (size_t)j * npts];
+        du += pp * Um[i + (size_t)j * n];
+        dd += pp * Dm[i + (size_t)j * n];
+        dn += pp * Nm[i + (size_t)j * n];
+      }
+    if (Ur) Ur[p] = du;
+    if (Dr) Dr[p] = dd;
+    if (Nr) Nr[p] = dn;
+    tu += w[p] * du; td += w[p] * dd; tn += w[p] * dn;
+  }
+  traces[0] = tu; traces[1] = td; traces[2] = tn;
+  free(Um);
+}
+
+/* Energy assembly of MCPDFTSolver::compute_energy, mcpdft_solver.cc:849-925:
+ *   one_electron = nuclear_attraction + kinetic                                   (:830)
+ *   two_electron = reference_energy - nuclear_repulsion - one_electron            (:852)
+ *   wf  = one_electron + lambda * two_electron                                    (:918)
+ *   dft = (1 - lambda) (coulomb + Ex) + (1 - lambda^2) Ec                         (:919)
+ *   E   = wf + dft + nuclear_repulsion                                            (:920)
+ *   1DH_MCPDFT only:  E += lambda * hf_exchange + lambda^2 * mp2_correlation      (:921-922)
+ * lambda is MCPDFT_LAMBDA for every method but "MCPDFT", where it stays 0 (:717-737).
+ * method: 0 MCPDFT, 1 1H_MCPDFT, 2 1DH_MCPDFT, 3 RS_MCPDFT, 4 RS1H_MCPDFT, 5 RS1DH_MCPDFT. */
+double orc_hybrid_energy(int method, double lambda, double e_ref, double e_nuc, double e_kin, double e_ne, double e_coulomb,
+                         double e_hf_x, double e_mp2, double ex, double ec) {
+  const double lmbd = method == 0 ? 0.0 : lambda;
+  const double one_electron = e_ne + e_kin;
+  const double two_electron = e_ref - e_nuc - one_electron;
+  const double wf = one_electron + lmbd * two_electron;
+  const double dft = (1.0 - lmbd) * (e_coulomb + ex) + (1.0 - lmbd * lmbd) * ec;
+  double total = wf + dft + e_nuc;
+  if (method == 2) total += (lmbd * e_hf_x) + (lmbd * lmbd * e_mp2);
+  return total;
+}

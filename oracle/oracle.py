@@ -173,6 +173,20 @@ class Port:
         self.omega = float(omega)
         self.lib.orc_set_omega(C.c_double(omega))
 
+    def polyradical(self, w, phi, D1a, D1b):
+        """MCPDFTSolver::polyradical_analysis restated (mcpdft_solver.cc:3001-3240): (traces[3], U(r), D(r), N(r))."""
+        phi = _f64(phi); npts, n = phi.shape
+        w, D1a, D1b = _f64(w), _f64(D1a), _f64(D1b)
+        U, D, N = (np.zeros(npts) for _ in range(3))
+        tr = (C.c_double * 3)()
+        self.lib.orc_polyradical(C.c_size_t(npts), n, _ptr(w), _ptr(phi), _ptr(D1a), _ptr(D1b), _ptr(U), _ptr(D), _ptr(N), tr)
+        return list(tr), U, D, N
+
+    def hybrid_energy(self, method, lam, e_ref, e_nuc, e_kin, e_ne, e_coulomb, e_hf_x, e_mp2, ex, ec) -> float:
+        """Energy assembly of MCPDFTSolver::compute_energy restated (mcpdft_solver.cc:849-925)."""
+        self.lib.orc_hybrid_energy.restype = C.c_double
+        return self.lib.orc_hybrid_energy(int(method), *(C.c_double(x) for x in (lam, e_ref, e_nuc, e_kin, e_ne, e_coulomb, e_hf_x, e_mp2, ex, ec)))
+
     def kron_tpdm(self, D1a, D1b):
         D1a, D1b = _f64(D1a), _f64(D1b)
         n = D1a.shape[0]

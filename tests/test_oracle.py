@@ -224,3 +224,31 @@ def test_psi4_plugin_functionals_energy_path(port, ref_psi4, fn):
     if fn == "BOP" and not np.isfinite(ec):
         pytest.skip("translated beta density hit zero")
     assert abs(r.scalars["ex"] - ex) <= 1e-13 * max(1, abs(ex)) and abs(r.scalars["ec"] - ec) <= 1e-13 * max(1, abs(ec))
+
+
+def test_hybrid_energy_assembly(ordm, port):
+    """ordm_hybrid_energy (host arithmetic, no GPU) against the restatement of MCPDFTSolver::compute_energy's assembly
+    (mcpdft_solver.cc:849-925) and against the formula written out: every method, lambda ignored for plain MCPDFT,
+    the double-hybrid terms only for 1DH_MCPDFT."""
+    rng = np.random.default_rng(9)
+    for method, mid in ordm.METHODS.items():
+        for lam in (0.0, 0.25, 0.7):
+            s = dict(e_reference=-108.9 + rng.random(), e_nuclear_repulsion=23.5 + rng.random(), e_kinetic=107.0 + rng.random(),
+                     e_nuclear_attraction=-302.0 + rng.random(), e_coulomb=61.0 + rng.random(), e_hf_exchange=-13.0 + rng.random(),
+                     e_mp2_correlation=-0.3 * rng.random())
+            ex, ec = -12.0 - rng.random(), -0.5 - rng.random()
+            got = ordm.hybrid_energy(method, lam, ex, ec, **s)
+            want = port.hybrid_energy(mid, lam, s["e_reference"], s["e_nuclear_repulsion"], s["e_kinetic"], s["e_nuclear_attraction"],
+                                      s["e_coulomb"], s["e_hf_exchange"], s["e_mp2_correlation"], ex, ec)
+            assert got["e_total"] == want
+            L = 0.0 if method == "MCPDFT" else lam
+            h = s["e_kinetic"] + s["e_nuclear_attraction"]
+            vee = s["e_reference"] - s["e_nuclear_repulsion"] - h
+            e = h + L * vee + (1 - L) * (s["e_coulomb"] + ex) + (1 - L * L) * ec + s["e_nuclear_repulsion"]
+            if method == "1DH_MCPDFT":
+                e += L * s["e_hf_exchange"] + L * L * s["e_mp2_correlation"]
+            assert abs(got["e_total"] - e) < 1e-12 and got["lambda_"] == L and abs(got["two_electron"] - vee) < 1e-12
+    # lambda = 0: E = h + J + Ex + Ec + Vnn, the plain MC-PDFT energy (eclass + Ex + Ec of energy.cc:181-183)
+    r = ordm.hybrid_energy("1H_MCPDFT", 0.0, -1.0, -0.1, e_reference=-5.0, e_nuclear_repulsion=1.0, e_kinetic=2.0, e_nuclear_attraction=-6.0,
+                           e_coulomb=1.5, e_hf_exchange=0.0, e_mp2_correlation=0.0)
+    assert abs(r["e_total"] - (2.0 - 6.0 + 1.5 - 1.0 - 0.1 + 1.0)) < 1e-14

@@ -650,3 +650,51 @@ def test_stale_vectors_are_errors_not_old_data(engine, ordm):
     engine.get_vector("rho")
     with pytest.raises(ordm.OrdmError):
         engine.get_vector("pi")
+
+
+# ---- rank-4 rows of SURVEY.md section 8f: the plugin's polyradical analysis and energy assembly ------------------------
+@pytest.mark.parametrize("ncore,nact,npts", [(0, 4, 513), (3, 8, 1000), (2, 20, 300), (1, 31, 130)])
+def test_polyradical_analysis_vs_restatement(engine, port, ordm, ncore, nact, npts):
+    """MCPDFTSolver::polyradical_analysis (mcpdft_solver.cc:3001-3240): U(r), D(r), N(r) and their traces against the C
+    restatement (the plugin itself needs Psi4 and cannot be compiled here: parity for this row is to the restatement),
+    plus two closed-form properties: doubly occupied core orbitals contribute nothing, and a closed-shell single
+    determinant has no effectively unpaired electrons at all."""
+    n = ncore + nact
+    w, phi, _ = ordm.synth_fill_host(70 + nact, npts, 0, npts, n, False)
+    A1a, A1b, _ = ordm.synth_rdms(70 + nact, nact, (nact + 1) // 2, nact // 2, 5, want_d2=False)
+    engine.set_grid(w); engine.set_orbitals(phi, None)
+    engine.set_active_space(ncore, A1a, A1b, None)
+    tr, U, D, N = engine.polyradical()
+    D1a = np.zeros((n, n)); D1b = np.zeros((n, n))
+    D1a[:ncore, :ncore] = D1b[:ncore, :ncore] = np.eye(ncore)
+    D1a[ncore:, ncore:] = A1a; D1b[ncore:, ncore:] = A1b
+    wtr, wU, wD, wN = port.polyradical(w, phi, D1a, D1b)     # dense, core orbitals included: their U = D = N = 0
+    for a, b in ((U, wU), (D, wD), (N, wN)):
+        assert (np.abs(a - b) <= 1e-12 * np.maximum(1.0, np.abs(b))).all()
+    assert np.allclose(tr, wtr, rtol=0, atol=1e-10)
+    # closed shell: n = 0 or 2 on the diagonal of the natural-orbital basis -> U = D = N = 0 everywhere
+    occ = np.diag([1.0] * (nact // 2) + [0.0] * (nact - nact // 2))
+    engine.set_active_space(ncore, occ, occ, None)
+    tr0, U0, D0, N0 = engine.polyradical()
+    assert max(np.abs(U0).max(), np.abs(D0).max(), np.abs(N0).max()) == 0.0 and tr0 == [0.0, 0.0, 0.0]
+
+
+@pytest.mark.parametrize("npts,nao,nmo,gga", [(2500, 200, 103, True), (130, 33, 64, False), (1029, 861, 20, False)])
+def test_ao_to_mo_kernel_shapes(engine, npts, nao, nmo, gga):
+    """K0 (csrc/k0_ao2mo.cuh), the library's own DMMA GEMM behind ordm_set_orbitals_ao: all three column-tile widths
+    (32 / 64 / 104), ragged row and K tails, odd K; 1e-13 of the row scale against numpy."""
+    rng = np.random.default_rng(nao)
+    ao = np.asfortranarray(rng.uniform(-1, 1, (npts, nao)))
+    C = np.asfortranarray(rng.normal(size=(nao, nmo)) / np.sqrt(nao))
+    g = [np.asfortranarray(rng.uniform(-1, 1, (npts, nao))) for _ in range(3)] if gga else None
+    engine.set_grid(np.ones(npts) / npts)
+    engine.set_orbitals_ao(ao, C, g)
+    out = np.zeros((npts, nmo), order="F")
+    gout = [np.zeros((npts, nmo), order="F") for _ in range(3)] if gga else None
+    engine.npts = npts
+    engine.get_orbitals(out, gout)
+    scale = np.abs(ao) @ np.abs(C)
+    assert (np.abs(out - ao @ C) <= 1e-13 * np.maximum(scale, 1.0)).all()
+    if gga:
+        for a, b in zip(gout, g):
+            assert (np.abs(a - b @ C) <= 1e-13 * np.maximum(np.abs(b) @ np.abs(C), 1.0)).all()
