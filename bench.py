@@ -186,9 +186,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="skip the config-5 sub-record (20 M points; needs ~64 GB per rank at N=1)")
+    ap.add_argument("--no-fp64", action="store_true", help="skip the extra FP64-pure (DMMA) loop")
+    ap.add_argument("--lean", action="store_true", help="profiling runs: only the resident loop (+ isolated stages): no e2e, CPU baseline, config 5, FP64-pure loop")
     ap.add_argument("--cpu-sample", type=int, default=0)
     args = ap.parse_args()
 
+    if args.lean:
+        args.no_e2e = args.no_cpu = args.no_config5 = args.no_fp64 = True
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -431,7 +435,7 @@ def main():
 
     # ---- the same step with Pi from the FP64 tensor-pipe kernels (no int8 path): the FP64-pure rate
     fp64_pure = None
-    if i8_pairs:
+    if i8_pairs and not args.no_fp64:
         v64, ms64, e64, _ = quick_rate(args.config, cfg["functional"], "0", max(3, min(steps, 10)))
         fp64_pure = {"value": v64, "ms_per_step": ms64, "pi_arithmetic": "FP64 (DMMA.8x8x4), ORDM_K2_INT8=0",
                      "abs_diff_e_tot_vs_int8_path": abs(e64 - res["e_tot"])}
