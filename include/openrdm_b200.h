@@ -278,6 +278,16 @@ int ordm_hybrid_energy(int method, double lambda, const ordm_hybrid_inputs* in, 
  * R/translate/XC -> quadrature (-> NCCL all-reduce when a communicator is attached). */
 int ordm_energy(ordm_ctx* ctx, int functional, double eclass, ordm_result* out);
 
+/* Stream-ordered form of ordm_energy: ordm_energy_async enqueues the whole step (kernels, all-reduce, D2H read of the
+ * result scalars into the context's pinned result block) on the context's stream and returns; ordm_energy_wait blocks
+ * for the LAST enqueued step and returns its result.  Several steps may be enqueued back to back -- an SCF driver
+ * that pipelines, a benchmark loop -- so that the host runs ahead of the GPU and the launch latency of a step
+ * disappears from the device timeline (at 8 GPUs a step is < 1 ms).  If the int8 on-top kernel's guard flagged
+ * points in any enqueued step, ordm_energy_wait repeats the last one with the FP64 kernels before returning.
+ * Inputs must not be changed between an async call and its wait; ordm_energy refuses to run while a step is pending. */
+int ordm_energy_async(ordm_ctx* ctx, int functional, double eclass);
+int ordm_energy_wait(ordm_ctx* ctx, ordm_result* out);
+
 /* Same, from HOST buffers: the grid is streamed through the device in point batches with
  * the H2D copies overlapped with compute; nothing but the RDMs has to be resident.  This is
  * the end-to-end call a host-memory caller (arma::mat) makes.  ncore/nact/A1a/A1b/D2act as

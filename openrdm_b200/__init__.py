@@ -158,6 +158,8 @@ def load(rebuild: bool = False) -> C.CDLL:
     lib.ordm_integrated_densities.argtypes = [P, D, D]
     lib.ordm_functional.argtypes = [P, I, S, D, D, D, D, D, D]
     lib.ordm_energy.argtypes = [P, I, C.c_double, C.POINTER(Result)]
+    lib.ordm_energy_async.argtypes = [P, I, C.c_double]
+    lib.ordm_energy_wait.argtypes = [P, C.POINTER(Result)]
     lib.ordm_energy_host.argtypes = [P, I, C.c_double, S, I, S, D, D, D, D, D, S, C.POINTER(Result)]
     lib.ordm_file_open.argtypes = [C.c_char_p, C.POINTER(P)]
     lib.ordm_file_close.argtypes = [P]
@@ -330,6 +332,15 @@ class Engine:
     def energy(self, functional=FUNC_SVWN, eclass=0.0) -> dict:
         r = Result()
         self._ck(self.lib.ordm_energy(self.ctx, functional, eclass, C.byref(r)))
+        return r.asdict()
+
+    def energy_async(self, functional=FUNC_SVWN, eclass=0.0):
+        """enqueue one step on the context's stream (ordm_energy_async); collect with energy_wait()"""
+        self._ck(self.lib.ordm_energy_async(self.ctx, functional, eclass))
+
+    def energy_wait(self) -> dict:
+        r = Result()
+        self._ck(self.lib.ordm_energy_wait(self.ctx, C.byref(r)))
         return r.asdict()
 
     def energy_host(self, functional, eclass, w, phi, grads=None, batch_points=0, ld=None) -> dict:

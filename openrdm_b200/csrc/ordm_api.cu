@@ -144,6 +144,7 @@ struct ordm_ctx {
   size_t k2p_smem = 0;
   int* d_i8_fail = nullptr;
   size_t k2i_smem = 0;
+  bool k1act_under = false;   // ORDM_K1ACT_UNDER=1: K1's active-space part also runs beside the int8 K2 (lab hook)
   bool k1_split = false;  // two-kernel K1 (k1_core + active) measured slower than the fused kernel; kept as a test hook
   uint16_t* d_pairs = nullptr;
   // grad-Pi variant of K2: the whole symmetric Dt in fragment order (built on first use)
@@ -159,7 +160,10 @@ struct ordm_ctx {
 
   // reductions
   double *d_partial = nullptr, *d_res = nullptr, *h_res = nullptr;
+  double* d_partial3 = nullptr;   // K3's block sums in the resident path (K1's stay in d_partial: one final kernel reads both)
   size_t partial_cap = 0;
+  // a step enqueued by ordm_energy_async and not yet collected by ordm_energy_wait
+  struct Pending { bool active = false, overlap = false, split = false, ft = false; int functional = 0, launches = 0; double eclass = 0.0; } pend;
   cudaEvent_t ev[8] = {};
 
   // streamed (host-buffer) path
@@ -228,7 +232,9 @@ bool want_pig(const ordm_ctx* c, bool gga) {
 int ensure_partials(ordm_ctx* c, size_t doubles) {
   if (doubles <= c->partial_cap) return ORDM_OK;
   dfree(c->d_partial);
+  dfree(c->d_partial3);
   CU(c, cudaMalloc(&c->d_partial, doubles * sizeof(double)));
+  CU(c, cudaMalloc(&c->d_partial3, doubles * sizeof(double)));
   c->partial_cap = doubles;
   return ORDM_OK;
 }
@@ -269,10 +275,14 @@ int ensure_vectors(ordm_ctx* c) {
 
 // ------------------------------------------------------------------ kernel launchers
 template <bool GGA>
-int launch_k1_np(ordm_ctx* c, const k1::Params& p, int grid, cudaStream_t st) {
+int launch_k1_np(ordm_ctx* c, const k1::Params& p, int grid, cudaStream_t st, bool under_k2 = false) {
   const int np = (int)round_up((size_t)std::max(c->nact, 1), 4);
   switch (np) {
-#define K1CASE(N) case N: k1::k1_density<N, GGA><<<grid, k1::THREADS, 0, st>>>(p); break;
+    // under_k2: the kernel is to run beside the int8 K2, which holds the SM at the maximum shared-memory carve-out;
+    // an SM does not re-partition while a CTA is resident, so this kernel has to ask for the same carve-out
+#define K1CASE(N) case N: \
+    if (under_k2) CU(c, cudaFuncSetAttribute(k1::k1_density<N, GGA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+    k1::k1_density<N, GGA><<<grid, k1::THREADS, 0, st>>>(p); break;
     K1CASE(4) K1CASE(8) K1CASE(12) K1CASE(16) K1CASE(20) K1CASE(24) K1CASE(28) K1CASE(32)
 #undef K1CASE
     default: k1::k1_density_generic<GGA><<<grid, k1::THREADS, 0, st>>>(p); break;
@@ -318,7 +328,10 @@ int run_k1_core_light(ordm_ctx* c, const GridView& v, int* launches, cudaStream_
 
 // core_ready: the core sums are already in v.core[] (run_k1_core_light); only the active-space part and
 // the assembly of rho, grad rho, pi_core are left
-int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaStream_t st = nullptr, bool core_ready = false) {
+// final_grid: when given, the one-block final pass is left to the caller (k4_final_all) and *final_grid receives the
+// number of partial rows in d_partial
+int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaStream_t st = nullptr, bool core_ready = false, bool under_k2 = false,
+           int* final_grid = nullptr) {
   if (!st) st = c->stream;
   // The __constant__ bank holding Ds is per device and shared by every context of the process
   // (kernel-parameter space was tried instead: ptxas then LDCs the coefficients into registers,
@@ -367,12 +380,13 @@ int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaSt
   int rc = ensure_partials(c, (size_t)c->sm_count * 16 * 8);
   if (rc) return rc;
   p.partial = c->d_partial;
-  rc = v.gga ? launch_k1_np<true>(c, p, grid, st) : launch_k1_np<false>(c, p, grid, st);
+  rc = v.gga ? launch_k1_np<true>(c, p, grid, st, under_k2) : launch_k1_np<false>(c, p, grid, st, under_k2);
   if (rc) return rc;
   if (use_bank) {
     CU(c, cudaEventRecord(bank[c->device & 63].last_k1, st));
     bank_lock.unlock();
   }
+  if (final_grid) { *final_grid = grid; *launches += 1; return ORDM_OK; }
   ordm::k4_finalize<3><<<1, 256, 0, st>>>(c->d_partial, grid, c->d_res, ordm::RES_N, accumulate);
   CU(c, cudaGetLastError());
   *launches += 2;
@@ -557,7 +571,7 @@ int run_k2(ordm_ctx* c, const GridView& v, int* launches, bool lean = false) {
 }
 
 int run_k3(ordm_ctx* c, const GridView& v, int functional, bool ft, int accumulate, int* launches, bool add_core = false,
-           const double* R_in = nullptr) {
+           const double* R_in = nullptr, int* final_grid = nullptr) {
   k3::Params p{};
   p.rho = v.vec[ORDM_VEC_RHO]; p.pi = v.vec[ORDM_VEC_PI]; p.w = v.w;
   p.R_in = R_in;
@@ -570,7 +584,7 @@ int run_k3(ordm_ctx* c, const GridView& v, int functional, bool ft, int accumula
   const int grid = k3_grid(c, v.npts);
   int rc = ensure_partials(c, (size_t)c->sm_count * 16 * 8);
   if (rc) return rc;
-  p.partial = c->d_partial;
+  p.partial = final_grid ? c->d_partial3 : c->d_partial;
   // energy.cc:114-120: "SVWN" -> LSDA+VWN3, else PBE.  Without orbital gradients the
   // translated sigma are zero vectors (energy.cc:63-65): PBE then runs with gx=gy=gz=0.
   if (functional != ORDM_FUNC_SVWN) {
@@ -588,6 +602,7 @@ int run_k3(ordm_ctx* c, const GridView& v, int functional, bool ft, int accumula
   }
 #undef K3CASE
   CU(c, cudaGetLastError());
+  if (final_grid) { *final_grid = grid; *launches += 1; return ORDM_OK; }
   ordm::k4_finalize<5><<<1, 256, 0, c->stream>>>(c->d_partial, grid, c->d_res, ordm::RES_TRN, accumulate);
   CU(c, cudaGetLastError());
   *launches += 2;
@@ -737,17 +752,22 @@ int check_inputs(ordm_ctx* c, bool need_rdm2) {
   return ORDM_OK;
 }
 
-int fetch_result(ordm_ctx* c, double eclass, ordm_result* out, uint64_t npts, int launches) {
+// the D2H read of the result scalars (and of the int8 kernel's / the peer all-reduce's status words), stream-ordered
+int fetch_enqueue(ordm_ctx* c) {
   CU(c, cudaMemcpyAsync(c->h_res, c->d_res, ordm::RES_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   int* h_i8_fail = reinterpret_cast<int*>(c->h_res + 12);   // the pinned block has room beyond the RES_COUNT scalars
-  *h_i8_fail = 0;
-  h_i8_fail[1] = 0;
   if (c->k2_i8 && c->d_i8_fail) CU(c, cudaMemcpyAsync(h_i8_fail, c->d_i8_fail, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  int* h_xerr = h_i8_fail + 2;
-  *h_xerr = 0;
-  if (c->comm && c->peer_ok && c->d_xerr) CU(c, cudaMemcpyAsync(h_xerr, c->d_xerr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (c->comm && c->peer_ok && c->d_xerr) CU(c, cudaMemcpyAsync(h_i8_fail + 2, c->d_xerr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaEventRecord(c->ev[5], c->stream));
+  return ORDM_OK;
+}
+
+int fetch_finish(ordm_ctx* c, double eclass, ordm_result* out, uint64_t npts, int launches) {
+  int* h_i8_fail = reinterpret_cast<int*>(c->h_res + 12);
+  int* h_xerr = h_i8_fail + 2;
   CU(c, cudaStreamSynchronize(c->stream));
+  if (!(c->k2_i8 && c->d_i8_fail)) h_i8_fail[0] = h_i8_fail[1] = 0;
+  if (!(c->comm && c->peer_ok && c->d_xerr)) *h_xerr = 0;
   if (*h_xerr)   // k_allreduce_peer (reduce.cuh): a peer's flag never arrived; the result scalars were set to NaN
     return fail(c, ORDM_ERR_NCCL, "peer all-reduce timed out waiting for another rank (rank %d of %d)", c->rank, c->nranks);
   if (*h_i8_fail) {   // a tcgen05 completion barrier never flipped (bounded spin in k2_int8.cuh): the Pi of this call is not valid
@@ -773,6 +793,11 @@ int fetch_result(ordm_ctx* c, double eclass, ordm_result* out, uint64_t npts, in
   out->gpu_launches = (uint32_t)launches;
   for (int i = 0; i < 3; ++i) { c->last_n[i] = r[ordm::RES_N + i]; c->last_trn[i] = r[ordm::RES_TRN + i]; }
   return ORDM_OK;
+}
+
+int fetch_result(ordm_ctx* c, double eclass, ordm_result* out, uint64_t npts, int launches) {
+  int rc = fetch_enqueue(c);
+  return rc ? rc : fetch_finish(c, eclass, out, npts, launches);
 }
 
 // all-reduce of d_res over the attached communicator: NVLink peer stores when the exchange buffers
@@ -1052,6 +1077,7 @@ int ordm_create(int device, ordm_ctx** out) {
   c->device = device;
   if (const char* e = getenv("ORDM_I8_NO_OVERLAP")) c->i8_no_overlap = (e[0] == '1');
   if (const char* e = getenv("ORDM_K2_INT8")) c->k2_i8_mode = atoi(e);   // 0: DMMA kernels only; 2: 21 slice pairs
+  if (const char* e = getenv("ORDM_K1ACT_UNDER")) c->k1act_under = (e[0] == '1');
   if (const char* e = getenv("ORDM_K2_PAIR")) c->k2_pair = (e[0] != '0');   // 0: single-CTA int8 kernel (k2_int8.cuh)
   if (const char* e = getenv("ORDM_K2_PLAIN")) c->k2_force_plain = (e[0] == '1');  // test hook: single-buffer K2
   if (const char* e = getenv("ORDM_K1_SPLIT")) c->k1_split = (e[0] == '1');         // test hook: two-kernel K1
@@ -1089,7 +1115,7 @@ void ordm_destroy(ordm_ctx* c) {
   for (int k = 0; k < 4; ++k) dfree(c->d_phi[k]);
   dfree(c->d_Dsa_g); dfree(c->d_Dsb_g); dfree(c->d_dfrag); dfree(c->d_tasks); dfree(c->d_pairs);
   dfree(c->d_timg); dfree(c->d_timg_pair); dfree(c->d_i8_fail);
-  dfree(c->d_partial); dfree(c->d_res);
+  dfree(c->d_partial); dfree(c->d_partial3); dfree(c->d_res);
   if (c->h_res) cudaFreeHost(c->h_res);
   for (auto& s : c->stage) {
     dfree(s.w);
@@ -1482,10 +1508,16 @@ int ordm_hybrid_energy(int method, double lambda, const ordm_hybrid_inputs* in, 
 }
 
 // ---- the path in one call -----------------------------------------------------------------
-static int energy_resident(ordm_ctx* c, int functional, double eclass, ordm_result* out);
+static int energy_enqueue(ordm_ctx* c, int functional, double eclass);
+static int energy_finish(ordm_ctx* c, ordm_result* out);
+static int energy_resident(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
+  int rc = energy_enqueue(c, functional, eclass);
+  return rc ? rc : energy_finish(c, out);
+}
 int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   CHECK_CTX(c);
   if (!out) return fail(c, ORDM_ERR_INVALID, "null result");
+  if (c->pend.active) return fail(c, ORDM_ERR_STATE, "a step enqueued by ordm_energy_async is still pending: collect it with ordm_energy_wait first");
   int rc = energy_resident(c, functional, eclass, out);
   if (rc == RETRY_FP64) {   // the int8 kernel's guard flagged points: same call again, Pi from the FP64 tensor-pipe kernels
     rc = energy_resident(c, functional, eclass, out);
@@ -1493,7 +1525,28 @@ int ordm_energy(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
   }
   return rc;
 }
-static int energy_resident(ordm_ctx* c, int functional, double eclass, ordm_result* out) {
+// Stream-ordered form: ordm_energy_async enqueues the whole step (kernels, all-reduce, D2H read of the scalars into the
+// context's pinned result block) and returns; ordm_energy_wait blocks for the LAST enqueued step and returns its
+// result.  Several steps may be enqueued back to back (an SCF driver that pipelines, a benchmark loop): the host then
+// runs ahead of the GPU and the per-step launch latency disappears from the device timeline.
+int ordm_energy_async(ordm_ctx* c, int functional, double eclass) {
+  CHECK_CTX(c);
+  return energy_enqueue(c, functional, eclass);
+}
+int ordm_energy_wait(ordm_ctx* c, ordm_result* out) {
+  CHECK_CTX(c);
+  if (!out) return fail(c, ORDM_ERR_INVALID, "null result");
+  if (!c->pend.active) return fail(c, ORDM_ERR_STATE, "ordm_energy_wait without a pending ordm_energy_async");
+  const int functional = c->pend.functional;
+  const double eclass = c->pend.eclass;
+  int rc = energy_finish(c, out);
+  if (rc == RETRY_FP64) {   // some enqueued step tripped the int8 guard: the last one is repeated with the FP64 kernels
+    rc = energy_resident(c, functional, eclass, out);
+    if (rc == ORDM_OK) out->pi_guard_points = c->guard_points;
+  }
+  return rc;
+}
+static int energy_enqueue(ordm_ctx* c, int functional, double eclass) {
   CU(c, cudaSetDevice(c->device));
   int rc = check_inputs(c, true);
   if (rc) return rc;
@@ -1503,6 +1556,7 @@ static int energy_resident(ordm_ctx* c, int functional, double eclass, ordm_resu
   const bool ft = (c->opts & ORDM_OPT_FULLY_TRANSLATED) != 0;
   c->inj_R = c->inj_grad = false;   // mcpdft_energy rebuilds every vector from the inputs (energy.cc:49-58)
   int launches = 0;
+  int grid1 = -1, grid3 = 0;   // rows of K1's / K3's block sums left for the final kernel (grid1 < 0: K1 finalised itself)
   // Overlapped mode (default): the tensor-bound K2 is launched first with a trimmed register
   // footprint, and the HBM-bound K1 streams underneath it on a second stream (one K1 CTA stays
   // co-resident per SM); K3 joins both and completes Pi = Pi_act + Pi_core.
@@ -1528,8 +1582,11 @@ static int energy_resident(ordm_ctx* c, int functional, double eclass, ordm_resu
       CU(c, cudaEventRecord(c->ev[2], c->stream));
     }
     CU(c, cudaEventRecord(c->ev_k1[0], c->side_stream));
-    if (split) { if ((rc = run_k1_core_light(c, c->g, &launches, c->side_stream, /*deep=*/c->k2_i8))) return rc; }
-    else if ((rc = run_k1(c, c->g, 0, &launches, c->side_stream))) return rc;
+    const bool act_under = split && c->k2_i8 && c->k1act_under;   // the active-space part too beside the int8 K2
+    if (split) {
+      if ((rc = run_k1_core_light(c, c->g, &launches, c->side_stream, /*deep=*/c->k2_i8))) return rc;
+      if (act_under && (rc = run_k1(c, c->g, 0, &launches, c->side_stream, /*core_ready=*/true, /*under_k2=*/true))) return rc;
+    } else if ((rc = run_k1(c, c->g, 0, &launches, c->side_stream))) return rc;
     CU(c, cudaEventRecord(c->ev_k1[1], c->side_stream));
     if (c->k2_i8) {
       if ((rc = run_k2(c, c->g, &launches, /*lean=*/true))) return rc;
@@ -1538,20 +1595,49 @@ static int energy_resident(ordm_ctx* c, int functional, double eclass, ordm_resu
     CU(c, cudaEventRecord(c->ev_join, c->side_stream));
     CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     CU(c, cudaEventRecord(c->ev[1], c->stream));  // = K2 and the side-stream part of K1 done
-    if (split && (rc = run_k1(c, c->g, 0, &launches, nullptr, /*core_ready=*/true))) return rc;
+    if (split && !act_under && (rc = run_k1(c, c->g, 0, &launches, nullptr, /*core_ready=*/true, false, &grid1))) return rc;
     CU(c, cudaEventRecord(c->ev[6], c->stream));
-    if ((rc = run_k3(c, c->g, functional, ft, 0, &launches, /*add_core=*/true))) return rc;
+    if ((rc = run_k3(c, c->g, functional, ft, 0, &launches, /*add_core=*/true, nullptr, &grid3))) return rc;
   } else {
-    if ((rc = run_k1(c, c->g, 0, &launches))) return rc;
+    if ((rc = run_k1(c, c->g, 0, &launches, nullptr, false, false, &grid1))) return rc;
     CU(c, cudaEventRecord(c->ev[1], c->stream));
     if ((rc = run_k2(c, c->g, &launches))) return rc;
     CU(c, cudaEventRecord(c->ev[2], c->stream));
-    if ((rc = run_k3(c, c->g, functional, ft, 0, &launches))) return rc;
+    if ((rc = run_k3(c, c->g, functional, ft, 0, &launches, false, nullptr, &grid3))) return rc;
   }
   CU(c, cudaEventRecord(c->ev[3], c->stream));
-  if ((rc = all_reduce_results(c, &launches))) return rc;
+  // one launch ends the step: final passes over K1's and K3's block sums + (peer-mapped communicator) the all-reduce
+  {
+    const bool peer = c->comm && c->peer_ok;
+    ordm::PeerXchg px = peer ? c->px : ordm::PeerXchg{};
+    if (!peer) px.nranks = 1;
+    if (grid1 < 0) {   // K1's final pass already ran on its own stream (overlap without split, or act_under): fold nothing here
+      static const double* none = nullptr;
+      ordm::k4_final_all<<<1, 256, 0, c->stream>>>(none, -1, c->d_partial3, grid3, c->d_res, px, peer ? ++c->xepoch : 0ull, c->d_xerr);
+    } else {
+      ordm::k4_final_all<<<1, 256, 0, c->stream>>>(c->d_partial, grid1, c->d_partial3, grid3, c->d_res, px, peer ? ++c->xepoch : 0ull, c->d_xerr);
+    }
+    CU(c, cudaGetLastError());
+    launches += 1;
+    if (c->comm && !peer) {   // NCCL fall-back
+      int nr = g_nccl.AllReduce(c->d_res, c->d_res, ordm::RES_COUNT, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream);
+      if (nr != 0) return fail(c, ORDM_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+      launches += 1;
+    }
+  }
   CU(c, cudaEventRecord(c->ev[4], c->stream));
-  if ((rc = fetch_result(c, eclass, out, c->g.npts, launches))) return rc;
+  if ((rc = fetch_enqueue(c))) return rc;
+  c->pend.active = true; c->pend.overlap = overlap; c->pend.split = split; c->pend.ft = ft;
+  c->pend.functional = functional; c->pend.launches = launches; c->pend.eclass = eclass;
+  return ORDM_OK;
+}
+
+static int energy_finish(ordm_ctx* c, ordm_result* out) {
+  const bool overlap = c->pend.overlap, split = c->pend.split, ft = c->pend.ft;
+  const int functional = c->pend.functional;
+  c->pend.active = false;
+  int rc;
+  if ((rc = fetch_finish(c, c->pend.eclass, out, c->g.npts, c->pend.launches))) return rc;
   float ms;
   if (overlap) {  // K1 (or its core part) and K2 ran concurrently: each is timed on its own stream
     CU(c, cudaEventElapsedTime(&ms, c->ev_k1[0], c->ev_k1[1])); out->ms_density = ms;

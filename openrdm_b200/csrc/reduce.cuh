@@ -106,4 +106,68 @@ __global__ void __launch_bounds__(128) k_allreduce_peer(double* __restrict__ res
   }
 }
 
+// The resident energy path ends in ONE launch: the final pass over K1's partial sums (3 values per block), the one
+// over K3's (5 values per block), and -- when a communicator with mapped peer buffers is attached -- the all-reduce
+// above, all in a single 256-thread block.  Same summation order as k4_finalize / k_allreduce_peer, so the results are
+// bitwise those of the three separate launches; what it saves is two launch latencies per step, which is what the
+// step consists of once the grid is spread over eight GPUs.
+__global__ void __launch_bounds__(256) k4_final_all(const double* __restrict__ part1, int n1, const double* __restrict__ part3, int n3,
+                                                    double* __restrict__ res, const PeerXchg px, unsigned long long epoch, int* __restrict__ err) {
+  __shared__ double scratch[5 * 32];
+  __shared__ double tot[5];
+  if (n1 >= 0) {   // n1 < 0: K1's final pass ran as its own launch on the side stream
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int r = threadIdx.x; r < n1; r += blockDim.x) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v[k] += part1[(size_t)r * 3 + k];
+    }
+    block_sum_store<3>(v, scratch, tot);
+    __syncthreads();
+    if (threadIdx.x < 3) res[RES_N + threadIdx.x] = tot[threadIdx.x];
+    __syncthreads();
+  }
+  {
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int r = threadIdx.x; r < n3; r += blockDim.x) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) v[k] += part3[(size_t)r * 5 + k];
+    }
+    block_sum_store<5>(v, scratch, tot);
+    __syncthreads();
+    if (threadIdx.x < 5) res[RES_TRN + threadIdx.x] = tot[threadIdx.x];
+  }
+  if (px.nranks < 2) return;
+  __threadfence();
+  __syncthreads();
+  // ---- k_allreduce_peer, verbatim (see above)
+  const int t = threadIdx.x, n = px.nranks;
+  const int par = (int)(epoch & 1);
+  if (t == 0) *err = 0;
+  if (t < n * RES_COUNT) {
+    const int r = t / RES_COUNT, k = t % RES_COUNT;
+    px.peer[r][((size_t)par * n + px.rank) * RES_COUNT + k] = res[k];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < n) {
+    unsigned long long* theirs = reinterpret_cast<unsigned long long*>(px.peer[t] + (size_t)2 * n * RES_COUNT) + px.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(px.peer[px.rank] + (size_t)2 * n * RES_COUNT) + t;
+    const long long t0 = clock64();
+    unsigned long long seen = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+      if (seen >= epoch) break;
+    } while (clock64() - t0 < 60000000000ll);
+    if (seen < epoch) *err = 1;
+  }
+  __syncthreads();
+  if (t < RES_COUNT) {
+    const double* v = px.peer[px.rank] + (size_t)par * n * RES_COUNT + t;
+    double s = 0.0;
+    for (int r = 0; r < n; ++r) s += v[(size_t)r * RES_COUNT];
+    res[t] = *err ? (0.0 / 0.0) : s;
+  }
+}
+
 }  // namespace ordm
