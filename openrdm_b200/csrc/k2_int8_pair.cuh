@@ -132,14 +132,18 @@ __host__ __device__ constexpr bool row_ends_at(int na, int I, int hi, int m) {
 #endif
 struct RowAcc { double d0, d1; float f0, f1; };
 
-template <int NA, int I, int IEND, bool F32>
+// FLYF (the streaming kernel for > 20 active orbitals, k2_int8_stream.cuh): no float copy of phi is kept -- 26 orbitals
+// as doubles AND floats do not fit the 128-register budget -- and the FP32 groups convert phi_u on the fly, unscaled
+// (amplitudes outside float's range only occur where the whole group is far below the parity bar)
+template <int NA, int I, int IEND, bool F32, bool FLYF = false>
 __device__ __forceinline__ void fold_elem(const double (&phi)[NA], const float (&phif)[NA], RowAcc& r, double& tot, uint32_t v) {
   constexpr int M = NA * (NA + 1) / 2;
   if constexpr (I < M) {
     constexpr int t = pair_t_of(NA, I), u = pair_u_of(NA, I);
     if constexpr (F32) {
       const float vf = __int2float_rn((int)v);
-      if constexpr (I & 1) r.f1 = fmaf(phif[u], vf, r.f1); else r.f0 = fmaf(phif[u], vf, r.f0);
+      const float pf = FLYF ? __double2float_rn(phi[u]) : phif[u];
+      if constexpr (I & 1) r.f1 = fmaf(pf, vf, r.f1); else r.f0 = fmaf(pf, vf, r.f0);
       if constexpr (row_ends_at(NA, I, IEND, M)) { tot = fma(phi[t], (double)(r.f0 + r.f1), tot); r.f0 = r.f1 = 0.f; }
     } else {
       double zd;
@@ -151,10 +155,10 @@ __device__ __forceinline__ void fold_elem(const double (&phi)[NA], const float (
   }
 }
 
-template <int NA, int U, int UEND, bool F32, int... Js>
+template <int NA, int U, int UEND, bool F32, bool FLYF, int... Js>
 __device__ __forceinline__ void fold_unit(const double (&phi)[NA], const float (&phif)[NA], RowAcc& r, double& tot, const uint32_t (&v)[16],
                                           std::integer_sequence<int, Js...>) {
-  (fold_elem<NA, 16 * U + Js, 16 * UEND, F32>(phi, phif, r, tot, v[Js]), ...);
+  (fold_elem<NA, 16 * U + Js, 16 * UEND, F32, FLYF>(phi, phif, r, tot, v[Js]), ...);
 }
 
 // tcgen05.wait::ld with the loaded registers as in/out operands: nothing that reads them can be scheduled above it
@@ -165,7 +169,7 @@ __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
                :: "memory");
 }
 
-template <int NA, int U, int U1, bool F32>
+template <int NA, int U, int U1, bool F32, bool FLYF = false>
 __device__ __forceinline__ void fold_units(const double (&phi)[NA], const float (&phif)[NA], RowAcc& r, double& tot, uint32_t tmem_row,
                                            uint32_t (&cur)[16], uint32_t (&nxt)[16], uint32_t drain_bar) {
 #ifndef K2P_LAB_NOLOAD   // lab switch (tools/ozlab): no TMEM loads, arithmetic on whatever the registers hold
@@ -180,14 +184,14 @@ __device__ __forceinline__ void fold_units(const double (&phi)[NA], const float 
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(drain_bar) : "memory");
   }
 #ifndef K2P_LAB_NOMATH   // lab switch: loads and barriers only
-  fold_unit<NA, U, U1, F32>(phi, phif, r, tot, cur, std::make_integer_sequence<int, 16>{});
+  fold_unit<NA, U, U1, F32, FLYF>(phi, phif, r, tot, cur, std::make_integer_sequence<int, 16>{});
 #else
   if (cur[0] == 0x12345678u && cur[15] == 0x9abcdefu) tot += 1.0;
 #endif
-  if constexpr (U + 1 < U1) fold_units<NA, U + 1, U1, F32>(phi, phif, r, tot, tmem_row, nxt, cur, drain_bar);
+  if constexpr (U + 1 < U1) fold_units<NA, U + 1, U1, F32, FLYF>(phi, phif, r, tot, tmem_row, nxt, cur, drain_bar);
 }
 
-template <int NA, int U0, int U1, bool F32>
+template <int NA, int U0, int U1, bool F32, bool FLYF = false>
 __device__ __forceinline__ double fold_group_units(const double (&phi)[NA], const float (&phif)[NA], uint32_t tmem_row, uint32_t drain_bar) {
   RowAcc r{0.0, 0.0, 0.f, 0.f};
   double tot = 0.0;
@@ -198,7 +202,7 @@ __device__ __forceinline__ double fold_group_units(const double (&phi)[NA], cons
 #pragma unroll
   for (int j = 0; j < 16; ++j) { va[j] = tmem_row * (j + 1); vb[j] = tmem_row * (j + 17); }
 #endif
-  fold_units<NA, U0, U1, F32>(phi, phif, r, tot, tmem_row, va, vb, drain_bar);
+  fold_units<NA, U0, U1, F32, FLYF>(phi, phif, r, tot, tmem_row, va, vb, drain_bar);
   return tot;
 }
 
