@@ -144,6 +144,7 @@ struct ordm_ctx {
   size_t k2p_smem = 0;
   int* d_i8_fail = nullptr;
   size_t k2i_smem = 0;
+  bool big_overlap = true;    // ORDM_BIG_OVERLAP=0 switches it off: the deep core kernel also beside a DMMA K2 that fills shared memory (26 active orbitals)
   bool k1act_under = false;   // ORDM_K1ACT_UNDER=1: K1's active-space part also runs beside the int8 K2 (lab hook)
   bool k1_split = false;  // two-kernel K1 (k1_core + active) measured slower than the fused kernel; kept as a test hook
   uint16_t* d_pairs = nullptr;
@@ -1078,6 +1079,7 @@ int ordm_create(int device, ordm_ctx** out) {
   if (const char* e = getenv("ORDM_I8_NO_OVERLAP")) c->i8_no_overlap = (e[0] == '1');
   if (const char* e = getenv("ORDM_K2_INT8")) c->k2_i8_mode = atoi(e);   // 0: DMMA kernels only; 2: 21 slice pairs
   if (const char* e = getenv("ORDM_K1ACT_UNDER")) c->k1act_under = (e[0] == '1');
+  if (const char* e = getenv("ORDM_BIG_OVERLAP")) c->big_overlap = (e[0] == '1');
   if (const char* e = getenv("ORDM_K2_PAIR")) c->k2_pair = (e[0] != '0');   // 0: single-CTA int8 kernel (k2_int8.cuh)
   if (const char* e = getenv("ORDM_K2_PLAIN")) c->k2_force_plain = (e[0] == '1');  // test hook: single-buffer K2
   if (const char* e = getenv("ORDM_K1_SPLIT")) c->k1_split = (e[0] == '1');         // test hook: two-kernel K1
@@ -1568,27 +1570,33 @@ static int energy_enqueue(ordm_ctx* c, int functional, double eclass) {
   const bool split_ok = c->core_form && c->ncore >= c->nact && c->g.core[0] && !c->no_split;
   // The int8 K2 owns the SM's shared memory and TMEM but leaves 17 K registers: only the split form fits beside it
   // (one deep-unrolled core CTA per SM); without core orbitals to stream the stages run back to back.
+  // A K2 that takes (almost) the whole shared memory -- 26 active orbitals: 219 KB -- still leaves room for the deep
+  // core-orbital kernel, which uses none: it is placed first (as beside the int8 K2) and streams the core columns
+  // while K2 owns the tensor pipe.
+  const bool k2_fills_smem = c->k2_smem + 32768 > (size_t)c->max_smem_optin;
+  const bool deep_beside_dmma = !c->k2_i8 && k2_fills_smem && split_ok && c->big_overlap;
   const bool overlap = !c->serial_stages && !(c->opts & ORDM_OPT_SERIAL_STAGES) && c->k2_ws && !want_pig(c, c->g.gga) &&
-                       c->k2_smem + 32768 <= (size_t)c->max_smem_optin && (!c->k2_i8 || (split_ok && !c->i8_no_overlap));
+                       (!k2_fills_smem || deep_beside_dmma) && (!c->k2_i8 || (split_ok && !c->i8_no_overlap));
   const bool split = overlap && split_ok;
+  const bool core_first = c->k2_i8 || deep_beside_dmma;   // the deep core CTA takes its slot on every SM before K2 arrives
   CU(c, cudaEventRecord(c->ev[0], c->stream));
   if (overlap) {
     CU(c, cudaEventRecord(c->ev_fork, c->stream));
     CU(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
     // Launch order: the DMMA K2 goes first and the light core kernel fills the registers it leaves; the int8 K2
     // takes one CTA slot per SM whatever is there, so the single deep core CTA per SM is placed first.
-    if (!c->k2_i8) {
+    if (!core_first) {
       if ((rc = run_k2(c, c->g, &launches, /*lean=*/true))) return rc;
       CU(c, cudaEventRecord(c->ev[2], c->stream));
     }
     CU(c, cudaEventRecord(c->ev_k1[0], c->side_stream));
     const bool act_under = split && c->k2_i8 && c->k1act_under;   // the active-space part too beside the int8 K2
     if (split) {
-      if ((rc = run_k1_core_light(c, c->g, &launches, c->side_stream, /*deep=*/c->k2_i8))) return rc;
+      if ((rc = run_k1_core_light(c, c->g, &launches, c->side_stream, /*deep=*/core_first))) return rc;
       if (act_under && (rc = run_k1(c, c->g, 0, &launches, c->side_stream, /*core_ready=*/true, /*under_k2=*/true))) return rc;
     } else if ((rc = run_k1(c, c->g, 0, &launches, c->side_stream))) return rc;
     CU(c, cudaEventRecord(c->ev_k1[1], c->side_stream));
-    if (c->k2_i8) {
+    if (core_first) {
       if ((rc = run_k2(c, c->g, &launches, /*lean=*/true))) return rc;
       CU(c, cudaEventRecord(c->ev[2], c->stream));
     }
