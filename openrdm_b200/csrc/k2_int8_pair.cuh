@@ -130,6 +130,9 @@ __host__ __device__ constexpr bool row_ends_at(int na, int I, int hi, int m) {
 #ifndef K2P_I2F_EVERY
 #define K2P_I2F_EVERY 3
 #endif
+#ifndef K2P_INTQ_MIN
+#define K2P_INTQ_MIN 8   // groups >= this carry the FP32 remainder terms in the integer fold (ifold_elem)
+#endif
 struct RowAcc { double d0, d1; float f0, f1; };
 
 // FLYF (the streaming kernel for > 20 active orbitals, k2_int8_stream.cuh): no float copy of phi is kept -- 26 orbitals
@@ -204,6 +207,90 @@ __device__ __forceinline__ double fold_group_units(const double (&phi)[NA], cons
 #endif
   fold_units<NA, U0, U1, F32, FLYF>(phi, phif, r, tot, tmem_row, va, vb, drain_bar);
   return tot;
+}
+
+// ---- the fold without the FP64 pipe ---------------------------------------------------------------------------------------
+// Measured (tools/microbench/mma_math_duty.cu, profiles/r02_mma_math_duty.log): while tcgen05.mma.kind::i8 runs, DFMA / DADD /
+// DMUL of the same SM issue 13x slower (0.29 -> 0.022 per clk per sub-partition) -- the FP64 pipe and the tensor core
+// exclude each other -- whereas FFMA, IMAD, IMAD.WIDE, I2FP and the conversion pipe keep their rate.  With the FP64 fold
+// above the kernel therefore time-shares: MMAs, then fold, never both.  The fold below does the same sums on the integer
+// and FP32 pipes; FP64 is left for three instructions per group.
+//   phi'_t = phi_t 2^-em (|.| < 1)  =  h_t 2^-27 + r_t,   h_t = rint(phi'_t 2^27) (int32),   |r_t| <= 2^-28 (float q_t = r_t 2^-27)
+//   row t of group G:   S_t = sum_u v h_u  (IMAD.WIDE, exact: |v| < 2^24, 20 terms -> |S| < 2^56)
+//                       s_t = sum_u v q_u  (I2FP + FFMA; a 2^-28 correction, so FP32's 2^-24 is 2^-52 of the group)
+//   group:  sum_t phi'_t (S_t 2^-27 + s_t 2^27)
+//         = 2^-54 sum_t h_t S_t                      exact in two int64: S_t = Sh 2^32 + Sl (Sl signed), PH += Sh h_t, PL += Sl h_t
+//         + 2^27 sum_t phi'_t s_t + sum_t q_t S_t    FP32 (Ca, Cb)
+// FOLD_INT_Q: as above (groups 10, 9, 8, which weigh >= 2^-16 of the total and need 2^-31 or better inside the group);
+// FOLD_INT: without the q terms (group 7: weight 2^-24, 27 bits of phi' are plenty);  FOLD_F32: FP32 throughout (groups
+// <= K2P_F32_MAX: weight <= 2^-32), row ends included.  The results are in units of 2^(2 em).
+enum { FOLD_INT_Q = 0, FOLD_INT = 1, FOLD_F32 = 2 };
+struct IRow { long long S, S1; float s, f0, f1; };   // two IMAD.WIDE chains per row (even / odd pair): one alone is latency-bound
+struct IGroup { long long PH, PL; float Ca, Cb; };
+
+template <int NA, int I, int IEND, int MODE>
+__device__ __forceinline__ void ifold_elem(const int (&h)[NA], const float (&q)[NA], const float (&phif)[NA], IRow& r, IGroup& g, uint32_t v) {
+  constexpr int M = NA * (NA + 1) / 2;
+  if constexpr (I < M) {
+    constexpr int t = pair_t_of(NA, I), u = pair_u_of(NA, I);
+    if constexpr (MODE == FOLD_F32) {
+      const float vf = __int2float_rn((int)v);
+      if constexpr (I & 1) r.f1 = fmaf(phif[u], vf, r.f1); else r.f0 = fmaf(phif[u], vf, r.f0);
+      if constexpr (row_ends_at(NA, I, IEND, M)) { g.Ca = fmaf(phif[t], r.f0 + r.f1, g.Ca); r.f0 = r.f1 = 0.f; }
+    } else {
+      if constexpr (I & 1) r.S1 += (long long)(int)v * (long long)h[u]; else r.S += (long long)(int)v * (long long)h[u];
+      if constexpr (MODE == FOLD_INT_Q) r.s = fmaf(__int2float_rn((int)v), q[u], r.s);
+      if constexpr (row_ends_at(NA, I, IEND, M)) {
+        r.S += r.S1;
+        r.S1 = 0;
+        const int sl = (int)(unsigned)r.S;
+        const int sh = (int)(r.S >> 32) - (sl >> 31);   // S = sh 2^32 + sl with sl signed
+        g.PH += (long long)sh * (long long)h[t];
+        g.PL += (long long)sl * (long long)h[t];
+        if constexpr (MODE == FOLD_INT_Q) {
+          g.Ca = fmaf(phif[t], r.s, g.Ca);
+          g.Cb = fmaf(q[t], __ll2float_rn(r.S), g.Cb);
+          r.s = 0.f;
+        }
+        r.S = 0;
+      }
+    }
+  }
+}
+
+template <int NA, int U, int UEND, int MODE, int... Js>
+__device__ __forceinline__ void ifold_unit(const int (&h)[NA], const float (&q)[NA], const float (&phif)[NA], IRow& r, IGroup& g, const uint32_t (&v)[16],
+                                           std::integer_sequence<int, Js...>) {
+  (ifold_elem<NA, 16 * U + Js, 16 * UEND, MODE>(h, q, phif, r, g, v[Js]), ...);
+}
+
+template <int NA, int U, int U1, int MODE>
+__device__ __forceinline__ void ifold_units(const int (&h)[NA], const float (&q)[NA], const float (&phif)[NA], IRow& r, IGroup& g, uint32_t tmem_row,
+                                            uint32_t (&cur)[16], uint32_t (&nxt)[16], uint32_t drain_bar) {
+  tmem_wait_ld16(cur);   // unit U is in `cur`
+  if constexpr (U + 1 < U1) {
+    tmem_ld16(tmem_row + (uint32_t)(16 * (U + 1)), nxt);
+  } else {   // every column of this thread's range has been read: the group after next may overwrite this accumulator
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(drain_bar) : "memory");
+  }
+  ifold_unit<NA, U, U1, MODE>(h, q, phif, r, g, cur, std::make_integer_sequence<int, 16>{});
+  if constexpr (U + 1 < U1) ifold_units<NA, U + 1, U1, MODE>(h, q, phif, r, g, tmem_row, nxt, cur, drain_bar);
+}
+
+// one group over this thread's units; the value (units of 2^(2 em), before the group's weight) as a double: the only FP64
+// instructions of the fold
+template <int NA, int U0, int U1, int MODE>
+__device__ __forceinline__ double ifold_group_units(const int (&h)[NA], const float (&q)[NA], const float (&phif)[NA], uint32_t tmem_row, uint32_t drain_bar) {
+  IRow r{0, 0, 0.f, 0.f, 0.f};
+  IGroup g{0, 0, 0.f, 0.f};
+  uint32_t va[16], vb[16];
+  tmem_ld16(tmem_row + (uint32_t)(16 * U0), va);
+  ifold_units<NA, U0, U1, MODE>(h, q, phif, r, g, tmem_row, va, vb, drain_bar);
+  if constexpr (MODE == FOLD_F32) return (double)g.Ca;
+  const double c = (MODE == FOLD_INT_Q) ? (double)fmaf(g.Ca, 134217728.0f, g.Cb) : 0.0;   // 2^27 Ca + Cb
+  // 2^-54 (PH 2^32 + PL) + c
+  return fma(__ll2double_rn(g.PH), 2.384185791015625e-07 /* 2^-22 */, fma(__ll2double_rn(g.PL), 5.5511151231257827e-17 /* 2^-54 */, c));
 }
 
 // every MMA of group G into the accumulator at tmem_acc: one per (slice pair, K chunk), N = the chunk's column range
@@ -308,11 +395,22 @@ __device__ __forceinline__ void pair_compute_role(const Params& P, const PairCtx
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if constexpr (PART == 0) s2 = sum_squares<NA>(phi);
-    float phif[NA];   // phi_u 2^-em as floats for the FP32 groups of the epilogue (|.| < 1: no range trouble whatever em)
+    // phi'_t = phi_t 2^-em (|.| < 1) in the three forms the fold uses (ifold_elem): float, 27-bit integer part, remainder
+    float phif[NA], q[NA];
+    int h[NA];
     {
       const double sc0 = __hiloint2double((2045 - e_raw) << 20, 0);   // 2^-em, em = e_raw - 1022
 #pragma unroll
-      for (int t = 0; t < NA; ++t) phif[t] = (float)(phi[t] * sc0);
+      for (int t = 0; t < NA; ++t) {
+        // ps + 1.5 2^25 has ulp 2^-27: its low mantissa word is h = rint(ps 2^27) (two's complement), and taking the
+        // constant off again leaves h 2^-27 exactly -- no F2I / I2F (16 per clk per SM) in the tile's prologue
+        const double ps = phi[t] * sc0;
+        const double hd = ps + 50331648.0;
+        h[t] = __double2loint(hd);
+        const float rf = (float)(ps - (hd - 50331648.0));         // |r| <= 2^-28, 24 bits of it
+        q[t] = rf * 7.450580596923828125e-9f;                      // r 2^-27
+        phif[t] = fmaf(__int2float_rn(h[t]), 7.450580596923828125e-9f, rf);
+      }
     }
     {   // next pair tile's orbitals towards L2 while this one is contracted
       const size_t pn = p0 + (size_t)(gridDim.x / 2) * 2 * TILE + p;
@@ -326,7 +424,7 @@ __device__ __forceinline__ void pair_compute_role(const Params& P, const PairCtx
     cluster_sync_all();   // both CTAs' operands are built
     K2P_LAP(1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    double pi_acc = 0.0, pi_acc32 = 0.0;   // FP64 groups; FP32 groups (in units of 2^em)
+    double pi_acc = 0.0;   // in units of 2^(2 em)
 #pragma unroll 1
     for (int gi = 0; gi < NGROUPS; ++gi, ++n) {
       const int G = group_at(gi, GMIN);
@@ -336,12 +434,15 @@ __device__ __forceinline__ void pair_compute_role(const Params& P, const PairCtx
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_row = c.tmem + c.lane_addr + (uint32_t)(b * ACC_COLS), db = c.drain_remote + 8 * b;
       const double wG = __hiloint2double((1023 + 8 * (G - GMIN)) << 20, 0);
-      if (G > K2P_F32_MAX) pi_acc = fma(fold_group_units<NA, U0, U1, false>(phi, phif, tmem_row, db), wG, pi_acc);
-      else pi_acc32 = fma(fold_group_units<NA, U0, U1, true>(phi, phif, tmem_row, db), wG, pi_acc32);
+      double vg;
+      if (G > K2P_INTQ_MIN - 1) vg = ifold_group_units<NA, U0, U1, FOLD_INT_Q>(h, q, phif, tmem_row, db);
+      else if (G > K2P_F32_MAX) vg = ifold_group_units<NA, U0, U1, FOLD_INT>(h, q, phif, tmem_row, db);
+      else vg = ifold_group_units<NA, U0, U1, FOLD_F32>(h, q, phif, tmem_row, db);
+      pi_acc = fma(vg, wG, pi_acc);
       K2P_LAP(6);
     }
     // every epilogue thread has seen the last group's "full": all MMAs of the tile are done, the X slices are dead
-    pi_acc = fma(pi_acc32, __hiloint2double((e_raw + 1) << 20, 0), pi_acc);   // 2^em
+    pi_acc *= __hiloint2double((2 * e_raw - 1021) << 20, 0);   // 2^(2 em), em = e_raw - 1022
     if constexpr (PART > 0) c.s_part[PART * TILE + p] = pi_acc;
     asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
     if constexpr (PART == 0) {
@@ -372,10 +473,15 @@ __device__ __forceinline__ void pair_mma_role(const Params& P, const PairCtx& c,
   constexpr int M = NA * (NA + 1) / 2, KP = (M + 31) / 32 * 32;
   constexpr int ACC_COLS = KP, X5_COL = 2 * KP;
   constexpr int NGROUPS = 2 * (NSLICE - 1) - GMIN + 1;
-  const int lane = threadIdx.x & 31;
+  // the issuing lane is chosen by elect.sync, not by lane id: inside a region ptxas knows to be single-lane the MMA's
+  // descriptor operands move to uniform registers with one R2UR each; behind `lane == 0` every tcgen05.mma costs a
+  // broadcast-and-retry loop (ELECT, R2UR.BROADCAST, BRA.U.ANY) -- instructions that compete with the epilogue warps of
+  // the same sub-partition for issue slots (tools/microbench/mma_math_duty.cu: that competition is what slows the MMAs)
+  uint32_t elected;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
 #ifdef K2I_PROF
   long long pf_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc_ = clock64();
-  const int prof_slot = (lane == 0) ? 2 : -1;
+  const int prof_slot = elected ? 2 : -1;
 #endif
   uint32_t n = 0;
   const size_t ntiles = (P.npts + 2 * TILE - 1) / (2 * TILE);
@@ -390,7 +496,7 @@ __device__ __forceinline__ void pair_mma_role(const Params& P, const PairCtx& c,
     for (int gi = 0; gi < NGROUPS; ++gi, ++n) {
       const int G = group_at(gi, GMIN);
       const uint32_t b = n & 1, use = n >> 1;
-      if (lane == 0 && c.crank == 0) {
+      if (elected && c.crank == 0) {
         if (use > 0) ok = wait_parity(c.bar_drain + 8 * b, (use - 1) & 1) && ok;   // both CTAs have read this accumulator's previous group
         K2P_LAP(2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -144,6 +144,7 @@ struct ordm_ctx {
   size_t k2p_smem = 0;
   int* d_i8_fail = nullptr;
   size_t k2i_smem = 0;
+  bool res_by_copy = false;   // ORDM_RES_COPY=1: result scalars by cudaMemcpyAsync instead of stores from the final kernel (lab)
   bool big_overlap = true;    // ORDM_BIG_OVERLAP=0 switches it off: the deep core kernel also beside a DMMA K2 that fills shared memory (26 active orbitals)
   bool k1act_under = false;   // ORDM_K1ACT_UNDER=1: K1's active-space part also runs beside the int8 K2 (lab hook)
   bool k1_split = false;  // two-kernel K1 (k1_core + active) measured slower than the fused kernel; kept as a test hook
@@ -754,7 +755,11 @@ int check_inputs(ordm_ctx* c, bool need_rdm2) {
 }
 
 // the D2H read of the result scalars (and of the int8 kernel's / the peer all-reduce's status words), stream-ordered
-int fetch_enqueue(ordm_ctx* c) {
+int fetch_enqueue(ordm_ctx* c, bool written_by_kernel = false) {
+  if (written_by_kernel) {   // k4_final_all stored scalars and status words into the pinned block itself
+    CU(c, cudaEventRecord(c->ev[5], c->stream));
+    return ORDM_OK;
+  }
   CU(c, cudaMemcpyAsync(c->h_res, c->d_res, ordm::RES_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   int* h_i8_fail = reinterpret_cast<int*>(c->h_res + 12);   // the pinned block has room beyond the RES_COUNT scalars
   if (c->k2_i8 && c->d_i8_fail) CU(c, cudaMemcpyAsync(h_i8_fail, c->d_i8_fail, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1079,6 +1084,7 @@ int ordm_create(int device, ordm_ctx** out) {
   if (const char* e = getenv("ORDM_I8_NO_OVERLAP")) c->i8_no_overlap = (e[0] == '1');
   if (const char* e = getenv("ORDM_K2_INT8")) c->k2_i8_mode = atoi(e);   // 0: DMMA kernels only; 2: 21 slice pairs
   if (const char* e = getenv("ORDM_K1ACT_UNDER")) c->k1act_under = (e[0] == '1');
+  if (const char* e = getenv("ORDM_RES_COPY")) c->res_by_copy = (e[0] == '1');
   if (const char* e = getenv("ORDM_BIG_OVERLAP")) c->big_overlap = (e[0] == '1');
   if (const char* e = getenv("ORDM_K2_PAIR")) c->k2_pair = (e[0] != '0');   // 0: single-CTA int8 kernel (k2_int8.cuh)
   if (const char* e = getenv("ORDM_K2_PLAIN")) c->k2_force_plain = (e[0] == '1');  // test hook: single-buffer K2
@@ -1615,15 +1621,20 @@ static int energy_enqueue(ordm_ctx* c, int functional, double eclass) {
   }
   CU(c, cudaEventRecord(c->ev[3], c->stream));
   // one launch ends the step: final passes over K1's and K3's block sums + (peer-mapped communicator) the all-reduce
+  bool host_direct = false;
   {
     const bool peer = c->comm && c->peer_ok;
     ordm::PeerXchg px = peer ? c->px : ordm::PeerXchg{};
     if (!peer) px.nranks = 1;
+    // (without the NCCL fall-back the kernel also delivers the result: scalars + status words into the pinned block)
+    host_direct = (!c->comm || peer) && !c->res_by_copy;
+    double* host_out = host_direct ? c->h_res : nullptr;
+    const int* status = (c->k2_i8 && c->d_i8_fail) ? c->d_i8_fail : nullptr;
     if (grid1 < 0) {   // K1's final pass already ran on its own stream (overlap without split, or act_under): fold nothing here
       static const double* none = nullptr;
-      ordm::k4_final_all<<<1, 256, 0, c->stream>>>(none, -1, c->d_partial3, grid3, c->d_res, px, peer ? ++c->xepoch : 0ull, c->d_xerr);
+      ordm::k4_final_all<<<1, 256, 0, c->stream>>>(none, -1, c->d_partial3, grid3, c->d_res, px, peer ? ++c->xepoch : 0ull, c->d_xerr, host_out, status);
     } else {
-      ordm::k4_final_all<<<1, 256, 0, c->stream>>>(c->d_partial, grid1, c->d_partial3, grid3, c->d_res, px, peer ? ++c->xepoch : 0ull, c->d_xerr);
+      ordm::k4_final_all<<<1, 256, 0, c->stream>>>(c->d_partial, grid1, c->d_partial3, grid3, c->d_res, px, peer ? ++c->xepoch : 0ull, c->d_xerr, host_out, status);
     }
     CU(c, cudaGetLastError());
     launches += 1;
@@ -1634,7 +1645,7 @@ static int energy_enqueue(ordm_ctx* c, int functional, double eclass) {
     }
   }
   CU(c, cudaEventRecord(c->ev[4], c->stream));
-  if ((rc = fetch_enqueue(c))) return rc;
+  if ((rc = fetch_enqueue(c, host_direct))) return rc;
   c->pend.active = true; c->pend.overlap = overlap; c->pend.split = split; c->pend.ft = ft;
   c->pend.functional = functional; c->pend.launches = launches; c->pend.eclass = eclass;
   return ORDM_OK;

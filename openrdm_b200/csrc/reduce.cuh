@@ -111,8 +111,12 @@ __global__ void __launch_bounds__(128) k_allreduce_peer(double* __restrict__ res
 // above, all in a single 256-thread block.  Same summation order as k4_finalize / k_allreduce_peer, so the results are
 // bitwise those of the three separate launches; what it saves is two launch latencies per step, which is what the
 // step consists of once the grid is spread over eight GPUs.
+// host_out (nullable): the context's pinned result block, written straight from here (the RES_COUNT scalars, then at
+// double offset 12 three status ints: the int8 kernel's two counters `status` points at, and the all-reduce time-out
+// flag) -- which spares the step its three small D2H copies, each a copy-engine round trip on the stream.
 __global__ void __launch_bounds__(256) k4_final_all(const double* __restrict__ part1, int n1, const double* __restrict__ part3, int n3,
-                                                    double* __restrict__ res, const PeerXchg px, unsigned long long epoch, int* __restrict__ err) {
+                                                    double* __restrict__ res, const PeerXchg px, unsigned long long epoch, int* __restrict__ err,
+                                                    double* __restrict__ host_out, const int* __restrict__ status) {
   __shared__ double scratch[5 * 32];
   __shared__ double tot[5];
   if (n1 >= 0) {   // n1 < 0: K1's final pass ran as its own launch on the side stream
@@ -136,7 +140,18 @@ __global__ void __launch_bounds__(256) k4_final_all(const double* __restrict__ p
     __syncthreads();
     if (threadIdx.x < 5) res[RES_TRN + threadIdx.x] = tot[threadIdx.x];
   }
-  if (px.nranks < 2) return;
+  if (px.nranks < 2) {
+    if (host_out) {
+      __syncthreads();
+      if (threadIdx.x < RES_COUNT) host_out[threadIdx.x] = res[threadIdx.x];
+      if (threadIdx.x == 0) {
+        int* hs = reinterpret_cast<int*>(host_out + 12);
+        hs[0] = status ? status[0] : 0; hs[1] = status ? status[1] : 0; hs[2] = 0;
+      }
+      __threadfence_system();
+    }
+    return;
+  }
   __threadfence();
   __syncthreads();
   // ---- k_allreduce_peer, verbatim (see above)
@@ -166,7 +181,16 @@ __global__ void __launch_bounds__(256) k4_final_all(const double* __restrict__ p
     const double* v = px.peer[px.rank] + (size_t)par * n * RES_COUNT + t;
     double s = 0.0;
     for (int r = 0; r < n; ++r) s += v[(size_t)r * RES_COUNT];
-    res[t] = *err ? (0.0 / 0.0) : s;
+    s = *err ? (0.0 / 0.0) : s;
+    res[t] = s;
+    if (host_out) host_out[t] = s;
+  }
+  if (host_out) {
+    if (t == 0) {
+      int* hs = reinterpret_cast<int*>(host_out + 12);
+      hs[0] = status ? status[0] : 0; hs[1] = status ? status[1] : 0; hs[2] = *err;
+    }
+    __threadfence_system();
   }
 }
 
