@@ -278,19 +278,36 @@ __device__ __forceinline__ void ifold_units(const int (&h)[NA], const float (&q)
   if constexpr (U + 1 < U1) ifold_units<NA, U + 1, U1, MODE>(h, q, phif, r, g, tmem_row, nxt, cur, drain_bar);
 }
 
-// one group over this thread's units; the value (units of 2^(2 em), before the group's weight) as a double: the only FP64
-// instructions of the fold
+// What a thread carries from group to group within a tile: not one FP64 instruction is issued between the tile's first
+// and last MMA (three DFMAs per group were a fifth of all stall samples, profiles/r02_ncu_full_k2i_intfold.csv).
+//   A: sum over the integer groups of (PH 2^32 + PL) 2^(8 (G - 7)), a 128-bit integer (< 2^112);
+//   C: the FP32 parts, same weights: remainder terms of groups >= K2P_INTQ_MIN and the groups <= K2P_F32_MAX whole.
+// value of the tile's groups in units of 2^(2 em) 2^(8 * 7):  A 2^-54 + C  (tile_acc_value, after the last MMA).
+struct TileAcc { __int128 A; float C; };
+
+__device__ __forceinline__ double tile_acc_value(const TileAcc& a) {
+  const long long hi = (long long)(a.A >> 64);
+  const unsigned long long lo = (unsigned long long)a.A;
+  const double v = fma(__ll2double_rn(hi), 18446744073709551616.0, __ull2double_rn(lo));   // |A| < 2^112: exact to 2^-53
+  return fma(v, 5.5511151231257827e-17 /* 2^-54 */, (double)a.C);
+}
+
+// one group (G) over this thread's units, added into the tile's accumulators
 template <int NA, int U0, int U1, int MODE>
-__device__ __forceinline__ double ifold_group_units(const int (&h)[NA], const float (&q)[NA], const float (&phif)[NA], uint32_t tmem_row, uint32_t drain_bar) {
+__device__ __forceinline__ void ifold_group_units(const int (&h)[NA], const float (&q)[NA], const float (&phif)[NA], uint32_t tmem_row, uint32_t drain_bar,
+                                                  int G, TileAcc& acc) {
   IRow r{0, 0, 0.f, 0.f, 0.f};
   IGroup g{0, 0, 0.f, 0.f};
   uint32_t va[16], vb[16];
   tmem_ld16(tmem_row + (uint32_t)(16 * U0), va);
   ifold_units<NA, U0, U1, MODE>(h, q, phif, r, g, tmem_row, va, vb, drain_bar);
-  if constexpr (MODE == FOLD_F32) return (double)g.Ca;
-  const double c = (MODE == FOLD_INT_Q) ? (double)fmaf(g.Ca, 134217728.0f, g.Cb) : 0.0;   // 2^27 Ca + Cb
-  // 2^-54 (PH 2^32 + PL) + c
-  return fma(__ll2double_rn(g.PH), 2.384185791015625e-07 /* 2^-22 */, fma(__ll2double_rn(g.PL), 5.5511151231257827e-17 /* 2^-54 */, c));
+  const float w = __int_as_float((127 + 8 * (G - 7)) << 23);   // 2^(8 (G - 7))
+  if constexpr (MODE == FOLD_F32) {
+    acc.C = fmaf(g.Ca, w, acc.C);
+  } else {
+    if constexpr (MODE == FOLD_INT_Q) acc.C = fmaf(fmaf(g.Ca, 134217728.0f, g.Cb), w, acc.C);   // (2^27 Ca + Cb) 2^(8 (G - 7))
+    acc.A += (((__int128)g.PH << 32) + (__int128)g.PL) << (8 * (G - 7));
+  }
 }
 
 // every MMA of group G into the accumulator at tmem_acc: one per (slice pair, K chunk), N = the chunk's column range
@@ -328,12 +345,15 @@ __device__ __forceinline__ void issue_group_pair_of(int G, uint32_t tmem_acc, ui
 // unit range of epilogue part `part` of EW: the KP / 16 units split as evenly as whole units allow, larger parts first
 __host__ __device__ constexpr int part_u0(int nunits, int ew, int part) { return part * (nunits / ew) + (part < nunits % ew ? part : nunits % ew); }
 
-// group order within a tile: light groups first (the epilogue starts early), the heaviest last (its MMAs cover the
-// epilogues before it and only one epilogue is left uncovered at the tile's end)
+// Group order within a tile.  Two accumulators ping-pong: the MMAs of group n + 2 wait for the fold of group n.  Groups
+// differ both ways -- MMAs: 1 .. 6 slice pairs (0.5 k .. 3.1 k clk); fold: integer + remainder terms (10, 9, 8), integer
+// (7), FP32 (<= 6) -- so heavy-MMA / light-fold groups alternate with light-MMA / heavy-fold ones, which keeps the tensor
+// pipe fed (a two-resource schedule simulation picked the order); the tile starts with the single-pair group (the epilogue
+// starts 0.5 k clk in) and ends with an FP32 group (the one fold nothing covers is the cheapest).
 __device__ __forceinline__ int group_at(int i, int gmin) {
-  // GMIN 4: 10 9 8 7 4 6 5 (1 2 3 4 5 5 6 slice pairs);  GMIN 5: 10 9 8 7 6 5
-  if (gmin == 4) return i < 4 ? 10 - i : (i == 4 ? 4 : (i == 5 ? 6 : 5));
-  return 10 - i;
+  // GMIN 4: 10 5 9 6 7 8 4;  GMIN 5: 10 5 9 7 8 6   (4-bit entries, first group in the low nibble)
+  const uint32_t order = gmin == 4 ? 0x487695Au : 0x68795Au;
+  return (int)((order >> (4 * i)) & 15u);
 }
 
 // register cap: 13 warps (EW = 3) are allocated as 16; at 96 registers the CTA leaves 16 K registers to a co-resident
@@ -424,7 +444,7 @@ __device__ __forceinline__ void pair_compute_role(const Params& P, const PairCtx
     cluster_sync_all();   // both CTAs' operands are built
     K2P_LAP(1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    double pi_acc = 0.0;   // in units of 2^(2 em)
+    TileAcc acc{0, 0.f};
 #pragma unroll 1
     for (int gi = 0; gi < NGROUPS; ++gi, ++n) {
       const int G = group_at(gi, GMIN);
@@ -433,16 +453,14 @@ __device__ __forceinline__ void pair_compute_role(const Params& P, const PairCtx
       K2P_LAP(5);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_row = c.tmem + c.lane_addr + (uint32_t)(b * ACC_COLS), db = c.drain_remote + 8 * b;
-      const double wG = __hiloint2double((1023 + 8 * (G - GMIN)) << 20, 0);
-      double vg;
-      if (G > K2P_INTQ_MIN - 1) vg = ifold_group_units<NA, U0, U1, FOLD_INT_Q>(h, q, phif, tmem_row, db);
-      else if (G > K2P_F32_MAX) vg = ifold_group_units<NA, U0, U1, FOLD_INT>(h, q, phif, tmem_row, db);
-      else vg = ifold_group_units<NA, U0, U1, FOLD_F32>(h, q, phif, tmem_row, db);
-      pi_acc = fma(vg, wG, pi_acc);
+      if (G > K2P_INTQ_MIN - 1) ifold_group_units<NA, U0, U1, FOLD_INT_Q>(h, q, phif, tmem_row, db, G, acc);
+      else if (G > K2P_F32_MAX) ifold_group_units<NA, U0, U1, FOLD_INT>(h, q, phif, tmem_row, db, G, acc);
+      else ifold_group_units<NA, U0, U1, FOLD_F32>(h, q, phif, tmem_row, db, G, acc);
       K2P_LAP(6);
     }
     // every epilogue thread has seen the last group's "full": all MMAs of the tile are done, the X slices are dead
-    pi_acc *= __hiloint2double((2 * e_raw - 1021) << 20, 0);   // 2^(2 em), em = e_raw - 1022
+    // (FP64 again: the tensor pipe is idle from here to the next tile's first MMA)
+    double pi_acc = tile_acc_value(acc) * __hiloint2double((2 * e_raw - 1021 + 8 * (7 - GMIN)) << 20, 0);   // 2^(2 em) 2^(8 (7 - GMIN)), em = e_raw - 1022
     if constexpr (PART > 0) c.s_part[PART * TILE + p] = pi_acc;
     asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
     if constexpr (PART == 0) {
@@ -522,6 +540,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(K2P_MAXREG) k2i_ontop_pair
   constexpr int ETHREADS = 4 * EW * 32;
   static_assert(2 * KP + KP / 4 <= 512, "TMEM columns");
   static_assert(NSLICE == 6 && (GMIN == 4 || GMIN == 5), "six slices, groups 10 .. GMIN");
+  static_assert(K2P_F32_MAX >= 6 && K2P_INTQ_MIN > K2P_F32_MAX, "the integer groups are weighted 2^(8 (G - 7)) >= 1 in TileAcc");
   static_assert(EW >= 2 && EW <= 4 && NUNITS >= EW, "epilogue warps per lane quadrant");
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_base_s;

@@ -3,6 +3,7 @@
 #define K2I_PROF 1
 #include "../../openrdm_b200/csrc/k2_int8_pair.cuh"
 #include "../../openrdm_b200/csrc/rdm_pack.h"
+#include "../../openrdm_b200/csrc/k1_density.cuh"
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -47,7 +48,26 @@ int main(int argc, char** argv) {
   const int threads = (4 * EW + 1) * 32;
   int grid = std::max(2, (int)std::min<size_t>((size_t)prop.multiProcessorCount, 2 * ((npts + 255) / 256)) / 2 * 2);
   if (argc > 4) grid = std::max(2, atoi(argv[4]) / 2 * 2);   // fewer CTA pairs: per-tile clocks with most of the chip idle
-  auto launch = [&]() { if (gmin == 4) k2i::k2i_ontop_pair<NA, 4, EW><<<grid, threads, smem>>>(P); else k2i::k2i_ontop_pair<NA, 5, EW><<<grid, threads, smem>>>(P); };
+  // LAB_CORE=<ncore>: the product's core-orbital stream (k1::k1_core_light<true, 8>, one CTA per SM, launched first on a
+  // second stream) beside the kernel, as ordm_energy runs it; LAB_CORE_MODE=1: the same loads without the DFMAs' results
+  // mattering is not possible here, so mode 1 = half as many core orbitals (half the bytes and DFMAs)
+  const int lab_core = getenv("LAB_CORE") ? atoi(getenv("LAB_CORE")) : 0;
+  cudaStream_t s2 = nullptr;
+  k1::Params kp{};
+  cudaEvent_t c0 = nullptr, c1 = nullptr;
+  if (lab_core > 0) {
+    CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    double* core; CK(cudaMalloc(&core, (size_t)4 * lab_core * npts * 8 + 4 * npts * 8));
+    CK(cudaMemset(core, 0, (size_t)4 * lab_core * npts * 8));
+    kp.phi = core; kp.phix = core + (size_t)lab_core * npts; kp.phiy = core + (size_t)2 * lab_core * npts; kp.phiz = core + (size_t)3 * lab_core * npts;
+    kp.ld = npts; kp.npts = npts; kp.ncore = lab_core; kp.nact = 0;
+    kp.core_rc = core + (size_t)4 * lab_core * npts; kp.core_cx = kp.core_rc + npts; kp.core_cy = kp.core_cx + npts; kp.core_cz = kp.core_cy + npts;
+    CK(cudaFuncSetAttribute(k1::k1_core_light<true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaEventCreate(&c0)); CK(cudaEventCreate(&c1));
+  }
+  auto launch = [&]() {
+    if (lab_core > 0) { CK(cudaEventRecord(c0, s2)); k1::k1_core_light<true, 8><<<prop.multiProcessorCount, k1::LIGHT_THREADS, 0, s2>>>(kp); CK(cudaEventRecord(c1, s2)); }
+    if (gmin == 4) k2i::k2i_ontop_pair<NA, 4, EW><<<grid, threads, smem>>>(P); else k2i::k2i_ontop_pair<NA, 5, EW><<<grid, threads, smem>>>(P); };
   launch();
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
@@ -57,6 +77,7 @@ int main(int argc, char** argv) {
     CK(cudaMemset(dfail, 0, 8));
     CK(cudaEventRecord(e0)); launch(); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = std::min(best, ms);
+    if (lab_core > 0) { float mc; CK(cudaEventElapsedTime(&mc, c0, c1)); printf("  rep %d: K2i %.3f ms beside the core stream of %d orbitals (%.3f ms, %.0f GB/s)\n", rep, ms, lab_core, mc, 32.0 * lab_core * npts / mc / 1e6); }
   }
   std::vector<double> pi(npts); int fail[2];
   CK(cudaMemcpy(pi.data(), dpi, npts * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(fail, dfail, 8, cudaMemcpyDeviceToHost));
