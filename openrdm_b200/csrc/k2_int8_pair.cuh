@@ -26,8 +26,7 @@
 
 namespace k2i {
 
-// shared-memory plan (dynamic) of one CTA of the pair: T half image | X slices 0..4 (the partial sums [EW][128] of the
-// tile's end alias the first KB of the X slices, which are dead by then)
+// shared-memory plan (dynamic) of one CTA of the pair: T half image | X slices 0..4
 struct PairSmem {
   __host__ __device__ static size_t t_bytes(int kp) { return (size_t)NSLICE * Geom::slice_bytes(kp) / 2; }
   __host__ __device__ static size_t x_off(int kp) { return t_bytes(kp); }
@@ -350,6 +349,7 @@ __host__ __device__ constexpr int part_u0(int nunits, int ew, int part) { return
 // (7), FP32 (<= 6) -- so heavy-MMA / light-fold groups alternate with light-MMA / heavy-fold ones, which keeps the tensor
 // pipe fed (a two-resource schedule simulation picked the order); the tile starts with the single-pair group (the epilogue
 // starts 0.5 k clk in) and ends with an FP32 group (the one fold nothing covers is the cheapest).
+__host__ __device__ constexpr int group_at_c(int i, int gmin) { return (int)(((gmin == 4 ? 0x487695Au : 0x68795Au) >> (4 * i)) & 15u); }
 __device__ __forceinline__ int group_at(int i, int gmin) {
   // GMIN 4: 10 5 9 6 7 8 4;  GMIN 5: 10 5 9 7 8 6   (4-bit entries, first group in the low nibble)
   const uint32_t order = gmin == 4 ? 0x487695Au : 0x68795Au;
@@ -374,7 +374,7 @@ struct PairCtx {
   uint32_t tmem, lane_addr, crank;
   uint32_t bar_full, bar_drain, drain_remote;   // shared-memory addresses; drain_remote = the leader's copy as seen from this CTA
   uint8_t* x_row;        // this thread's row of the X operand (slice 0) in shared memory
-  double* s_part;        // [EW][TILE] partial sums (alias the X slices, dead at the tile's end)
+  double* s_part;        // [EW - 1][TILE] partial sums of parts 1 .. EW - 1
   uint64_t tdesc0, xdesc0;
   uint32_t idesc0;
   int p;                 // point within the CTA's 128-point tile
@@ -396,17 +396,25 @@ __device__ __forceinline__ void pair_compute_role(const Params& P, const PairCtx
 #endif
   uint32_t n = 0;   // groups consumed so far (each accumulator sees every other one)
   const size_t ntiles = (P.npts + 2 * TILE - 1) / (2 * TILE);   // pair tiles of 256 points
-  for (size_t tile = blockIdx.x / 2; tile < ntiles; tile += gridDim.x / 2) {
+  const size_t tstride = gridDim.x / 2;
+  // The orbital values of a tile are loaded during the LAST group of the tile before it: that group is folded in FP32
+  // (static_assert below), which needs neither h nor q, so their 40 registers are free for the 20 doubles and the load
+  // latency (1.4 k clk of every tile alone, 3 k beside the core-orbital stream) disappears behind that group's MMAs.
+  static_assert(group_at_c(NGROUPS - 1, GMIN) <= K2P_F32_MAX, "the tile's last group must be an FP32 one");
+  double phi[NA];
+  auto load_phi = [&](size_t tile) {
+    const size_t pp = tile * 2 * TILE + (size_t)c.crank * TILE + p;
+#pragma unroll
+    for (int t = 0; t < NA; ++t) phi[t] = (tile < ntiles && pp < P.npts) ? __ldg(P.phi_act + (size_t)t * P.ld + pp) : 0.0;
+  };
+  load_phi(blockIdx.x / 2);
+  for (size_t tile = blockIdx.x / 2; tile < ntiles; tile += tstride) {
     const size_t p0 = tile * 2 * TILE + (size_t)c.crank * TILE;
-    double phi[NA];
     double s2 = 0.0;   // sum_t phi_t^2 for the error guard
     K2P_LAP(7);
     uint32_t mh = 0;   // max over t of the high word of |phi_t|: its exponent field is that of max |phi_t|
 #pragma unroll
-    for (int t = 0; t < NA; ++t) {
-      phi[t] = (p0 + p < P.npts) ? __ldg(P.phi_act + (size_t)t * P.ld + p0 + p) : 0.0;
-      mh = max(mh, (uint32_t)__double2hiint(phi[t]) & 0x7FFFFFFFu);
-    }
+    for (int t = 0; t < NA; ++t) mh = max(mh, (uint32_t)__double2hiint(phi[t]) & 0x7FFFFFFFu);
     // row scale: max |X| = (max_t |phi_t|)^2 < 2^(2 em); the clamps keep the scale factors finite normal numbers
     const int e_raw = min(max((int)(mh >> 20), 534), 1500);
     const double scale = __hiloint2double((3113 - 2 * e_raw + (FIX_BITS - 46)) << 20, 0);  // 2^(FIX_BITS - 2 em)
@@ -433,7 +441,7 @@ __device__ __forceinline__ void pair_compute_role(const Params& P, const PairCtx
       }
     }
     {   // next pair tile's orbitals towards L2 while this one is contracted
-      const size_t pn = p0 + (size_t)(gridDim.x / 2) * 2 * TILE + p;
+      const size_t pn = p0 + tstride * 2 * TILE + p;
       if (pn < P.npts) {
 #pragma unroll
         for (int t = PART; t < NA; t += EW) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.phi_act + (size_t)t * P.ld + pn));
@@ -446,7 +454,7 @@ __device__ __forceinline__ void pair_compute_role(const Params& P, const PairCtx
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     TileAcc acc{0, 0.f};
 #pragma unroll 1
-    for (int gi = 0; gi < NGROUPS; ++gi, ++n) {
+    for (int gi = 0; gi < NGROUPS - 1; ++gi, ++n) {
       const int G = group_at(gi, GMIN);
       const uint32_t b = n & 1, use = n >> 1;   // accumulator, and how often it has been used before
       ok = wait_parity(c.bar_full + 8 * b, use & 1) && ok;
@@ -458,26 +466,40 @@ __device__ __forceinline__ void pair_compute_role(const Params& P, const PairCtx
       else ifold_group_units<NA, U0, U1, FOLD_F32>(h, q, phif, tmem_row, db, G, acc);
       K2P_LAP(6);
     }
+    // the next tile's orbitals (and this tile's core term) are asked for now, the tile's last group is folded meanwhile
+    load_phi(tile + tstride);
+    double pi_core_p = 0.0;
+    if constexpr (PART == 0) pi_core_p = (P.pi_core && p0 + p < P.npts) ? __ldg(P.pi_core + p0 + p) : 0.0;
+    {
+      constexpr int G = group_at_c(NGROUPS - 1, GMIN);
+      const uint32_t b = n & 1, use = n >> 1;
+      ok = wait_parity(c.bar_full + 8 * b, use & 1) && ok;
+      K2P_LAP(5);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      ifold_group_units<NA, U0, U1, FOLD_F32>(h, q, phif, c.tmem + c.lane_addr + (uint32_t)(b * ACC_COLS), c.drain_remote + 8 * b, G, acc);
+      ++n;
+      K2P_LAP(6);
+    }
     // every epilogue thread has seen the last group's "full": all MMAs of the tile are done, the X slices are dead
     // (FP64 again: the tensor pipe is idle from here to the next tile's first MMA)
     double pi_acc = tile_acc_value(acc) * __hiloint2double((2 * e_raw - 1021 + 8 * (7 - GMIN)) << 20, 0);   // 2^(2 em) 2^(8 (7 - GMIN)), em = e_raw - 1022
-    if constexpr (PART > 0) c.s_part[PART * TILE + p] = pi_acc;
+    if constexpr (PART > 0) c.s_part[(PART - 1) * TILE + p] = pi_acc;
     asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
     if constexpr (PART == 0) {
       double s = pi_acc;
 #pragma unroll
-      for (int k = 1; k < EW; ++k) s += c.s_part[k * TILE + p];
+      for (int k = 1; k < EW; ++k) s += c.s_part[(k - 1) * TILE + p];
       // Pi = 2 * 2^(2 em - FIX) * 2^(t_exp - FIX) * 2^(8 GMIN) * (sum over the parts)
       const double f1 = __hiloint2double((2 * e_raw - 1067 - (FIX_BITS - 46)) << 20, 0);        // 2^(2 em - FIX_BITS)
       const double f2 = __hiloint2double((1023 + P.t_exp - FIX_BITS + 8 * GMIN + 1) << 20, 0);  // 2 * 2^(t_exp - FIX_BITS + 8 GMIN)
       const double pi_act = s * f1 * f2;
       if (p0 + p < P.npts) {
-        const double pi_tot = P.pi_core ? pi_act + P.pi_core[p0 + p] : pi_act;
+        const double pi_tot = pi_act + pi_core_p;
         P.pi[p0 + p] = pi_tot;
         if (guard_flag(s2, e_raw, fabs(pi_tot), P.guard_g1, P.guard_g2)) ++nflag;
       }
     }
-    asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");   // the partial sums alias the X slices: read before the next tile's build writes them
+    // (s_part has its own shared memory: its next writer is a whole tile and a cluster barrier away)
     K2P_LAP(4);
   }
 #ifdef K2I_PROF
@@ -541,9 +563,10 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(K2P_MAXREG) k2i_ontop_pair
   static_assert(2 * KP + KP / 4 <= 512, "TMEM columns");
   static_assert(NSLICE == 6 && (GMIN == 4 || GMIN == 5), "six slices, groups 10 .. GMIN");
   static_assert(K2P_F32_MAX >= 6 && K2P_INTQ_MIN > K2P_F32_MAX, "the integer groups are weighted 2^(8 (G - 7)) >= 1 in TileAcc");
-  static_assert(EW >= 2 && EW <= 4 && NUNITS >= EW, "epilogue warps per lane quadrant");
+  static_assert(EW >= 2 && EW <= 3 && NUNITS >= EW, "epilogue warps per lane quadrant (EW = 4: no room for s_part_s)");
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_base_s;
+  __shared__ double s_part_s[(EW - 1) * TILE];   // the other parts' per-point sums on their way to part 0
   __shared__ __align__(8) uint64_t bar_s[4];   // [0..1] accumulator b complete (multicast commit); [2..3] (leader's copy) accumulator b drained by both CTAs
   uint8_t* s_t = smem;
   uint8_t* s_x = smem + PairSmem::x_off(KP);
@@ -578,7 +601,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(K2P_MAXREG) k2i_ontop_pair
   c.idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * TILE) >> 4) << 24);   // M = 256 over the pair
   c.p = 32 * q + lane;
   c.x_row = s_x + (c.p >> 3) * 128 + (c.p & 7) * 16;
-  c.s_part = (double*)s_x;
+  c.s_part = s_part_s;
   c.tdesc0 = smem_desc((uint32_t)__cvta_generic_to_shared(s_t), 0, 128);
   c.xdesc0 = smem_desc((uint32_t)__cvta_generic_to_shared(s_x), (TILE / 8) * 128, 128);
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(c.drain_remote) : "r"(c.bar_drain), "r"(0));
