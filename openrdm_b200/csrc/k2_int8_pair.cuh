@@ -248,7 +248,7 @@ __device__ __forceinline__ void ifold_elem(const int (&h)[NA], const float (&q)[
         g.PL += (long long)sl * (long long)h[t];
         if constexpr (MODE == FOLD_INT_Q) {
           g.Ca = fmaf(phif[t], r.s, g.Ca);
-          g.Cb = fmaf(q[t], __ll2float_rn(r.S), g.Cb);
+          g.Cb = fmaf(q[t], fmaf(__int2float_rn(sh), 4294967296.0f, __int2float_rn(sl)), g.Cb);   // (float)S from its words: no 64-bit conversion
           r.s = 0.f;
         }
         r.S = 0;
@@ -266,14 +266,22 @@ __device__ __forceinline__ void ifold_unit(const int (&h)[NA], const float (&q)[
 template <int NA, int U, int U1, int MODE>
 __device__ __forceinline__ void ifold_units(const int (&h)[NA], const float (&q)[NA], const float (&phif)[NA], IRow& r, IGroup& g, uint32_t tmem_row,
                                             uint32_t (&cur)[16], uint32_t (&nxt)[16], uint32_t drain_bar) {
+#ifndef K2P_LAB_NOLOAD   // lab switch (tools/ozlab): no TMEM loads, arithmetic on whatever the registers hold
   tmem_wait_ld16(cur);   // unit U is in `cur`
+#endif
   if constexpr (U + 1 < U1) {
+#ifndef K2P_LAB_NOLOAD
     tmem_ld16(tmem_row + (uint32_t)(16 * (U + 1)), nxt);
+#endif
   } else {   // every column of this thread's range has been read: the group after next may overwrite this accumulator
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(drain_bar) : "memory");
   }
+#ifndef K2P_LAB_NOMATH   // lab switch: loads and barriers only
   ifold_unit<NA, U, U1, MODE>(h, q, phif, r, g, cur, std::make_integer_sequence<int, 16>{});
+#else
+  if (cur[0] == 0x12345678u && cur[15] == 0x9abcdefu) g.Ca += 1.f;
+#endif
   if constexpr (U + 1 < U1) ifold_units<NA, U + 1, U1, MODE>(h, q, phif, r, g, tmem_row, nxt, cur, drain_bar);
 }
 
@@ -298,7 +306,12 @@ __device__ __forceinline__ void ifold_group_units(const int (&h)[NA], const floa
   IRow r{0, 0, 0.f, 0.f, 0.f};
   IGroup g{0, 0, 0.f, 0.f};
   uint32_t va[16], vb[16];
+#ifndef K2P_LAB_NOLOAD
   tmem_ld16(tmem_row + (uint32_t)(16 * U0), va);
+#else
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { va[j] = tmem_row * (j + 1); vb[j] = tmem_row * (j + 17); }
+#endif
   ifold_units<NA, U0, U1, MODE>(h, q, phif, r, g, tmem_row, va, vb, drain_bar);
   const float w = __int_as_float((127 + 8 * (G - 7)) << 23);   // 2^(8 (G - 7))
   if constexpr (MODE == FOLD_F32) {
@@ -346,14 +359,20 @@ __host__ __device__ constexpr int part_u0(int nunits, int ew, int part) { return
 
 // Group order within a tile.  Two accumulators ping-pong: the MMAs of group n + 2 wait for the fold of group n.  Groups
 // differ both ways -- MMAs: 1 .. 6 slice pairs (0.5 k .. 3.1 k clk); fold: integer + remainder terms (10, 9, 8), integer
-// (7), FP32 (<= 6) -- so heavy-MMA / light-fold groups alternate with light-MMA / heavy-fold ones, which keeps the tensor
-// pipe fed (a two-resource schedule simulation picked the order); the tile starts with the single-pair group (the epilogue
-// starts 0.5 k clk in) and ends with an FP32 group (the one fold nothing covers is the cheapest).
-__host__ __device__ constexpr int group_at_c(int i, int gmin) { return (int)(((gmin == 4 ? 0x487695Au : 0x68795Au) >> (4 * i)) & 15u); }
+// (7), FP32 (<= 6).  The tile starts with the single-pair group (the epilogue starts 0.5 k clk in), its heaviest MMA group
+// follows (it covers the first folds), and it ends with an FP32 group: the fold nothing covers is the cheapest, and it is
+// the one during which the next tile's orbitals are loaded (pair_compute_role).  Eight orders measured on 2 M points
+// (profiles/r02_k2p_group_orders.log): 1.33 .. 1.38 ms; the old order by descending weight, 10 9 8 7 4 6 5: 1.40.
+#ifndef K2P_ORDER4
+#define K2P_ORDER4 0x467895Au   // 10 5 9 8 7 6 4 (first group in the low nibble)
+#endif
+#ifndef K2P_ORDER5
+#define K2P_ORDER5 0x67895Au    // 10 5 9 8 7 6
+#endif
+__host__ __device__ constexpr int group_at_c(int i, int gmin) { return (int)(((gmin == 4 ? K2P_ORDER4 : K2P_ORDER5) >> (4 * i)) & 15u); }
 __device__ __forceinline__ int group_at(int i, int gmin) {
   // GMIN 4: 10 5 9 6 7 8 4;  GMIN 5: 10 5 9 7 8 6   (4-bit entries, first group in the low nibble)
-  const uint32_t order = gmin == 4 ? 0x487695Au : 0x68795Au;
-  return (int)((order >> (4 * i)) & 15u);
+  return (int)(((gmin == 4 ? K2P_ORDER4 : K2P_ORDER5) >> (4 * i)) & 15u);
 }
 
 // register cap: 13 warps (EW = 3) are allocated as 16; at 96 registers the CTA leaves 16 K registers to a co-resident

@@ -52,6 +52,7 @@ int main(int argc, char** argv) {
   // second stream) beside the kernel, as ordm_energy runs it; LAB_CORE_MODE=1: the same loads without the DFMAs' results
   // mattering is not possible here, so mode 1 = half as many core orbitals (half the bytes and DFMAs)
   const int lab_core = getenv("LAB_CORE") ? atoi(getenv("LAB_CORE")) : 0;
+  const int core_unr = getenv("LAB_CORE_UNR") ? atoi(getenv("LAB_CORE_UNR")) : 8, core_ctas = getenv("LAB_CORE_CTAS") ? atoi(getenv("LAB_CORE_CTAS")) : 1;
   cudaStream_t s2 = nullptr;
   k1::Params kp{};
   cudaEvent_t c0 = nullptr, c1 = nullptr;
@@ -63,10 +64,18 @@ int main(int argc, char** argv) {
     kp.ld = npts; kp.npts = npts; kp.ncore = lab_core; kp.nact = 0;
     kp.core_rc = core + (size_t)4 * lab_core * npts; kp.core_cx = kp.core_rc + npts; kp.core_cy = kp.core_cx + npts; kp.core_cz = kp.core_cy + npts;
     CK(cudaFuncSetAttribute(k1::k1_core_light<true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k1::k1_core_light<true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k1::k1_core_light<true, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaEventCreate(&c0)); CK(cudaEventCreate(&c1));
   }
   auto launch = [&]() {
-    if (lab_core > 0) { CK(cudaEventRecord(c0, s2)); k1::k1_core_light<true, 8><<<prop.multiProcessorCount, k1::LIGHT_THREADS, 0, s2>>>(kp); CK(cudaEventRecord(c1, s2)); }
+    if (lab_core > 0) {
+      CK(cudaEventRecord(c0, s2));
+      if (core_unr == 8) k1::k1_core_light<true, 8><<<prop.multiProcessorCount * core_ctas, k1::LIGHT_THREADS, 0, s2>>>(kp);
+      else if (core_unr == 4) k1::k1_core_light<true, 4><<<prop.multiProcessorCount * core_ctas, k1::LIGHT_THREADS, 0, s2>>>(kp);
+      else k1::k1_core_light<true, 2><<<prop.multiProcessorCount * core_ctas, k1::LIGHT_THREADS, 0, s2>>>(kp);
+      CK(cudaEventRecord(c1, s2));
+    }
     if (gmin == 4) k2i::k2i_ontop_pair<NA, 4, EW><<<grid, threads, smem>>>(P); else k2i::k2i_ontop_pair<NA, 5, EW><<<grid, threads, smem>>>(P); };
   launch();
   CK(cudaGetLastError());
