@@ -57,6 +57,7 @@ struct Params {
   const double* Dsb_g;
   // core partial sums produced by k1_core (rc = sum phi_i^2, c{x,y,z} = sum phi_i d phi_i); when
   // core_rc is set the kernels below skip their own core loop and read these instead
+  int core_done;     // with core_rc set: the partials cover core orbitals [0, core_done); the density kernels sum [core_done, ncore) themselves
   double* core_rc;
   double* core_cx;
   double* core_cy;
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(CORE_THREADS) k1_core(const Params P) {
   for (size_t p = (size_t)blockIdx.x * CORE_THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * CORE_THREADS) {
     double rc = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
     int i = 0;
-    for (; i + 4 <= P.ncore; i += 4) {
+    const int nc = P.core_done > 0 ? P.core_done : P.ncore;
+    for (; i + 4 <= nc; i += 4) {
       double v[4], vx[4], vy[4], vz[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(CORE_THREADS) k1_core(const Params P) {
         if (GGA) { cx = fma(v[j], vx[j], cx); cy = fma(v[j], vy[j], cy); cz = fma(v[j], vz[j], cz); }
       }
     }
-    for (; i < P.ncore; ++i) {
+    for (; i < nc; ++i) {
       const size_t o = (size_t)i * ld + p;
       const double v = __ldcs(P.phi + o);
       rc = fma(v, v, rc);
@@ -120,7 +122,8 @@ __global__ void __launch_bounds__(LIGHT_THREADS, UNR <= 2 ? 8 : 4) k1_core_light
   for (size_t p = (size_t)blockIdx.x * LIGHT_THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * LIGHT_THREADS) {
     double rc = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
     int i = 0;
-    for (; i + UNR <= P.ncore; i += UNR) {
+    const int nc = P.core_done > 0 ? P.core_done : P.ncore;
+    for (; i + UNR <= nc; i += UNR) {
       double v[UNR], vx[UNR], vy[UNR], vz[UNR];
 #pragma unroll
       for (int j = 0; j < UNR; ++j) {
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(LIGHT_THREADS, UNR <= 2 ? 8 : 4) k1_core_light
         if (GGA) { cx = fma(v[j], vx[j], cx); cy = fma(v[j], vy[j], cy); cz = fma(v[j], vz[j], cz); }
       }
     }
-    for (; i < P.ncore; ++i) {
+    for (; i < nc; ++i) {
       const size_t o = (size_t)i * ld + p;
       const double v = __ldcs(P.phi + o);
       rc = fma(v, v, rc);
@@ -157,11 +160,14 @@ __device__ __forceinline__ void density_point(const Params& P, const size_t p, d
   const size_t ld = P.ld;
   // ---- core orbitals: closed form (from k1_core's partials when those were produced) ----
   double rc = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+  int i0 = 0;
   if (P.core_rc) {
     rc = P.core_rc[p];
     if (GGA) { cx = P.core_cx[p]; cy = P.core_cy[p]; cz = P.core_cz[p]; }
-  } else {
-    for (int i = 0; i < P.ncore; ++i) {
+    i0 = P.core_done > 0 ? P.core_done : P.ncore;
+  }
+  {
+    for (int i = i0; i < P.ncore; ++i) {
       const size_t o = (size_t)i * ld + p;
       const double v = __ldcs(P.phi + o);
       rc = fma(v, v, rc);
@@ -241,8 +247,10 @@ __device__ __forceinline__ void density_point(const Params& P, const size_t p, d
   acc[2] = fma(rhob, wp, acc[2]);
 }
 
+// (min blocks per SM pinned to what the kernel had before the core loop moved in beside the partials: 128 registers up to
+//  24 active orbitals, 168 above)
 template <int NP, bool GGA>
-__global__ void __launch_bounds__(THREADS) k1_density(const Params P) {
+__global__ void __launch_bounds__(THREADS, NP <= 24 ? 4 : 3) k1_density(const Params P) {
   __shared__ double scratch[3 * 32];
   double acc[3] = {0.0, 0.0, 0.0};
   for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS)
@@ -310,11 +318,14 @@ __global__ void __launch_bounds__(THREADS) k1_density_generic(const Params P) {
   const int na = P.nact;
   for (size_t p = (size_t)blockIdx.x * THREADS + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * THREADS) {
     double rc = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+    int i0 = 0;
     if (P.core_rc) {
       rc = P.core_rc[p];
       if (GGA) { cx = P.core_cx[p]; cy = P.core_cy[p]; cz = P.core_cz[p]; }
-    } else {
-      for (int i = 0; i < P.ncore; ++i) {
+      i0 = P.core_done > 0 ? P.core_done : P.ncore;
+    }
+    {
+      for (int i = i0; i < P.ncore; ++i) {
         const size_t o = (size_t)i * ld + p;
         const double v = __ldcs(P.phi + o);
         rc = fma(v, v, rc);

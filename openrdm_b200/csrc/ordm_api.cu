@@ -144,6 +144,7 @@ struct ordm_ctx {
   size_t k2p_smem = 0;
   int* d_i8_fail = nullptr;
   size_t k2i_smem = 0;
+  int core_keep = -1, core_keep_pct = 25;   // core orbitals left to the density kernel in split mode (ORDM_CORE_KEEP, ORDM_CORE_KEEP_PCT)
   bool res_by_copy = false;   // ORDM_RES_COPY=1: result scalars by cudaMemcpyAsync instead of stores from the final kernel (lab)
   bool big_overlap = true;    // ORDM_BIG_OVERLAP=0 switches it off: the deep core kernel also beside a DMMA K2 that fills shared memory (26 active orbitals)
   bool k1act_under = false;   // ORDM_K1ACT_UNDER=1: K1's active-space part also runs beside the int8 K2 (lab hook)
@@ -303,11 +304,22 @@ int k3_grid(const ordm_ctx* c, size_t npts) {
 }
 
 // The core sums alone (rc, cx, cy, cz -> v.core[]), in the register-light shape that runs underneath K2.
+// How many of the core orbitals the side kernel sums while K2 runs; the rest is left to the density kernel that follows.
+// Beside the int8 K2 the side kernel's DFMAs only get the FP64 pipe between the MMAs (the pipe stalls 13x while
+// tcgen05.mma runs), so it ends after K2 does: handing the last few columns to the density kernel,
+// which has the pipe to itself, shortens the step.  ORDM_CORE_KEEP=<n> overrides the number left behind.
+int core_done_beside_k2(const ordm_ctx* c) {
+  int keep = c->core_keep >= 0 ? c->core_keep : (c->k2_i8 ? (c->ncore * c->core_keep_pct + 50) / 100 : 0);
+  keep = std::min(keep, std::max(c->ncore - 8, 0));
+  return c->ncore - keep;   // (= ncore: the side kernel does them all)
+}
+
 int run_k1_core_light(ordm_ctx* c, const GridView& v, int* launches, cudaStream_t st, bool deep = false) {
   k1::Params p{};
   p.phi = v.phi; p.phix = v.phix; p.phiy = v.phiy; p.phiz = v.phiz;
   p.ld = v.ld; p.npts = v.npts; p.ncore = c->ncore; p.nact = c->nact;
   p.core_rc = v.core[0]; p.core_cx = v.core[1]; p.core_cy = v.core[2]; p.core_cz = v.core[3];
+  p.core_done = core_done_beside_k2(c);
   const size_t want = (v.npts + k1::LIGHT_THREADS - 1) / k1::LIGHT_THREADS;
   const int grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * (deep ? 1 : 16)));
   if (deep) {   // next to the int8 K2: one CTA per SM with 32 loads in flight per thread
@@ -369,6 +381,7 @@ int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaSt
   p.Dsa_g = c->d_Dsa_g; p.Dsb_g = c->d_Dsb_g;
   if (core_ready) {
     p.core_rc = v.core[0]; p.core_cx = v.core[1]; p.core_cy = v.core[2]; p.core_cz = v.core[3];
+    p.core_done = core_done_beside_k2(c);
     } else if (c->k1_split && c->ncore >= 8 && v.core[0]) {  // K1a: stream the core columns at full occupancy first
     p.core_rc = v.core[0]; p.core_cx = v.core[1]; p.core_cy = v.core[2]; p.core_cz = v.core[3];
     const size_t want = (v.npts + k1::CORE_THREADS - 1) / k1::CORE_THREADS;
@@ -1084,6 +1097,8 @@ int ordm_create(int device, ordm_ctx** out) {
   if (const char* e = getenv("ORDM_I8_NO_OVERLAP")) c->i8_no_overlap = (e[0] == '1');
   if (const char* e = getenv("ORDM_K2_INT8")) c->k2_i8_mode = atoi(e);   // 0: DMMA kernels only; 2: 21 slice pairs
   if (const char* e = getenv("ORDM_K1ACT_UNDER")) c->k1act_under = (e[0] == '1');
+  if (const char* e = getenv("ORDM_CORE_KEEP")) c->core_keep = atoi(e);
+  if (const char* e = getenv("ORDM_CORE_KEEP_PCT")) c->core_keep_pct = atoi(e);
   if (const char* e = getenv("ORDM_RES_COPY")) c->res_by_copy = (e[0] == '1');
   if (const char* e = getenv("ORDM_BIG_OVERLAP")) c->big_overlap = (e[0] == '1');
   if (const char* e = getenv("ORDM_K2_PAIR")) c->k2_pair = (e[0] != '0');   // 0: single-CTA int8 kernel (k2_int8.cuh)

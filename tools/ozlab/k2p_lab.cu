@@ -14,6 +14,27 @@
 #endif
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
+// lab: the core-orbital stream's loads without its FP64 arithmetic (the values are xor-ed together): separates what the
+// stream costs the kernel beside it through HBM / L2 / issue slots from what its DFMAs cost
+__global__ void __launch_bounds__(128, 4) core_stream_nofp64(const k1::Params P) {
+  const size_t ld = P.ld;
+  for (size_t p = (size_t)blockIdx.x * 128 + threadIdx.x; p < P.npts; p += (size_t)gridDim.x * 128) {
+    unsigned long long a = 0, b = 0, c = 0, d = 0;
+    int i = 0;
+    for (; i + 8 <= P.ncore; i += 8) {
+      double v[8], vx[8], vy[8], vz[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const size_t o = (size_t)(i + j) * ld + p;
+        v[j] = __ldcs(P.phi + o); vx[j] = __ldcs(P.phix + o); vy[j] = __ldcs(P.phiy + o); vz[j] = __ldcs(P.phiz + o);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a ^= __double_as_longlong(v[j]); b ^= __double_as_longlong(vx[j]); c ^= __double_as_longlong(vy[j]); d ^= __double_as_longlong(vz[j]); }
+    }
+    P.core_rc[p] = __longlong_as_double(a ^ b ^ c ^ d);
+  }
+}
+
 int main(int argc, char** argv) {
   const size_t npts = argc > 1 ? (size_t)atoll(argv[1]) : 2000000;
   const size_t ncheck = std::min(npts, argc > 2 ? (size_t)atoll(argv[2]) : (size_t)2048);
@@ -66,12 +87,14 @@ int main(int argc, char** argv) {
     CK(cudaFuncSetAttribute(k1::k1_core_light<true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k1::k1_core_light<true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k1::k1_core_light<true, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(core_stream_nofp64, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaEventCreate(&c0)); CK(cudaEventCreate(&c1));
   }
   auto launch = [&]() {
     if (lab_core > 0) {
       CK(cudaEventRecord(c0, s2));
-      if (core_unr == 8) k1::k1_core_light<true, 8><<<prop.multiProcessorCount * core_ctas, k1::LIGHT_THREADS, 0, s2>>>(kp);
+      if (core_unr == 0) core_stream_nofp64<<<prop.multiProcessorCount * core_ctas, 128, 0, s2>>>(kp);
+      else if (core_unr == 8) k1::k1_core_light<true, 8><<<prop.multiProcessorCount * core_ctas, k1::LIGHT_THREADS, 0, s2>>>(kp);
       else if (core_unr == 4) k1::k1_core_light<true, 4><<<prop.multiProcessorCount * core_ctas, k1::LIGHT_THREADS, 0, s2>>>(kp);
       else k1::k1_core_light<true, 2><<<prop.multiProcessorCount * core_ctas, k1::LIGHT_THREADS, 0, s2>>>(kp);
       CK(cudaEventRecord(c1, s2));
