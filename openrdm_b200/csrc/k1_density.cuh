@@ -148,6 +148,61 @@ __global__ void __launch_bounds__(LIGHT_THREADS, UNR <= 2 ? 8 : 4) k1_core_light
   }
 }
 
+// The deep shape with 16-byte loads: a thread owns two adjacent points, 4 orbitals x 4 arrays = 16 LDG.128 in flight (the
+// same 256 bytes per thread as UNR = 8 above) for half as many load instructions -- beside the int8 K2, whose epilogue
+// warps are bound by instruction issue, every instruction this kernel does not issue is one they can
+// (profiles/r02_k2p_core_stream_fp64_vs_loads_only.log: a loads-only stream slows K2 as much as the full kernel does).
+// Points are paired (p, p + 1) with p even; ld is a multiple of 256 and the arrays are ld long, so the odd tail is in bounds.
+__device__ __forceinline__ double2 ldcs2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+template <bool GGA>
+__global__ void __launch_bounds__(LIGHT_THREADS, 4) k1_core_pairs(const Params P) {
+  const size_t ld = P.ld;
+  const int nc = P.core_done > 0 ? P.core_done : P.ncore;
+  for (size_t p = 2 * ((size_t)blockIdx.x * LIGHT_THREADS + threadIdx.x); p < P.npts; p += 2 * (size_t)gridDim.x * LIGHT_THREADS) {
+    double2 rc = {0.0, 0.0}, cx = {0.0, 0.0}, cy = {0.0, 0.0}, cz = {0.0, 0.0};
+    int i = 0;
+    for (; i + 4 <= nc; i += 4) {
+      double2 v[4], vx[4], vy[4], vz[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const size_t o = (size_t)(i + j) * ld + p;
+        v[j] = ldcs2(P.phi + o);
+        if (GGA) { vx[j] = ldcs2(P.phix + o); vy[j] = ldcs2(P.phiy + o); vz[j] = ldcs2(P.phiz + o); }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rc.x = fma(v[j].x, v[j].x, rc.x); rc.y = fma(v[j].y, v[j].y, rc.y);
+        if (GGA) {
+          cx.x = fma(v[j].x, vx[j].x, cx.x); cx.y = fma(v[j].y, vx[j].y, cx.y);
+          cy.x = fma(v[j].x, vy[j].x, cy.x); cy.y = fma(v[j].y, vy[j].y, cy.y);
+          cz.x = fma(v[j].x, vz[j].x, cz.x); cz.y = fma(v[j].y, vz[j].y, cz.y);
+        }
+      }
+    }
+    for (; i < nc; ++i) {
+      const size_t o = (size_t)i * ld + p;
+      const double2 v = ldcs2(P.phi + o);
+      rc.x = fma(v.x, v.x, rc.x); rc.y = fma(v.y, v.y, rc.y);
+      if (GGA) {
+        const double2 a = ldcs2(P.phix + o), b = ldcs2(P.phiy + o), c = ldcs2(P.phiz + o);
+        cx.x = fma(v.x, a.x, cx.x); cx.y = fma(v.y, a.y, cx.y);
+        cy.x = fma(v.x, b.x, cy.x); cy.y = fma(v.y, b.y, cy.y);
+        cz.x = fma(v.x, c.x, cz.x); cz.y = fma(v.y, c.y, cz.y);
+      }
+    }
+    *reinterpret_cast<double2*>(P.core_rc + p) = rc;
+    if (GGA) {
+      *reinterpret_cast<double2*>(P.core_cx + p) = cx;
+      *reinterpret_cast<double2*>(P.core_cy + p) = cy;
+      *reinterpret_cast<double2*>(P.core_cz + p) = cz;
+    }
+  }
+}
+
 __device__ __forceinline__ void st(double* p, size_t i, double v) {
   if (p) p[i] = v;
 }

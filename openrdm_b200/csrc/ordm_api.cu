@@ -144,7 +144,8 @@ struct ordm_ctx {
   size_t k2p_smem = 0;
   int* d_i8_fail = nullptr;
   size_t k2i_smem = 0;
-  int core_keep = -1, core_keep_pct = 25;   // core orbitals left to the density kernel in split mode (ORDM_CORE_KEEP, ORDM_CORE_KEEP_PCT)
+  int core_keep = -1, core_keep_pct = 6;   // core orbitals left to the density kernel in split mode (ORDM_CORE_KEEP, ORDM_CORE_KEEP_PCT)
+  bool core_pairs = true;     // ORDM_CORE_PAIRS=0: the deep core kernel with 8-byte loads (k1_core_light<., 8>)
   bool res_by_copy = false;   // ORDM_RES_COPY=1: result scalars by cudaMemcpyAsync instead of stores from the final kernel (lab)
   bool big_overlap = true;    // ORDM_BIG_OVERLAP=0 switches it off: the deep core kernel also beside a DMMA K2 that fills shared memory (26 active orbitals)
   bool k1act_under = false;   // ORDM_K1ACT_UNDER=1: K1's active-space part also runs beside the int8 K2 (lab hook)
@@ -329,9 +330,15 @@ int run_k1_core_light(ordm_ctx* c, const GridView& v, int* launches, cudaStream_
     if (carve_dev != c->device) {
       CU(c, cudaFuncSetAttribute(k1::k1_core_light<true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       CU(c, cudaFuncSetAttribute(k1::k1_core_light<false, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CU(c, cudaFuncSetAttribute(k1::k1_core_pairs<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CU(c, cudaFuncSetAttribute(k1::k1_core_pairs<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       carve_dev = c->device;
     }
-    if (v.gga) k1::k1_core_light<true, 8><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    if (c->core_pairs && v.ld % 2 == 0 && al16(v.phi) && al16(v.phix) && al16(v.phiy) && al16(v.phiz) && al16(v.core[0])) {   // two points per thread, 16-byte loads (the arrays are ld long and 16-byte aligned)
+      if (v.gga) k1::k1_core_pairs<true><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
+      else k1::k1_core_pairs<false><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
+    } else if (v.gga) k1::k1_core_light<true, 8><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
     else k1::k1_core_light<false, 8><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
   } else if (v.gga) k1::k1_core_light<true, 2><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
   else k1::k1_core_light<false, 2><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
@@ -1099,6 +1106,7 @@ int ordm_create(int device, ordm_ctx** out) {
   if (const char* e = getenv("ORDM_K1ACT_UNDER")) c->k1act_under = (e[0] == '1');
   if (const char* e = getenv("ORDM_CORE_KEEP")) c->core_keep = atoi(e);
   if (const char* e = getenv("ORDM_CORE_KEEP_PCT")) c->core_keep_pct = atoi(e);
+  if (const char* e = getenv("ORDM_CORE_PAIRS")) c->core_pairs = (e[0] == '1');
   if (const char* e = getenv("ORDM_RES_COPY")) c->res_by_copy = (e[0] == '1');
   if (const char* e = getenv("ORDM_BIG_OVERLAP")) c->big_overlap = (e[0] == '1');
   if (const char* e = getenv("ORDM_K2_PAIR")) c->k2_pair = (e[0] != '0');   // 0: single-CTA int8 kernel (k2_int8.cuh)
