@@ -256,7 +256,7 @@ def main():
     pik = eng.pi_kernel_info()   # int8 tensor-core K2 (18..20 active orbitals) or the FP64 DMMA kernels
     i8_pairs, i8_mma = pik["int8_slice_pairs"], pik["mma_per_tile"]
     pi_arithmetic = (f"exact int8 tensor-core products (tcgen05.mma kind::i8, CTA pairs) of {i8_pairs} byte-slice pairs of 46-bit fixed-point images; "
-                     "epilogue FP64 for the four high-order groups, FP32 for the three that weigh <= 2^-32; guarded by an a-posteriori error estimate "
+                     "epilogue on the integer and FP32 pipes (exact int64 sums against 27-bit orbital images + FP32 remainder terms for the four high-order groups, FP32 for the three that weigh <= 2^-32; FP64 only outside the MMA phase); guarded by an a-posteriori error estimate "
                      "with FP64 (DMMA) retry" if i8_pairs else "FP64 (DMMA.8x8x4)")
     p0, cnt = ordm.shard_range(cfg["npts"], world, rank)
     eng.synth_fill(cfg["seed"], cfg["npts"], p0, cnt, n, gga)
