@@ -278,8 +278,9 @@ int ordm_hybrid_energy(int method, double lambda, const ordm_hybrid_inputs* in, 
  * R/translate/XC -> quadrature (-> NCCL all-reduce when a communicator is attached). */
 int ordm_energy(ordm_ctx* ctx, int functional, double eclass, ordm_result* out);
 
-/* Stream-ordered form of ordm_energy: ordm_energy_async enqueues the whole step (kernels, all-reduce, D2H read of the
- * result scalars into the context's pinned result block) on the context's stream and returns; ordm_energy_wait blocks
+/* Stream-ordered form of ordm_energy: ordm_energy_async enqueues the whole step (kernels; the last one does the final
+ * passes, the all-reduce and stores the result scalars into the context's pinned result block) on the context's stream
+ * and returns; ordm_energy_wait blocks
  * for the LAST enqueued step and returns its result.  Several steps may be enqueued back to back -- an SCF driver
  * that pipelines, a benchmark loop -- so that the host runs ahead of the GPU and the launch latency of a step
  * disappears from the device timeline (at 8 GPUs a step is < 1 ms).  If the int8 on-top kernel's guard flagged
