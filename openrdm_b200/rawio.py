@@ -104,3 +104,10 @@ def make_data_h5_dict(w, phi_mo=None, grads_mo=None, ncore=0, A1a=None, A1b=None
         d[base + "NNZ"], d[base + "VAL"] = np.int64(len(v)), v
         d[base + "DIM1_IDX"], d[base + "DIM2_IDX"], d[base + "DIM3_IDX"], d[base + "DIM4_IDX"] = i, j, k, l
     return d
+
+
+if __name__ == "__main__":   # python -m openrdm_b200.rawio data.h5 data.ordmraw   (needs h5py)
+    import sys
+    if len(sys.argv) != 3:
+        sys.exit("usage: python -m openrdm_b200.rawio <data.h5> <out.ordmraw>")
+    convert_h5(sys.argv[1], sys.argv[2])
