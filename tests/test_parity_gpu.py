@@ -379,6 +379,7 @@ def test_psi4_plugin_functionals_energy_path(engine, port, ordm, fn, ncore):
 
 @pytest.mark.parametrize("nact,ncore,npts,opts", [
     (26, 2, 160, {}),                         # config 5's active space: two X buffers just fit (224 KB)
+    (26, 30, 131, {}),                        # ... with core orbitals to stream: the paired core kernel beside the DMMA K2, odd tail
     (26, 0, 96, {"pi_gradient": True}),       # grad Pi there: single-buffer WS variant (NBUF = 1)
     (28, 1, 130, {}),                         # beyond the WS kernel: single-buffer k2_ontop<NPG,MT> family
     (32, 0, 70, {}),                          # largest register-tiled K1 (MAX_ACT) / M = 528
@@ -483,7 +484,8 @@ def int8_kernel(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("nact,ncore,npts,mode", [(20, 3, 300, "1"), (20, 0, 131, "2"), (19, 2, 257, "1"), (18, 1, 200, "1"), (18, 25, 129, "2"), (20, 5, 1301, "1")])
+@pytest.mark.parametrize("nact,ncore,npts,mode", [(20, 3, 300, "1"), (20, 0, 131, "2"), (19, 2, 257, "1"), (18, 1, 200, "1"), (18, 25, 129, "2"), (20, 5, 1301, "1"),
+                                                  (20, 31, 1303, "1"), (19, 40, 77, "1")])   # split mode: core stream (16-byte loads, odd tails) beside K2i, part of the core left to the density kernel
 def test_int8_tensor_core_pi_vs_oracle(port, ordm, monkeypatch, int8_kernel, nact, ncore, npts, mode):
     """18..20 active orbitals: Pi comes from the int8 tensor-core kernel (k2_int8.cuh; exact integer slice products
     of 46-bit fixed-point images, 26 (mode 1, default) or 21 (mode 2) slice pairs).  Same bar as the FP64 kernels:
