@@ -2,16 +2,17 @@
 //     Pi_act(p) = sum_{I,J} X_pI D~_IJ X_pJ,   X_pI = phi_t(p) phi_u(p)   (I = packed pair t <= u),
 // i.e. MCPDFT::build_ontop_pair_density (/root/reference/src/libmcpdft/mcpdft.cc:185-212) restricted to the active
 // orbitals.  Same arithmetic as k2_int8.cuh (exact int8 products of the byte slices of 46-bit fixed-point images,
-// D~ = T + T^T with T block-upper-triangular, slice pairs k + l >= GMIN, FP64 dot with the unquantised X; DESIGN.md
-// section 4 "K2i"); what changes is where things live and who does what:
+// D~ = T + T^T with T block-upper-triangular, slice pairs k + l >= GMIN, final dot with the unquantised X -- here with
+// the orbital values to 51 bits; DESIGN.md section 4 "K2i"); what changes is where things live and who does what:
 //   * two SMs of a cluster run tcgen05.mma.cta_group::2 (M = 256: 128 points per CTA); each CTA keeps only HALF of the
 //     rows of every T chunk in shared memory (84 KB), which makes room for X slices 0..4 there (140 KB);
 //   * TMEM then holds TWO full-width accumulators (2 x KP columns) + X slice 5: consecutive slice-pair groups alternate
 //     between them, so the epilogue of one group runs under the MMAs of the next;
 //   * the epilogue is spread over EW warps per TMEM lane quadrant (= per SM sub-partition): each thread owns one point
 //     and a contiguous range of 16-pair units of its accumulator row, read with tcgen05.ld.x16 one unit ahead and folded
-//     as sum_t phi_t (sum_u phi_u acc_tu) with the pair -> (t, u) map resolved at compile time; the three low-order
-//     groups, which weigh <= 2^-32 of the top one, are folded in FP32 (2 instructions per element instead of 4);
+//     as sum_t phi_t (sum_u phi_u acc_tu) with the pair -> (t, u) map resolved at compile time -- on the INTEGER and FP32
+//     pipes (ifold_elem below): while tcgen05.mma runs the SM's FP64 pipe issues 13x slower, so no FP64 instruction is
+//     issued between a tile's first and last MMA;
 //   * the same threads build the X slices of their pair range: one DFMA per pair leaves the balanced image in the
 //     mantissa (the re-centring constant rides in the FMA addend), byte transposes cut it into slices;
 //   * every point carries an a-posteriori error estimate of the 46-bit scheme (guard_flag below): points whose estimate
@@ -112,7 +113,8 @@ __host__ __device__ constexpr bool row_ends_at(int na, int I, int hi, int m) {
   return I + 1 >= hi || I + 1 >= m || pair_t_of(na, I + 1) != pair_t_of(na, I);
 }
 
-// Arithmetic of the fold, per accumulator element v (an exact int32) of pair (t, u):
+// The FP64 form of the fold (round 2's first version; still used by the streamed-T lab kernel, tools/ozlab/
+// k2_int8_stream.cuh; the product kernel below folds with ifold_elem).  Per accumulator element v (an exact int32) of pair (t, u):
 //   groups G >  K2P_F32_MAX:  FP64.  v -> double exactly (2^52 bit trick: xor, hi word, DADD; every K2P_I2F_EVERY-th
 //       element through I2F.F64.S32 instead, which runs on the otherwise idle conversion pipe), then one DFMA into the
 //       row's running sum  sum_u phi_u v.

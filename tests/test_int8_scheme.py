@@ -148,3 +148,62 @@ def test_error_guard_covers_the_measured_error(tmp_path, nact):
                 assert flagged.any(), (name, gmin)
     print("max measured error / 4-sigma estimate:", worst)
     assert worst < 0.8      # the model is conservative: measured <= 2.5 sigma of 4 (tools/ozlab calibration run)
+
+
+# ---- the epilogue on the integer and FP32 pipes (k2_int8_pair.cuh: ifold_elem, ifold_group_units, tile_acc_value) -----
+def test_integer_fold_restatement():
+    """The pair kernel folds an accumulator row as sum_t phi'_t sum_u phi'_u v_tu without the FP64 pipe: phi' = h 2^-27 + r
+    (h an int32, r a float), row sums of v h_u in int64, remainder terms in FP32.  Restated here with Python integers
+    and numpy float32, against exact rational arithmetic.  The remainders are rounded to FP32 at an ABSOLUTE 2^-52 (of the row maximum, not
+    of each orbital), so over a 20-term row the fold's own error is a few 2^-52 of sum |terms|: 2^-48 is asked for in the
+    groups that carry the remainder terms (the 46-bit images' rounding is 2^-47); without them (group 7, weight 2^-24)
+    2^-25, in FP32 throughout (groups <= 6, weight <= 2^-32) 2^-20."""
+    from fractions import Fraction
+    rng = np.random.default_rng(5)
+    f32 = np.float32
+    na = 20
+    pairs = [(t, u) for t in range(na) for u in range(t, na)]
+    worst = {"intq": 0.0, "int": 0.0, "f32": 0.0}
+    for trial in range(40):
+        phi = rng.uniform(-1, 1, na) * np.exp(-6 * rng.random(na))           # |phi'| < 1, a few decades
+        phi[rng.integers(na)] = rng.choice([-1, 1]) * rng.uniform(0.5, 1.0)   # the row maximum sits in [0.5, 1)
+        v = rng.integers(-(1 << 23), 1 << 23, len(pairs))                     # accumulator elements, |v| < 2^24
+        hd = phi + 50331648.0                                                 # 1.5 2^25: ulp 2^-27
+        h = [int(np.float64(x).view(np.int64) & 0xFFFFFFFF) for x in hd]
+        h = [x - (1 << 32) if x >= (1 << 31) else x for x in h]
+        assert all(hh == int(np.rint(p * 2.0 ** 27)) for hh, p in zip(h, phi))
+        rf = (phi - (hd - 50331648.0)).astype(f32)
+        q = (rf * f32(2.0 ** -27)).astype(f32)
+        pf = np.array([f32(f32(hh) * f32(2.0 ** -27) + r) for hh, r in zip(h, rf)], dtype=f32)   # fmaf: one rounding
+        exact = sum(Fraction(float(phi[t])) * Fraction(float(phi[u])) * int(vv) for (t, u), vv in zip(pairs, v))
+        scale = sum(abs(float(phi[t]) * float(phi[u]) * int(vv)) for (t, u), vv in zip(pairs, v))
+        PH = PL = 0
+        Ca = Cb = f32(0)
+        F = f32(0)
+        i = 0
+        for t in range(na):
+            S, s, f = 0, f32(0), f32(0)
+            for u in range(t, na):
+                S += int(v[i]) * h[u]
+                s = f32(np.float64(f32(v[i])) * np.float64(q[u]) + np.float64(s))        # FFMA: exact product, one rounding
+                f = f32(np.float64(pf[u]) * np.float64(f32(v[i])) + np.float64(f))
+                i += 1
+            assert abs(S) < 1 << 56
+            sl = ((S + (1 << 31)) % (1 << 32)) - (1 << 31)                               # signed low word
+            sh = (S - sl) >> 32
+            assert sh * (1 << 32) + sl == S and abs(sh) < 1 << 31
+            PH += sh * h[t]; PL += sl * h[t]
+            Sf = f32(np.float64(f32(sh)) * 4294967296.0 + np.float64(f32(sl)))
+            Ca = f32(np.float64(pf[t]) * np.float64(s) + np.float64(Ca))
+            Cb = f32(np.float64(q[t]) * np.float64(Sf) + np.float64(Cb))
+            F = f32(np.float64(pf[t]) * np.float64(f) + np.float64(F))
+        assert abs(PH) < 1 << 63 and abs(PL) < 1 << 63                                   # fit the kernel's int64
+        A = (PH << 32) + PL
+        val_int = Fraction(A, 1 << 54)
+        val_intq = val_int + Fraction(float(f32(np.float64(Ca) * 134217728.0 + np.float64(Cb))))
+        for key, got in (("intq", val_intq), ("int", val_int), ("f32", Fraction(float(F)))):
+            worst[key] = max(worst[key], abs(float(got - exact)) / scale)
+    print({k: np.log2(x) for k, x in worst.items()})
+    assert worst["intq"] < 2.0 ** -48
+    assert worst["int"] < 2.0 ** -25
+    assert worst["f32"] < 2.0 ** -20
