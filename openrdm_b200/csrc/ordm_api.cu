@@ -22,6 +22,7 @@
 #include "../../include/ordm_synth.h"
 #include "k0_ao2mo.cuh"
 #include "k1_density.cuh"
+#include "k1_tile.cuh"
 #include "k2_ontop.cuh"
 #include "k2_int8.cuh"
 #include "k2_int8_pair.cuh"
@@ -122,6 +123,13 @@ struct ordm_ctx {
   std::vector<double> h_Dsa, h_Dsb;  // symmetrised, row-major stride k1::MAX_ACT (or nact when generic)
   std::vector<double> h_A1a, h_A1b;  // the active 1-RDM blocks as given (nact x nact column-major): polyradical analysis
   double *d_Dsa_g = nullptr, *d_Dsb_g = nullptr;
+  // K1t (k1_tile.cuh): Dsa + Dsb | Dsa - Dsb, stride k1::MAX_ACT, uploaded on the launching stream when the version moves
+  std::vector<double> h_dmat;
+  double* d_dmat = nullptr;
+  uint64_t dmat_version = 0;
+  bool have_diff = false;
+  bool k1_tile = true;        // ORDM_K1_TILE=0: the thread-per-point k1_density for every request (lab / test hook)
+  struct { const double* phi = nullptr; size_t ld = 0, npts = 0; int c0 = -1, ncols = 0; bool gga = false; k1t::Maps maps; } tmap;
   // K2 operands
   int k2_npg = 0, k2_mt = 0;
   k2::Params k2p{};
@@ -295,6 +303,91 @@ int launch_k1_np(ordm_ctx* c, const k1::Params& p, int grid, cudaStream_t st, bo
   return ORDM_OK;
 }
 
+// ---- K1t: the active-space part on TMA-staged tiles (k1_tile.cuh).  Returns K1T_NO when the request is not one it
+// serves (diagnostic vectors, grad Pi's core part, too many staged columns, unaligned views, no tensor-map entry point):
+// the caller then launches k1_density.
+constexpr int K1T_NO = -2000;
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return (TmapEncodeFn)f;
+  }();
+  return fn;
+}
+
+template <int NP, bool GGA>
+int launch_k1_tile(ordm_ctx* c, const k1t::Maps& maps, const k1t::Params& p, int grid, size_t smem, cudaStream_t st) {
+  static thread_local int dev = -1;
+  static thread_local size_t bytes = 0;
+  if (dev != c->device || bytes < smem) {
+    CU(c, cudaFuncSetAttribute(k1t::k1_tile<NP, GGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dev = c->device; bytes = smem;
+  }
+  k1t::k1_tile<NP, GGA><<<grid, k1t::THREADS, smem, st>>>(maps, p);
+  CU(c, cudaGetLastError());
+  return ORDM_OK;
+}
+
+int run_k1_tile(ordm_ctx* c, const GridView& v, const k1::Params& kp, cudaStream_t st, int* grid_out) {
+  if (!c->k1_tile || c->nact < 1 || c->nact > 28 || c->d_dmat == nullptr) return K1T_NO;
+  if (kp.rhoa || kp.rhob || kp.saa || kp.sab || kp.sbb || kp.pcg[0] || !kp.rho || (v.gga && !kp.gx)) return K1T_NO;
+  for (int i = 0; i < 6; ++i) if (kp.grad[i]) return K1T_NO;
+  const int c0 = kp.core_rc ? (kp.core_done > 0 ? kp.core_done : c->ncore) : 0;   // first staged column
+  const int nlead = c->ncore - c0, ncols = nlead + c->nact, np = (int)round_up((size_t)c->nact, 4);
+  if (nlead < 0 || nlead > k1t::MAX_LEAD) return K1T_NO;
+  const size_t fixed = (k1t::EXCH_DOUBLES + k1t::dmat_doubles(np)) * sizeof(double) + 16 * (12 + 8) + 1024 /* static + reserved */;
+  const size_t slot = k1t::slot_doubles(ncols, v.gga) * sizeof(double);
+  if ((size_t)c->max_smem_optin < fixed + slot) return K1T_NO;
+  const int nslots = (int)std::min<size_t>(12, ((size_t)c->max_smem_optin - fixed) / slot);
+  if (nslots < (v.gga ? 5 : 2)) return K1T_NO;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  if (!al16(v.phi) || (v.gga && (!al16(v.phix) || !al16(v.phiy) || !al16(v.phiz))) || !al16(v.w) || v.ld % 2 != 0 ||
+      (kp.core_rc && (!al16(kp.core_rc) || !al16(kp.core_cx) || !al16(kp.core_cy) || !al16(kp.core_cz))) ||
+      v.npts > (size_t)0x7fffff00u)
+    return K1T_NO;
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc) return K1T_NO;
+  auto& tm = c->tmap;
+  if (tm.phi != v.phi || tm.ld != v.ld || tm.npts != v.npts || tm.c0 != c0 || tm.ncols != ncols || tm.gga != v.gga) {
+    const double* base[4] = {v.phi, v.phix, v.phiy, v.phiz};
+    for (int a = 0; a < (v.gga ? 4 : 1); ++a) {
+      cuuint64_t gdim[2] = {(cuuint64_t)v.npts, (cuuint64_t)ncols}, gstr[1] = {(cuuint64_t)v.ld * 8};
+      cuuint32_t box[2] = {(cuuint32_t)k1t::TILE, (cuuint32_t)ncols}, estr[2] = {1, 1};
+      const CUresult r = enc(&tm.maps.m[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base[a]) + (size_t)c0 * v.ld, gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { tm.phi = nullptr; return K1T_NO; }
+    }
+    tm.phi = v.phi; tm.ld = v.ld; tm.npts = v.npts; tm.c0 = c0; tm.ncols = ncols; tm.gga = v.gga;
+  }
+  if (c->dmat_version != c->rdm1_version) {
+    CU(c, cudaMemcpyAsync(c->d_dmat, c->h_dmat.data(), c->h_dmat.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    c->dmat_version = c->rdm1_version;
+  }
+  k1t::Params p{};
+  p.w = v.w; p.core_rc = kp.core_rc; p.core_cx = kp.core_cx; p.core_cy = kp.core_cy; p.core_cz = kp.core_cz;
+  p.npts = v.npts; p.ntiles = (int)((v.npts + k1t::TILE - 1) / k1t::TILE);
+  p.nlead = nlead; p.nact = c->nact; p.have_diff = c->have_diff ? 1 : 0; p.nslots = nslots;
+  p.rho = kp.rho; p.gx = kp.gx; p.gy = kp.gy; p.gz = kp.gz; p.pi_core = kp.pi_core;
+  p.partial = kp.partial; p.dmat = c->d_dmat;
+  p.xc = -1;
+  const int grid = std::max(1, std::min(p.ntiles, c->sm_count));
+  const size_t smem = k1t::smem_bytes(ncols, v.gga, nslots, np);
+  int rc = ORDM_OK;
+  switch (np) {
+#define K1TCASE(N) case N: rc = v.gga ? launch_k1_tile<N, true>(c, tm.maps, p, grid, smem, st) : launch_k1_tile<N, false>(c, tm.maps, p, grid, smem, st); break;
+    K1TCASE(4) K1TCASE(8) K1TCASE(12) K1TCASE(16) K1TCASE(20) K1TCASE(24) K1TCASE(28)
+#undef K1TCASE
+    default: return K1T_NO;
+  }
+  if (rc) return rc;
+  *grid_out = grid;
+  return ORDM_OK;
+}
+
 int k1_grid(const ordm_ctx* c, size_t npts) {
   const size_t want = (npts + k1::THREADS - 1) / k1::THREADS;
   return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 16));
@@ -360,21 +453,6 @@ int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaSt
   // another stream used it last.  The lock is held from the ownership check to the K1 launch, and
   // the last user's K1 is followed by an event that the next uploader's stream waits for: two
   // contexts on one device (two host threads) serialise their K1s on the GPU instead of racing.
-  static std::mutex bank_mu;
-  static struct { uint64_t owner_id; uint64_t version; cudaStream_t stream; cudaEvent_t last_k1; } bank[64] = {};
-  std::unique_lock<std::mutex> bank_lock(bank_mu, std::defer_lock);
-  const bool use_bank = c->nact <= k1::MAX_ACT;
-  if (use_bank) {
-    bank_lock.lock();
-    auto& b = bank[c->device & 63];
-    if (!b.last_k1) CU(c, cudaEventCreateWithFlags(&b.last_k1, cudaEventDisableTiming));
-    if (b.owner_id != c->ctx_id || b.version != c->rdm1_version || b.stream != st) {
-      if (b.owner_id && b.stream != st) CU(c, cudaStreamWaitEvent(st, b.last_k1, 0));  // the last user's K1 may still read the bank
-      CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsa, c->h_Dsa.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, st));
-      CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsb, c->h_Dsb.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, st));
-      b.owner_id = c->ctx_id; b.version = c->rdm1_version; b.stream = st;
-    }
-  }
   k1::Params p{};
   p.phi = v.phi; p.phix = v.phix; p.phiy = v.phiy; p.phiz = v.phiz; p.w = v.w;
   p.ld = v.ld; p.npts = v.npts; p.ncore = c->ncore; p.nact = c->nact;
@@ -398,10 +476,37 @@ int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaSt
     CU(c, cudaGetLastError());
     *launches += 1;
   }
-  const int grid = k1_grid(c, v.npts);
   int rc = ensure_partials(c, (size_t)c->sm_count * 16 * 8);
   if (rc) return rc;
   p.partial = c->d_partial;
+  if (!under_k2) {   // the tiled kernel takes the energy-path requests (it needs the SM's shared memory: not beside K2)
+    int tgrid = 0;
+    rc = run_k1_tile(c, v, p, st, &tgrid);
+    if (rc == ORDM_OK) {
+      if (final_grid) { *final_grid = tgrid; *launches += 1; return ORDM_OK; }
+      ordm::k4_finalize<3><<<1, 256, 0, st>>>(c->d_partial, tgrid, c->d_res, ordm::RES_N, accumulate);
+      CU(c, cudaGetLastError());
+      *launches += 2;
+      return ORDM_OK;
+    }
+    if (rc != K1T_NO) return rc;
+  }
+  static std::mutex bank_mu;
+  static struct { uint64_t owner_id; uint64_t version; cudaStream_t stream; cudaEvent_t last_k1; } bank[64] = {};
+  std::unique_lock<std::mutex> bank_lock(bank_mu, std::defer_lock);
+  const bool use_bank = c->nact <= k1::MAX_ACT;
+  if (use_bank) {
+    bank_lock.lock();
+    auto& b = bank[c->device & 63];
+    if (!b.last_k1) CU(c, cudaEventCreateWithFlags(&b.last_k1, cudaEventDisableTiming));
+    if (b.owner_id != c->ctx_id || b.version != c->rdm1_version || b.stream != st) {
+      if (b.owner_id && b.stream != st) CU(c, cudaStreamWaitEvent(st, b.last_k1, 0));  // the last user's K1 may still read the bank
+      CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsa, c->h_Dsa.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, st));
+      CU(c, cudaMemcpyToSymbolAsync(k1::c_Dsb, c->h_Dsb.data(), sizeof(double) * k1::MAX_ACT * k1::MAX_ACT, 0, cudaMemcpyHostToDevice, st));
+      b.owner_id = c->ctx_id; b.version = c->rdm1_version; b.stream = st;
+    }
+  }
+  const int grid = k1_grid(c, v.npts);
   rc = v.gga ? launch_k1_np<true>(c, p, grid, st, under_k2) : launch_k1_np<false>(c, p, grid, st, under_k2);
   if (rc) return rc;
   if (use_bank) {
@@ -758,6 +863,17 @@ int install_rdm1(ordm_ctx* c, int ncore, int nact, const double* A1a, const doub
     CU(c, cudaMemcpy(c->d_Dsa_g, c->h_Dsa.data(), b, cudaMemcpyHostToDevice));
     CU(c, cudaMemcpy(c->d_Dsb_g, c->h_Dsb.data(), b, cudaMemcpyHostToDevice));
   }
+  if (nact <= k1::MAX_ACT) {   // K1t's coefficient block: Dsa + Dsb | Dsa - Dsb (both symmetric), stride k1::MAX_ACT
+    const size_t m = (size_t)k1::MAX_ACT * k1::MAX_ACT;
+    c->h_dmat.assign(2 * m, 0.0);
+    c->have_diff = false;
+    for (size_t i = 0; i < m; ++i) {
+      c->h_dmat[i] = c->h_Dsa[i] + c->h_Dsb[i];
+      c->h_dmat[m + i] = c->h_Dsa[i] - c->h_Dsb[i];
+      if (c->h_dmat[m + i] != 0.0) c->have_diff = true;
+    }
+    if (!c->d_dmat) CU(c, cudaMalloc(&c->d_dmat, 2 * m * sizeof(double)));
+  }
   c->have_rdm1 = true;
   static std::atomic<uint64_t> next_version{0};
   c->rdm1_version = ++next_version;
@@ -1104,6 +1220,7 @@ int ordm_create(int device, ordm_ctx** out) {
   if (const char* e = getenv("ORDM_I8_NO_OVERLAP")) c->i8_no_overlap = (e[0] == '1');
   if (const char* e = getenv("ORDM_K2_INT8")) c->k2_i8_mode = atoi(e);   // 0: DMMA kernels only; 2: 21 slice pairs
   if (const char* e = getenv("ORDM_K1ACT_UNDER")) c->k1act_under = (e[0] == '1');
+  if (const char* e = getenv("ORDM_K1_TILE")) c->k1_tile = atoi(e) != 0;
   if (const char* e = getenv("ORDM_CORE_KEEP")) c->core_keep = atoi(e);
   if (const char* e = getenv("ORDM_CORE_KEEP_PCT")) c->core_keep_pct = atoi(e);
   if (const char* e = getenv("ORDM_CORE_PAIRS")) c->core_pairs = (e[0] == '1');
@@ -1144,6 +1261,7 @@ void ordm_destroy(ordm_ctx* c) {
   dfree(c->d_dfrag_full); dfree(c->d_tasks_full);
   dfree(c->d_w);
   for (int k = 0; k < 4; ++k) dfree(c->d_phi[k]);
+  dfree(c->d_dmat);
   dfree(c->d_Dsa_g); dfree(c->d_Dsb_g); dfree(c->d_dfrag); dfree(c->d_tasks); dfree(c->d_pairs);
   dfree(c->d_timg); dfree(c->d_timg_pair); dfree(c->d_i8_fail);
   dfree(c->d_partial); dfree(c->d_partial3); dfree(c->d_res);
