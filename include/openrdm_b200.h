@@ -101,7 +101,8 @@ typedef struct {
                              (its a-posteriori estimate exceeded 1e-12 max(1, |Pi|)), and the whole call was
                              repeated with the FP64 tensor-pipe kernels -- which then stay selected until the
                              RDMs or the orbitals change; this result is the FP64 one */
-  uint32_t reserved_;
+  uint32_t density_tiled; /* launches of the TMA-tiled density kernel (k1_tile.cuh) in this call; 0: the thread-per-point
+                             k1_density served it (diagnostic vectors requested, no orbital gradients, > 28 active orbitals ...) */
 } ordm_result;
 
 /* Which kernel computes the active-space on-top pair density for the RDMs currently set (no reference

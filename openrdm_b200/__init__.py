@@ -45,7 +45,7 @@ class Result(C.Structure):
         "e_tot", "ex", "ec", "eclass", "n_tot", "n_a", "n_b", "trn_tot", "trn_a", "trn_b",
         "ms_density", "ms_pi", "ms_xc", "ms_reduce", "ms_total")] + [
         ("npts", C.c_uint64), ("gpu_launches", C.c_uint32), ("overlapped", C.c_uint32),
-        ("pi_guard_points", C.c_uint32), ("reserved_", C.c_uint32)]
+        ("pi_guard_points", C.c_uint32), ("density_tiled", C.c_uint32)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ }

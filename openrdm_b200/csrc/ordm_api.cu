@@ -128,6 +128,7 @@ struct ordm_ctx {
   double* d_dmat = nullptr;
   uint64_t dmat_version = 0;
   bool have_diff = false;
+  uint32_t k1t_in_call = 0;   // k1_tile launches since the last result was delivered (ordm_result.density_tiled)
   bool k1_tile = true;        // ORDM_K1_TILE=0: the thread-per-point k1_density for every request (lab / test hook)
   struct { const double* phi = nullptr; size_t ld = 0, npts = 0; int c0 = -1, ncols = 0; bool gga = false; k1t::Maps maps; } tmap;
   // K2 operands
@@ -319,31 +320,33 @@ TmapEncodeFn tmap_encoder() {
   return fn;
 }
 
-template <int NP, bool GGA>
+template <int NP>
 int launch_k1_tile(ordm_ctx* c, const k1t::Maps& maps, const k1t::Params& p, int grid, size_t smem, cudaStream_t st) {
   static thread_local int dev = -1;
   static thread_local size_t bytes = 0;
   if (dev != c->device || bytes < smem) {
-    CU(c, cudaFuncSetAttribute(k1t::k1_tile<NP, GGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(c, cudaFuncSetAttribute(k1t::k1_tile<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dev = c->device; bytes = smem;
   }
-  k1t::k1_tile<NP, GGA><<<grid, k1t::THREADS, smem, st>>>(maps, p);
+  k1t::k1_tile<NP><<<grid, k1t::THREADS, smem, st>>>(maps, p);
   CU(c, cudaGetLastError());
   return ORDM_OK;
 }
 
 int run_k1_tile(ordm_ctx* c, const GridView& v, const k1::Params& kp, cudaStream_t st, int* grid_out) {
-  if (!c->k1_tile || c->nact < 1 || c->nact > 28 || c->d_dmat == nullptr) return K1T_NO;
+  // (without orbital gradients a tile is one 1 KB-row chunk of ~20 columns and the thread-per-point kernel streams as fast:
+  //  0.249 vs 0.267 ms per 2 M points, profiles/r02_k1_tile_lab.log; the tiled kernel serves the GGA layouts)
+  if (!c->k1_tile || !v.gga || c->nact < 1 || c->nact > 28 || c->d_dmat == nullptr) return K1T_NO;
   if (kp.rhoa || kp.rhob || kp.saa || kp.sab || kp.sbb || kp.pcg[0] || !kp.rho || (v.gga && !kp.gx)) return K1T_NO;
   for (int i = 0; i < 6; ++i) if (kp.grad[i]) return K1T_NO;
   const int c0 = kp.core_rc ? (kp.core_done > 0 ? kp.core_done : c->ncore) : 0;   // first staged column
   const int nlead = c->ncore - c0, ncols = nlead + c->nact, np = (int)round_up((size_t)c->nact, 4);
   if (nlead < 0 || nlead > k1t::MAX_LEAD) return K1T_NO;
-  const size_t fixed = (k1t::EXCH_DOUBLES + k1t::dmat_doubles(np)) * sizeof(double) + 16 * (12 + 8) + 1024 /* static + reserved */;
-  const size_t slot = k1t::slot_doubles(ncols, v.gga) * sizeof(double);
+  const size_t fixed = k1t::dmat_doubles(np) * sizeof(double) + 16 * 12 + 1024 /* static shared memory */ + 1024 /* reserved per CTA */;
+  const size_t slot = k1t::slot_doubles(ncols) * sizeof(double);
   if ((size_t)c->max_smem_optin < fixed + slot) return K1T_NO;
   const int nslots = (int)std::min<size_t>(12, ((size_t)c->max_smem_optin - fixed) / slot);
-  if (nslots < (v.gga ? 5 : 2)) return K1T_NO;
+  if (nslots < 5) return K1T_NO;   // a tile's four chunks are held together + one in flight
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   if (!al16(v.phi) || (v.gga && (!al16(v.phix) || !al16(v.phiy) || !al16(v.phiz))) || !al16(v.w) || v.ld % 2 != 0 ||
       (kp.core_rc && (!al16(kp.core_rc) || !al16(kp.core_cx) || !al16(kp.core_cy) || !al16(kp.core_cz))) ||
@@ -354,7 +357,7 @@ int run_k1_tile(ordm_ctx* c, const GridView& v, const k1::Params& kp, cudaStream
   auto& tm = c->tmap;
   if (tm.phi != v.phi || tm.ld != v.ld || tm.npts != v.npts || tm.c0 != c0 || tm.ncols != ncols || tm.gga != v.gga) {
     const double* base[4] = {v.phi, v.phix, v.phiy, v.phiz};
-    for (int a = 0; a < (v.gga ? 4 : 1); ++a) {
+    for (int a = 0; a < 4; ++a) {
       cuuint64_t gdim[2] = {(cuuint64_t)v.npts, (cuuint64_t)ncols}, gstr[1] = {(cuuint64_t)v.ld * 8};
       cuuint32_t box[2] = {(cuuint32_t)k1t::TILE, (cuuint32_t)ncols}, estr[2] = {1, 1};
       const CUresult r = enc(&tm.maps.m[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base[a]) + (size_t)c0 * v.ld, gdim, gstr, box, estr,
@@ -373,18 +376,18 @@ int run_k1_tile(ordm_ctx* c, const GridView& v, const k1::Params& kp, cudaStream
   p.nlead = nlead; p.nact = c->nact; p.have_diff = c->have_diff ? 1 : 0; p.nslots = nslots;
   p.rho = kp.rho; p.gx = kp.gx; p.gy = kp.gy; p.gz = kp.gz; p.pi_core = kp.pi_core;
   p.partial = kp.partial; p.dmat = c->d_dmat;
-  p.xc = -1;
   const int grid = std::max(1, std::min(p.ntiles, c->sm_count));
-  const size_t smem = k1t::smem_bytes(ncols, v.gga, nslots, np);
+  const size_t smem = k1t::smem_bytes(ncols, nslots, np);
   int rc = ORDM_OK;
   switch (np) {
-#define K1TCASE(N) case N: rc = v.gga ? launch_k1_tile<N, true>(c, tm.maps, p, grid, smem, st) : launch_k1_tile<N, false>(c, tm.maps, p, grid, smem, st); break;
+#define K1TCASE(N) case N: rc = launch_k1_tile<N>(c, tm.maps, p, grid, smem, st); break;
     K1TCASE(4) K1TCASE(8) K1TCASE(12) K1TCASE(16) K1TCASE(20) K1TCASE(24) K1TCASE(28)
 #undef K1TCASE
     default: return K1T_NO;
   }
   if (rc) return rc;
   *grid_out = grid;
+  c->k1t_in_call += 1;
   return ORDM_OK;
 }
 
@@ -933,6 +936,8 @@ int fetch_finish(ordm_ctx* c, double eclass, ordm_result* out, uint64_t npts, in
   out->trn_tot = r[ordm::RES_TRN]; out->trn_a = r[ordm::RES_TRNA]; out->trn_b = r[ordm::RES_TRNB];
   out->npts = npts;
   out->gpu_launches = (uint32_t)launches;
+  out->density_tiled = c->k1t_in_call;
+  c->k1t_in_call = 0;
   for (int i = 0; i < 3; ++i) { c->last_n[i] = r[ordm::RES_N + i]; c->last_trn[i] = r[ordm::RES_TRN + i]; }
   return ORDM_OK;
 }

@@ -1,13 +1,19 @@
 // k1lab -- lab harness for K1's active-space part: k1::k1_density on the core partials (the round-1 kernel) against
 // k1t::k1_tile (TMA-staged tiles, sum / difference roles).  Synthetic data, parity of every output and event times.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -I../../include -I../../openrdm_b200/csrc -o k1lab k1lab.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -I../../include -I../../openrdm_b200/csrc -I. -o k1lab k1lab.cu
+//   (add -DK1LAB_FUSED -o k1lab_fused for the fused-XC lab variant; K1T_FUNC / K1T_GGA / K1T_SLOTS in the environment)
 //   ./k1lab [npts] [nact] [nlead] [reps]
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
 #include <vector>
 #include <algorithm>
+// -DK1LAB_FUSED: the lab variant with K3 fused behind the density (k1_tile_fused.cuh, 13 warps) instead of the product kernel
+#ifdef K1LAB_FUSED
+#include "k1_tile_fused.cuh"
+#else
 #include "k1_tile.cuh"
+#endif
 #include "k3_xc.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
@@ -23,19 +29,31 @@ __global__ void fill(double* p, size_t n, unsigned long long seed, double scale)
   }
 }
 
+static bool g_gga = true;
 template <int NP>
 void launch_tile(const k1t::Maps& maps, const k1t::Params& P, int grid, size_t smem) {
-  CK(cudaFuncSetAttribute(k1t::k1_tile<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k1t::k1_tile<NP, true><<<grid, k1t::THREADS, smem>>>(maps, P);
+#ifdef K1LAB_FUSED
+  if (g_gga) {
+    CK(cudaFuncSetAttribute(k1t::k1_tile<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k1t::k1_tile<NP, true><<<grid, k1t::THREADS, smem>>>(maps, P);
+  } else {
+    CK(cudaFuncSetAttribute(k1t::k1_tile<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k1t::k1_tile<NP, false><<<grid, k1t::THREADS, smem>>>(maps, P);
+  }
+#else
+  CK(cudaFuncSetAttribute(k1t::k1_tile<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k1t::k1_tile<NP><<<grid, k1t::THREADS, smem>>>(maps, P);
+#endif
 }
 template <int NP>
-void launch_old(const k1::Params& p, int grid) { k1::k1_density<NP, true><<<grid, k1::THREADS>>>(p); }
+void launch_old(const k1::Params& p, int grid) { if (g_gga) k1::k1_density<NP, true><<<grid, k1::THREADS>>>(p); else k1::k1_density<NP, false><<<grid, k1::THREADS>>>(p); }
 
 int main(int argc, char** argv) {
   const size_t npts = argc > 1 ? strtoull(argv[1], 0, 10) : 2000000;
   const int nact = argc > 2 ? atoi(argv[2]) : 20;
   const int nlead = argc > 3 ? atoi(argv[3]) : 5;
   const int reps = argc > 4 ? atoi(argv[4]) : 5;
+  g_gga = !(getenv("K1T_GGA") && atoi(getenv("K1T_GGA")) == 0);
   const int c0 = 3, ncore = c0 + nlead, n = ncore + nact, ncols = nlead + nact;
   const size_t ld = (npts + 255) / 256 * 256;
   int dev = 0, sms = 0;
@@ -94,14 +112,23 @@ int main(int argc, char** argv) {
   k1t::Params pn{};
   pn.w = w; pn.core_rc = core[0]; pn.core_cx = core[1]; pn.core_cy = core[2]; pn.core_cz = core[3];
   pn.npts = npts; pn.ntiles = (int)((npts + k1t::TILE - 1) / k1t::TILE); pn.nlead = nlead; pn.nact = nact; pn.have_diff = 1;
-  pn.xc = -1; pn.dmat = dmat; pn.rho = out_new[0]; pn.gx = out_new[1]; pn.gy = out_new[2]; pn.gz = out_new[3]; pn.pi_core = out_new[4]; pn.partial = part_new;
+  pn.dmat = dmat; pn.rho = out_new[0]; pn.gx = out_new[1]; pn.gy = out_new[2]; pn.gz = out_new[3]; pn.pi_core = out_new[4]; pn.partial = part_new;
   const int func = getenv("K1T_FUNC") ? atoi(getenv("K1T_FUNC")) : 1;
   const int np = (nact + 3) / 4 * 4;
-  int nslots = (int)((232448 - 16 * 20 - 1024 - (k1t::EXCH_DOUBLES + k1t::dmat_doubles(np)) * 8) / (k1t::slot_doubles(ncols, true) * 8));
+#ifdef K1LAB_FUSED
+  int nslots = (int)((232448 - 16 * 28 - 3072 - (k1t::EXCH_DOUBLES + k1t::dmat_doubles(np)) * 8) / (k1t::slot_doubles(ncols, g_gga) * 8));
+#else
+  if (!g_gga) { printf("the product kernel serves GGA layouts only (build with -DK1LAB_FUSED for the lab variant)\n"); return 1; }
+  int nslots = (int)((232448 - 16 * 12 - 2048 - k1t::dmat_doubles(np) * 8) / (k1t::slot_doubles(ncols) * 8));
+#endif
   if (getenv("K1T_SLOTS")) nslots = atoi(getenv("K1T_SLOTS"));
   nslots = std::min(nslots, 12);
   pn.nslots = nslots;
-  const size_t smem = k1t::smem_bytes(ncols, true, nslots, np);
+#ifdef K1LAB_FUSED
+  const size_t smem = k1t::smem_bytes(ncols, g_gga, nslots, np);
+#else
+  const size_t smem = k1t::smem_bytes(ncols, nslots, np);
+#endif
   const int grid_new = std::min(pn.ntiles, sms);
   printf("npts %zu nact %d nlead %d: old grid %d, new grid %d, slots %d, smem %zu, functional %d\n", npts, nact, nlead, grid_old, grid_new, nslots, smem, func);
   // Pi_act and the K3 of the separate path
@@ -111,7 +138,7 @@ int main(int argc, char** argv) {
   fill<<<592, 256>>>(pi_in, npts, 4242, 0.5);   // both signs: the pi < 0 branch of the translation is hit
   CK(cudaMalloc(&part3_old, sms * 16 * 5 * 8)); CK(cudaMalloc(&part3_new, sms * 16 * 5 * 8));
   k3::Params p3{};
-  p3.rho = out_old[0]; p3.pi = pi_old; p3.pi_core = out_old[4]; p3.pi_out = pi_old; p3.w = w; p3.gx = out_old[1]; p3.gy = out_old[2]; p3.gz = out_old[3];
+  p3.rho = out_old[0]; p3.pi = pi_old; p3.pi_core = out_old[4]; p3.pi_out = pi_old; p3.w = w; p3.gx = g_gga ? out_old[1] : nullptr; p3.gy = g_gga ? out_old[2] : nullptr; p3.gz = g_gga ? out_old[3] : nullptr;
   p3.npts = npts; p3.omega = 0.3; p3.partial = part3_old;
   const int grid3 = (int)std::min<size_t>((npts + k3::THREADS - 1) / k3::THREADS, (size_t)sms * 8);
   auto run_k3 = [&]() {
@@ -122,14 +149,23 @@ int main(int argc, char** argv) {
       default: k3::k3_translate_xc<5, false><<<grid3, k3::THREADS>>>(p3); break;
     }
   };
-  pn.pi = pi_new; pn.partial3 = part3_new; pn.omega = 0.3;
+#ifdef K1LAB_FUSED
+  pn.xc = -1; pn.pi = pi_new; pn.partial3 = part3_new; pn.omega = 0.3;
+#endif
   auto run_old = [&]() { switch (np) { case 8: launch_old<8>(po, grid_old); break; case 20: launch_old<20>(po, grid_old); break; case 28: launch_old<28>(po, grid_old); break; default: launch_old<24>(po, grid_old); } };
   auto run_new = [&]() { switch (np) { case 8: launch_tile<8>(maps, pn, grid_new, smem); break; case 20: launch_tile<20>(maps, pn, grid_new, smem); break; case 28: launch_tile<28>(maps, pn, grid_new, smem); break; default: launch_tile<24>(maps, pn, grid_new, smem); } };
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   const char* what[4] = {"k1_density        ", "k1_density + k3   ", "k1_tile           ", "k1_tile, fused XC "};
-  for (int which = 0; which < 4; ++which) {
+#ifdef K1LAB_FUSED
+  const int nwhich = 4;
+#else
+  const int nwhich = 3;
+#endif
+  for (int which = 0; which < nwhich; ++which) {
     float best = 1e9f, sum = 0.f;
+#ifdef K1LAB_FUSED
     pn.xc = which == 3 ? func : -1;
+#endif
     for (int r = 0; r < reps + 1; ++r) {
       if (which < 2) CK(cudaMemcpy(pi_old, pi_in, ld * 8, cudaMemcpyDeviceToDevice));
       CK(cudaMemcpy(pi_new, pi_in, ld * 8, cudaMemcpyDeviceToDevice));
