@@ -19,8 +19,8 @@
 //     constant-bank form that was tried first;
 //   * everything that needs the finished T (rho_t and the three gradient dots) is one straight-line block after all four
 //     chunks of the tile have been waited for: eight independent chains whose shared-memory loads can move to the top.
-// Measured (tools/k1lab, 2 M points, 20 active + 5 staged core columns, profiles/r02_k1_tile_lab.log): 0.295 ms = 5.96 TB/s
-// = 91 % of the measured HBM copy bandwidth, against 0.345 ms for k1_density; config 4's 5 M points: 0.74 vs 0.85 ms.
+// Measured (tools/k1lab, 2 M points, 20 active + 5 staged core columns, profiles/r02_k1_tile_lab.log): 0.317 ms = 5.55 TB/s
+// = 85 % of the measured HBM copy bandwidth, against 0.342 ms for k1_density; config 4's 5 M points: 0.78 vs 0.85 ms.
 // Columns staged per array: [c0, n_occ) = the core columns the side kernel left behind (k1::Params::core_done) followed
 // by the active block.  Diagnostic vectors (rho_a, rho_b, spin gradients, sigma) and the core part of grad Pi are not
 // produced here: those requests keep k1_density, as do grids without orbital gradients (one 20-column chunk per tile

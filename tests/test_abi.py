@@ -33,6 +33,7 @@ def test_library_carries_sm100a_tensor_and_tma_code():
     assert "sm_100a" in sass
     assert "DMMA.8x8x4" in sass      # FP64 tensor pipe (K2)
     assert "UBLKCP" in sass          # TMA bulk copy (K2 tile loads)
+    assert "UTMALDG" in sass         # cp.async.bulk.tensor.2d: the tiled density kernel's orbital chunks (csrc/k1_tile.cuh)
     assert "SYNCS" in sass           # mbarrier
     assert "UTCIMMA" in sass         # tcgen05.mma kind::i8 (K2 for 18..20 active orbitals, csrc/k2_int8.cuh)
     assert "LDTM" in sass and "STTM" in sass   # tcgen05.ld / tcgen05.st: TMEM accumulators and A operand
