@@ -203,6 +203,57 @@ __global__ void __launch_bounds__(LIGHT_THREADS, 4) k1_core_pairs(const Params P
   }
 }
 
+// ... and with 32-byte loads (LDG.E.256, new with sm_100): a thread owns four adjacent points, 2 orbitals x 4 arrays = 8 loads
+// in flight (again 256 bytes per thread), a warp instruction covers 1 KB of one column.  Half the load instructions of
+// k1_core_pairs for the same bytes and DFMAs.  Points are grouped (p .. p + 3) with p a multiple of 4; ld is a multiple of 256
+// and the arrays are ld long and 32-byte aligned (checked by the launcher), so the tail group is in bounds.
+struct double4v { double x, y, z, w; };
+__device__ __forceinline__ double4v ldcs4(const double* p) {
+  double4v v;
+  asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stcg4(double* p, const double4v& v) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ void fma4(double4v& a, const double4v& x, const double4v& y) {
+  a.x = fma(x.x, y.x, a.x); a.y = fma(x.y, y.y, a.y); a.z = fma(x.z, y.z, a.z); a.w = fma(x.w, y.w, a.w);
+}
+template <bool GGA>
+__global__ void __launch_bounds__(LIGHT_THREADS, 4) k1_core_quads(const Params P) {
+  const size_t ld = P.ld;
+  const int nc = P.core_done > 0 ? P.core_done : P.ncore;
+  for (size_t p = 4 * ((size_t)blockIdx.x * LIGHT_THREADS + threadIdx.x); p < P.npts; p += 4 * (size_t)gridDim.x * LIGHT_THREADS) {
+    double4v rc = {0.0, 0.0, 0.0, 0.0}, cx = rc, cy = rc, cz = rc;
+    int i = 0;
+    for (; i + 2 <= nc; i += 2) {
+      double4v v[2], vx[2], vy[2], vz[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const size_t o = (size_t)(i + j) * ld + p;
+        v[j] = ldcs4(P.phi + o);
+        if (GGA) { vx[j] = ldcs4(P.phix + o); vy[j] = ldcs4(P.phiy + o); vz[j] = ldcs4(P.phiz + o); }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        fma4(rc, v[j], v[j]);
+        if (GGA) { fma4(cx, v[j], vx[j]); fma4(cy, v[j], vy[j]); fma4(cz, v[j], vz[j]); }
+      }
+    }
+    for (; i < nc; ++i) {
+      const size_t o = (size_t)i * ld + p;
+      const double4v v = ldcs4(P.phi + o);
+      fma4(rc, v, v);
+      if (GGA) {
+        const double4v a = ldcs4(P.phix + o), b = ldcs4(P.phiy + o), c = ldcs4(P.phiz + o);
+        fma4(cx, v, a); fma4(cy, v, b); fma4(cz, v, c);
+      }
+    }
+    stcg4(P.core_rc + p, rc);
+    if (GGA) { stcg4(P.core_cx + p, cx); stcg4(P.core_cy + p, cy); stcg4(P.core_cz + p, cz); }
+  }
+}
+
 __device__ __forceinline__ void st(double* p, size_t i, double v) {
   if (p) p[i] = v;
 }

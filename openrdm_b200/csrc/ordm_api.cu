@@ -154,6 +154,7 @@ struct ordm_ctx {
   int* d_i8_fail = nullptr;
   size_t k2i_smem = 0;
   int core_keep = -1, core_keep_pct = 6;   // core orbitals left to the density kernel in split mode (ORDM_CORE_KEEP, ORDM_CORE_KEEP_PCT)
+  bool core_quads = true;     // ORDM_CORE_QUADS=0: two points per thread (k1_core_pairs) instead of four (k1_core_quads)
   bool core_pairs = true;     // ORDM_CORE_PAIRS=0: the deep core kernel with 8-byte loads (k1_core_light<., 8>)
   bool res_by_copy = false;   // ORDM_RES_COPY=1: result scalars by cudaMemcpyAsync instead of stores from the final kernel (lab)
   bool big_overlap = true;    // ORDM_BIG_OVERLAP=0 switches it off: the deep core kernel also beside a DMMA K2 that fills shared memory (26 active orbitals)
@@ -429,6 +430,21 @@ int run_k1_core_light(ordm_ctx* c, const GridView& v, int* launches, cudaStream_
       CU(c, cudaFuncSetAttribute(k1::k1_core_pairs<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       CU(c, cudaFuncSetAttribute(k1::k1_core_pairs<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       carve_dev = c->device;
+    }
+    auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
+    if (c->core_quads && v.ld % 4 == 0 && al32(v.phi) && al32(v.phix) && al32(v.phiy) && al32(v.phiz) && al32(v.core[0]) && al32(v.core[1]) && al32(v.core[2]) &&
+        al32(v.core[3])) {   // four points per thread, 32-byte loads
+      static thread_local int carve_q = -1;
+      if (carve_q != c->device) {
+        CU(c, cudaFuncSetAttribute(k1::k1_core_quads<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU(c, cudaFuncSetAttribute(k1::k1_core_quads<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        carve_q = c->device;
+      }
+      if (v.gga) k1::k1_core_quads<true><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
+      else k1::k1_core_quads<false><<<grid, k1::LIGHT_THREADS, 0, st>>>(p);
+      CU(c, cudaGetLastError());
+      *launches += 1;
+      return ORDM_OK;
     }
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     if (c->core_pairs && v.ld % 2 == 0 && al16(v.phi) && al16(v.phix) && al16(v.phiy) && al16(v.phiz) && al16(v.core[0])) {   // two points per thread, 16-byte loads (the arrays are ld long and 16-byte aligned)
@@ -1226,6 +1242,7 @@ int ordm_create(int device, ordm_ctx** out) {
   if (const char* e = getenv("ORDM_K2_INT8")) c->k2_i8_mode = atoi(e);   // 0: DMMA kernels only; 2: 21 slice pairs
   if (const char* e = getenv("ORDM_K1ACT_UNDER")) c->k1act_under = (e[0] == '1');
   if (const char* e = getenv("ORDM_K1_TILE")) c->k1_tile = atoi(e) != 0;
+  if (const char* e = getenv("ORDM_CORE_QUADS")) c->core_quads = atoi(e) != 0;
   if (const char* e = getenv("ORDM_CORE_KEEP")) c->core_keep = atoi(e);
   if (const char* e = getenv("ORDM_CORE_KEEP_PCT")) c->core_keep_pct = atoi(e);
   if (const char* e = getenv("ORDM_CORE_PAIRS")) c->core_pairs = (e[0] == '1');
