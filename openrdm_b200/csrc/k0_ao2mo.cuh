@@ -5,9 +5,11 @@
 // all column-major, with m = grid points of a batch (large), K = nao (hundreds), N = occupied MOs (~100): tall and
 // skinny, A read once, B L2-resident.  FP64 has no tcgen05 kind; the tensor path is DMMA (mma.sync.m8n8k4.f64), as in K2.
 //
-// CTA = 128 rows x (8 NT) columns, 8 warps, warp w owns rows [16 w, 16 w + 16) x all 8 NT columns: 2 x NT accumulator
-// fragments (4 NT doubles per thread), so a k-step of 4 costs 2 + NT fragment loads for 2 NT DMMAs.  K is streamed in
-// chunks of 16 through a two-stage cp.async pipeline: A chunk [16][128 + 8] (the + 8 makes the A-fragment loads
+// CTA = 128 rows x (8 NT) columns, 16 warps: warp (r, h) owns rows [16 r, 16 r + 16) x column half h (ceil(NT / 2) n-tiles):
+// 2 x ceil(NT / 2) accumulator fragments per thread.  (Round 2's first version gave a warp all NT n-tiles: 170 registers,
+// one 8-warp CTA per SM and two CTA barriers per chunk -- 21.2 TFLOP/s, 0.76 of cuBLAS; twice the warps at ~100 registers,
+// a three-stage pipeline and one barrier per chunk hide the fragment-load and cp.async latencies.)  K is streamed in
+// chunks of 16 through a three-stage cp.async pipeline: A chunk [16][128 + 8] (the + 8 makes the A-fragment loads
 // conflict-free: 4 k-rows x 8 rows hit 32 distinct 8-byte banks), B chunk [8 NT][16 + 4] (ditto for B fragments).
 // Rows beyond m and K beyond nao are zero-filled in shared memory; columns beyond N are not stored.
 // A may also be given ROW-major (element (p, mu) at A[p * lda + mu], the layout numpy / data.h5 hold the AO values
@@ -18,7 +20,14 @@
 
 namespace k0 {
 
-constexpr int BM = 128, KC = 16, THREADS = 256;
+constexpr int BM = 128, KC = 16;
+// pipeline depth: three stages for wide CTAs (one per SM anyway), two for narrow ones (N <= 32 streams A at ~3 TB/s and
+// wants five CTAs per SM rather than deeper buffers)
+template <int NT> __host__ __device__ constexpr int stages_of() { return NT >= 8 ? 3 : 2; }
+// WC = column groups of warps (8 warps each): 2 for wide CTAs (NT >= 8), 1 for narrow ones (NT = 4: two n-tiles per warp
+// are too little work per barrier: 14.8 vs 16.3 TFLOP/s at N = 20)
+template <int NT> __host__ __device__ constexpr int wc_of() { return NT >= 8 ? 2 : 1; }
+template <int NT> __host__ __device__ constexpr int threads_of() { return 256 * wc_of<NT>(); }
 constexpr int LDA_S = BM + 8, LDB_S = KC + 4;
 
 struct Params {
@@ -35,7 +44,7 @@ struct Params {
 template <int NT>
 struct Smem {
   static constexpr int A_DOUBLES = KC * LDA_S, B_DOUBLES = 8 * NT * LDB_S;
-  static constexpr size_t bytes = (size_t)2 * (A_DOUBLES + B_DOUBLES) * sizeof(double);
+  static constexpr size_t bytes = (size_t)stages_of<NT>() * (A_DOUBLES + B_DOUBLES) * sizeof(double);
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
@@ -50,11 +59,15 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool pre
 }
 
 template <int NT>
-__global__ void __launch_bounds__(THREADS) k0_ao2mo(const Params P) {
+__global__ void __launch_bounds__(threads_of<NT>()) k0_ao2mo(const Params P) {
+  constexpr int THREADS = threads_of<NT>(), WC = wc_of<NT>(), NSTAGE = stages_of<NT>();
   extern __shared__ __align__(16) double smem_d[];
-  double* sA[2] = {smem_d, smem_d + Smem<NT>::A_DOUBLES};
-  double* sB[2] = {smem_d + 2 * Smem<NT>::A_DOUBLES, smem_d + 2 * Smem<NT>::A_DOUBLES + Smem<NT>::B_DOUBLES};
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double *sA[NSTAGE], *sB[NSTAGE];
+#pragma unroll
+  for (int i = 0; i < NSTAGE; ++i) { sA[i] = smem_d + i * Smem<NT>::A_DOUBLES; sB[i] = smem_d + NSTAGE * Smem<NT>::A_DOUBLES + i * Smem<NT>::B_DOUBLES; }
+  const int tid = threadIdx.x, warp = (tid >> 5) & 7, half = tid >> 8, lane = tid & 31;
+  constexpr int NTW = (NT + WC - 1) / WC;   // n-tiles per warp
+  const int b0 = half * NTW;
   const int g = lane >> 2, q = lane & 3;   // fragment coordinates: A row / B column g, k index q; C row g, columns 2q, 2q + 1
   const size_t row0 = (size_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * 8 * NT;
@@ -90,43 +103,46 @@ __global__ void __launch_bounds__(THREADS) k0_ao2mo(const Params P) {
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  double acc[2][NT][2];
+  double acc[2][NTW][2];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int b = 0; b < NTW; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-  load_chunk(0, 0);
+  // (an empty commit keeps the group count in step when there is nothing left to load)
+  for (int s = 0; s < NSTAGE - 1; ++s) {
+    if (s < nchunks) load_chunk(s, s);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (int kc = 0; kc < nchunks; ++kc) {
-    const int buf = kc & 1;
-    if (kc + 1 < nchunks) {
-      load_chunk(kc + 1, buf ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
+    const int buf = kc % NSTAGE;
+    asm volatile("cp.async.wait_group %0;" ::"n"(NSTAGE - 2) : "memory");   // chunk kc has landed (this thread's part)
+    __syncthreads();   // ... everybody's part; and everybody is done with chunk kc - 1, whose buffer is refilled next
+    if (kc + NSTAGE - 1 < nchunks) load_chunk(kc + NSTAGE - 1, (kc + NSTAGE - 1) % NSTAGE);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
     const double* a_s = sA[buf] + 16 * warp + g;
-    const double* b_s = sB[buf] + g * LDB_S;
+    const double* b_s = sB[buf] + (size_t)(b0 * 8 + g) * LDB_S;
 #pragma unroll
     for (int ks = 0; ks < KC; ks += 4) {
       const double a0 = a_s[(ks + q) * LDA_S], a1 = a_s[(ks + q) * LDA_S + 8];
 #pragma unroll
-      for (int b = 0; b < NT; ++b) {
-        const double bf = b_s[b * 8 * LDB_S + ks + q];
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};" : "+d"(acc[0][b][0]), "+d"(acc[0][b][1]) : "d"(a0), "d"(bf));
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};" : "+d"(acc[1][b][0]), "+d"(acc[1][b][1]) : "d"(a1), "d"(bf));
+      for (int b = 0; b < NTW; ++b) {
+        if (b0 + b < NT) {
+          const double bf = b_s[b * 8 * LDB_S + ks + q];
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};" : "+d"(acc[0][b][0]), "+d"(acc[0][b][1]) : "d"(a0), "d"(bf));
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};" : "+d"(acc[1][b][0]), "+d"(acc[1][b][1]) : "d"(a1), "d"(bf));
+        }
       }
     }
-    __syncthreads();   // the buffer is refilled two iterations from now, by the load issued at the top of the next one
   }
 #pragma unroll
   for (int a = 0; a < 2; ++a) {
     const size_t r = row0 + 16 * warp + 8 * a + g;
     if (r >= P.m) continue;
 #pragma unroll
-    for (int b = 0; b < NT; ++b) {
-      const int c = n0 + 8 * b + 2 * q;
+    for (int b = 0; b < NTW; ++b) {
+      if (b0 + b >= NT) continue;
+      const int c = n0 + 8 * (b0 + b) + 2 * q;
       if (c < P.N) P.C[(size_t)c * P.ldc + r] = acc[a][b][0];
       if (c + 1 < P.N) P.C[(size_t)(c + 1) * P.ldc + r] = acc[a][b][1];
     }

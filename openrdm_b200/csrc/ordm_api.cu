@@ -1139,7 +1139,7 @@ int launch_k0(ordm_ctx* c, const k0::Params& p) {
     dev = c->device;
   }
   dim3 grid((unsigned)((p.m + k0::BM - 1) / k0::BM), (unsigned)((p.N + 8 * NT - 1) / (8 * NT)));
-  k0::k0_ao2mo<NT><<<grid, k0::THREADS, k0::Smem<NT>::bytes, c->stream>>>(p);
+  k0::k0_ao2mo<NT><<<grid, k0::threads_of<NT>(), k0::Smem<NT>::bytes, c->stream>>>(p);
   CU(c, cudaGetLastError());
   return ORDM_OK;
 }
@@ -1339,7 +1339,10 @@ int ordm_synchronize(ordm_ctx* c) {
 
 int ordm_host_alloc(size_t bytes, void** out) {
   if (!out) return fail(nullptr, ORDM_ERR_INVALID, "null output pointer");
-  CU(nullptr, cudaMallocHost(out, bytes ? bytes : 1));
+  // ORDM_HOST_WC=1 (lab switch): write-combined pages -- not snooped during the DMA reads of an H2D copy; slow to read
+  // back on the host, so only for buffers the host merely fills
+  static const bool wc = [] { const char* e = getenv("ORDM_HOST_WC"); return e && e[0] == '1'; }();
+  CU(nullptr, cudaHostAlloc(out, bytes ? bytes : 1, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
   return ORDM_OK;
 }
 int ordm_host_free(void* p) {

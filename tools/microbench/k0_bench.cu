@@ -12,7 +12,7 @@
 template <int NT> void launch(const k0::Params& p) {
   CK(cudaFuncSetAttribute(k0::k0_ao2mo<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k0::Smem<NT>::bytes));
   dim3 grid((unsigned)((p.m + k0::BM - 1) / k0::BM), (unsigned)((p.N + 8 * NT - 1) / (8 * NT)));
-  k0::k0_ao2mo<NT><<<grid, k0::THREADS, k0::Smem<NT>::bytes>>>(p);
+  k0::k0_ao2mo<NT><<<grid, k0::threads_of<NT>(), k0::Smem<NT>::bytes>>>(p);
 }
 
 int main(int argc, char** argv) {
