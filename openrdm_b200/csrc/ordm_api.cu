@@ -130,7 +130,7 @@ struct ordm_ctx {
   bool have_diff = false;
   uint32_t k1t_in_call = 0;   // k1_tile launches since the last result was delivered (ordm_result.density_tiled)
   bool k1_tile = true;        // ORDM_K1_TILE=0: the thread-per-point k1_density for every request (lab / test hook)
-  struct { const double* phi = nullptr; size_t ld = 0, npts = 0; int c0 = -1, ncols = 0; bool gga = false; k1t::Maps maps; } tmap;
+  struct { const double* phi[4] = {nullptr, nullptr, nullptr, nullptr}; size_t ld = 0, npts = 0; int c0 = -1, ncols = 0; k1t::Maps maps; } tmap;   // K1t's tensor maps are re-encoded when the view changes
   // K2 operands
   int k2_npg = 0, k2_mt = 0;
   k2::Params k2p{};
@@ -356,16 +356,18 @@ int run_k1_tile(ordm_ctx* c, const GridView& v, const k1::Params& kp, cudaStream
   TmapEncodeFn enc = tmap_encoder();
   if (!enc) return K1T_NO;
   auto& tm = c->tmap;
-  if (tm.phi != v.phi || tm.ld != v.ld || tm.npts != v.npts || tm.c0 != c0 || tm.ncols != ncols || tm.gga != v.gga) {
-    const double* base[4] = {v.phi, v.phix, v.phiy, v.phiz};
+  const double* base[4] = {v.phi, v.phix, v.phiy, v.phiz};
+  if (tm.phi[0] != base[0] || tm.phi[1] != base[1] || tm.phi[2] != base[2] || tm.phi[3] != base[3] || tm.ld != v.ld || tm.npts != v.npts ||
+      tm.c0 != c0 || tm.ncols != ncols) {
     for (int a = 0; a < 4; ++a) {
       cuuint64_t gdim[2] = {(cuuint64_t)v.npts, (cuuint64_t)ncols}, gstr[1] = {(cuuint64_t)v.ld * 8};
       cuuint32_t box[2] = {(cuuint32_t)k1t::TILE, (cuuint32_t)ncols}, estr[2] = {1, 1};
       const CUresult r = enc(&tm.maps.m[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base[a]) + (size_t)c0 * v.ld, gdim, gstr, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) { tm.phi = nullptr; return K1T_NO; }
+      if (r != CUDA_SUCCESS) { tm.phi[0] = nullptr; return K1T_NO; }
     }
-    tm.phi = v.phi; tm.ld = v.ld; tm.npts = v.npts; tm.c0 = c0; tm.ncols = ncols; tm.gga = v.gga;
+    for (int a = 0; a < 4; ++a) tm.phi[a] = base[a];
+    tm.ld = v.ld; tm.npts = v.npts; tm.c0 = c0; tm.ncols = ncols;
   }
   if (c->dmat_version != c->rdm1_version) {
     CU(c, cudaMemcpyAsync(c->d_dmat, c->h_dmat.data(), c->h_dmat.size() * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -498,7 +500,7 @@ int run_k1(ordm_ctx* c, const GridView& v, int accumulate, int* launches, cudaSt
   int rc = ensure_partials(c, (size_t)c->sm_count * 16 * 8);
   if (rc) return rc;
   p.partial = c->d_partial;
-  if (!under_k2) {   // the tiled kernel takes the energy-path requests (it needs the SM's shared memory: not beside K2)
+  if (!under_k2 && st != c->side_stream) {   // the tiled kernel takes the energy-path requests; it needs the SM's shared memory, so not beside K2 (side stream)
     int tgrid = 0;
     rc = run_k1_tile(c, v, p, st, &tgrid);
     if (rc == ORDM_OK) {

@@ -60,7 +60,12 @@ def test_tiled_density_matches_oracle_and_plain_kernel(ordm, port, monkeypatch, 
     A1a, A1b, D2 = ordm.synth_rdms(seed, nact, max(1, nact // 2), max(1, (nact + 1) // 3), 3)   # alpha != beta: both roles work
     want = port.energy_coreactive(w, phi, ncore, A1a, A1b, D2, "PBE", grads, eclass=0.0)
     tiled, plain = both_kernels(ordm, monkeypatch, w, phi, grads, ncore, A1a, A1b, D2)
-    assert tiled[0]["density_tiled"] >= 1, "the tiled kernel declined an energy-path request it should serve"
+    # (overlapped == 1: few core orbitals beside a warp-specialised K2 -- the whole density kernel streams underneath K2 on
+    #  the side stream, where the tiled kernel's 220 KB of shared memory would not fit beside K2's: k1_density keeps that mode)
+    if tiled[0]["overlapped"] != 1:
+        assert tiled[0]["density_tiled"] >= 1, "the tiled kernel declined an energy-path request it should serve"
+    else:
+        assert tiled[0]["density_tiled"] == 0
     check_pair(tiled, plain, want)
 
 
