@@ -69,7 +69,7 @@ def test_tiled_density_matches_oracle_and_plain_kernel(ordm, port, monkeypatch, 
     check_pair(tiled, plain, want)
 
 
-@pytest.mark.parametrize("keep", [0, 1, 5, 8])
+@pytest.mark.parametrize("keep", [0, 1, 5, 8, 11])
 def test_staged_core_columns_in_split_mode(ordm, port, monkeypatch, keep):
     """ncore >= nact: the core sums run on the side stream beside K2 and leave `keep` columns (ORDM_CORE_KEEP) to the
     density kernel, which stages them in front of the active block."""
