@@ -91,17 +91,18 @@ class ClockSampler:
         rows = [r[1:] for r in self.rows if t_begin is None or (t_begin - 0.05 <= r[0] <= t_end + 0.05)]
         if len(rows) < 3:  # timed region shorter than the sampling period: use every sample under load
             rows = [r[1:] for r in self.rows]
-        sm, mx, reasons = [], 0.0, set()
+        sm, mx, reasons, pw = [], 0.0, set(), []
         for r in rows:
             try:
-                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                sm.append(float(r[1])); mx = max(mx, float(r[2])); pw.append(float(r[3]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        sm.sort(); pw.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": pw[len(pw) // 2] if pw else None}
 
 
 def measured_peaks():

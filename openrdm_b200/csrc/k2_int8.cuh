@@ -60,11 +60,17 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint3
 __device__ __forceinline__ void commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+#ifndef K2I_WAIT_NAP_NS
+#define K2I_WAIT_NAP_NS 0
+#endif
 __device__ __forceinline__ bool wait_parity(uint32_t bar, uint32_t parity) {
   for (long spin = 0; spin < (1l << 24); ++spin) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) return true;
+#if K2I_WAIT_NAP_NS > 0
+    __nanosleep(K2I_WAIT_NAP_NS);   // (lab switch: the step runs under the board's power cap; does a quieter wait buy clocks?)
+#endif
   }
   return false;
 }
