@@ -136,6 +136,7 @@ struct ordm_ctx {
   k2::Params k2p{};
   double* d_dfrag = nullptr;
   void* d_tasks = nullptr;
+  size_t cap_dfrag = 0, cap_tasks = 0, cap_pairs = 0, cap_timg = 0, cap_timg_pair = 0;   // bytes allocated (ensure_dev)
   bool k2_ws = false, k2_force_plain = false;
   // K2 on the int8 tensor cores (k2_int8.cuh): 18..20 active orbitals, Pi only (grad Pi keeps the DMMA kernel)
   int k2_i8_mode = 1;          // ORDM_K2_INT8: 0 off, 1 on with 26 slice pairs (default), 2 on with 21 slice pairs
@@ -236,6 +237,18 @@ template <typename T>
 void dfree(T*& p) {
   if (p) cudaFree(p);
   p = nullptr;
+}
+
+// Device buffer that is re-used across RDM updates (an SCF loop calls ordm_set_active_space every iteration: a
+// cudaFree / cudaMalloc pair per operand costs more than packing and uploading it)
+template <typename T>
+cudaError_t ensure_dev(T*& p, size_t& cap, size_t bytes) {
+  if (p && bytes <= cap) return cudaSuccess;
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+  const cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+  if (e == cudaSuccess) cap = bytes;
+  return e;
 }
 
 // grad Pi is built when asked for, or when the fully-translated GGA gradients need it
@@ -785,13 +798,13 @@ int configure_k2(ordm_ctx* c) {
   static_assert(sizeof(ordm::SegDesc) == sizeof(k2::SegDesc) && sizeof(ordm::SegDesc) == 8, "segment descriptor layout");
   std::vector<uint16_t> tab;
   ordm::pair_table(c->nact, tab);
-  dfree(c->d_dfrag);
-  dfree(c->d_tasks);
-  dfree(c->d_pairs);
-  CU(c, cudaMalloc(&c->d_pairs, tab.size() * sizeof(uint16_t)));
+  // the operands are overwritten in place: nothing enqueued earlier may still be reading them
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (c->side_stream) CU(c, cudaStreamSynchronize(c->side_stream));
+  CU(c, ensure_dev(c->d_pairs, c->cap_pairs, tab.size() * sizeof(uint16_t)));
   CU(c, cudaMemcpy(c->d_pairs, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-  CU(c, cudaMalloc(&c->d_dfrag, lay.data.size() * sizeof(double)));
-  CU(c, cudaMalloc(&c->d_tasks, lay.segs.size() * sizeof(ordm::SegDesc)));
+  CU(c, ensure_dev(c->d_dfrag, c->cap_dfrag, lay.data.size() * sizeof(double)));
+  CU(c, ensure_dev(c->d_tasks, c->cap_tasks, lay.segs.size() * sizeof(ordm::SegDesc)));
   CU(c, cudaMemcpy(c->d_dfrag, lay.data.data(), lay.data.size() * sizeof(double), cudaMemcpyHostToDevice));
   CU(c, cudaMemcpy(c->d_tasks, lay.segs.data(), lay.segs.size() * sizeof(ordm::SegDesc), cudaMemcpyHostToDevice));
   c->k2p = k2::Params{};
@@ -809,32 +822,30 @@ int configure_k2(ordm_ctx* c) {
   c->k2_i8 = c->k2_i8_cfg;
   if (c->k2_i8) {
     static_assert(k2i::NSLICE == 6 && k2i::FIX_BITS == 46, "ordm::pack_t_int8 is written for six byte slices of a 46-bit image");
-    std::vector<uint8_t> img;
     int t_exp = 0;
-    ordm::pack_t_int8(M, c->h_Dt, kp, img, t_exp);
-    if (img.size() != k2i::Smem::t_bytes(kp) || ordm::t_int8_slice_bytes(kp) != k2i::Geom::slice_bytes(kp))
-      return fail(c, ORDM_ERR_UNSUPPORTED, "int8 on-top path: host image and kernel geometry disagree");
-    dfree(c->d_timg);
-    CU(c, cudaMalloc(&c->d_timg, img.size()));
-    CU(c, cudaMemcpy(c->d_timg, img.data(), img.size(), cudaMemcpyHostToDevice));
+    c->k2_pair = c->k2_pair && k2i::PairSmem::bytes(kp) + 1024 <= (size_t)c->max_smem_optin;
     if (!c->d_i8_fail) { CU(c, cudaMalloc(&c->d_i8_fail, 2 * sizeof(int))); CU(c, cudaMemset(c->d_i8_fail, 0, 2 * sizeof(int))); }
     c->k2ip = k2i::Params{};
+    if (c->k2_pair) {   // the image cut in two: each CTA of a pair keeps half of the rows of every chunk (the single-CTA image is not built)
+      std::vector<uint8_t> pimg;
+      ordm::pack_t_int8_pair(M, c->h_Dt, kp, pimg, t_exp);
+      if (pimg.size() != 2 * k2i::PairSmem::t_bytes(kp))
+        return fail(c, ORDM_ERR_UNSUPPORTED, "int8 on-top path: pair image and kernel geometry disagree");
+      CU(c, ensure_dev(c->d_timg_pair, c->cap_timg_pair, pimg.size()));
+      CU(c, cudaMemcpy(c->d_timg_pair, pimg.data(), pimg.size(), cudaMemcpyHostToDevice));
+      c->k2p_smem = k2i::PairSmem::bytes(kp);
+    } else {
+      std::vector<uint8_t> img;
+      ordm::pack_t_int8(M, c->h_Dt, kp, img, t_exp);
+      if (img.size() != k2i::Smem::t_bytes(kp) || ordm::t_int8_slice_bytes(kp) != k2i::Geom::slice_bytes(kp))
+        return fail(c, ORDM_ERR_UNSUPPORTED, "int8 on-top path: host image and kernel geometry disagree");
+      CU(c, ensure_dev(c->d_timg, c->cap_timg, img.size()));
+      CU(c, cudaMemcpy(c->d_timg, img.data(), img.size(), cudaMemcpyHostToDevice));
+    }
     c->k2ip.timg = c->d_timg; c->k2ip.t_exp = t_exp; c->k2ip.fail = c->d_i8_fail;
     ordm::int8_guard_constants(M, c->h_Dt, t_exp, c->k2_i8_mode == 1 ? 4 : 5, c->k2ip.guard_g1, c->k2ip.guard_g2);
-    c->k2_pair = c->k2_pair && k2i::PairSmem::bytes(kp) + 1024 <= (size_t)c->max_smem_optin;
-    if (c->k2_pair) {   // the same image cut in two: each CTA of a pair keeps half of the rows of every chunk
-      std::vector<uint8_t> pimg;
-      int te2 = 0;
-      ordm::pack_t_int8_pair(M, c->h_Dt, kp, pimg, te2);
-      if (pimg.size() != 2 * k2i::PairSmem::t_bytes(kp) || te2 != t_exp)
-        return fail(c, ORDM_ERR_UNSUPPORTED, "int8 on-top path: pair image and kernel geometry disagree");
-      dfree(c->d_timg_pair);
-      CU(c, cudaMalloc(&c->d_timg_pair, pimg.size()));
-      CU(c, cudaMemcpy(c->d_timg_pair, pimg.data(), pimg.size(), cudaMemcpyHostToDevice));
-      c->k2pp = c->k2ip;
-      c->k2pp.timg = c->d_timg_pair;
-      c->k2p_smem = k2i::PairSmem::bytes(kp);
-    }
+    c->k2pp = c->k2ip;
+    c->k2pp.timg = c->d_timg_pair;
     c->k2i_smem = k2i::Smem::bytes(kp, c->nact);
   }
   return ORDM_OK;

@@ -40,12 +40,15 @@ inline void fold_tpdm(int n, const double* D2, std::vector<double>& Dt) {
   const int M = pair_count(n);
   const size_t n2 = (size_t)n * n;
   Dt.assign((size_t)M * M, 0.0);
+  std::vector<int> pidx(n2);   // (nu, mu) -> packed pair, looked up instead of recomputed for each of the n^4 elements
+  for (int nu = 0; nu < n; ++nu)
+    for (int mu = 0; mu < n; ++mu) pidx[(size_t)nu * n + mu] = pair_index(n, nu, mu);
   for (int si = 0; si < n; ++si)
     for (int la = 0; la < n; ++la) {
-      const int J = pair_index(n, si, la);
+      const int J = pidx[(size_t)si * n + la];
       const double* col = D2 + ((size_t)si * n + la) * n2;
-      for (int nu = 0; nu < n; ++nu)
-        for (int mu = 0; mu < n; ++mu) Dt[(size_t)pair_index(n, nu, mu) * M + J] += col[(size_t)nu * n + mu];
+      double* dst = Dt.data() + J;
+      for (size_t e = 0; e < n2; ++e) dst[(size_t)pidx[e] * M] += col[e];
     }
   for (int I = 0; I < M; ++I)
     for (int J = I + 1; J < M; ++J) {
@@ -294,22 +297,41 @@ inline void pack_t_int8(int M, const std::vector<double>& Dt, int kp, std::vecto
 // N from each CTA), each half chunk a K-major no-swizzle operand of rows/2 rows.  Slice stride and chunk offsets
 // are half of pack_t_int8's.
 inline void pack_t_int8_pair(int M, const std::vector<double>& Dt, int kp, std::vector<uint8_t>& img, int& t_exp) {
-  std::vector<uint8_t> whole;
-  pack_t_int8(M, Dt, kp, whole, t_exp);
-  const int nslice = 6;
-  const size_t slice = (size_t)t_int8_slice_bytes(kp), half = slice / 2;
+  // one pass, straight into the pair layout (an SCF loop re-packs T every iteration: this is the largest host cost of
+  // ordm_set_active_space); byte for byte what splitting pack_t_int8's image would give
+  const int fix_bits = 46, nslice = 6;
+  auto T = [&](int I, int J) -> double {
+    if (I >= M || J >= M) return 0.0;
+    const int bi = I / 32, bj = J / 32;
+    return bi < bj ? Dt[(size_t)I * M + J] : (bi == bj ? 0.5 * Dt[(size_t)I * M + J] : 0.0);
+  };
+  double tmax = 0.0;
+  for (int I = 0; I < M; ++I) {
+    const int bi = I / 32;
+    for (int J = bi * 32; J < M; ++J) tmax = std::max(tmax, std::fabs(T(I, J)));   // (T vanishes below the block diagonal)
+  }
+  t_exp = 0;
+  if (tmax > 0.0) (void)std::frexp(tmax, &t_exp);   // tmax < 2^t_exp
+  const double scale = std::ldexp(1.0, fix_bits - t_exp);   // exact power of two: v * scale == ldexp(v, fix_bits - t_exp)
+  const size_t half = (size_t)t_int8_slice_bytes(kp) / 2;
   img.assign((size_t)2 * nslice * half, 0);
-  for (int l = 0; l < nslice; ++l)
-    for (int kc = 0; kc < kp / 32; ++kc) {
-      const int rows = kp - 32 * kc, hr = rows / 2;
-      for (int n = 0; n < rows; ++n)
-        for (int k = 0; k < 32; ++k) {
-          const size_t from = (size_t)l * slice + (size_t)t_int8_chunk_off(kp, kc) + (size_t)((k >> 4) * (rows >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (k & 15);
-          const int c = n / hr, nl = n % hr;
-          const size_t to = ((size_t)c * nslice + l) * half + (size_t)t_int8_chunk_off(kp, kc) / 2 + (size_t)((k >> 4) * (hr >> 3) + (nl >> 3)) * 128 + (nl & 7) * 16 + (k & 15);
-          img[to] = whole[from];
-        }
+  for (int kc = 0; kc < kp / 32; ++kc) {
+    const int rows = kp - 32 * kc, hr = rows / 2;
+    const size_t coff = (size_t)t_int8_chunk_off(kp, kc) / 2;
+    for (int k = 0; k < 32; ++k) {   // (row I = 32 kc + k of Dt is read contiguously)
+      const int I = 32 * kc + k;
+      const size_t koff = (size_t)(k >> 4) * (hr >> 3) * 128 + (k & 15);
+      for (int n = 0; n < rows; ++n) {
+        const int c = n >= hr ? 1 : 0, nl = n - c * hr;
+        // round to nearest even as llrint does, without the libm call: |x| <= 2^46, so x + 1.5 2^52 has ulp 1
+        const double r = (T(I, 32 * kc + n) * scale + 6755399441055744.0) - 6755399441055744.0;
+        const unsigned long long v = (unsigned long long)((long long)r + 0x0000008080808080ll);
+        uint8_t* at = img.data() + (size_t)c * nslice * half + coff + (size_t)(nl >> 3) * 128 + (nl & 7) * 16 + koff;
+        for (int l = 0; l < nslice - 1; ++l) at[(size_t)l * half] = (uint8_t)(v >> (8 * l)) ^ 0x80;
+        at[(size_t)(nslice - 1) * half] = (uint8_t)(v >> 40);
+      }
     }
+  }
 }
 
 // Constants of the int8 path's a-posteriori error estimate (k2_int8_pair.cuh: guard_flag):
