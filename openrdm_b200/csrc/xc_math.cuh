@@ -361,20 +361,28 @@ __device__ __forceinline__ void pbe_pair_pt(double ra, double rb, double saa, do
     ex = ra * (c * ka) * FXa + rb * (c * kb) * FXb;
   }
   // ---- correlation (functional.cc:296-302; PW92 :243-261, H :210-233,263-271)
+  // Seven of the reference's divisions share two reciprocals here (K3 is bound by its instruction count: ~12 instructions
+  // per FP64 division): 1 / (k0 fi^3 rho^2) serves rs = C / k0, t^2 = sigma / (4 ks^2 fi^2 rho^2) and ec / (fi^3 gamma);
+  // 1 / (p_A p_P p_F) serves the three 0.5 / poly of PW92's G; the constant divisors become multiplications.
   const double sig = fmax(0.0, saa) + fmax(0.0, sbb) + 2.0 * sab;
-  const double rs = C_RS_KF / k0;
-  const double sr = sqrt(rs);
-  const double mAc = pw92_G(rs, sr, 0.0168869, 0.11125, 10.357, 3.6231, 0.88026, 0.49671);
-  const double eP = pw92_G(rs, sr, 0.0310907, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294);
-  const double eF = pw92_G(rs, sr, 0.01554535, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517);
-  const double fz = spin_f(zeta, cu, cd);
-  const double z2 = zeta * zeta, z4 = z2 * z2;
-  const double ec = eP + ((-mAc) * fz * (1.0 - z4)) / D2FZ + (eF - eP) * fz * z4;
   const double fi = 0.5 * (cu * cu + cd * cd);
-  const double fi3 = fi * fi * fi;
-  const double ks2 = 4.0 * k0 / PI;
-  const double t2 = sig / (4.0 * ks2 * (fi * fi) * (rho * rho));
-  const double A = (PBE_BETA / PBE_GAMMA) / (exp(-ec / (fi3 * PBE_GAMMA)) - 1.0);
+  const double fi2 = fi * fi, fi3 = fi2 * fi, rho2 = rho * rho;
+  const double rD = 1.0 / (k0 * fi3 * rho2);
+  const double rs = C_RS_KF * (rD * (fi3 * rho2));     // C / k0
+  const double sr = sqrt(rs);
+  const double rsr = rs * sr, rs2 = rs * rs;
+  const double pA = 0.0168869 * (10.357 * sr + 3.6231 * rs + 0.88026 * rsr + 0.49671 * rs2);
+  const double pP = 0.0310907 * (7.5957 * sr + 3.5876 * rs + 1.6382 * rsr + 0.49294 * rs2);
+  const double pF = 0.01554535 * (14.1189 * sr + 6.1977 * rs + 3.3662 * rsr + 0.62517 * rs2);
+  const double rp = 0.5 / (pA * pP * pF);
+  const double mAc = -2.0 * 0.0168869 * (1.0 + 0.11125 * rs) * log(1.0 + rp * (pP * pF));
+  const double eP = -2.0 * 0.0310907 * (1.0 + 0.21370 * rs) * log(1.0 + rp * (pA * pF));
+  const double eF = -2.0 * 0.01554535 * (1.0 + 0.20548 * rs) * log(1.0 + rp * (pA * pP));
+  const double fz = ((1.0 + zeta) * cu + (1.0 - zeta) * cd - 2.0) * (1.0 / FZ_DEN);
+  const double z2 = zeta * zeta, z4 = z2 * z2;
+  const double ec = eP + ((-mAc) * fz * (1.0 - z4)) * (1.0 / D2FZ) + (eF - eP) * fz * z4;
+  const double t2 = sig * ((PI / 16.0) * (rD * fi));    // sigma / (4 ks^2 fi^2 rho^2), ks^2 = 4 k0 / pi
+  const double A = (PBE_BETA / PBE_GAMMA) / (exp(-ec * (rD * (k0 * rho2)) * (1.0 / PBE_GAMMA)) - 1.0);
   const double At2 = A * t2;
   const double H = fi3 * PBE_GAMMA * log(1.0 + (PBE_BETA / PBE_GAMMA) * t2 * (1.0 + At2) / (1.0 + At2 + At2 * At2));
   ec_out = rho * (H + ec);
