@@ -140,3 +140,29 @@ def test_streamed_batches_through_the_tiled_kernel(ordm, port, monkeypatch):
             check_scalars(st, want.scalars)
     finally:
         eng.close()
+
+
+def test_rdm_updates_on_one_engine_reuse_the_device_operands(ordm, port):
+    """An SCF loop calls ordm_set_active_space every iteration: the device operands (DMMA fragments, int8 image, pair table,
+    K1t's coefficient block and tensor maps) are re-used or re-sized in place.  Growing, shrinking and repeating the active
+    space on ONE engine must give what a fresh engine gives."""
+    seed, npts, ncore = 31, 900, 3
+    cases = [20, 6, 20, 13, 6]      # int8 path -> small wide-tile K2 -> int8 again (same sizes: buffers re-used) -> WS K2 -> small
+    nmax = ncore + max(cases)
+    w, phi, grads = ordm.synth_fill_host(seed, npts, 0, npts, nmax, True)
+    eng = ordm.Engine(0)
+    try:
+        eng.set_grid(w)
+        for i, nact in enumerate(cases):
+            n = ncore + nact
+            ph = np.asfortranarray(phi[:, :n]); gr = [np.asfortranarray(g[:, :n]) for g in grads]
+            A1a, A1b, D2 = ordm.synth_rdms(seed + i, nact, max(1, nact // 2), max(1, nact // 3), 3)
+            eng.set_orbitals(ph, gr); eng.set_active_space(ncore, A1a, A1b, D2)
+            got = eng.energy(FN["PBE"], 0.0)
+            fresh, _ = run(ordm, w, ph, gr, ncore, A1a, A1b, D2)
+            check_scalars(got, fresh, tol=1e-13)
+            if nact <= 13:
+                want = port.energy_coreactive(w, ph, ncore, A1a, A1b, D2, "PBE", gr, eclass=0.0, want_vecs=False)
+                check_scalars(got, want.scalars)
+    finally:
+        eng.close()
